@@ -1,0 +1,81 @@
+#!/usr/bin/env python3
+"""tests/golden/make_golden.py — regenerate the committed golden fixtures.
+
+Run in the build container, where /root/reference is mounted and oracle/_ref has been built
+(``python oracle/build.py``).  The GPU box has neither, so everything the tests need at run time is
+committed here as small files:
+
+  lz4_input.txt / lz4_compressed.bin   the reference's OWN golden vector, copied verbatim from
+                                       Output-Input/input/input.txt and Output-Input/out/compressed.bin
+  Metamorphosis.txt                    the text corpus the reference's workload generator samples
+                                       (Output-Input/input/Metamorphosis.txt; public-domain text, data not code)
+  og_crop.png + og_crop_{lum,cb,cr}.png  a 256x100 crop (x=768, y=200) of Assets/Images/og.png and the
+                                       same crop of the reference's committed colour-plane renderings
+                                       Output-Input/Images/{luminance,bChrominance,rChrominance}.png
+  lz4_ref_vectors.json                 sha256/size/offsets of streams produced by the REFERENCE build
+                                       (oracle/_ref/libref_lz4.so, bounded variant) on seeded inputs
+  jpeg_ref_vectors.npz                 coefficients / bit streams produced by the REFERENCE build
+                                       (oracle/_ref/libref_jpeg.so) on og_crop, seeded noise, the
+                                       SURVEY.md Appendix C block and a few degenerate blocks
+"""
+from __future__ import annotations
+
+import hashlib
+import json
+import os
+import shutil
+import sys
+
+import numpy as np
+from PIL import Image
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from oracle.pyoracle import Oracle, Ref  # noqa: E402
+import cases  # noqa: E402  (tests/cases.py: the seeded inputs shared with the tests)
+
+REF = "/root/reference"
+
+
+def main() -> None:
+    shutil.copy(f"{REF}/Output-Input/input/input.txt", f"{HERE}/lz4_input.txt")
+    shutil.copy(f"{REF}/Output-Input/out/compressed.bin", f"{HERE}/lz4_compressed.bin")
+    shutil.copy(f"{REF}/Output-Input/input/Metamorphosis.txt", f"{HERE}/Metamorphosis.txt")
+
+    x0, y0, cw, ch = 768, 200, 256, 100
+    for src, dst in (("Assets/Images/og.png", "og_crop.png"),
+                     ("Output-Input/Images/luminance.png", "og_crop_lum.png"),
+                     ("Output-Input/Images/bChrominance.png", "og_crop_cb.png"),
+                     ("Output-Input/Images/rChrominance.png", "og_crop_cr.png")):
+        im = Image.open(f"{REF}/{src}").convert("RGBA").crop((x0, y0, x0 + cw, y0 + ch))
+        im.save(f"{HERE}/{dst}", optimize=True)
+
+    # ---- LZ4: reference (bounded) streams on the shared seeded cases -------------------------
+    ref = Ref("lz4")
+    vec = {}
+    for name, data, block_len in cases.lz4_cases():
+        stream, offs, _ = ref.lz4_compress(data, block_len)
+        vec[name] = {"n": int(data.size), "block_len": block_len, "size": int(stream.size),
+                     "sha256": hashlib.sha256(stream.tobytes()).hexdigest(),
+                     "offsets_sha256": hashlib.sha256(offs.tobytes()).hexdigest()}
+    with open(f"{HERE}/lz4_ref_vectors.json", "w") as f:
+        json.dump(vec, f, indent=1, sort_keys=True)
+
+    # ---- JPEG: reference coefficients + streams ------------------------------------------------
+    rj = Ref("jpeg")
+    out = {}
+    for name, rgba in cases.jpeg_cases():
+        r = rj.jpeg_encode(rgba)
+        assert r["max_code_len"] <= 31, (name, r["max_code_len"])
+        out[f"{name}__coefs"] = r["coefs"]
+        out[f"{name}__stream"] = r["stream"]
+        out[f"{name}__bits"] = r["bits"]
+        out[f"{name}__offsets"] = r["offsets"]
+    np.savez_compressed(f"{HERE}/jpeg_ref_vectors.npz", **out)
+    print("golden fixtures written:", sorted(os.listdir(HERE)))
+
+
+if __name__ == "__main__":
+    main()
