@@ -1,0 +1,142 @@
+/*
+ * include/lz4jpeg_b200.h — C ABI of the B200-native LZ4 / JPEG block codecs.
+ *
+ * Drop-in boundary for the two per-block hot paths of CyrilMorel42/LZ4-JPEG.  The reference has no
+ * library boundary of its own: each codec is one C file with a main(), and the timing harnesses
+ * (Experiment/*_experiment.c) popen() an executable.  The functions below are the buffer-level
+ * operations those programs are made of; each cites the reference interface it replaces.  Host code
+ * stays plain C: include this header, link liblz4jpeg_b200.so (INTEGRATION.md shows the exact edits).
+ *
+ * Conventions
+ *   - every function returns LJB_OK (0) or a negative LJB_E_* code and never calls exit() (the reference
+ *     perror()+exit(1)s: Algorithms/sequential/LZ4/LZ4.c:113-118, :632-637);
+ *   - pointers named d_* are CUDA device pointers, all others are host pointers;
+ *   - the library is CUDA-only: there is no CPU fallback; without a usable device every entry point
+ *     returns LJB_E_CUDA.
+ */
+#ifndef LZ4JPEG_B200_H
+#define LZ4JPEG_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LJB_OK 0
+#define LJB_E_ARG (-1)         /* invalid argument (NULL, zero size, block_len > 65536, odd image width ...) */
+#define LJB_E_CUDA (-2)        /* CUDA runtime error or no device; ljb_last_cuda_error() has the text */
+#define LJB_E_CAPACITY (-3)    /* output buffer too small; *out_len holds the required size where known */
+#define LJB_E_FORMAT (-4)      /* decoder: stream is inconsistent / ambiguous (SURVEY.md A.3-b phantom sequences) */
+#define LJB_E_UNSUPPORTED (-5) /* input outside the reference's defined behaviour (e.g. code longer than 31 bits) */
+
+#define LJB_LZ4_MAX_BLOCK 65536u /* uint16 offsets / WINDOW_SIZE 65535 (LZ4.c:22) bound a block to 64 KiB */
+#define LJB_LZ4_REF_BLOCK 300u   /* DEFAULT_BLOCK_LENGTH (LZ4.c:23) */
+
+typedef struct ljb_ctx ljb_ctx; /* one per (process, GPU): device id, stream, persistent scratch */
+
+/* Context: replaces the implicit process-global state of the reference programs. */
+int ljb_ctx_create(int device, ljb_ctx **out);
+void ljb_ctx_destroy(ljb_ctx *ctx);
+/* The CUDA stream (cudaStream_t) all work of this context is enqueued on. */
+void *ljb_ctx_stream(ljb_ctx *ctx);
+const char *ljb_strerror(int code);
+const char *ljb_last_cuda_error(void);
+/* Number of kernels this library has launched on ctx since creation (bench.py's gpu_launches). */
+uint64_t ljb_ctx_launch_count(const ljb_ctx *ctx);
+/* Duration in ms of the most recent ljb_*_dev call's dominant kernel (CUDA events on the ctx stream). */
+float ljb_ctx_last_kernel_ms(const ljb_ctx *ctx);
+
+/* ------------------------------------------------------------------------------------------------
+ * LZ4 (reference dialect)
+ *
+ * ljb_lz4_compress replaces lz4_encode()'s compute: divide_input -> block_encode per block ->
+ * write_output (Algorithms/sequential/LZ4/LZ4.c:123, :506, :427; thread-per-block form
+ * parallel_LZ4_encode, Algorithms/parallel/LZ4/LZ4.c:680).  Output bytes are identical to the
+ * reference's compressed.bin for the same input and block_len (match extension bounded at the block
+ * end):  u8 nblocks_lo8 | { u8 nseq_lo8, u16 size, sequences }*.
+ *
+ *   in, n          input bytes (n >= 1)
+ *   block_len      1..65536; the reference's compile-time DEFAULT_BLOCK_LENGTH
+ *   out, out_cap   receives the stream; ljb_lz4_bound(n, block_len) is always enough
+ *   block_offsets  optional, nblocks+1 entries: byte offset of every block in out, and the end.  The
+ *                  in-band size fields are 8/16-bit and wrap at this block size, so this table is the
+ *                  authoritative framing.
+ *   out_len        receives the stream length
+ *   phantom        optional: number of sequences whose size field counts a byte that is not written
+ *                  (match lengths 257..259 mod 256) — such streams are not decodable,
+ *                  by the reference or by anyone
+ * ------------------------------------------------------------------------------------------------ */
+size_t ljb_lz4_bound(size_t n, size_t block_len);
+size_t ljb_lz4_block_count(size_t n, size_t block_len);
+
+int ljb_lz4_compress(ljb_ctx *ctx, const uint8_t *in, size_t n, size_t block_len, uint8_t *out, size_t out_cap,
+                     uint64_t *block_offsets, size_t *out_len, uint64_t *phantom);
+
+/* Same operation on device-resident buffers, asynchronous on the context stream.
+ *   d_block_offsets  nblocks+1 device entries (required)
+ *   d_result         3 device uint64: [0] stream length, [1] phantom count, [2] error flags (0 = ok,
+ *                    bit0 = out_cap exceeded)
+ *   first_block / frame_blocks: this call encodes a shard of a larger frame — blocks are numbered from
+ *   first_block and the leading frame byte (low 8 bits of frame_blocks, LZ4.c:429) is written only when
+ *   first_block == 0.  Single-GPU callers pass 0 and the total block count. */
+int ljb_lz4_compress_dev(ljb_ctx *ctx, const uint8_t *d_in, size_t n, size_t block_len, uint8_t *d_out, size_t out_cap,
+                         uint64_t *d_block_offsets, uint64_t *d_result, size_t first_block, size_t frame_blocks);
+
+/* Per-position longest match of ONE block (n <= 65536): len[p] in {0,4..1024}, dist[p] = p - earliest
+ * position.  Exposes the kernel stage that replaces find_longest_match (LZ4.c:290-323) for parity tests. */
+int ljb_lz4_block_matches(ljb_ctx *ctx, const uint8_t *in, size_t n, uint16_t *len, uint16_t *dist);
+
+/* Format-level decoder (replaces LZ4_decode's compute, LZ4.c:1038; block-parallel like
+ * parallel_LZ4_decode, Algorithms/parallel/LZ4/LZ4.c:1105).  Needs the out-of-band block_offsets. */
+int ljb_lz4_decompress(ljb_ctx *ctx, const uint8_t *comp, size_t comp_len, const uint64_t *block_offsets,
+                       size_t nblocks, size_t block_len, uint8_t *out, size_t out_cap, size_t *out_len);
+
+/* ------------------------------------------------------------------------------------------------
+ * JPEG-like encoder
+ *
+ * ljb_jpeg_encode_rgba replaces the encode half of the reference's main()/process():
+ * build_{luminance,rChrominance,bChrominance}_matrix -> chroma_subsample -> divide_image ->
+ * discrete_cosine_transform -> Quantize -> zigzag_pattern -> RLE -> encode_huffman ->
+ * generate_encoded_sequence (Algorithms/sequential/JPEG/JPEG.c:114-185, :302, :496, :451, :621, :693,
+ * :767, :1035, :993; fused per-block form Algorithms/parallel/JPEG/JPEG.c:1103-1252).
+ *
+ *   rgba, w, h, stride  8-bit RGBA pixels as the reference's Pixel (JPEG.c:29-32); w must be even
+ *   first_group, ngroups  which 8x8 groups to encode (row-major over ceil(w/8) columns); the reference
+ *                       processes groups [0, ceil(w*h/64)) (JPEG.c:1131) = ljb_jpeg_group_count(w,h).
+ *                       Shards of one image pass sub-ranges; rgba always points at the whole image.
+ *   out, out_cap        packed code bits: per group the luma, Cr, Cb strings (reference order,
+ *                       JPEG.c:1242-1321) concatenated MSB-first and zero-padded to a byte boundary
+ *   group_offsets       optional, ngroups+1 byte offsets into out
+ *   group_bits          optional, 3 uint16 per group: bit lengths of the three strings
+ *   coefs               optional, 128 int16 per group: quantised coefficients before zig-zag,
+ *                       lum[64] (u*8+v), Cr[32], Cb[32] (u*4+v)
+ *   out_len             receives the stream length in bytes
+ * Returns LJB_E_UNSUPPORTED if some code is longer than 31 bits or a string is longer than the
+ * reference's fixed buffers allow (1023 / 511 chars): the reference itself overflows there.
+ * ------------------------------------------------------------------------------------------------ */
+size_t ljb_jpeg_group_count(int w, int h);
+size_t ljb_jpeg_bound(size_t ngroups);
+
+int ljb_jpeg_encode_rgba(ljb_ctx *ctx, const uint8_t *rgba, int w, int h, size_t stride, size_t first_group,
+                         size_t ngroups, uint8_t *out, size_t out_cap, uint64_t *group_offsets, uint16_t *group_bits,
+                         int16_t *coefs, size_t *out_len);
+
+/* Device-resident form, asynchronous on the context stream.  d_result: 3 device uint64:
+ * [0] stream length, [1] groups outside the reference's defined behaviour, [2] error flags. */
+int ljb_jpeg_encode_rgba_dev(ljb_ctx *ctx, const uint8_t *d_rgba, int w, int h, size_t stride, size_t first_group,
+                             size_t ngroups, uint8_t *d_out, size_t out_cap, uint64_t *d_group_offsets,
+                             uint16_t *d_group_bits, int16_t *d_coefs, uint64_t *d_result);
+
+/* ------------------------------------------------------------------------------------------------
+ * Workload generators (host code): the reference's Experiment/random_extract.c:8-71 and
+ * Experiment/random_image.c:58-77 with an explicit seed (the reference uses time() / unseeded rand()).
+ * ------------------------------------------------------------------------------------------------ */
+void ljb_synth_text(const uint8_t *corpus, size_t corpus_len, uint64_t seed, size_t passage, uint8_t *out, size_t n);
+void ljb_synth_image(uint64_t seed, int w, int h, uint8_t *rgba);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LZ4JPEG_B200_H */

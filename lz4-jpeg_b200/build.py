@@ -1,0 +1,62 @@
+"""lz4-jpeg_b200/build.py — compile the CUDA kernels + C ABI into lz4-jpeg_b200/liblz4jpeg_b200.so.
+
+sm_100a only (``-gencode arch=compute_100a,code=sm_100a``); nvcc cross-compiles without a GPU.
+The .so is built in-tree (git-ignored) so that it travels with the repo snapshot to the GPU box.
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "liblz4jpeg_b200.so")
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+CU_SOURCES = ["api.cu", "lz4_encode.cu", "lz4_decode.cu", "jpeg_encode.cu"]
+C_SOURCES = ["synth.c"]
+
+
+def sources() -> list[str]:
+    return [os.path.join(CSRC, s) for s in CU_SOURCES + C_SOURCES if os.path.exists(os.path.join(CSRC, s))]
+
+
+def _stale() -> bool:
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    deps = sources() + [os.path.join(CSRC, "common.cuh"), os.path.join(os.path.dirname(HERE), "include", "lz4jpeg_b200.h"),
+                        os.path.abspath(__file__)]
+    return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if not force and not _stale():
+        return LIB
+    objdir = os.path.join(HERE, "build")
+    os.makedirs(objdir, exist_ok=True)
+    objs = []
+    for src in sources():
+        obj = os.path.join(objdir, os.path.basename(src) + ".o")
+        if src.endswith(".cu"):
+            cmd = [NVCC, *ARCH, "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-Xptxas", "-v", "-c", src, "-o", obj]
+        else:
+            cmd = ["gcc", "-O2", "-fPIC", "-c", src, "-o", obj]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            sys.stderr.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
+            raise RuntimeError(f"compile failed: {src}")
+        if verbose:
+            sys.stderr.write(r.stderr)
+        objs.append(obj)
+    cmd = [NVCC, *ARCH, "-shared", "-o", LIB, *objs, "-lcudart"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
+        raise RuntimeError("link failed")
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose=True))

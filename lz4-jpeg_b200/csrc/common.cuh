@@ -1,0 +1,99 @@
+// lz4-jpeg_b200/csrc/common.cuh — shared device helpers and the context object (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+
+#include "../../include/lz4jpeg_b200.h"
+
+#ifndef __CUDA_ARCH__
+#define LJB_HOST_ONLY 1
+#endif
+
+struct ljb_ctx {
+    int device;
+    int num_sms;
+    cudaStream_t stream;
+    cudaEvent_t ev0, ev1;
+    uint64_t launches;
+    float last_kernel_ms;
+    // persistent scratch (grown on demand, never shrunk)
+    void *d_scratch;      // per-CTA match records etc.
+    size_t scratch_bytes;
+    void *d_status;       // ticket counter + decoupled look-back status words
+    size_t status_bytes;
+    void *d_stage_in;     // device staging for the host-buffer entry points
+    size_t stage_in_bytes;
+    void *d_stage_out;
+    size_t stage_out_bytes;
+    void *d_small;        // offsets / results staging
+    size_t small_bytes;
+};
+
+int ljb_set_cuda_error(cudaError_t e, const char *what, int line);
+int ljb_ensure(void **p, size_t *have, size_t want);
+
+#define LJB_CUDA(x)                                                        \
+    do {                                                                   \
+        cudaError_t e__ = (x);                                             \
+        if (e__ != cudaSuccess) return ljb_set_cuda_error(e__, #x, __LINE__); \
+    } while (0)
+
+// ---- decoupled look-back (single-pass chained scan of per-block byte counts) -------------------------
+// status word: bits 63..62 = state (0 invalid, 1 aggregate published, 2 inclusive prefix published),
+// bits 61..0 = value.  One 64-bit word carries flag and value together, so no fence is needed.
+#define LJB_ST_AGG (1ull << 62)
+#define LJB_ST_INC (2ull << 62)
+#define LJB_ST_MASK (3ull << 62)
+
+#ifdef __CUDACC__
+__device__ __forceinline__ uint64_t ljb_ld_volatile(const uint64_t *p)
+{
+    uint64_t v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void ljb_st_volatile(uint64_t *p, uint64_t v)
+{
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// Called by one full warp.  Publishes `mine` for unit `idx` and returns the exclusive prefix
+// (`lead` + sum of all earlier units).  Units must have been claimed in increasing order by CTAs that
+// are resident (ticket counter), so every predecessor is running or finished: no deadlock.
+__device__ __forceinline__ uint64_t ljb_lookback(uint64_t *status, long long idx, uint64_t mine, uint64_t lead)
+{
+    const unsigned lane = threadIdx.x & 31;
+    if (idx == 0) {
+        if (lane == 0) ljb_st_volatile(&status[0], LJB_ST_INC | (lead + mine));
+        return lead;
+    }
+    if (lane == 0) ljb_st_volatile(&status[idx], LJB_ST_AGG | mine);
+    uint64_t excl = 0;
+    long long at = idx - 1;
+    for (;;) {
+        long long j = at - (long long)lane;
+        uint64_t w;
+        if (j < 0) {
+            w = LJB_ST_INC | lead; // virtual unit -1 holds the inclusive prefix `lead`
+        } else {
+            do {
+                w = ljb_ld_volatile(&status[j]);
+            } while ((w & LJB_ST_MASK) == 0);
+        }
+        unsigned inc = __ballot_sync(0xffffffffu, (w & LJB_ST_MASK) == LJB_ST_INC);
+        uint64_t v = w & ~LJB_ST_MASK;
+        if (inc) {
+            int first = __ffs(inc) - 1; // nearest predecessor holding an inclusive prefix
+            if ((int)lane > first) v = 0;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        excl += v;
+        if (inc) break;
+        at -= 32;
+    }
+    if (lane == 0) ljb_st_volatile(&status[idx], LJB_ST_INC | (excl + mine));
+    return excl;
+}
+#endif

@@ -1,0 +1,143 @@
+// lz4-jpeg_b200/csrc/lz4_decode.cu — format-level LZ4 (reference dialect) block decoder for sm_100a.
+//
+// Replaces the compute of LZ4_decode() / block_decode() / sequence_decode() / interpret_sequence()
+// (Algorithms/sequential/LZ4/LZ4.c:1038, :845, :744, :937; "parallel" form parallel_LZ4_decode,
+// Algorithms/parallel/LZ4/LZ4.c:1105).  The reference decoder is count-driven (its u8 counters wrap
+// beyond 255 sequences / 127 blocks) and does signed-char arithmetic, so it cannot decode what its own
+// encoder writes at 64 KiB blocks.  This decoder follows the wire format instead:
+// blocks are delimited by the out-of-band offset table, sequences are walked structurally, literal
+// counts >= 271 are recovered from the sequence size field, matches are copied with overlap semantics
+// (LZ4.c:956-977).  One warp decodes one block; blocks are independent (offsets never reach before the
+// block start), which is the reference's own thread-per-block decomposition.
+#include "common.cuh"
+
+namespace lz4d {
+
+constexpr int WARPS_PER_CTA = 8;
+
+struct Params {
+    const uint8_t *comp;
+    const uint64_t *offs; // nblocks + 1
+    uint32_t nblocks;
+    uint32_t block_len;
+    uint8_t *out;
+    size_t out_cap;
+    uint32_t *block_out_len; // per block decoded length
+    uint64_t *result;        // [0] unused, [1] unused, [2] error flags: bit0 capacity, bit1 format
+};
+
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32) lz4_decode_kernel(Params P)
+{
+    const uint32_t b = blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5);
+    const uint32_t lane = threadIdx.x & 31;
+    if (b >= P.nblocks) return;
+    const uint8_t *c = P.comp;
+    size_t s = (size_t)P.offs[b], e = (size_t)P.offs[b + 1];
+    const size_t out0 = (size_t)b * P.block_len;
+    const size_t out_lim = min(P.out_cap, out0 + (size_t)P.block_len);
+    uint8_t *out = P.out;
+    size_t o = out0;
+    unsigned err = 0;
+    if (e < s + 3) err = 2;
+    s += 3; // block header: u8 nseq_lo8, u16 size (both wrap; the offset table is authoritative)
+    while (!err && s < e) {
+        if (s + 3 > e) { err = 2; break; }
+        const uint32_t token = c[s];
+        size_t size16 = (size_t)c[s + 1] | ((size_t)c[s + 2] << 8);
+        size_t q = s + 3;
+        size_t lit = token >> 4;
+        const uint32_t mtok = token & 15;
+        if (s + size16 + 65536 <= e) size16 += 65536; // u16 wrap of the size field (>= 65531 literals)
+        if (lit == 15) {
+            if (q >= e) { err = 2; break; }
+            const uint32_t e1 = c[q];
+            const uint32_t next = e1 == 255 ? 2 : 1;
+            const size_t fixed = 5 + next + (mtok == 15 ? 1 : 0);
+            if (size16 < fixed + 15) { err = 2; break; }
+            lit = size16 - fixed;
+            if (((lit - 15) & 0xFF) != (next == 2 ? 255u : e1)) { err = 2; break; }
+            q += next;
+        }
+        if (q + lit + 2 > e) { err = 2; break; }
+        if (o + lit > out_lim) { err = (o + lit > P.out_cap) ? 1 : 2; break; }
+        for (size_t k = lane; k < lit; k += 32) out[o + k] = c[q + k];
+        o += lit;
+        q += lit;
+        const size_t off = (size_t)c[q] | ((size_t)c[q + 1] << 8);
+        q += 2;
+        if (off != 0) {
+            size_t mlen = mtok + 4;
+            if (mtok == 15) {
+                if (q >= e) { err = 2; break; }
+                mlen = (size_t)c[q++] + 19;
+            }
+            if (off > o - out0) { err = 2; break; }
+            if (o + mlen > out_lim) { err = (o + mlen > P.out_cap) ? 1 : 2; break; }
+            __syncwarp(); // literals written by other lanes may be match source
+            // overlapping forward copy == periodic extension of the last `off` bytes
+            for (size_t k = lane; k < mlen; k += 32) out[o + k] = out[o - off + (k % off)];
+            o += mlen;
+            __syncwarp();
+        } else if (mtok != 0) {
+            err = 2;
+            break;
+        }
+        s = q;
+    }
+    if (lane == 0) {
+        P.block_out_len[b] = (uint32_t)(o - out0);
+        if (err) atomicOr((unsigned long long *)&P.result[2], (unsigned long long)err);
+    }
+}
+
+} // namespace lz4d
+
+extern "C" int ljb_lz4_decompress(ljb_ctx *ctx, const uint8_t *comp, size_t comp_len, const uint64_t *block_offsets,
+                                  size_t nblocks, size_t block_len, uint8_t *out, size_t out_cap, size_t *out_len)
+{
+    using namespace lz4d;
+    if (!ctx || !comp || !block_offsets || !out || nblocks == 0 || block_len == 0 || block_len > 65536) return LJB_E_ARG;
+    if (block_offsets[nblocks] > comp_len) return LJB_E_ARG;
+    LJB_CUDA(cudaSetDevice(ctx->device));
+    int rc;
+    const size_t need_out = nblocks * block_len;
+    const size_t dcap = need_out < out_cap ? need_out : out_cap;
+    if ((rc = ljb_ensure(&ctx->d_stage_in, &ctx->stage_in_bytes, comp_len + 64)) != 0) return rc;
+    if ((rc = ljb_ensure(&ctx->d_stage_out, &ctx->stage_out_bytes, dcap + 64)) != 0) return rc;
+    if ((rc = ljb_ensure(&ctx->d_small, &ctx->small_bytes, (nblocks + 1 + 3) * sizeof(uint64_t) + nblocks * sizeof(uint32_t))) != 0)
+        return rc;
+    uint64_t *d_offs = (uint64_t *)ctx->d_small;
+    uint64_t *d_res = d_offs + nblocks + 1;
+    uint32_t *d_len = (uint32_t *)(d_res + 3);
+    LJB_CUDA(cudaMemcpyAsync(ctx->d_stage_in, comp, comp_len, cudaMemcpyHostToDevice, ctx->stream));
+    LJB_CUDA(cudaMemcpyAsync(d_offs, block_offsets, (nblocks + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+    LJB_CUDA(cudaMemsetAsync(d_res, 0, 3 * sizeof(uint64_t), ctx->stream));
+    Params P;
+    P.comp = (const uint8_t *)ctx->d_stage_in;
+    P.offs = d_offs;
+    P.nblocks = (uint32_t)nblocks;
+    P.block_len = (uint32_t)block_len;
+    P.out = (uint8_t *)ctx->d_stage_out;
+    P.out_cap = dcap;
+    P.block_out_len = d_len;
+    P.result = d_res;
+    const unsigned grid = (unsigned)((nblocks + WARPS_PER_CTA - 1) / WARPS_PER_CTA);
+    LJB_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+    lz4_decode_kernel<<<grid, WARPS_PER_CTA * 32, 0, ctx->stream>>>(P);
+    LJB_CUDA(cudaGetLastError());
+    LJB_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+    ctx->launches += 1;
+    uint64_t res[3];
+    uint32_t last_len = 0;
+    LJB_CUDA(cudaMemcpyAsync(res, d_res, sizeof res, cudaMemcpyDeviceToHost, ctx->stream));
+    LJB_CUDA(cudaMemcpyAsync(&last_len, d_len + (nblocks - 1), sizeof last_len, cudaMemcpyDeviceToHost, ctx->stream));
+    LJB_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (res[2] & 2) return LJB_E_FORMAT;
+    if (res[2] & 1) return LJB_E_CAPACITY;
+    const size_t total = (nblocks - 1) * block_len + last_len;
+    if (out_len) *out_len = total;
+    if (total > out_cap) return LJB_E_CAPACITY;
+    LJB_CUDA(cudaMemcpyAsync(out, ctx->d_stage_out, total, cudaMemcpyDeviceToHost, ctx->stream));
+    LJB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return LJB_OK;
+}

@@ -1,0 +1,81 @@
+"""Host-side mirror of the reference's JPEG interface (Algorithms/sequential/JPEG/JPEG.c) over the C ABI.
+
+reference stages fused in one kernel                                 here
+  build_{luminance,rChrominance,bChrominance}_matrix  JPEG.c:114-185
+  chroma_subsample / divide_image                     JPEG.c:302 / :496
+  discrete_cosine_transform / Quantize                JPEG.c:451 / :621
+  zigzag_pattern / RLE                                JPEG.c:693 / :767
+  encode_huffman / generate_encoded_sequence          JPEG.c:1035 / :993    process(rgba) -> EncodedImage
+(`process` is the reference's fused per-block function, Algorithms/parallel/JPEG/JPEG.c:1103.)
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _native as N
+
+GROUP_SIZE = 8
+
+
+@dataclass
+class EncodedImage:
+    stream: np.ndarray         # uint8: per group lum|Cr|Cb code bits, MSB first, group records byte aligned
+    group_offsets: np.ndarray  # uint64[ngroups+1]
+    group_bits: np.ndarray     # uint16[ngroups,3]: bit lengths of the lum, r, b strings
+    coefs: np.ndarray | None   # int16[ngroups,128]: quantised lum[64], Cr[32], Cb[32] (row-major, before zig-zag)
+    width: int
+    height: int
+    first_group: int
+
+    def bit_string(self, g: int, channel: int) -> str:
+        """The '0'/'1' string generate_encoded_sequence (JPEG.c:993) builds for group g, channel 0/1/2 = lum/r/b."""
+        o = int(self.group_offsets[g])
+        nb = [int(x) for x in self.group_bits[g]]
+        rec = self.stream[o:int(self.group_offsets[g + 1])]
+        bits = "".join(f"{b:08b}" for b in rec)
+        start = sum(nb[:channel])
+        return bits[start:start + nb[channel]]
+
+
+def group_count(w: int, h: int) -> int:
+    """Groups the reference processes: ceil(w*h/64) (JPEG.c:1131)."""
+    return int(N.lib().ljb_jpeg_group_count(w, h))
+
+
+def process(rgba, first_group: int = 0, ngroups: int | None = None, want_coefs: bool = True,
+            ctx: N.Context | None = None) -> EncodedImage:
+    """Encode the 8x8 groups [first_group, first_group+ngroups) of an H x W x 4 uint8 image."""
+    a = np.ascontiguousarray(rgba, dtype=np.uint8)
+    if a.ndim != 3 or a.shape[2] != 4:
+        raise ValueError("expect an H x W x 4 uint8 array (the reference's Pixel, JPEG.c:29-32)")
+    h, w, _ = a.shape
+    total = group_count(w, h)
+    if ngroups is None:
+        ngroups = total - first_group
+    ctx = ctx or N.default_context()
+    cap = int(N.lib().ljb_jpeg_bound(ngroups))
+    out = np.empty(cap, dtype=np.uint8)
+    offs = np.zeros(ngroups + 1, dtype=np.uint64)
+    bits = np.zeros((ngroups, 3), dtype=np.uint16)
+    coefs = np.zeros((ngroups, 128), dtype=np.int16) if want_coefs else None
+    out_len = C.c_size_t(0)
+    rc = N.lib().ljb_jpeg_encode_rgba(ctx.handle, a.ctypes.data, w, h, 4 * w, first_group, ngroups, out.ctypes.data, cap,
+                                      offs.ctypes.data, bits.ctypes.data, coefs.ctypes.data if want_coefs else None,
+                                      C.byref(out_len))
+    N.check(rc, "ljb_jpeg_encode_rgba")
+    return EncodedImage(out[: out_len.value].copy(), offs, bits, coefs, w, h, first_group)
+
+
+def encode_device(d_rgba, w: int, h: int, d_out, d_group_offsets, d_group_bits, d_result, ctx: N.Context,
+                  first_group: int = 0, ngroups: int | None = None, d_coefs=None) -> None:
+    """Asynchronous on ctx.stream; d_* are torch CUDA tensors (pointers only)."""
+    if ngroups is None:
+        ngroups = group_count(w, h) - first_group
+    rc = N.lib().ljb_jpeg_encode_rgba_dev(ctx.handle, d_rgba.data_ptr(), w, h, 4 * w, first_group, ngroups, d_out.data_ptr(),
+                                          d_out.numel(), d_group_offsets.data_ptr(),
+                                          d_group_bits.data_ptr() if d_group_bits is not None else None,
+                                          d_coefs.data_ptr() if d_coefs is not None else None, d_result.data_ptr())
+    N.check(rc, "ljb_jpeg_encode_rgba_dev")
