@@ -11,14 +11,24 @@
 //                 histogram, exclusive scan, scatter in 64 position-ordered rounds)
 //   P3 search   : exact longest-previous-match for EVERY position — equivalent to the reference's
 //                 exhaustive scan because a match of length >= 4 shares its 4-gram with the current
-//                 position; teams of TEAM lanes walk one bucket cooperatively, ties resolved to the
-//                 earliest position (strict '>' in LZ4.c:307), length capped at min(1024, block end)
+//                 position; ties resolved to the earliest position (strict '>' in LZ4.c:307), length
+//                 capped at min(1024, block end).  Two phases:
+//                 A  threads walk the index in SORTED order, so the lanes of a warp sit in the same
+//                    bucket: equal trip counts, and the candidate's bytes are one broadcast load.  Only
+//                    the first 8 bytes are compared: matches shorter than 8 are final here.
+//                 B  positions that have an 8-byte match are resolved from a second index keyed by the
+//                    8-gram (tiny buckets), in position order, each thread inheriting the previous
+//                    position's match along its diagonal instead of re-comparing up to 1024 bytes.
 //   P4 parse    : the greedy chain 0 -> p+step[p] is resolved in parallel with per-segment exit tables,
 //                 then sequences are sized with the reference's uint8/uint16 wrap rules
 //   P5 place    : decoupled look-back over the per-block byte counts gives the block's output offset
 //   P6 emit     : sequences are serialised straight to their final position in the output stream
 // HBM traffic per block is therefore N_in + N_out (+ a per-CTA scratch that stays in L2).
 #include "common.cuh"
+
+#include <stdio.h>
+#include <stdlib.h>
+#include <type_traits>
 
 namespace lz4k {
 
@@ -42,9 +52,10 @@ constexpr int SM_DIR = SM_S + 2 * MAXB;            // u32 dirw[4096 + 1]    pack
 constexpr int SM_STEP = SM_B;                      // u8 step[65536 + 64]
 constexpr int SM_FLAG = SM_STEP + MAXB + 64;       // u8 x1/flag[65536 + 64]
 constexpr int SM_ENTRY = SM_FLAG + MAXB + 64;      // u8 entry[1024]
-constexpr int SM_MISC = SM_DIR + 4 * (NBUCKET / 2 + 4); // after the larger of the two views
+constexpr int SM_LONG = SM_DIR + 4 * (NBUCKET / 2 + 4); // u32 longbits[2048]: positions that have an >= 8 byte match
+constexpr int SM_MISC = SM_LONG + MAXB / 8;
 constexpr int SM_TOTAL = SM_MISC + 1024;
-static_assert(SM_ENTRY + 1024 <= SM_MISC, "parse view must fit inside region B");
+static_assert(SM_ENTRY + 1024 <= SM_LONG, "parse view must fit inside region B");
 static_assert(SM_TOTAL <= 227 * 1024, "exceeds B200 shared memory per CTA");
 
 struct Misc {
@@ -74,6 +85,7 @@ struct Params {
     uint32_t frame_byte;
     uint16_t *dump_len;      // optional single-block stage dump
     uint16_t *dump_dist;
+    unsigned long long *phase_cycles; // optional: per-phase SM cycles summed over CTAs (profiling aid)
 };
 
 __device__ __forceinline__ uint32_t load32u(const uint32_t *w, uint32_t a)
@@ -82,6 +94,16 @@ __device__ __forceinline__ uint32_t load32u(const uint32_t *w, uint32_t a)
     return __funnelshift_r(w[i], w[i + 1], s);
 }
 __device__ __forceinline__ uint32_t hash4(uint32_t key) { return (key * 2654435761u) >> (32 - HASH_BITS); }
+__device__ __forceinline__ uint32_t hash8(uint32_t k0, uint32_t k1)
+{
+    return ((k0 * 2654435761u) ^ (k1 * 2246822519u) ^ ((k1 * 3266489917u) >> 15)) >> (32 - HASH_BITS);
+}
+template <int GRAM>
+__device__ __forceinline__ uint32_t hash_at(const uint32_t *w, uint32_t p)
+{
+    if (GRAM == 4) return hash4(load32u(w, p));
+    return hash8(load32u(w, p), load32u(w, p + 4));
+}
 
 // Longest common prefix of data[c..] and data[p..], p-side first 8 bytes given; result clamped to cap.
 __device__ __forceinline__ uint32_t lcp_from(const uint32_t *w, uint32_t c, uint32_t p, uint32_t P0, uint32_t P1,
@@ -95,12 +117,17 @@ __device__ __forceinline__ uint32_t lcp_from(const uint32_t *w, uint32_t c, uint
     if (x) return min(4u + ((uint32_t)(__ffs(x) - 1) >> 3), cap);
     uint32_t l = 8;
     uint32_t pi = p >> 2, ps = (p & 3) * 8;
+    uint32_t cw = a2, pw = w[pi + 2]; // words straddling offset 8 on either side
     while (l < cap) {
-        uint32_t ca = w[ci + (l >> 2)], cb = w[ci + (l >> 2) + 1];
-        uint32_t pa = w[pi + (l >> 2)], pb = w[pi + (l >> 2) + 1];
-        x = __funnelshift_r(ca, cb, cs) ^ __funnelshift_r(pa, pb, ps);
+        const uint32_t c1 = w[ci + (l >> 2) + 1], c2 = w[ci + (l >> 2) + 2];
+        const uint32_t p1 = w[pi + (l >> 2) + 1], p2 = w[pi + (l >> 2) + 2];
+        x = __funnelshift_r(cw, c1, cs) ^ __funnelshift_r(pw, p1, ps);
         if (x) return min(l + ((uint32_t)(__ffs(x) - 1) >> 3), cap);
-        l += 4;
+        x = __funnelshift_r(c1, c2, cs) ^ __funnelshift_r(p1, p2, ps);
+        if (x) return min(l + 4 + ((uint32_t)(__ffs(x) - 1) >> 3), cap);
+        cw = c2;
+        pw = p2;
+        l += 8;
     }
     return cap;
 }
@@ -141,6 +168,15 @@ __global__ void __launch_bounds__(THREADS, 1) lz4_encode_kernel(Params P)
     const int warp = tid >> 5;
     uint32_t *R = P.scratch + (size_t)blockIdx.x * MAXB;
 
+    long long t_prev = clock64();
+#define LJB_PHASE(idx)                                                                      \
+    do {                                                                                    \
+        if (P.phase_cycles && tid == 0) {                                                   \
+            long long t_now = clock64();                                                    \
+            atomicAdd(&P.phase_cycles[idx], (unsigned long long)(t_now - t_prev));          \
+            t_prev = t_now;                                                                 \
+        }                                                                                   \
+    } while (0)
     for (;;) {
         // ---------------- ticket ----------------
         if (tid == 0) M.ticket = (long long)atomicAdd((unsigned long long *)&P.status[0], 1ull);
@@ -166,114 +202,174 @@ __global__ void __launch_bounds__(THREADS, 1) lz4_encode_kernel(Params P)
             for (int i = tid; i < NBUCKET / 2 + 1; i += THREADS) dirw[i] = 0;
         }
         __syncthreads();
+        LJB_PHASE(0); // stage
 
         const uint32_t npos = nb >= 4 ? nb - 3 : 0; // positions that still have a 4-gram inside the block
 
-        // ---------------- P2: index = counting sort by hash of the 4-gram ----------------
-        for (uint32_t p = tid; p < npos; p += THREADS) {
-            uint32_t h = hash4(load32u(dataw, p));
-            atomicAdd(&dirw[h >> 1], (h & 1) ? 0x10000u : 1u);
-        }
-        __syncthreads();
-        {
-            // exclusive scan of 8192 u16 counts; thread t owns buckets 8t .. 8t+7 (4 packed words)
-            uint32_t c[8], sum = 0;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                uint32_t wv = dirw[tid * 4 + k];
-                c[2 * k] = wv & 0xFFFF;
-                c[2 * k + 1] = wv >> 16;
-            }
-#pragma unroll
-            for (int k = 0; k < 8; ++k) sum += c[k];
-            uint32_t inc = sum;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
-                if (lane >= o) inc += v;
-            }
-            if (lane == 31) M.scan_tmp[warp] = inc;
-            __syncthreads();
-            uint32_t wbase = 0;
-            for (int k = 0; k < warp; ++k) wbase += M.scan_tmp[k];
-            uint32_t run = wbase + inc - sum;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                uint32_t lo = run;
-                run += c[2 * k];
-                uint32_t hi = run;
-                run += c[2 * k + 1];
-                dirw[tid * 4 + k] = (lo & 0xFFFF) | (hi << 16);
-            }
-        }
-        __syncthreads();
-        // scatter in position-ordered rounds: inside a bucket, entries of an earlier 1024-chunk come first
-        for (uint32_t base = 0; base < npos; base += THREADS) {
-            uint32_t p = base + tid;
-            if (p < npos) {
-                uint32_t h = hash4(load32u(dataw, p));
-                uint32_t old = atomicAdd(&dirw[h >> 1], (h & 1) ? 0x10000u : 1u);
-                uint32_t slot = (h & 1) ? (old >> 16) : (old & 0xFFFF);
-                S[slot] = (uint16_t)p;
-            }
-            __syncthreads();
-        }
-        // now dir16[h] = end of bucket h = start of bucket h+1
+        // ---------------- P2/P3 ----------------
+        uint32_t *longbits = reinterpret_cast<uint32_t *>(smem + SM_LONG);
+        for (int i = tid; i < MAXB / 32; i += THREADS) longbits[i] = 0;
 
-        // ---------------- P3: exact longest previous match for every position ----------------
+        // index = counting sort of positions [0, cnt) by the hash of their GRAM-gram.  Afterwards
+        // dir16[h] = end of bucket h = start of bucket h+1; inside a bucket, entries of an earlier
+        // 1024-position chunk come first (the scatter runs in position-ordered rounds).
+        auto build_index = [&](auto gram_tag, uint32_t cnt) {
+            constexpr int GRAM = decltype(gram_tag)::value;
+            for (uint32_t p = tid; p < cnt; p += THREADS) {
+                uint32_t h = hash_at<GRAM>(dataw, p);
+                atomicAdd(&dirw[h >> 1], (h & 1) ? 0x10000u : 1u);
+            }
+            __syncthreads();
+            {
+                // exclusive scan of 8192 u16 counts; thread t owns buckets 8t .. 8t+7 (4 packed words)
+                uint32_t c[8], sum = 0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    uint32_t wv = dirw[tid * 4 + k];
+                    c[2 * k] = wv & 0xFFFF;
+                    c[2 * k + 1] = wv >> 16;
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) sum += c[k];
+                uint32_t inc = sum;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
+                    if (lane >= o) inc += v;
+                }
+                if (lane == 31) M.scan_tmp[warp] = inc;
+                __syncthreads();
+                uint32_t wbase = 0;
+                for (int k = 0; k < warp; ++k) wbase += M.scan_tmp[k];
+                uint32_t run = wbase + inc - sum;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    uint32_t lo = run;
+                    run += c[2 * k];
+                    uint32_t hi = run;
+                    run += c[2 * k + 1];
+                    dirw[tid * 4 + k] = (lo & 0xFFFF) | (hi << 16);
+                }
+            }
+            __syncthreads();
+            for (uint32_t base = 0; base < cnt; base += THREADS) {
+                uint32_t p = base + tid;
+                if (p < cnt) {
+                    uint32_t h = hash_at<GRAM>(dataw, p);
+                    uint32_t old = atomicAdd(&dirw[h >> 1], (h & 1) ? 0x10000u : 1u);
+                    uint32_t slot = (h & 1) ? (old >> 16) : (old & 0xFFFF);
+                    S[slot] = (uint16_t)p;
+                }
+                __syncthreads();
+            }
+        };
+
+        build_index(std::integral_constant<int, 4>{}, npos);
+        LJB_PHASE(1); // index (4-gram)
+
+        // ---- phase A: sorted-order walk, first 8 bytes only
+        for (uint32_t j = tid; j < npos; j += THREADS) {
+            const uint32_t p = S[j];
+            const uint32_t P0 = load32u(dataw, p), P1 = load32u(dataw, p + 4);
+            const uint32_t h = hash4(P0);
+            const uint32_t lo = h ? dir16[h - 1] : 0u, hi = dir16[h];
+            const uint32_t cap8 = min(8u, nb - p);
+            const uint32_t pch = p >> 10;
+            uint32_t best = 0;
+            for (uint32_t i = lo; i < hi; ++i) {
+                const uint32_t c = S[i];
+                const uint32_t cch = c >> 10;
+                if (cch > pch) break; // only later positions from here on
+                // an 8-byte (or block-end) match from an earlier chunk cannot be beaten by later positions
+                if ((best >> 16) == cap8 && cch > ((0xFFFFu - (best & 0xFFFFu)) >> 10)) break;
+                if (c < p) {
+                    const uint32_t ci = c >> 2, cs = (c & 3) * 8;
+                    const uint32_t a0 = dataw[ci], a1 = dataw[ci + 1];
+                    if (__funnelshift_r(a0, a1, cs) == P0) {
+                        const uint32_t x = __funnelshift_r(a1, dataw[ci + 2], cs) ^ P1;
+                        uint32_t l = x ? 4u + ((uint32_t)(__ffs(x) - 1) >> 3) : 8u;
+                        l = min(l, cap8);
+                        best = max(best, (l << 16) | (0xFFFFu - c));
+                    }
+                }
+            }
+            const uint32_t bl = best >> 16, bp = 0xFFFFu - (best & 0xFFFFu);
+            R[p] = bl ? ((bl << 16) | bp) : 0u;
+            if (bl == 8 && nb - p > 8) atomicOr(&longbits[p >> 5], 1u << (p & 31)); // may be longer: phase B decides
+        }
+        for (uint32_t p = npos + tid; p < nb; p += THREADS) R[p] = 0; // the last 3 positions cannot start a match
+        __syncthreads();
+        LJB_PHASE(2); // search phase A
+
+        // ---- phase B: positions with an >= 8 byte match, from the 8-gram index
         {
-            const int team = tid / TEAM;
-            const int tl = tid % TEAM;
-            const unsigned tmask = (TEAM == 32) ? 0xffffffffu : (((1u << TEAM) - 1u) << (lane & ~(TEAM - 1)));
-            constexpr int NTEAMS = THREADS / TEAM;
-            for (uint32_t p = team; p < nb; p += NTEAMS) {
-                uint32_t bestkey = 0;
-                if (p < npos) {
-                    const uint32_t P0 = load32u(dataw, p), P1 = load32u(dataw, p + 4);
-                    const uint32_t h = hash4(P0);
-                    const uint32_t lo = h ? dir16[h - 1] : 0u;
-                    const uint32_t hi = dir16[h]; // bucket ends are <= 65533: fit u16
-                    const uint32_t cap = min((uint32_t)MAX_MATCH, nb - p);
-                    const uint32_t pchunk = p >> 10;
-                    for (uint32_t k0 = lo; k0 < hi; k0 += TEAM) {
-                        const uint32_t k = k0 + tl;
-                        uint32_t c = 0xFFFFFFFFu;
-                        if (k < hi) c = S[k];
-                        const bool past = (k >= hi) || ((c >> 10) > pchunk);
-                        if (c < p) {
-                            const uint32_t bl = bestkey >> 16, bp = 0xFFFFu - (bestkey & 0xFFFFu);
-                            // a candidate matters only if it beats the best length, or ties it from an earlier position
-                            const uint32_t need = bl == 0 ? 4u : (c < bp ? bl : bl + 1);
-                            if (need <= cap) {
-                                bool ok = true;
-                                if (bl != 0) ok = data[c + need - 1] == data[p + need - 1];
-                                if (ok) {
-                                    uint32_t l = lcp_from(dataw, c, p, P0, P1, cap);
-                                    if (l >= 4) {
-                                        uint32_t key = (l << 16) | (0xFFFFu - c);
-                                        bestkey = max(bestkey, key);
+            uint32_t any = 0;
+            for (int i = tid; i < MAXB / 32; i += THREADS) any |= longbits[i];
+            any = __syncthreads_or(any != 0);
+            if (any) {
+                for (int i = tid; i < NBUCKET / 2 + 1; i += THREADS) dirw[i] = 0;
+                __syncthreads();
+                const uint32_t npos8 = nb >= 8 ? nb - 7 : 0;
+                build_index(std::integral_constant<int, 8>{}, npos8);
+                LJB_PHASE(3); // index (8-gram)
+                // thread t owns the 32-position chunks t, t + 1024: one word of longbits each
+                for (uint32_t ch = tid; ch * 32 < nb; ch += THREADS) {
+                    uint32_t bits = longbits[ch];
+                    uint32_t prev_len = 0, prev_pos = 0, prev_p = 0xFFFFFFFFu;
+                    bool prev_capped = false;
+                    while (bits) {
+                        const uint32_t p = ch * 32 + (__ffs(bits) - 1);
+                        bits &= bits - 1;
+                        const uint32_t cap = min((uint32_t)MAX_MATCH, nb - p);
+                        const uint32_t P0 = load32u(dataw, p), P1 = load32u(dataw, p + 4);
+                        uint32_t bestkey = 0;
+                        if (prev_p + 1 == p && prev_len >= 5) { // inherited candidate on the previous best's diagonal
+                            const uint32_t c0 = prev_pos + 1;
+                            uint32_t l0 = prev_len - 1;
+                            if (prev_capped) // the previous run was cut by the cap, not by a mismatch: it may go on
+                                while (l0 < cap && data[c0 + l0] == data[p + l0]) ++l0;
+                            l0 = min(l0, cap);
+                            bestkey = (l0 << 16) | (0xFFFFu - c0);
+                        }
+                        // a capped 1024 match becomes a literal step ((uint8_t)1024 == 0, LZ4.c:317) whose distance
+                        // is never used: no need to look for an earlier one
+                        if ((bestkey >> 16) != (uint32_t)MAX_MATCH) {
+                            const uint32_t h = hash8(P0, P1);
+                            const uint32_t lo = h ? dir16[h - 1] : 0u, hi = dir16[h];
+                            const uint32_t pch = p >> 10;
+                            for (uint32_t k = lo; k < hi; ++k) {
+                                const uint32_t c = S[k];
+                                const uint32_t cch = c >> 10;
+                                if (cch > pch) break;
+                                const uint32_t bl = bestkey >> 16, bp = 0xFFFFu - (bestkey & 0xFFFFu);
+                                if (bl == cap && cch > (bp >> 10)) break; // later positions cannot win a tie
+                                if (c < p) {
+                                    // a candidate matters only if it beats the best length, or ties it from an earlier position
+                                    const uint32_t need = bl == 0 ? 8u : (c < bp ? bl : bl + 1);
+                                    if (need <= cap) {
+                                        bool ok = true;
+                                        if (bl != 0) ok = data[c + need - 1] == data[p + need - 1];
+                                        if (ok) {
+                                            const uint32_t l = lcp_from(dataw, c, p, P0, P1, cap);
+                                            if (l >= 8) bestkey = max(bestkey, (l << 16) | (0xFFFFu - c));
+                                            if (l == (uint32_t)MAX_MATCH) break;
+                                        }
                                     }
                                 }
                             }
                         }
-                        // share the team's best so far: sharper pruning for everyone
-#pragma unroll
-                        for (int o = TEAM / 2; o > 0; o >>= 1) bestkey = max(bestkey, __shfl_xor_sync(tmask, bestkey, o));
-                        // stop when every remaining entry lies in a later 1024-chunk than p, or — once the
-                        // length cap is reached — in a later chunk than the best position (cannot win a tie)
-                        const uint32_t tbl = bestkey >> 16, tbp = 0xFFFFu - (bestkey & 0xFFFFu);
-                        const bool done = past || (tbl == cap && (c >> 10) > (tbp >> 10));
-                        const unsigned alldone = __ballot_sync(tmask, done);
-                        if ((alldone & tmask) == tmask) break;
+                        const uint32_t bl = bestkey >> 16, bp = 0xFFFFu - (bestkey & 0xFFFFu);
+                        prev_len = bl;
+                        prev_pos = bp;
+                        prev_p = p;
+                        prev_capped = bl == cap;
+                        R[p] = (bl << 16) | bp; // bl >= 8 here: phase A proved an 8-byte match exists
                     }
-                }
-                if (tl == 0) {
-                    uint32_t bl = bestkey >> 16, bp = 0xFFFFu - (bestkey & 0xFFFFu);
-                    R[p] = bl ? ((bl << 16) | bp) : 0u;
                 }
             }
         }
         __syncthreads();
+        LJB_PHASE(4); // search phase B
         if (P.dump_len) { // stage dump for parity tests of the search (single block calls only)
             for (uint32_t p = tid; p < nb; p += THREADS) {
                 uint32_t r = R[p];
@@ -324,6 +420,7 @@ __global__ void __launch_bounds__(THREADS, 1) lz4_encode_kernel(Params P)
         }
         __syncthreads();
 
+        LJB_PHASE(5); // parse: chain resolution
         // sequence pass 1: last match end per warp region
         const uint32_t r0 = warp * REGION;
         {
@@ -438,6 +535,7 @@ __global__ void __launch_bounds__(THREADS, 1) lz4_encode_kernel(Params P)
             nseq += 1;
         }
 
+        LJB_PHASE(6); // sequence sizing
         // ---------------- P5: place (decoupled look-back) ----------------
         if (warp == 0) {
             unsigned long long base = ljb_lookback(P.status + 1, b, pay, P.lead);
@@ -455,6 +553,7 @@ __global__ void __launch_bounds__(THREADS, 1) lz4_encode_kernel(Params P)
         }
         __syncthreads();
 
+        LJB_PHASE(7); // look-back
         // ---------------- P6: emit ----------------
         if (M.emit_ok) {
             const unsigned long long base = M.base;
@@ -488,7 +587,9 @@ __global__ void __launch_bounds__(THREADS, 1) lz4_encode_kernel(Params P)
             }
         }
         __syncthreads(); // region B and data are reused by the next block
+        LJB_PHASE(8); // emit
     }
+#undef LJB_PHASE
 }
 
 } // namespace lz4k
@@ -515,8 +616,8 @@ static int lz4_launch(ljb_ctx *ctx, const uint8_t *d_in, size_t n, size_t block_
     const int grid = (int)((nblocks < (size_t)ctx->num_sms) ? nblocks : (size_t)ctx->num_sms);
     int rc;
     if ((rc = ljb_ensure(&ctx->d_scratch, &ctx->scratch_bytes, (size_t)ctx->num_sms * MAXB * sizeof(uint32_t))) != 0) return rc;
-    if ((rc = ljb_ensure(&ctx->d_status, &ctx->status_bytes, (nblocks + 2) * sizeof(uint64_t))) != 0) return rc;
-    LJB_CUDA(cudaMemsetAsync(ctx->d_status, 0, (nblocks + 2) * sizeof(uint64_t), ctx->stream));
+    if ((rc = ljb_ensure(&ctx->d_status, &ctx->status_bytes, (nblocks + 2 + 16) * sizeof(uint64_t))) != 0) return rc;
+    LJB_CUDA(cudaMemsetAsync(ctx->d_status, 0, (nblocks + 2 + 16) * sizeof(uint64_t), ctx->stream));
     LJB_CUDA(cudaMemsetAsync(d_result, 0, 3 * sizeof(uint64_t), ctx->stream));
     Params P;
     P.in = d_in;
@@ -533,6 +634,10 @@ static int lz4_launch(ljb_ctx *ctx, const uint8_t *d_in, size_t n, size_t block_
     P.frame_byte = (uint32_t)(frame_blocks & 0xFF);
     P.dump_len = d_dump_len;
     P.dump_dist = d_dump_dist;
+    P.phase_cycles = nullptr;
+    if (getenv("LJB_LZ4_PHASES")) { // profiling aid: per-phase cycle counters behind the status words
+        P.phase_cycles = (unsigned long long *)ctx->d_status + (nblocks + 2);
+    }
     static bool attr_done = false;
     if (!attr_done) {
         LJB_CUDA(cudaFuncSetAttribute(lz4_encode_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
@@ -543,6 +648,17 @@ static int lz4_launch(ljb_ctx *ctx, const uint8_t *d_in, size_t n, size_t block_
     LJB_CUDA(cudaGetLastError());
     LJB_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
     ctx->launches += 1;
+    if (P.phase_cycles) {
+        unsigned long long ph[16];
+        LJB_CUDA(cudaMemcpyAsync(ph, P.phase_cycles, sizeof ph, cudaMemcpyDeviceToHost, ctx->stream));
+        LJB_CUDA(cudaStreamSynchronize(ctx->stream));
+        static const char *names[9] = {"stage", "index4", "phaseA", "index8", "phaseB", "parse", "sizing", "lookback", "emit"};
+        unsigned long long tot = 0;
+        for (int i = 0; i < 9; ++i) tot += ph[i];
+        fprintf(stderr, "[ljb lz4 phases] cycles per block:");
+        for (int i = 0; i < 9; ++i) fprintf(stderr, " %s=%.0f(%.0f%%)", names[i], (double)ph[i] / (double)nblocks, 100.0 * (double)ph[i] / (double)tot);
+        fprintf(stderr, " total=%.0f\n", (double)tot / (double)nblocks);
+    }
     return LJB_OK;
 }
 

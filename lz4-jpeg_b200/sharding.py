@@ -73,3 +73,16 @@ def gather_totals(local_total: int, device=None, group=None):
     allv = torch.empty(world, dtype=torch.int64, device=mine.device)
     dist.all_gather_into_tensor(allv, mine, group=group)
     return exclusive_bases(allv.tolist())
+
+
+def gather_totals_device(d_total, group=None):
+    """Device-side form of gather_totals for the timed path: `d_total` is a 1-element int64 CUDA tensor written by
+    the encode kernel; returns the world-size int64 tensor of all ranks' totals without a host round trip.
+    Issued on torch's current stream (callers make that the context stream so it is ordered after the kernel)."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    allv = torch.empty(world, dtype=torch.int64, device=d_total.device)
+    dist.all_gather_into_tensor(allv, d_total.contiguous(), group=group)
+    return allv
