@@ -53,7 +53,8 @@ constexpr int SM_STEP = SM_B;                      // u8 step[65536 + 64]
 constexpr int SM_FLAG = SM_STEP + MAXB + 64;       // u8 x1/flag[65536 + 64]
 constexpr int SM_ENTRY = SM_FLAG + MAXB + 64;      // u8 entry[1024]
 constexpr int SM_LONG = SM_DIR + 4 * (NBUCKET / 2 + 4); // u32 longbits[2048]: positions that have an >= 8 byte match
-constexpr int SM_MISC = SM_LONG + MAXB / 8;
+constexpr int SM_FIRST = SM_LONG + MAXB / 8;             // u32 firstbits[2048]: first occurrences of a repeated 8-gram
+constexpr int SM_MISC = SM_FIRST + MAXB / 8;
 constexpr int SM_TOTAL = SM_MISC + 1024;
 static_assert(SM_ENTRY + 1024 <= SM_LONG, "parse view must fit inside region B");
 static_assert(SM_TOTAL <= 227 * 1024, "exceeds B200 shared memory per CTA");
@@ -166,7 +167,7 @@ __global__ void __launch_bounds__(THREADS, 1) lz4_encode_kernel(Params P)
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
-    uint32_t *R = P.scratch + (size_t)blockIdx.x * MAXB;
+    uint32_t *R = P.scratch + (size_t)blockIdx.x * MAXB; // match records, one per position
 
     long long t_prev = clock64();
 #define LJB_PHASE(idx)                                                                      \
@@ -208,14 +209,21 @@ __global__ void __launch_bounds__(THREADS, 1) lz4_encode_kernel(Params P)
 
         // ---------------- P2/P3 ----------------
         uint32_t *longbits = reinterpret_cast<uint32_t *>(smem + SM_LONG);
-        for (int i = tid; i < MAXB / 32; i += THREADS) longbits[i] = 0;
+        uint32_t *firstbits = reinterpret_cast<uint32_t *>(smem + SM_FIRST);
+        for (int i = tid; i < MAXB / 32; i += THREADS) {
+            longbits[i] = 0;
+            firstbits[i] = 0;
+        }
 
         // index = counting sort of positions [0, cnt) by the hash of their GRAM-gram.  Afterwards
         // dir16[h] = end of bucket h = start of bucket h+1; inside a bucket, entries of an earlier
         // 1024-position chunk come first (the scatter runs in position-ordered rounds).
+        // Only positions whose 8-gram occurs more than once are indexed (flagged ones and the first occurrences
+        // they point at): everything else can never be a candidate.
         auto build_index = [&](auto gram_tag, uint32_t cnt) {
             constexpr int GRAM = decltype(gram_tag)::value;
             for (uint32_t p = tid; p < cnt; p += THREADS) {
+                if (!(((longbits[p >> 5] | firstbits[p >> 5]) >> (p & 31)) & 1u)) continue;
                 uint32_t h = hash_at<GRAM>(dataw, p);
                 atomicAdd(&dirw[h >> 1], (h & 1) ? 0x10000u : 1u);
             }
@@ -254,7 +262,7 @@ __global__ void __launch_bounds__(THREADS, 1) lz4_encode_kernel(Params P)
             __syncthreads();
             for (uint32_t base = 0; base < cnt; base += THREADS) {
                 uint32_t p = base + tid;
-                if (p < cnt) {
+                if (p < cnt && ((((longbits[p >> 5] | firstbits[p >> 5]) >> (p & 31)) & 1u))) {
                     uint32_t h = hash_at<GRAM>(dataw, p);
                     uint32_t old = atomicAdd(&dirw[h >> 1], (h & 1) ? 0x10000u : 1u);
                     uint32_t slot = (h & 1) ? (old >> 16) : (old & 0xFFFF);
@@ -264,42 +272,109 @@ __global__ void __launch_bounds__(THREADS, 1) lz4_encode_kernel(Params P)
             }
         };
 
-        build_index(std::integral_constant<int, 4>{}, npos);
-        LJB_PHASE(1); // index (4-gram)
-
-        // ---- phase A: sorted-order walk, first 8 bytes only
-        for (uint32_t j = tid; j < npos; j += THREADS) {
-            const uint32_t p = S[j];
-            const uint32_t P0 = load32u(dataw, p), P1 = load32u(dataw, p + 4);
-            const uint32_t h = hash4(P0);
-            const uint32_t lo = h ? dir16[h - 1] : 0u, hi = dir16[h];
-            const uint32_t cap8 = min(8u, nb - p);
-            const uint32_t pch = p >> 10;
-            uint32_t best = 0;
-            for (uint32_t i = lo; i < hi; ++i) {
-                const uint32_t c = S[i];
-                const uint32_t cch = c >> 10;
-                if (cch > pch) break; // only later positions from here on
-                // an 8-byte (or block-end) match from an earlier chunk cannot be beaten by later positions
-                if ((best >> 16) == cap8 && cch > ((0xFFFFu - (best & 0xFFFFu)) >> 10)) break;
-                if (c < p) {
-                    const uint32_t ci = c >> 2, cs = (c & 3) * 8;
-                    const uint32_t a0 = dataw[ci], a1 = dataw[ci + 1];
-                    if (__funnelshift_r(a0, a1, cs) == P0) {
-                        const uint32_t x = __funnelshift_r(a1, dataw[ci + 2], cs) ^ P1;
-                        uint32_t l = x ? 4u + ((uint32_t)(__ffs(x) - 1) >> 3) : 8u;
-                        l = min(l, cap8);
-                        best = max(best, (l << 16) | (0xFFFFu - c));
+        // ---- phase A: first-occurrence ladder, k = 8, 7, 6, 5, 4
+        // Level k puts every still-unresolved position into a table keyed by a hash of its k-gram that keeps
+        // the MINIMUM position (atomicMin).  A position whose slot holds an earlier position with the same
+        // k-gram has found the first occurrence F_k(p) of that gram: the longest match is >= k, and because
+        // no earlier position shares its (k+1)-gram (it would have been resolved one level up) every earlier
+        // occurrence matches exactly k bytes, so (k, F_k(p)) IS the reference's answer (earliest of the
+        // longest).  Resolved positions are never a first occurrence of any shorter gram either, so they
+        // leave the ladder.  Slots owned by a different gram ("losers") are re-hashed in further rounds; all
+        // occurrences of a gram win or lose together, which keeps the minimum exact.  Level 8 only flags:
+        // matches of 8+ bytes get their true length in phase B.
+        {
+            uint32_t *T = reinterpret_cast<uint32_t *>(smem + SM_S); // 32768 slots
+            constexpr int TBITS = 15;
+            constexpr int MAXR = 12;
+            unsigned long long unres = 0;
+#pragma unroll 1
+            for (int i = 0; i < 64; ++i)
+                if ((uint32_t)tid + 1024u * i < nb) unres |= 1ull << i;
+#pragma unroll 1
+            for (int k = 8; k >= 4; --k) {
+                const uint32_t npk = nb >= (uint32_t)k ? nb - k + 1 : 0;
+                const uint32_t m1 = k >= 8 ? 0xFFFFFFFFu : (k == 4 ? 0u : ((1u << (8 * (k - 4))) - 1u));
+                unsigned long long ins = 0;
+                for (unsigned long long m = unres; m;) {
+                    const int i = __ffsll((long long)m) - 1;
+                    m &= m - 1;
+                    if ((uint32_t)tid + 1024u * i < npk) ins |= 1ull << i;
+                }
+                int round = 0;
+                for (;;) {
+                    {
+                        uint4 *T4 = reinterpret_cast<uint4 *>(T);
+                        const uint4 ff = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+                        for (int i = tid; i < (1 << TBITS) / 4; i += THREADS) T4[i] = ff;
+                    }
+                    __syncthreads();
+                    const uint32_t A = 2654435761u + 0x9E3779B1u * (uint32_t)round * 2u;
+                    const uint32_t B = 2246822519u + 0x85EBCA77u * (uint32_t)round * 2u;
+                    for (unsigned long long m = ins; m;) {
+                        const int i = __ffsll((long long)m) - 1;
+                        m &= m - 1;
+                        const uint32_t p = (uint32_t)tid + 1024u * i;
+                        const uint32_t P0 = load32u(dataw, p), P1 = load32u(dataw, p + 4) & m1;
+                        uint32_t h = (P0 * A) ^ (P1 * B);
+                        h = ((h ^ (h >> 15)) * 2246822519u) >> (32 - TBITS);
+                        atomicMin(&T[h], p);
+                    }
+                    __syncthreads();
+                    unsigned long long next = 0;
+                    for (unsigned long long m = ins; m;) {
+                        const int i = __ffsll((long long)m) - 1;
+                        m &= m - 1;
+                        const uint32_t p = (uint32_t)tid + 1024u * i;
+                        const uint32_t P0 = load32u(dataw, p), P1 = load32u(dataw, p + 4) & m1;
+                        uint32_t h = (P0 * A) ^ (P1 * B);
+                        h = ((h ^ (h >> 15)) * 2246822519u) >> (32 - TBITS);
+                        const uint32_t q = T[h];
+                        if (q != p) { // q < p: the earliest position that hashes here
+                            const uint32_t Q0 = load32u(dataw, q), Q1 = load32u(dataw, q + 4) & m1;
+                            if (Q0 == P0 && Q1 == P1) {
+                                R[p] = ((uint32_t)k << 16) | q;
+                                unres &= ~(1ull << i);
+                                if (k == 8 && nb - p > 8) {
+                                    atomicOr(&longbits[p >> 5], 1u << (p & 31));
+                                    atomicOr(&firstbits[q >> 5], 1u << (q & 31));
+                                }
+                            } else {
+                                next |= 1ull << i; // slot owned by another gram: try again with another hash
+                            }
+                        }
+                    }
+                    ins = next;
+                    ++round;
+                    if (!__syncthreads_or(ins != 0)) break;
+                    if (round >= MAXR) break;
+                }
+                // practically unreachable: grams that kept colliding through MAXR independent hashes
+                for (unsigned long long m = ins; m;) {
+                    const int i = __ffsll((long long)m) - 1;
+                    m &= m - 1;
+                    const uint32_t p = (uint32_t)tid + 1024u * i;
+                    const uint32_t P0 = load32u(dataw, p), P1 = load32u(dataw, p + 4) & m1;
+                    for (uint32_t q = 0; q < p; ++q) {
+                        if (load32u(dataw, q) == P0 && (load32u(dataw, q + 4) & m1) == P1) {
+                            R[p] = ((uint32_t)k << 16) | q;
+                            unres &= ~(1ull << i);
+                            if (k == 8 && nb - p > 8) {
+                                atomicOr(&longbits[p >> 5], 1u << (p & 31));
+                                atomicOr(&firstbits[q >> 5], 1u << (q & 31));
+                            }
+                            break;
+                        }
                     }
                 }
             }
-            const uint32_t bl = best >> 16, bp = 0xFFFFu - (best & 0xFFFFu);
-            R[p] = bl ? ((bl << 16) | bp) : 0u;
-            if (bl == 8 && nb - p > 8) atomicOr(&longbits[p >> 5], 1u << (p & 31)); // may be longer: phase B decides
+            for (unsigned long long m = unres; m;) { // no earlier occurrence of even the 4-gram: literal
+                const int i = __ffsll((long long)m) - 1;
+                m &= m - 1;
+                R[(uint32_t)tid + 1024u * i] = 0;
+            }
         }
-        for (uint32_t p = npos + tid; p < nb; p += THREADS) R[p] = 0; // the last 3 positions cannot start a match
         __syncthreads();
-        LJB_PHASE(2); // search phase A
+        LJB_PHASE(2); // search phase A (ladder)
 
         // ---- phase B: positions with an >= 8 byte match, from the 8-gram index
         {
@@ -312,61 +387,278 @@ __global__ void __launch_bounds__(THREADS, 1) lz4_encode_kernel(Params P)
                 const uint32_t npos8 = nb >= 8 ? nb - 7 : 0;
                 build_index(std::integral_constant<int, 8>{}, npos8);
                 LJB_PHASE(3); // index (8-gram)
-                // thread t owns the 32-position chunks t, t + 1024: one word of longbits each
-                for (uint32_t ch = tid; ch * 32 < nb; ch += THREADS) {
-                    uint32_t bits = longbits[ch];
-                    uint32_t prev_len = 0, prev_pos = 0, prev_p = 0xFFFFFFFFu;
-                    bool prev_capped = false;
-                    while (bits) {
-                        const uint32_t p = ch * 32 + (__ffs(bits) - 1);
-                        bits &= bits - 1;
-                        const uint32_t cap = min((uint32_t)MAX_MATCH, nb - p);
-                        const uint32_t P0 = load32u(dataw, p), P1 = load32u(dataw, p + 4);
-                        uint32_t bestkey = 0;
-                        if (prev_p + 1 == p && prev_len >= 5) { // inherited candidate on the previous best's diagonal
-                            const uint32_t c0 = prev_pos + 1;
-                            uint32_t l0 = prev_len - 1;
-                            if (prev_capped) // the previous run was cut by the cap, not by a mismatch: it may go on
-                                while (l0 < cap && data[c0 + l0] == data[p + l0]) ++l0;
-                            l0 = min(l0, cap);
-                            bestkey = (l0 << 16) | (0xFFFFu - c0);
-                        }
-                        // a capped 1024 match becomes a literal step ((uint8_t)1024 == 0, LZ4.c:317) whose distance
-                        // is never used: no need to look for an earlier one
-                        if ((bestkey >> 16) != (uint32_t)MAX_MATCH) {
-                            const uint32_t h = hash8(P0, P1);
-                            const uint32_t lo = h ? dir16[h - 1] : 0u, hi = dir16[h];
-                            const uint32_t pch = p >> 10;
-                            for (uint32_t k = lo; k < hi; ++k) {
-                                const uint32_t c = S[k];
-                                const uint32_t cch = c >> 10;
-                                if (cch > pch) break;
-                                const uint32_t bl = bestkey >> 16, bp = 0xFFFFu - (bestkey & 0xFFFFu);
-                                if (bl == cap && cch > (bp >> 10)) break; // later positions cannot win a tie
-                                if (c < p) {
-                                    // a candidate matters only if it beats the best length, or ties it from an earlier position
-                                    const uint32_t need = bl == 0 ? 8u : (c < bp ? bl : bl + 1);
-                                    if (need <= cap) {
-                                        bool ok = true;
-                                        if (bl != 0) ok = data[c + need - 1] == data[p + need - 1];
-                                        if (ok) {
-                                            const uint32_t l = lcp_from(dataw, c, p, P0, P1, cap);
-                                            if (l >= 8) bestkey = max(bestkey, (l << 16) | (0xFFFFu - c));
-                                            if (l == (uint32_t)MAX_MATCH) break;
-                                        }
+                // ---- B1: sorted-order walk of the 8-gram index, first 16 bytes only.  The lanes of a warp sit in
+                // the same bucket (equal trip counts, broadcast loads).  A position whose best candidate is
+                // shorter than 16 bytes is final here; the others ("very long") go to B2.
+                uint32_t *vlong = firstbits; // the first-occurrence bits are dead once the index is built
+                for (int i = tid; i < MAXB / 32; i += THREADS) vlong[i] = 0;
+                __syncthreads();
+                {
+                    const uint32_t nidx = dir16[NBUCKET - 1];
+                    for (uint32_t j = tid; j < nidx; j += THREADS) {
+                        const uint32_t p = S[j];
+                        if (!((longbits[p >> 5] >> (p & 31)) & 1u)) continue; // a first occurrence: candidate only
+                        const uint32_t pi = p >> 2, ps = (p & 3) * 8;
+                        const uint32_t w0 = dataw[pi], w1 = dataw[pi + 1], w2 = dataw[pi + 2], w3 = dataw[pi + 3], w4 = dataw[pi + 4];
+                        const uint32_t P0 = __funnelshift_r(w0, w1, ps), P1 = __funnelshift_r(w1, w2, ps);
+                        const uint32_t P2 = __funnelshift_r(w2, w3, ps), P3 = __funnelshift_r(w3, w4, ps);
+                        const uint32_t h = hash8(P0, P1);
+                        const uint32_t lo = h ? dir16[h - 1] : 0u, hi = dir16[h];
+                        const uint32_t cap16 = min(16u, nb - p);
+                        const uint32_t pch = p >> 10;
+                        uint32_t best = 0, n16 = 0, cand = 0xFFFFFFFFu;
+                        for (uint32_t i = lo; i < hi; ++i) {
+                            const uint32_t c = S[i];
+                            const uint32_t cch = c >> 10;
+                            if (cch > pch) break; // only later positions from here on
+                            // later positions cannot win a tie; but B2 needs EVERY 16-byte candidate unless it walks the bucket itself
+                            if ((best >> 16) == cap16 && (cap16 < 16 || n16 > 2) && cch > ((0xFFFFu - (best & 0xFFFFu)) >> 10)) break;
+                            if (c < p) {
+                                const uint32_t ci = c >> 2, cs = (c & 3) * 8;
+                                const uint32_t a0 = dataw[ci], a1 = dataw[ci + 1], a2 = dataw[ci + 2];
+                                if (__funnelshift_r(a0, a1, cs) == P0 && __funnelshift_r(a1, a2, cs) == P1) {
+                                    const uint32_t a3 = dataw[ci + 3], a4 = dataw[ci + 4];
+                                    const uint32_t x2 = __funnelshift_r(a2, a3, cs) ^ P2, x3 = __funnelshift_r(a3, a4, cs) ^ P3;
+                                    uint32_t l = x2 ? 8u + ((uint32_t)(__ffs(x2) - 1) >> 3) : (x3 ? 12u + ((uint32_t)(__ffs(x3) - 1) >> 3) : 16u);
+                                    l = min(l, cap16);
+                                    best = max(best, (l << 16) | (0xFFFFu - c));
+                                    if (l == 16) { // remember up to 2 candidates that may be longer; B2 measures only these
+                                        if (n16 == 0) cand = (cand & 0xFFFF0000u) | c;
+                                        if (n16 == 1) cand = (cand & 0xFFFFu) | (c << 16);
+                                        ++n16;
                                     }
                                 }
                             }
                         }
-                        const uint32_t bl = bestkey >> 16, bp = 0xFFFFu - (bestkey & 0xFFFFu);
-                        prev_len = bl;
-                        prev_pos = bp;
-                        prev_p = p;
-                        prev_capped = bl == cap;
-                        R[p] = (bl << 16) | bp; // bl >= 8 here: phase A proved an 8-byte match exists
+                        const uint32_t bl = best >> 16, bp = 0xFFFFu - (best & 0xFFFFu);
+                        if (bl == 16 && nb - p > 16) { // may be longer: B2 decides
+                            atomicOr(&vlong[p >> 5], 1u << (p & 31));
+                            if (n16 > 2) cand = (cand & 0xFFFFu) | 0xFFFE0000u; // overflow: B2 walks the bucket itself
+                            R[p] = cand; // provisional: the two candidates, in place of (length, position)
+                        } else {
+                            R[p] = (bl << 16) | bp; // bl >= 8: the ladder proved an earlier occurrence of the 8-gram
+                        }
                     }
                 }
+                __syncthreads();
+                LJB_PHASE(1); // search phase B1
+                // ---- B2: very long matches, in position order.
+                // Each thread walks one 32-position chunk (one word of vlong) in position order and keeps
+                constexpr int KEEP = 4;
+                constexpr uint32_t SHORT = 32; // a lane compares this much on its own; longer runs are compared by the whole warp
+                if (tid == 0) M.scan_tmp[0] = 0;
+                __syncthreads();
+                const uint32_t nrows = (nb + 1023) >> 10;
+                for (;;) {
+                    uint32_t row = 0;
+                    if (lane == 0) row = atomicAdd(&M.scan_tmp[0], 1u);
+                    row = __shfl_sync(0xffffffffu, row, 0);
+                    if (row >= nrows) break;
+                    const uint32_t ch = row * 32 + lane;
+                    const uint32_t bits = (ch * 32 < nb) ? vlong[ch] : 0u;
+                    uint32_t pc[KEEP], pl[KEEP]; // candidates of the previous position: position, length | capped << 16
+                    uint32_t pn = 0;
+                    uint32_t dbg_pos = 0, dbg_vis = 0, dbg_scratch = 0, dbg_bytes = 0, dbg_inh = 0;
+                    long long tA = 0, tB = 0, tC = 0, tD = 0, tcur = clock64();
+                    const long long trow0 = tcur;
+#define LJB_T(acc) do { long long tn = clock64(); acc += tn - tcur; tcur = tn; } while (0)
+                    // all lanes step through the 32 positions of their chunks together (warp-uniform control flow),
+                    // so that long compares can be done by the whole warp
+                    uint32_t steps = __reduce_or_sync(0xffffffffu, bits);
+                    // the candidates of the next step are fetched (one L2 round trip) while this step is processed
+                    uint32_t sl_next = 0xFFFFFFFFu;
+                    if (steps) {
+                        const int i0 = __ffs(steps) - 1;
+                        if ((bits >> i0) & 1u) sl_next = R[ch * 32 + i0];
+                    }
+                    while (steps) {
+                        const int i = __ffs(steps) - 1;
+                        steps &= steps - 1;
+                        const uint32_t sl = sl_next;
+                        sl_next = 0xFFFFFFFFu;
+                        if (steps) {
+                            const int i1 = __ffs(steps) - 1;
+                            if ((bits >> i1) & 1u) sl_next = R[ch * 32 + i1];
+                        }
+                        const bool active = (bits >> i) & 1u;
+                        const uint32_t p = ch * 32 + i;
+                        const bool chained = active && i > 0 && ((bits >> (i - 1)) & 1u);
+                        if (!chained) pn = 0;
+                        uint32_t cap = 0, P0 = 0, P1 = 0, bestkey = 0;
+                        bool overflow = false;
+                        if (active) {
+                            ++dbg_pos;
+                            cap = min((uint32_t)MAX_MATCH, nb - p);
+                            P0 = load32u(dataw, p);
+                            P1 = load32u(dataw, p + 4);
+                            overflow = (sl >> 16) == 0xFFFEu;
+                        }
+                        uint32_t nc[KEEP], nl[KEEP], nn = 0;
+                        if (__shfl_sync(0xffffffffu, sl, 0) == 0x12345u) tA += 1; // keep the loads before the timer
+                        LJB_T(tA);
+                        // the (at most 2) candidates B1 found with >= 16 matching bytes: measure each, reusing the
+                        // previous position's result when the pair continues that diagonal
+#pragma unroll
+                        for (int q = 0; q < 2; ++q) {
+                            const uint32_t c = (sl >> (q * 16)) & 0xFFFFu;
+                            const bool eval = active && !overflow && c != 0xFFFFu && (bestkey >> 16) != (uint32_t)MAX_MATCH;
+                            uint32_t l = 0xFFFFFFFFu;
+                            bool fresh = false;
+                            if (eval) {
+#pragma unroll
+                                for (int t = 0; t < KEEP; ++t) {
+                                    if ((uint32_t)t < pn && pc[t] + 1 == c) {
+                                        l = (pl[t] & 0xFFFF) - 1;
+                                        if (pl[t] >> 16) // previous length was cut by the cap, not by a mismatch: it may go on
+                                            while (l < cap && data[c + l] == data[p + l]) ++l;
+                                        l = min(l, cap);
+                                        ++dbg_inh;
+                                    }
+                                }
+                                if (l == 0xFFFFFFFFu) {
+                                    l = lcp_from(dataw, c, p, P0, P1, min(cap, SHORT));
+                                    fresh = true;
+                                    ++dbg_scratch;
+                                }
+                            }
+                            // runs that are still matching after SHORT bytes: the warp compares 256 bytes per step
+                            LJB_T(tB);
+                            // (inherited lengths are exact or already extended; only from-scratch results can be cut at SHORT)
+                            unsigned pend = __ballot_sync(0xffffffffu, fresh && l == SHORT && cap > SHORT);
+                            while (pend) {
+                                const int src = __ffs(pend) - 1;
+                                pend &= pend - 1;
+                                const uint32_t bc = __shfl_sync(0xffffffffu, c, src), bp_ = __shfl_sync(0xffffffffu, p, src);
+                                const uint32_t bcap = __shfl_sync(0xffffffffu, cap, src);
+                                uint32_t res = bcap;
+                                for (uint32_t base = SHORT; base < bcap; base += 256) {
+                                    const uint32_t off = base + 8 * lane;
+                                    uint32_t x0 = 0, x1 = 0;
+                                    if (off < bcap) {
+                                        const uint32_t ci = (bc + off) >> 2, cs = ((bc + off) & 3) * 8;
+                                        const uint32_t pi = (bp_ + off) >> 2, ps = ((bp_ + off) & 3) * 8;
+                                        const uint32_t a0 = dataw[ci], a1 = dataw[ci + 1], a2 = dataw[ci + 2];
+                                        const uint32_t b0 = dataw[pi], b1 = dataw[pi + 1], b2 = dataw[pi + 2];
+                                        x0 = __funnelshift_r(a0, a1, cs) ^ __funnelshift_r(b0, b1, ps);
+                                        x1 = __funnelshift_r(a1, a2, cs) ^ __funnelshift_r(b1, b2, ps);
+                                    }
+                                    const unsigned mm = __ballot_sync(0xffffffffu, (x0 | x1) != 0);
+                                    if (mm) {
+                                        const int f = __ffs(mm) - 1;
+                                        const uint32_t mine = off + (x0 ? ((uint32_t)(__ffs(x0) - 1) >> 3) : 4u + ((uint32_t)(__ffs(x1) - 1) >> 3));
+                                        res = min(__shfl_sync(0xffffffffu, mine, f), bcap);
+                                        break;
+                                    }
+                                }
+                                if (lane == src) {
+                                    l = res;
+                                    dbg_bytes += res;
+                                }
+                            }
+                            LJB_T(tC);
+                            if (eval) {
+                                bestkey = max(bestkey, (l << 16) | (0xFFFFu - c));
+#pragma unroll
+                                for (int u = 0; u < KEEP; ++u)
+                                    if ((uint32_t)u == nn) {
+                                        nc[u] = c;
+                                        nl[u] = l | ((l == cap) ? 0x10000u : 0u);
+                                    }
+                                ++nn;
+                            }
+                        }
+                        LJB_T(tB);
+                        if (active && overflow) {
+                            // more than 4 long candidates (highly repetitive data): walk the bucket with pruning
+                            // 1. candidates inherited along the diagonals of the previous position's long matches
+#pragma unroll
+                            for (int t = 0; t < KEEP; ++t) {
+                                if ((uint32_t)t < pn) {
+                                    const uint32_t c = pc[t] + 1;
+                                    uint32_t l = (pl[t] & 0xFFFF) - 1;
+                                    if (pl[t] >> 16)
+                                        while (l < cap && data[c + l] == data[p + l]) ++l;
+                                    l = min(l, cap);
+                                    bestkey = max(bestkey, (l << 16) | (0xFFFFu - c));
+                                    pc[t] = c; // now holds this position's candidate (used for the duplicate test below)
+                                    if (l >= 16) {
+#pragma unroll
+                                        for (int u = 0; u < KEEP; ++u)
+                                            if ((uint32_t)u == nn) {
+                                                nc[u] = c;
+                                                nl[u] = l | ((l == cap) ? 0x10000u : 0u);
+                                            }
+                                        ++nn;
+                                    }
+                                }
+                            }
+                            // 2. the rest of the bucket; a capped 1024 match becomes a literal step ((uint8_t)1024 == 0,
+                            //    LZ4.c:317) whose distance is never used, so nothing else needs to be looked at
+                            if ((bestkey >> 16) != (uint32_t)MAX_MATCH) {
+                                const uint32_t h = hash8(P0, P1);
+                                const uint32_t lo = h ? dir16[h - 1] : 0u, hi = dir16[h];
+                                const uint32_t pch = p >> 10;
+                                for (uint32_t k = lo; k < hi; ++k) {
+                                    const uint32_t c = S[k];
+                                    if ((c >> 10) > pch) break; // only later positions from here on
+                                    ++dbg_vis;
+                                    if (c >= p) continue;
+                                    const uint32_t bl = bestkey >> 16, bp = 0xFFFFu - (bestkey & 0xFFFFu);
+                                    if (bl == cap && (c >> 10) > (bp >> 10)) break; // later positions cannot win a tie
+                                    // a candidate matters only if it beats the best length, or ties it from an earlier position
+                                    const uint32_t need = bl < 16 ? 16u : (c < bp ? bl : bl + 1); // B1 proved a 16-byte match exists
+                                    if (need > cap) continue;
+                                    bool dup = false;
+#pragma unroll
+                                    for (int t = 0; t < KEEP; ++t) dup |= ((uint32_t)t < pn && pc[t] == c);
+                                    if (dup) continue; // already evaluated as an inherited candidate
+                                    if (data[c + need - 1] != data[p + need - 1]) continue;
+                                    const uint32_t l = lcp_from(dataw, c, p, P0, P1, cap);
+                                    if (l < 16) continue; // cannot be the answer: a 16-byte match exists
+                                    bestkey = max(bestkey, (l << 16) | (0xFFFFu - c));
+                                    if (nn < KEEP) {
+#pragma unroll
+                                        for (int u = 0; u < KEEP; ++u)
+                                            if ((uint32_t)u == nn) {
+                                                nc[u] = c;
+                                                nl[u] = l | ((l == cap) ? 0x10000u : 0u);
+                                            }
+                                        ++nn;
+                                    }
+                                    if (l == (uint32_t)MAX_MATCH) break;
+                                }
+                            }
+                        }
+                        LJB_T(tD);
+                        if (active) {
+#pragma unroll
+                            for (int t = 0; t < KEEP; ++t) {
+                                pc[t] = nc[t];
+                                pl[t] = nl[t];
+                            }
+                            pn = nn;
+                            const uint32_t bl = bestkey >> 16, bp = 0xFFFFu - (bestkey & 0xFFFFu);
+                            R[p] = (bl << 16) | bp; // bl >= 16 here
+                        }
+                    }
+                    if (P.phase_cycles) {
+                        atomicAdd(&P.phase_cycles[9], (unsigned long long)dbg_pos);
+                        (void)dbg_vis; (void)dbg_scratch; (void)dbg_bytes;
+                        atomicAdd(&P.phase_cycles[13], (unsigned long long)dbg_inh);
+                        if (lane == 0) {
+                            atomicAdd(&P.phase_cycles[14], (unsigned long long)(clock64() - trow0));
+                            atomicAdd(&P.phase_cycles[15], (unsigned long long)tA);
+                            atomicAdd(&P.phase_cycles[10], (unsigned long long)tB);
+                            atomicAdd(&P.phase_cycles[11], (unsigned long long)tC);
+                            atomicAdd(&P.phase_cycles[12], (unsigned long long)tD);
+                        }
+                    }
+#undef LJB_T
+                }
             }
+        }
+        if (P.phase_cycles && lane == 0) {
+            // (profiling aid) how long this warp was busy in B2, and the slowest warp
         }
         __syncthreads();
         LJB_PHASE(4); // search phase B
@@ -652,12 +944,14 @@ static int lz4_launch(ljb_ctx *ctx, const uint8_t *d_in, size_t n, size_t block_
         unsigned long long ph[16];
         LJB_CUDA(cudaMemcpyAsync(ph, P.phase_cycles, sizeof ph, cudaMemcpyDeviceToHost, ctx->stream));
         LJB_CUDA(cudaStreamSynchronize(ctx->stream));
-        static const char *names[9] = {"stage", "index4", "phaseA", "index8", "phaseB", "parse", "sizing", "lookback", "emit"};
+        static const char *names[9] = {"stage", "phaseB1", "ladderA", "index8", "phaseB", "parse", "sizing", "lookback", "emit"};
         unsigned long long tot = 0;
         for (int i = 0; i < 9; ++i) tot += ph[i];
         fprintf(stderr, "[ljb lz4 phases] cycles per block:");
         for (int i = 0; i < 9; ++i) fprintf(stderr, " %s=%.0f(%.0f%%)", names[i], (double)ph[i] / (double)nblocks, 100.0 * (double)ph[i] / (double)tot);
         fprintf(stderr, " total=%.0f\n", (double)tot / (double)nblocks);
+        fprintf(stderr, "[ljb lz4 phaseB2] per block: positions=%.0f inherited=%.0f | warp-cycles: rows=%.0f load=%.0f eval=%.0f coop=%.0f fallback=%.0f\n",
+                (double)ph[9] / nblocks, (double)ph[13] / nblocks, (double)ph[14] / nblocks, (double)ph[15] / nblocks, (double)ph[10] / nblocks, (double)ph[11] / nblocks, (double)ph[12] / nblocks);
     }
     return LJB_OK;
 }
