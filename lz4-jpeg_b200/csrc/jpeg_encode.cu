@@ -11,45 +11,58 @@
 // the per-group records (device-wide decoupled look-back over record sizes).
 //
 // Work decomposition: the reference spawns one thread per 8x8 group (P-JPG:1297-1302); here one CUDA
-// thread owns one group, 192 groups per CTA tile, persistent CTAs pull tiles from a ticket counter.
+// thread owns one group, 512 groups per CTA tile, one persistent CTA per SM pulling tiles from a ticket
+// counter.  Every per-thread array lives in shared memory WORD-INTERLEAVED across the 32 lanes of its warp
+// (word w of lane l at warp_base + (w*32 + l)*4): whatever data-dependent index a lane uses, it stays in
+// its own bank, so the divergent heap / table walks of the Huffman construction are bank-conflict free.
+// 112 words per thread (LUT 64 | heap+codes 32 | parents 16) let 16 warps share the 227 KB of one SM.
 //
-// Exactness: colour conversion is evaluated in IEEE double with explicit round-to-nearest mul/add in
-// the reference's left-to-right order (no FMA contraction).  The DCT is evaluated twice at most: a
-// separable double-precision fast path, and — only for a coefficient whose quotient lies within 1e-6
-// of a non-zero integer, where truncation could go either way — the reference's own summation order
-// (x outer, y inner, (corr*cos_x)*cos_y, no FMA) with the exact cos()/sqrt() doubles glibc returns
-// (jpeg_tables.inc).  The result is bit-identical quantised coefficients, hence identical bit strings.
+// Exactness (results are bit-identical to the reference built with gcc x86-64 SSE2 -O2 -ffp-contract=off):
+//   colour   the reference evaluates 0.299*r+0.587*g+0.114*b (etc.) in double and truncates.  The exact
+//            rational value is S/1000 with S an integer; unless S is a multiple of 1000 it is >= 1e-3 away
+//            from every integer while the double evaluation errs by < 1e-12, so floor(S/1000) is the
+//            answer; for S % 1000 == 0 (one pixel in a thousand) the double expression itself is evaluated
+//            with explicit round-to-nearest mul/add in the reference's left-to-right order (no FMA).
+//   DCT      a separable double-precision evaluation with even/odd butterflies gives every quotient to
+//            ~1e-12; a coefficient whose quotient lies within 1e-6 of a non-zero integer (where truncation
+//            could go either way) is re-evaluated in the reference's own summation order (x outer, y
+//            inner, (corr*cos_x)*cos_y, no FMA) with the exact cos()/sqrt() doubles glibc returns
+//            (jpeg_tables.inc).
+//   Huffman  the reference's array-heap procedure is simulated step by step per (group, channel).
+// Channels outside the fast path's limits (a quantised value outside int8, more than 32 distinct symbols,
+// a code longer than 26 bits) are redone by a general per-thread routine on local-memory arrays.
 #include "common.cuh"
+
+#include <stdlib.h>
 
 namespace jpgk {
 
 #include "jpeg_tables.inc"
 
-constexpr int THREADS = 192;       // groups per tile
+constexpr int THREADS = 512;       // groups per tile
+constexpr int NWARPS = THREADS / 32;
 constexpr int REC_BYTES = 256;     // max packed record: (1023 + 511 + 511) bits (JPEG.c:1248, :1286, :1320)
-constexpr int MAXSYM = 72;         // <= 64 distinct values + <= 10 distinct run lengths
-constexpr int MAXNODE = 2 * MAXSYM;
+constexpr int REC_WORDS = REC_BYTES / 4;
 
-// per-thread scratch in shared memory (bytes); the stride is an odd number of words so that threads
-// touching the same logical index fall into different banks
-constexpr int OFF_COEF = 0;        // int16[128]: zig-zag ordered quantised lum[64], r[32], b[32]
-constexpr int OFF_LUT = 256;       // uint8[320]: symbol value+160 -> slot   (aliased by samples u8[128] before entropy)
-constexpr int OFF_X = 576;         // 288 B: while building: cnt u8[144] | heap u8[72]; afterwards code u32[72]
-constexpr int OFF_PAR = 864;       // uint8[144] parent node
-constexpr int OFF_PBIT = 1008;     // uint32[5]  bit of each node under its parent
-constexpr int OFF_LEN = 1028;      // uint8[72]  code length per slot
-constexpr int STRIDE = 1100;
-static_assert((STRIDE / 4) % 2 == 1 && STRIDE % 4 == 0, "stride must be an odd number of words");
-constexpr int SM_THREADS = THREADS * STRIDE;
-constexpr int SM_COS8 = SM_THREADS;            // double[64]
-constexpr int SM_COS4 = SM_COS8 + 512;         // double[16]
-constexpr int SM_MISC = SM_COS4 + 128;
-constexpr int SM_TOTAL = SM_MISC + 2048;
+// per-thread workspace, in 32-bit words (interleaved across the warp)
+constexpr int W_LUT = 0;           // u8[256]: symbol+128 -> (epoch << 5) | slot
+constexpr int W_HEAP = 64;         // u16[34]: 1-based array heap of (count << 8) | node id     (17 words)
+constexpr int W_CODE = 64;         // u32[32]: (length << 27) | code per leaf slot; aliases the heap once the tree is built
+constexpr int W_PAR = 96;          // u8[64]: parent node id | 0x80 if the node is a right child
+constexpr int WS_WORDS = 112;
+// DCT phase view of the same words
+constexpr int W_T = 0;             // double[32]: row-pass results (8 rows x 4 columns), 64-bit interleaved
+constexpr int W_SMP = 64;          // u8[128]: samples lum[64] | Cr[32] | Cb[32]
+constexpr int FAST_MAXSYM = 32;
+constexpr int FAST_MAXLEN = 26;
+
+constexpr int SM_WS = THREADS * WS_WORDS * 4; // 229376
+constexpr int SM_MISC = SM_WS;
+constexpr int SM_TOTAL = SM_MISC + 256;
 static_assert(SM_TOTAL <= 227 * 1024, "exceeds B200 shared memory per CTA");
 
 struct Misc {
-    unsigned int rec_off[THREADS + 1]; // exclusive scan of record sizes inside the tile
-    unsigned int warp_sum[THREADS / 32];
+    unsigned int warp_sum[NWARPS];
     long long ticket;
     unsigned long long base;
     int emit_ok;
@@ -67,8 +80,9 @@ struct Params {
     int16_t *coefs;          // optional, 128 per group
     uint64_t *result;        // [0] length, [1] groups outside the reference's defined behaviour, [2] error flags
     uint64_t *status;        // [0] ticket, [1..] look-back words (one per tile)
-    uint32_t *scratch;       // per CTA: THREADS * 64 words of record staging
+    uint32_t *scratch;       // per CTA: REC_WORDS x THREADS words of record staging, word-major
     uint32_t ntiles;
+    int force_slow;          // test hook: route every channel through the general routine
 };
 
 // JPEG.c:12-27 as doubles, and their reciprocals for the fast path (the chroma table is consumed as
@@ -130,35 +144,76 @@ struct ZigZag {
         }
     }
 };
+__constant__ const ZigZag<8, 8> kZZ8 = ZigZag<8, 8>(); // dynamically indexed copies for the general routine
+__constant__ const ZigZag<4, 8> kZZ4 = ZigZag<4, 8>();
 
-// ---- colour conversion, JPEG.c:127, :157, :180 (double, left to right, no contraction) ---------------
-__device__ __forceinline__ int luma_of(int r, int g, int b)
+// ---- interleaved workspace accessors: wl = warp workspace base + lane ------------------------------------
+__device__ __forceinline__ uint32_t &ws_w(uint32_t *wl, int word) { return wl[word * 32]; }
+__device__ __forceinline__ uint8_t &ws_b(uint32_t *wl, int word0, int byte)
+{
+    return reinterpret_cast<uint8_t *>(wl + (word0 + (byte >> 2)) * 32)[byte & 3];
+}
+__device__ __forceinline__ uint16_t &ws_h(uint32_t *wl, int word0, int half)
+{
+    return reinterpret_cast<uint16_t *>(wl + (word0 + (half >> 1)) * 32)[half & 1];
+}
+// 64-bit interleaved view of words [0, 64): double d of lane l at warp_base + (d*32 + l)*8
+__device__ __forceinline__ double &ws_d(uint32_t *wbase, int lane, int d) { return reinterpret_cast<double *>(wbase)[d * 32 + lane]; }
+
+// ---- colour conversion, JPEG.c:127, :157, :180 ------------------------------------------------------------
+__device__ __noinline__ int luma_exact(int r, int g, int b)
 {
     double y = __dadd_rn(__dadd_rn(__dmul_rn(0.299, (double)r), __dmul_rn(0.587, (double)g)), __dmul_rn(0.114, (double)b));
     return (int)y & 0xFF; // implicit double -> uint8_t conversion of a value in [0, 255]
 }
 __device__ __forceinline__ int clamp255(int v) { return v < 0 ? 0 : (v > 255 ? 255 : v); }
-__device__ __forceinline__ int cr_of(int r, int g, int b)
+__device__ __noinline__ int cr_exact(int r, int g, int b)
 {
     double v = __dadd_rn(__dsub_rn(__dsub_rn(__dmul_rn(0.439, (double)r), __dmul_rn(0.368, (double)g)), __dmul_rn(0.071, (double)b)), 128.0);
     return clamp255((int)v);
 }
-__device__ __forceinline__ int cb_of(int r, int g, int b)
+__device__ __noinline__ int cb_exact(int r, int g, int b)
 {
     double v = __dadd_rn(__dadd_rn(__dsub_rn(__dmul_rn(-0.148, (double)r), __dmul_rn(0.291, (double)g)), __dmul_rn(0.439, (double)b)), 128.0);
     return clamp255((int)v);
 }
+// floor(s / 1000) for 0 <= s < 2^18, and whether s is a multiple of 1000
+__device__ __forceinline__ int div1000(int s, bool &tie)
+{
+    const int q = (int)__umulhi((unsigned)s, 4294968u); // ceil(2^32 / 1000): exact for s < 2^22
+    tie = (s - q * 1000) == 0;
+    return q;
+}
+__device__ __forceinline__ int luma_of(int r, int g, int b)
+{
+    bool tie;
+    const int q = div1000(299 * r + 587 * g + 114 * b, tie);
+    return tie ? luma_exact(r, g, b) : q;
+}
+__device__ __forceinline__ int cr_of(int r, int g, int b)
+{
+    bool tie; // 439r - 368g - 71b + 128000 lies in [16055, 239945]: positive, so (int) truncation is floor and clamp is idle
+    const int q = div1000(439 * r - 368 * g - 71 * b + 128000, tie);
+    return tie ? cr_exact(r, g, b) : q;
+}
+__device__ __forceinline__ int cb_of(int r, int g, int b)
+{
+    bool tie;
+    const int q = div1000(-148 * r - 291 * g + 439 * b + 128000, tie);
+    return tie ? cb_exact(r, g, b) : q;
+}
 
-// ---- the reference's own summation, JPEG.c:471-490, for one coefficient ------------------------------
-template <int W>
-__device__ __noinline__ double exact_coef(const uint8_t *smp, int u, int v, const double *c8, const double *c4)
+// ---- the reference's own summation, JPEG.c:471-490, for one coefficient ------------------------------------
+// smp(i) returns sample i of the channel (row-major, W columns)
+template <int W, class F>
+__device__ __forceinline__ double exact_coef_t(F smp, int u, int v)
 {
     double sum = 0.0;
     for (int x = 0; x < 8; ++x) {
-        const double cx = c8[x * 8 + u];
+        const double cx = kCos8[x * 8 + u];
         for (int y = 0; y < W; ++y) {
-            const double cy = (W == 8) ? c8[y * 8 + v] : c4[y * 4 + v];
-            const double corr = (double)((int)smp[x * W + y] - 128);
+            const double cy = (W == 8) ? kCos8[y * 8 + v] : kCos4[y * 4 + v];
+            const double corr = (double)(smp(x * W + y) - 128);
             sum = __dadd_rn(sum, __dmul_rn(__dmul_rn(corr, cx), cy));
         }
     }
@@ -166,66 +221,135 @@ __device__ __noinline__ double exact_coef(const uint8_t *smp, int u, int v, cons
     const double av = (W == 8) ? (v == 0 ? kAlpha8[0] : kAlpha8[1]) : (v == 0 ? kAlpha4[0] : kAlpha4[1]);
     return __dmul_rn(__dmul_rn(au, av), sum);
 }
-
-// DCT + quantise + zig-zag of one channel (W = 8 luma, W = 4 chroma; 8 rows).
 template <int W>
-__device__ __forceinline__ void transform_channel(const uint8_t *smp, int16_t *cz, int16_t *coefs_out, const double *c8s,
-                                                  const double *c4s)
+__device__ __noinline__ int exact_quant_ws(uint32_t *wl, int byte0, int u, int v)
 {
-    constexpr ZigZag<W, 8> zz;
-    double T[8][W];
-    // row pass: T[x][v] = sum_y corr[x][y] * cos_y[y][v]
-#pragma unroll
-    for (int x = 0; x < 8; ++x) {
-        double c[W];
-#pragma unroll
-        for (int y = 0; y < W; ++y) c[y] = (double)((int)smp[x * W + y] - 128);
-#pragma unroll
-        for (int v = 0; v < W; ++v) {
-            double acc = 0.0;
-#pragma unroll
-            for (int y = 0; y < W; ++y) acc = fma(c[y], (W == 8) ? kCos8[y * 8 + v] : kCos4[y * 4 + v], acc);
-            T[x][v] = acc;
-        }
-    }
-    // column pass + quantise
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-#pragma unroll
-        for (int v = 0; v < W; ++v) {
-            double acc = 0.0;
-#pragma unroll
-            for (int x = 0; x < 8; ++x) acc = fma(T[x][v], kCos8[x * 8 + u], acc);
-            const double au = u == 0 ? kAlpha8[0] : kAlpha8[1];
-            const double av = (W == 8) ? (v == 0 ? kAlpha8[0] : kAlpha8[1]) : (v == 0 ? kAlpha4[0] : kAlpha4[1]);
-            const double q = (W == 8) ? kQLum[u * W + v] : kQChr[u * W + v];
-            const double qf = ((au * av) * acc) * ((W == 8) ? kRLum[u * W + v] : kRChr[u * W + v]); // within 2 ulp of the quotient
-            int t = (int)qf; // truncation toward zero, JPEG.c:627
-            // |qf| < 1 - 1e-6 truncates to 0 whatever the last bits are; otherwise a quotient within 1e-6
-            // of an integer is re-evaluated in the reference's own order (fast-path error is < 1e-9)
-            if (fabs(qf) >= 0.999999 && fabs(qf - rint(qf)) < 1e-6) {
-                const double ce = exact_coef<W>(smp, u, v, c8s, c4s);
-                t = (int)__ddiv_rn(ce, q);
-            }
-            cz[zz.pos[u * W + v]] = (int16_t)t;
-            if (coefs_out) coefs_out[u * W + v] = (int16_t)t;
-        }
-    }
+    const double ce = exact_coef_t<W>([&](int i) { return (int)ws_b(wl, W_SMP, byte0 + i); }, u, v);
+    return (int)__ddiv_rn(ce, (W == 8) ? kQLum[u * W + v] : kQChr[u * W + v]);
 }
 
-// ---- per-channel adaptive Huffman code + emission -----------------------------------------------------
+// quantise one fast-path coefficient value (already scaled by alpha_u*alpha_v); returns true if the
+// truncation is safe, i.e. the quotient is not within 1e-6 of a non-zero integer
+__device__ __forceinline__ bool quant_fast(double scaled, double recip, int &t)
+{
+    const double qf = scaled * recip; // within 2 ulp of the quotient
+    t = (int)qf;                      // truncation toward zero, JPEG.c:627
+    return !(fabs(qf) >= 0.999999 && fabs(qf - rint(qf)) < 1e-6);
+}
+
+__device__ __forceinline__ void put_i8(uint32_t &reg, int byte, int t)
+{
+    reg = (reg & ~(0xFFu << (8 * byte))) | (((uint32_t)t & 0xFFu) << (8 * byte));
+}
+
+// Luma: 8x8 DCT + quantise + zig-zag -> 64 int8 packed in L[16]; returns true if some value is outside int8.
+__device__ __forceinline__ bool dct_luma(uint32_t *wl, uint32_t *wbase, int lane, uint32_t (&L)[16], int16_t *co)
+{
+    constexpr ZigZag<8, 8> zz;
+    bool wide = false;
+#pragma unroll
+    for (int par = 0; par < 2; ++par) { // even / odd output columns v
+        // row pass: T[x][vi] = sum_y corr[x][y] * cos8[y][v], v = 2 vi + par, using cos8[7-y][v] = (-1)^v cos8[y][v]
+#pragma unroll
+        for (int x = 0; x < 8; ++x) {
+            const uint32_t w0 = ws_w(wl, W_SMP + 2 * x), w1 = ws_w(wl, W_SMP + 2 * x + 1);
+            double e[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int a = (w0 >> (8 * j)) & 0xFF, b = (w1 >> (8 * (3 - j))) & 0xFF; // y = j and y = 7 - j
+                e[j] = (double)(par == 0 ? a + b - 256 : a - b);
+            }
+#pragma unroll
+            for (int vi = 0; vi < 4; ++vi) {
+                const int v = 2 * vi + par;
+                double acc = e[0] * kCos8[0 * 8 + v];
+#pragma unroll
+                for (int j = 1; j < 4; ++j) acc = fma(e[j], kCos8[j * 8 + v], acc);
+                ws_d(wbase, lane, x * 4 + vi) = acc;
+            }
+        }
+        // column pass + quantise
+#pragma unroll
+        for (int vi = 0; vi < 4; ++vi) {
+            const int v = 2 * vi + par;
+            double s[4], d[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const double a = ws_d(wbase, lane, j * 4 + vi), b = ws_d(wbase, lane, (7 - j) * 4 + vi);
+                s[j] = a + b;
+                d[j] = a - b;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                double acc = ((u & 1) ? d[0] : s[0]) * kCos8[0 * 8 + u];
+#pragma unroll
+                for (int j = 1; j < 4; ++j) acc = fma((u & 1) ? d[j] : s[j], kCos8[j * 8 + u], acc);
+                const double au = u == 0 ? kAlpha8[0] : kAlpha8[1], av = v == 0 ? kAlpha8[0] : kAlpha8[1];
+                int t;
+                if (!quant_fast((au * av) * acc, kRLum[u * 8 + v], t)) t = exact_quant_ws<8>(wl, 0, u, v);
+                wide |= (t < -128) | (t > 127);
+                put_i8(L[zz.pos[u * 8 + v] >> 2], zz.pos[u * 8 + v] & 3, t);
+                if (co) co[u * 8 + v] = (int16_t)t;
+            }
+        }
+    }
+    return wide;
+}
+
+// Chroma: 8 rows x 4 columns -> 32 int8 packed in C[8]
+__device__ __forceinline__ bool dct_chroma(uint32_t *wl, uint32_t *wbase, int lane, int byte0, uint32_t (&C)[8], int16_t *co)
+{
+    constexpr ZigZag<4, 8> zz;
+    bool wide = false;
+#pragma unroll
+    for (int x = 0; x < 8; ++x) {
+        const uint32_t w0 = ws_w(wl, W_SMP + (byte0 >> 2) + x);
+        const int c0 = w0 & 0xFF, c1 = (w0 >> 8) & 0xFF, c2 = (w0 >> 16) & 0xFF, c3 = w0 >> 24;
+        const double s0 = (double)(c0 + c3 - 256), s1 = (double)(c1 + c2 - 256), d0 = (double)(c0 - c3), d1 = (double)(c1 - c2);
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+            const double a = (v & 1) ? d0 : s0, b = (v & 1) ? d1 : s1;
+            ws_d(wbase, lane, x * 4 + v) = fma(b, kCos4[1 * 4 + v], a * kCos4[0 * 4 + v]);
+        }
+    }
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+        double s[4], d[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const double a = ws_d(wbase, lane, j * 4 + v), b = ws_d(wbase, lane, (7 - j) * 4 + v);
+            s[j] = a + b;
+            d[j] = a - b;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            double acc = ((u & 1) ? d[0] : s[0]) * kCos8[0 * 8 + u];
+#pragma unroll
+            for (int j = 1; j < 4; ++j) acc = fma((u & 1) ? d[j] : s[j], kCos8[j * 8 + u], acc);
+            const double au = u == 0 ? kAlpha8[0] : kAlpha8[1], av = v == 0 ? kAlpha4[0] : kAlpha4[1];
+            int t;
+            if (!quant_fast((au * av) * acc, kRChr[u * 4 + v], t)) t = exact_quant_ws<4>(wl, byte0, u, v);
+            wide |= (t < -128) | (t > 127);
+            put_i8(C[zz.pos[u * 4 + v] >> 2], zz.pos[u * 4 + v] & 3, t);
+            if (co) co[u * 4 + v] = (int16_t)t;
+        }
+    }
+    return wide;
+}
+
+// ---- bit packing: records are staged word-major ([word][thread]) so that a warp's stores coalesce ----------
 struct BitWriter {
     unsigned long long acc;
     int nbits;          // bits pending in acc (< 32 between calls)
-    uint32_t *dst;      // record staging, REC_BYTES / 4 words
+    uint32_t *dst;      // this thread's column of the CTA's staging area
     int wpos;
     __device__ __forceinline__ void put(uint32_t code, int len)
     {
         acc = (acc << len) | code;
         nbits += len;
         if (nbits >= 32) {
-            uint32_t wv = (uint32_t)(acc >> (nbits - 32));
-            if (wpos < REC_BYTES / 4) dst[wpos] = __byte_perm(wv, 0, 0x0123); // MSB-first bytes
+            const uint32_t wv = (uint32_t)(acc >> (nbits - 32));
+            if (wpos < REC_WORDS) dst[wpos * THREADS] = __byte_perm(wv, 0, 0x0123); // MSB-first bytes
             ++wpos;
             nbits -= 32;
         }
@@ -233,120 +357,285 @@ struct BitWriter {
     __device__ __forceinline__ void finish()
     {
         if (nbits > 0) {
-            uint32_t wv = (uint32_t)(acc << (32 - nbits));
-            if (wpos < REC_BYTES / 4) dst[wpos] = __byte_perm(wv, 0, 0x0123);
+            const uint32_t wv = (uint32_t)(acc << (32 - nbits));
+            if (wpos < REC_WORDS) dst[wpos * THREADS] = __byte_perm(wv, 0, 0x0123);
         }
     }
 };
 
-__device__ __forceinline__ void heapify(uint8_t *heap, const uint8_t *cnt, int size, int i) // JPEG.c:894-911
+// ---- general routine (local-memory arrays): any values, any number of symbols -------------------------------
+// Recomputes the channel from the pixels.  Follows JPEG.c:864-1007 literally (linear-search symbol table).
+__device__ __noinline__ int slow_channel(const uint8_t *rgba, int w, int h, size_t stride, size_t g, int ch, int16_t *co,
+                                         BitWriter *bwp, int max_bits, int *bad)
 {
-    for (;;) {
-        int smallest = i, l = 2 * i + 1, r = 2 * i + 2;
-        if (l < size && cnt[heap[l]] < cnt[heap[smallest]]) smallest = l;
-        if (r < size && cnt[heap[r]] < cnt[heap[smallest]]) smallest = r;
-        if (smallest == i) return;
-        uint8_t t = heap[i];
-        heap[i] = heap[smallest];
-        heap[smallest] = t;
-        i = smallest;
-    }
-}
-
-// Returns the number of bits emitted; sets *bad when the reference itself would overflow.
-template <int N>
-__device__ __noinline__ int entropy_channel(uint8_t *ts, const int16_t *cz, BitWriter &bw, int max_bits, int *bad)
-{
-    uint8_t *lut = ts + OFF_LUT;
-    uint8_t *cnt = ts + OFF_X;
-    uint8_t *heap = ts + OFF_X + MAXNODE;
-    uint32_t *code = reinterpret_cast<uint32_t *>(ts + OFF_X);
-    uint8_t *par = ts + OFF_PAR;
-    uint32_t *pbit = reinterpret_cast<uint32_t *>(ts + OFF_PBIT);
-    uint8_t *len = ts + OFF_LEN;
-
-    // calculate_frequency (JPEG.c:864-885): symbols in first-appearance order; RLE emits (count, value)
-    int k = 0;
-    for (int i = 0; i < N;) {
-        const int v = cz[i];
-        int j = i + 1;
-        while (j < N && cz[j] == v) ++j;
-        const int sym[2] = {j - i, v};
-#pragma unroll
-        for (int s = 0; s < 2; ++s) {
-            const int idx = sym[s] + 160;
-            const int slot = lut[idx];
-            if (slot == 0xFF) {
-                lut[idx] = (uint8_t)k;
-                cnt[k] = 1;
-                ++k;
-            } else {
-                cnt[slot]++;
+    const int W = ch == 0 ? 8 : 4, N = 8 * W;
+    uint8_t smp[64];
+    int16_t z[64];
+    {
+        const size_t bpr = ((size_t)w + 7) / 8;
+        const size_t brow = g / bpr, bcol = g % bpr;
+        for (int lr = 0; lr < 8; ++lr)
+            for (int c = 0; c < W; ++c) {
+                const size_t row = brow * 8 + lr;
+                const size_t col = bcol * 8 + (ch == 0 ? c : 2 * c + 1); // chroma keeps the odd columns (JPEG.c:302-375)
+                const size_t gate = bcol * 8 + (ch == 0 ? c : 2 * c);    // ... filed under the even column (JPEG.c:543)
+                int s = 0;
+                if (row < (size_t)h && gate < (size_t)w && col < (size_t)w) {
+                    const uint8_t *q = rgba + row * stride + col * 4;
+                    s = ch == 0 ? luma_of(q[0], q[1], q[2]) : (ch == 1 ? cr_of(q[0], q[1], q[2]) : cb_of(q[0], q[1], q[2]));
+                }
+                smp[lr * W + c] = (uint8_t)s;
             }
+    }
+    for (int u = 0; u < 8; ++u)
+        for (int v = 0; v < W; ++v) {
+            // separable evaluation is not worth its code here: evaluate the double sum with FMAs, then fall back like the fast path
+            double acc = 0.0;
+            for (int x = 0; x < 8; ++x) {
+                double row = 0.0;
+                for (int y = 0; y < W; ++y)
+                    row = fma((double)((int)smp[x * W + y] - 128), (W == 8) ? kCos8[y * 8 + v] : kCos4[y * 4 + v], row);
+                acc = fma(row, kCos8[x * 8 + u], acc);
+            }
+            const double au = u == 0 ? kAlpha8[0] : kAlpha8[1];
+            const double av = (W == 8) ? (v == 0 ? kAlpha8[0] : kAlpha8[1]) : (v == 0 ? kAlpha4[0] : kAlpha4[1]);
+            int t;
+            if (!quant_fast((au * av) * acc, (W == 8) ? kRLum[u * 8 + v] : kRChr[u * 4 + v], t)) {
+                const double ce = (W == 8) ? exact_coef_t<8>([&](int i) { return (int)smp[i]; }, u, v)
+                                           : exact_coef_t<4>([&](int i) { return (int)smp[i]; }, u, v);
+                t = (int)__ddiv_rn(ce, (W == 8) ? kQLum[u * 8 + v] : kQChr[u * 4 + v]);
+            }
+            z[(W == 8) ? kZZ8.pos[u * 8 + v] : kZZ4.pos[u * 4 + v]] = (int16_t)t;
+            if (co) co[u * W + v] = (int16_t)t;
+        }
+    // RLE (JPEG.c:767-809) + calculate_frequency (JPEG.c:864-885)
+    int16_t sym[130];
+    uint8_t cnt[260], heap[130], par[260], rbit[260], seq[130];
+    int k = 0, m = 0;
+    for (int i = 0; i < N;) {
+        const int v = z[i];
+        int j = i + 1;
+        while (j < N && z[j] == v) ++j;
+        const int two[2] = {j - i, v};
+        for (int s = 0; s < 2; ++s) {
+            int slot = -1;
+            for (int q = 0; q < k; ++q)
+                if (sym[q] == two[s]) {
+                    slot = q;
+                    break;
+                }
+            if (slot < 0) {
+                slot = k++;
+                sym[slot] = (int16_t)two[s];
+                cnt[slot] = 0;
+            }
+            cnt[slot]++;
+            seq[m++] = (uint8_t)slot;
         }
         i = j;
     }
-    // build_heap (JPEG.c:913-934)
+    auto heapify = [&](int size, int i) { // JPEG.c:894-911
+        for (;;) {
+            int smallest = i, l = 2 * i + 1, r = 2 * i + 2;
+            if (l < size && cnt[heap[l]] < cnt[heap[smallest]]) smallest = l;
+            if (r < size && cnt[heap[r]] < cnt[heap[smallest]]) smallest = r;
+            if (smallest == i) return;
+            const uint8_t t = heap[i];
+            heap[i] = heap[smallest];
+            heap[smallest] = t;
+            i = smallest;
+        }
+    };
     for (int i = 0; i < k; ++i) heap[i] = (uint8_t)i;
-    for (int i = k / 2 - 1; i >= 0; --i) heapify(heap, cnt, k, i);
-    // build_huffman_tree (JPEG.c:936-961): pop two, append their parent at the END of the array (no sift-up)
-#pragma unroll
-    for (int i = 0; i < 5; ++i) pbit[i] = 0;
+    for (int i = k / 2 - 1; i >= 0; --i) heapify(k, i); // JPEG.c:913-934
     int size = k, next = k;
-    while (size > 1) {
+    while (size > 1) { // JPEG.c:936-961: pop two, append their parent at the END of the array (no sift-up)
         const int left = heap[0];
         heap[0] = heap[--size];
-        heapify(heap, cnt, size, 0);
+        heapify(size, 0);
         const int right = heap[0];
         heap[0] = heap[--size];
-        heapify(heap, cnt, size, 0);
+        heapify(size, 0);
         cnt[next] = (uint8_t)(cnt[left] + cnt[right]);
         par[left] = (uint8_t)next;
         par[right] = (uint8_t)next;
-        pbit[right >> 5] |= 1u << (right & 31);
+        rbit[left] = 0;
+        rbit[right] = 1;
         heap[size++] = (uint8_t)next;
         ++next;
     }
     const int root = heap[0];
-    // assign_codes (JPEG.c:963-982): left = '0', right = '1'; a leaf's code is read off its path to the root.
-    // (cnt/heap are dead from here on; code[] reuses their storage.)
-    uint32_t codes_tmp;
+    // assign_codes (JPEG.c:963-982) read bottom-up, then generate_encoded_sequence (JPEG.c:993-1007)
+    BitWriter bw = *bwp;
+    int bits = 0;
+    for (int i = 0; i < m; ++i) {
+        uint32_t c = 0;
+        int l = 0, node = seq[i];
+        while (node != root) {
+            if (l < 32) c |= (uint32_t)rbit[node] << l;
+            ++l;
+            node = par[node];
+        }
+        if (l > 31) { // HuffmanCode.code is char[32] (JPEG.c:861)
+            *bad = 1;
+            l = 31;
+        }
+        if (l > 16) {
+            bw.put(c >> 16, l - 16);
+            bw.put(c & 0xFFFF, 16);
+        } else {
+            bw.put(c, l);
+        }
+        bits += l;
+    }
+    if (bits > max_bits) *bad = 1; // char encoded_sequence[1024] / [512] (JPEG.c:1248, :1286)
+    *bwp = bw;
+    return bits;
+}
+
+// ---- fast path: symbol table + array heap in the interleaved workspace --------------------------------------
+struct Ent {
+    uint32_t *wl;
+    uint32_t epoch; // pre-shifted: epoch << 5
+    int k;
+    bool over;
+};
+__device__ __forceinline__ void sym_count(Ent &E, int sym) // calculate_frequency, JPEG.c:864-885
+{
+    uint8_t &l = ws_b(E.wl, W_LUT, sym + 128);
+    const uint32_t e = l;
+    if ((e & 0xE0u) == E.epoch) {
+        ws_h(E.wl, W_HEAP, (e & 31) + 1) += 0x100;
+    } else if (E.k >= FAST_MAXSYM) {
+        E.over = true;
+    } else {
+        l = (uint8_t)(E.epoch | E.k);
+        ws_h(E.wl, W_HEAP, E.k + 1) = (uint16_t)(0x100 | E.k);
+        ++E.k;
+    }
+}
+__device__ __forceinline__ void sym_emit(const Ent &E, BitWriter &bw, int sym) // generate_encoded_sequence, JPEG.c:993-1007
+{
+    const uint32_t slot = ws_b(E.wl, W_LUT, sym + 128) & 31u;
+    const uint32_t cw = ws_w(E.wl, W_CODE + slot);
+    bw.put(cw & 0x07FFFFFFu, cw >> 27);
+}
+// sift entry e down from 1-based position j in a heap of n entries (heapify, JPEG.c:894-911)
+__device__ __forceinline__ void sift(uint32_t *wl, int n, int j, uint32_t e)
+{
+    const uint32_t ec = e >> 8;
+    while (2 * j <= n) {
+        const uint32_t pair = ws_w(wl, W_HEAP + j); // children 2j (low half) and 2j+1 (high half)
+        const uint32_t lo = pair & 0xFFFFu, hi = pair >> 16;
+        const uint32_t lc = lo >> 8, hc = (2 * j + 1 <= n) ? (hi >> 8) : 0x1FFu;
+        uint32_t sc = ec;
+        int s = 0;
+        if (lc < sc) {
+            sc = lc;
+            s = 1;
+        }
+        if (hc < sc) s = 2;
+        if (s == 0) break;
+        ws_h(wl, W_HEAP, j) = (uint16_t)(s == 1 ? lo : hi);
+        j = 2 * j + (s - 1);
+    }
+    ws_h(wl, W_HEAP, j) = (uint16_t)e;
+}
+
+// Scan 32 int8 coefficients (8 registers) for runs; F is called with (count, value) for every finished run.
+template <class F>
+__device__ __forceinline__ void scan32(const uint32_t (&r)[8], bool first, int &prev, int &run, F flush)
+{
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+        const int v = (int)(int8_t)(r[i >> 2] >> (8 * (i & 3)));
+        if (i == 0 && first) {
+            prev = v;
+            run = 1;
+        } else if (v != prev) {
+            flush(run, prev);
+            prev = v;
+            run = 1;
+        } else {
+            ++run;
+        }
+    }
+}
+
+// One channel through RLE + Huffman + emission.  cur[0..nh*8) hold N = 32*nh int8 coefficients in zig-zag order.
+// Returns the number of bits, or -1 if the channel has to go through slow_channel.
+__device__ __forceinline__ int entropy_fast(uint32_t *wl, uint32_t epoch, uint32_t (&cur)[16], int nh, BitWriter &bw)
+{
+    Ent E;
+    E.wl = wl;
+    E.epoch = epoch << 5;
+    E.k = 0;
+    E.over = false;
+    int prev = 0, run = 0;
+    uint32_t r[8];
+    // pass 1: RLE (JPEG.c:767-809) feeding the symbol table in first-appearance order
+#pragma unroll 1
+    for (int h = 0; h < nh; ++h) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r[i] = h == 0 ? cur[i] : cur[8 + i];
+        scan32(r, h == 0, prev, run, [&](int c, int v) {
+            sym_count(E, c);
+            sym_count(E, v);
+        });
+    }
+    sym_count(E, run);
+    sym_count(E, prev);
+    if (E.over) return -1;
+    const int k = E.k;
+    // build_heap (JPEG.c:913-934)
+    for (int j = k >> 1; j >= 1; --j) sift(wl, k, j, ws_h(wl, W_HEAP, j));
+    // build_huffman_tree (JPEG.c:936-961): pop two, append their parent at the END of the array (no sift-up)
+    int n = k, next = k, bits = 0;
+    while (n > 1) {
+        const uint32_t left = ws_h(wl, W_HEAP, 1);
+        uint32_t e = ws_h(wl, W_HEAP, n);
+        --n;
+        sift(wl, n, 1, e);
+        const uint32_t right = ws_h(wl, W_HEAP, 1);
+        e = ws_h(wl, W_HEAP, n);
+        --n;
+        if (n >= 1) sift(wl, n, 1, e);
+        const uint32_t c = (left >> 8) + (right >> 8);
+        bits += (int)c; // total code length = sum of the internal nodes' counts
+        ws_b(wl, W_PAR, left & 0xFF) = (uint8_t)next;
+        ws_b(wl, W_PAR, right & 0xFF) = (uint8_t)(next | 0x80);
+        ++n;
+        ws_h(wl, W_HEAP, n) = (uint16_t)((c << 8) | next);
+        ++next;
+    }
+    const int root = k > 1 ? next - 1 : 0;
+    // assign_codes (JPEG.c:963-982): left = '0', right = '1'; a leaf's code is read off its path to the root
+    bool deep = false;
     for (int s = 0; s < k; ++s) {
         uint32_t c = 0;
         int l = 0, node = s;
         while (node != root) {
-            if (l < 32) c |= ((pbit[node >> 5] >> (node & 31)) & 1u) << l;
+            const uint32_t b = ws_b(wl, W_PAR, node);
+            c |= (b >> 7) << (l & 31);
             ++l;
-            node = par[node];
+            node = b & 0x7F;
         }
-        if (l > 31) *bad = 1; // HuffmanCode.code is char[32] (JPEG.c:861)
-        len[s] = (uint8_t)(l > 31 ? 31 : l);
-        codes_tmp = c;
-        // code[] aliases cnt[]/heap[]: slots >= s*4 bytes may still hold parents' cnt, which are no longer read
-        code[s] = codes_tmp;
+        deep |= l > FAST_MAXLEN;
+        ws_w(wl, W_CODE + s) = ((uint32_t)l << 27) | (c & 0x07FFFFFFu); // the heap is dead: codes reuse its words
     }
-    // generate_encoded_sequence (JPEG.c:993-1007)
-    int bits = 0;
-    for (int i = 0; i < N;) {
-        const int v = cz[i];
-        int j = i + 1;
-        while (j < N && cz[j] == v) ++j;
-        const int s0 = lut[(j - i) + 160], s1 = lut[v + 160];
-        bw.put(code[s0], len[s0]);
-        bw.put(code[s1], len[s1]);
-        bits += len[s0] + len[s1];
-        i = j;
+    if (deep) return -1;
+    // pass 2: generate_encoded_sequence (JPEG.c:993-1007)
+#pragma unroll 1
+    for (int h = 0; h < nh; ++h) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r[i] = h == 0 ? cur[i] : cur[8 + i];
+        scan32(r, h == 0, prev, run, [&](int c, int v) {
+            sym_emit(E, bw, c);
+            sym_emit(E, bw, v);
+        });
     }
-    if (bits > max_bits) *bad = 1; // char encoded_sequence[1024] / [512] (JPEG.c:1248, :1286)
-    // reset the lookup table for the next channel
-    for (int i = 0; i < N;) {
-        const int v = cz[i];
-        int j = i + 1;
-        while (j < N && cz[j] == v) ++j;
-        lut[(j - i) + 160] = 0xFF;
-        lut[v + 160] = 0xFF;
-        i = j;
-    }
+    sym_emit(E, bw, run);
+    sym_emit(E, bw, prev);
     return bits;
 }
 
@@ -355,13 +644,10 @@ __global__ void __launch_bounds__(THREADS, 1) jpeg_encode_kernel(Params P)
     extern __shared__ __align__(16) uint8_t smem[];
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
-    uint8_t *ts = smem + tid * STRIDE;
-    double *c8s = reinterpret_cast<double *>(smem + SM_COS8);
-    double *c4s = reinterpret_cast<double *>(smem + SM_COS4);
+    uint32_t *wbase = reinterpret_cast<uint32_t *>(smem) + warp * (WS_WORDS * 32);
+    uint32_t *wl = wbase + lane;
     Misc &M = *reinterpret_cast<Misc *>(smem + SM_MISC);
-    for (int i = tid; i < 64; i += THREADS) c8s[i] = kCos8[i];
-    for (int i = tid; i < 16; i += THREADS) c4s[i] = kCos4[i];
-    uint32_t *stage = P.scratch + ((size_t)blockIdx.x * THREADS + tid) * (REC_BYTES / 4);
+    uint32_t *stage = P.scratch + (size_t)blockIdx.x * (REC_WORDS * THREADS) + tid;
     const size_t bpr = ((size_t)P.w + 7) / 8;
     const bool aligned = ((reinterpret_cast<uintptr_t>(P.rgba) | P.stride) & 15) == 0;
 
@@ -377,64 +663,102 @@ __global__ void __launch_bounds__(THREADS, 1) jpeg_encode_kernel(Params P)
         if (active) {
             const size_t g = P.first_group + gl;
             const size_t brow = g / bpr, bcol = g % bpr;
+            const size_t col0 = bcol * 8;
             // ---- colour conversion + 4:2:2 point subsampling + tiling -> samples u8[64 | 32 | 32]
-            uint8_t *smp = ts + OFF_LUT;
-            for (int lr = 0; lr < 8; ++lr) {
-                const size_t row = brow * 8 + lr;
-                uint32_t px[8];
-                const size_t col0 = bcol * 8;
-                if (row < (size_t)P.h) {
-                    const uint8_t *rp = P.rgba + row * P.stride + col0 * 4;
-                    if (aligned && col0 + 8 <= (size_t)P.w) {
-                        const uint4 a = __ldg(reinterpret_cast<const uint4 *>(rp));
-                        const uint4 b = __ldg(reinterpret_cast<const uint4 *>(rp) + 1);
-                        px[0] = a.x; px[1] = a.y; px[2] = a.z; px[3] = a.w;
-                        px[4] = b.x; px[5] = b.y; px[6] = b.z; px[7] = b.w;
-                    } else {
+            const bool full = brow * 8 + 8 <= (size_t)P.h && col0 + 8 <= (size_t)P.w;
+            if (full && aligned) {
+                const uint8_t *rp = P.rgba + brow * 8 * P.stride + col0 * 4;
 #pragma unroll
-                        for (int lc = 0; lc < 8; ++lc) {
-                            px[lc] = 0xFFFFFFFFu; // marks "outside the image": sample stays 0
-                            if (col0 + lc < (size_t)P.w) {
-                                const uint8_t *q = rp + 4 * lc;
-                                px[lc] = (uint32_t)q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16);
+                for (int lr = 0; lr < 8; ++lr) {
+                    const uint4 a = __ldg(reinterpret_cast<const uint4 *>(rp + lr * P.stride));
+                    const uint4 b = __ldg(reinterpret_cast<const uint4 *>(rp + lr * P.stride) + 1);
+                    const uint32_t px[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+                    uint32_t y0 = 0, y1 = 0, cr = 0, cb = 0;
+#pragma unroll
+                    for (int lc = 0; lc < 8; ++lc) {
+                        const int r = px[lc] & 0xFF, gg = (px[lc] >> 8) & 0xFF, bq = (px[lc] >> 16) & 0xFF;
+                        const uint32_t y = (uint32_t)luma_of(r, gg, bq);
+                        if (lc < 4) y0 |= y << (8 * lc);
+                        else y1 |= y << (8 * (lc - 4));
+                        if (lc & 1) { // chroma sample of local column lc-1 is the original chroma at column lc
+                            cr |= (uint32_t)cr_of(r, gg, bq) << (8 * (lc >> 1));
+                            cb |= (uint32_t)cb_of(r, gg, bq) << (8 * (lc >> 1));
+                        }
+                    }
+                    ws_w(wl, W_SMP + 2 * lr) = y0;
+                    ws_w(wl, W_SMP + 2 * lr + 1) = y1;
+                    ws_w(wl, W_SMP + 16 + lr) = cr;
+                    ws_w(wl, W_SMP + 24 + lr) = cb;
+                }
+            } else {
+#pragma unroll 1
+                for (int lr = 0; lr < 8; ++lr) {
+                    const size_t row = brow * 8 + lr;
+                    uint32_t y0 = 0, y1 = 0, cr = 0, cb = 0;
+#pragma unroll 1
+                    for (int lc = 0; lc < 8; ++lc) {
+                        if (row < (size_t)P.h && col0 + lc < (size_t)P.w) {
+                            const uint8_t *q = P.rgba + row * P.stride + (col0 + lc) * 4;
+                            const int r = q[0], gg = q[1], bq = q[2];
+                            const uint32_t y = (uint32_t)luma_of(r, gg, bq);
+                            if (lc < 4) y0 |= y << (8 * lc);
+                            else y1 |= y << (8 * (lc - 4));
+                            if (lc & 1) {
+                                cr |= (uint32_t)cr_of(r, gg, bq) << (8 * (lc >> 1));
+                                cb |= (uint32_t)cb_of(r, gg, bq) << (8 * (lc >> 1));
                             }
                         }
                     }
-                } else {
-#pragma unroll
-                    for (int lc = 0; lc < 8; ++lc) px[lc] = 0xFFFFFFFFu;
-                }
-                const bool full = row < (size_t)P.h && col0 + 8 <= (size_t)P.w;
-#pragma unroll
-                for (int lc = 0; lc < 8; ++lc) {
-                    const bool inside = full || (row < (size_t)P.h && col0 + lc < (size_t)P.w);
-                    const int r = px[lc] & 0xFF, gg = (px[lc] >> 8) & 0xFF, b = (px[lc] >> 16) & 0xFF;
-                    smp[lr * 8 + lc] = inside ? (uint8_t)luma_of(r, gg, b) : 0;
-                    if (lc & 1) { // chroma sample of local column lc-1 is the original chroma at column lc
-                        smp[64 + lr * 4 + (lc >> 1)] = inside ? (uint8_t)cr_of(r, gg, b) : 0;
-                        smp[96 + lr * 4 + (lc >> 1)] = inside ? (uint8_t)cb_of(r, gg, b) : 0;
-                    }
+                    ws_w(wl, W_SMP + 2 * lr) = y0;
+                    ws_w(wl, W_SMP + 2 * lr + 1) = y1;
+                    ws_w(wl, W_SMP + 16 + lr) = cr;
+                    ws_w(wl, W_SMP + 24 + lr) = cb;
                 }
             }
-            // ---- DCT + quantise + zig-zag
-            int16_t *cz = reinterpret_cast<int16_t *>(ts + OFF_COEF);
+            // ---- DCT + quantise + zig-zag of the three channels -> int8 coefficients in registers
+            uint32_t L[16], R[8], B[8];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) L[i] = 0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) R[i] = B[i] = 0;
             int16_t *co = P.coefs ? P.coefs + gl * 128 : nullptr;
-            transform_channel<8>(smp, cz, co, c8s, c4s);
-            transform_channel<4>(smp + 64, cz + 64, co ? co + 64 : nullptr, c8s, c4s);
-            transform_channel<4>(smp + 96, cz + 96, co ? co + 96 : nullptr, c8s, c4s);
+            unsigned widemask = P.force_slow ? 7u : 0u;
+            if (dct_luma(wl, wbase, lane, L, co)) widemask |= 1u;
+            if (dct_chroma(wl, wbase, lane, 64, R, co ? co + 64 : nullptr)) widemask |= 2u;
+            if (dct_chroma(wl, wbase, lane, 96, B, co ? co + 96 : nullptr)) widemask |= 4u;
             // ---- entropy coding of lum, r, b (reference order JPEG.c:1242, :1284, :1318)
-            uint32_t *lutw = reinterpret_cast<uint32_t *>(ts + OFF_LUT);
-#pragma unroll 4
-            for (int i = 0; i < 80; ++i) lutw[i] = 0xFFFFFFFFu;
+            // The symbol table shares its words with the DCT's row-pass results: clear it once per group; the three
+            // channels then tag their entries with epochs 1, 2, 3.
+#pragma unroll 8
+            for (int i = 0; i < 64; ++i) ws_w(wl, W_LUT + i) = 0;
             BitWriter bw;
             bw.acc = 0;
             bw.nbits = 0;
             bw.dst = stage;
             bw.wpos = 0;
             int bad = 0;
-            bl = entropy_channel<64>(ts, cz, bw, 1023, &bad);
-            br = entropy_channel<32>(ts, cz + 64, bw, 511, &bad);
-            bb = entropy_channel<32>(ts, cz + 96, bw, 511, &bad);
+#pragma unroll 1
+            for (int ch = 0; ch < 3; ++ch) {
+                uint32_t cur[16];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    cur[i] = ch == 0 ? L[i] : (ch == 1 ? R[i] : B[i]);
+                    cur[8 + i] = L[8 + i];
+                }
+                const int max_bits = ch == 0 ? 1023 : 511;
+                int bits = -1;
+                if (!((widemask >> ch) & 1u)) bits = entropy_fast(wl, (uint32_t)ch + 1u, cur, ch == 0 ? 2 : 1, bw);
+                if (bits < 0) {
+                    BitWriter tmp = bw;
+                    bits = slow_channel(P.rgba, P.w, P.h, P.stride, g, ch, nullptr, &tmp, max_bits, &bad);
+                    bw = tmp;
+                } else if (bits > max_bits) {
+                    bad = 1; // char encoded_sequence[1024] / [512] (JPEG.c:1248, :1286)
+                }
+                if (ch == 0) bl = bits;
+                else if (ch == 1) br = bits;
+                else bb = bits;
+            }
             bw.finish();
             if (bad) {
                 atomicAdd((unsigned long long *)&P.result[1], 1ull);
@@ -452,13 +776,14 @@ __global__ void __launch_bounds__(THREADS, 1) jpeg_encode_kernel(Params P)
         }
         if (lane == 31) M.warp_sum[warp] = inc;
         __syncthreads();
-        unsigned int wbase = 0, tile_total = 0;
-        for (int k = 0; k < THREADS / 32; ++k) {
-            if (k < warp) wbase += M.warp_sum[k];
-            tile_total += M.warp_sum[k];
+        unsigned int wsum = 0, tile_total = 0;
+#pragma unroll
+        for (int k = 0; k < NWARPS; ++k) {
+            const unsigned int s = M.warp_sum[k];
+            if (k < warp) wsum += s;
+            tile_total += s;
         }
-        M.rec_off[tid] = wbase + inc - rec_bytes;
-        if (tid == 0) M.rec_off[THREADS] = tile_total;
+        const unsigned int my_off = wsum + inc - rec_bytes;
         // ---- place the tile in the output stream
         if (warp == 0) {
             unsigned long long base = ljb_lookback(P.status + 1, tile, tile_total, 0);
@@ -475,24 +800,34 @@ __global__ void __launch_bounds__(THREADS, 1) jpeg_encode_kernel(Params P)
         __syncthreads();
         const unsigned long long base = M.base;
         if (active) {
-            P.group_offsets[gl] = base + M.rec_off[tid];
+            P.group_offsets[gl] = base + my_off;
             if (P.group_bits) {
                 P.group_bits[3 * gl + 0] = (uint16_t)bl;
                 P.group_bits[3 * gl + 1] = (uint16_t)br;
                 P.group_bits[3 * gl + 2] = (uint16_t)bb;
             }
-        }
-        // ---- gather the staged records into the stream: one warp per record, coalesced byte runs
-        if (M.emit_ok) {
-            const uint8_t *tile_stage = reinterpret_cast<const uint8_t *>(P.scratch + (size_t)blockIdx.x * THREADS * (REC_BYTES / 4));
-            for (int r = warp; r < THREADS; r += THREADS / 32) {
-                const unsigned int o0 = M.rec_off[r], o1 = M.rec_off[r + 1];
-                const uint8_t *srcp = tile_stage + (size_t)r * REC_BYTES;
-                uint8_t *dstp = P.out + base + o0;
-                for (unsigned int k = lane; k < o1 - o0; k += 32) dstp[k] = srcp[k];
+            // ---- move the staged record to its place: head bytes, aligned words, tail bytes
+            if (M.emit_ok && rec_bytes) {
+                uint8_t *dst = P.out + base + my_off;
+                const unsigned int head = min((unsigned int)((4 - (reinterpret_cast<uintptr_t>(dst) & 3)) & 3), rec_bytes);
+                uint32_t w0 = stage[0];
+                for (unsigned int i = 0; i < head; ++i) dst[i] = (uint8_t)(w0 >> (8 * i));
+                const unsigned int nwords = (rec_bytes - head) >> 2;
+                uint32_t *d4 = reinterpret_cast<uint32_t *>(dst + head);
+                unsigned int j = 0;
+                for (; j < nwords; ++j) {
+                    const uint32_t w1 = (j + 1 < REC_WORDS) ? stage[(j + 1) * THREADS] : 0u;
+                    d4[j] = __funnelshift_r(w0, w1, 8 * head);
+                    w0 = w1;
+                }
+                const unsigned int done = head + 4 * nwords;
+                if (done < rec_bytes) {
+                    const uint32_t w1 = (j + 1 < REC_WORDS) ? stage[(j + 1) * THREADS] : 0u;
+                    const uint32_t t = __funnelshift_r(w0, w1, 8 * head);
+                    for (unsigned int i = 0; done + i < rec_bytes; ++i) dst[done + i] = (uint8_t)(t >> (8 * i));
+                }
             }
         }
-        __syncthreads();
     }
 }
 
@@ -540,6 +875,7 @@ extern "C" int ljb_jpeg_encode_rgba_dev(ljb_ctx *ctx, const uint8_t *d_rgba, int
     P.status = (uint64_t *)ctx->d_status;
     P.scratch = (uint32_t *)ctx->d_scratch;
     P.ntiles = (uint32_t)ntiles;
+    P.force_slow = getenv("LJB_JPEG_FORCE_SLOW") ? 1 : 0; // test hook
     static bool attr_done = false;
     if (!attr_done) {
         LJB_CUDA(cudaFuncSetAttribute(jpeg_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));

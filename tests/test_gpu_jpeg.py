@@ -83,3 +83,49 @@ def test_full_size_properties(ljb, ctx):
     last = enc.stream[enc.group_offsets[1:].astype(np.int64) - 1].astype(np.int64)
     pad = (8 - bits % 8) % 8
     assert ((last & ((1 << pad) - 1)) == 0).all()
+
+
+def _binary_noise(w, h, seed):
+    rng = np.random.default_rng(seed)
+    img = np.empty((h, w, 4), np.uint8)
+    img[..., :3] = rng.integers(0, 2, size=(h, w, 3), dtype=np.uint8) * 255
+    img[..., 3] = 255
+    return img
+
+
+def test_extreme_contrast_vs_oracle(ljb, ctx, oracle):
+    """0/255 pixels give the widest coefficient spread (values outside int8, > 32 distinct symbols per channel):
+    exercises the hand-over from the shared-memory fast path to the general routine."""
+    img = _binary_noise(128, 64, 3)
+    img[:16, :16, :3] = np.indices((16, 16)).sum(0)[..., None] % 2 * 255  # checkerboard: one huge coefficient
+    img[16:32, :16, :3] = (np.arange(16)[None, :, None] >= 8) * 255       # vertical edge
+    enc = ljb.jpeg.process(img, ctx=ctx)
+    ref = oracle.jpeg_encode(img)
+    assert np.array_equal(enc.coefs, ref["coefs"])
+    assert np.array_equal(enc.group_bits, ref["bits"])
+    assert np.array_equal(enc.stream, ref["stream"])
+
+
+@pytest.mark.parametrize("name", ["og_crop", "noise_64x48", "noise_18x13", "appendix_c", "white_16x16"])
+def test_general_routine_alone(ljb, ctx, name, monkeypatch):
+    """LJB_JPEG_FORCE_SLOW routes every channel through the general (local-memory) routine: same bytes."""
+    monkeypatch.setenv("LJB_JPEG_FORCE_SLOW", "1")
+    enc = ljb.jpeg.process(ALL[name], ctx=ctx)
+    assert np.array_equal(enc.coefs, VEC[f"{name}__coefs"])
+    assert np.array_equal(enc.group_bits, VEC[f"{name}__bits"])
+    assert np.array_equal(enc.stream, VEC[f"{name}__stream"])
+
+
+def test_photo_like_vs_oracle(ljb, ctx, oracle):
+    """Smooth gradients + texture (large DC, many zero runs): the typical photographic case."""
+    yy, xx = np.mgrid[0:96, 0:160]
+    rng = np.random.default_rng(12)
+    base = 128 + 100 * np.sin(xx / 23.0) * np.cos(yy / 17.0)
+    img = np.empty((96, 160, 4), np.uint8)
+    for c in range(3):
+        img[..., c] = np.clip(base + (c - 1) * 30 + rng.normal(0, 6, base.shape), 0, 255).astype(np.uint8)
+    img[..., 3] = 255
+    enc = ljb.jpeg.process(img, ctx=ctx)
+    ref = oracle.jpeg_encode(img)
+    assert np.array_equal(enc.coefs, ref["coefs"])
+    assert np.array_equal(enc.stream, ref["stream"])
