@@ -46,15 +46,14 @@ constexpr int REC_WORDS = REC_BYTES / 4;
 
 // per-thread workspace, in 32-bit words (interleaved across the warp)
 constexpr int W_LUT = 0;           // u8[256]: symbol+128 -> (epoch << 5) | slot
-constexpr int W_HEAP = 64;         // u16[34]: 1-based array heap of (count << 8) | node id     (17 words)
-constexpr int W_CODE = 64;         // u32[32]: (length << 27) | code per leaf slot; aliases the heap once the tree is built
-constexpr int W_PAR = 96;          // u8[64]: parent node id | 0x80 if the node is a right child
+constexpr int W_CNT = 64;          // u32[32] counts -> u16 heap -> u16[63] code words (see entropy_fast)
+constexpr int W_PAR = 96;          // u16[31]: children of the internal nodes; int8 coefficients while the DCT runs
 constexpr int WS_WORDS = 112;
 // DCT phase view of the same words
 constexpr int W_T = 0;             // double[32]: row-pass results (8 rows x 4 columns), 64-bit interleaved
 constexpr int W_SMP = 64;          // u8[128]: samples lum[64] | Cr[32] | Cb[32]
 constexpr int FAST_MAXSYM = 32;
-constexpr int FAST_MAXLEN = 26;
+constexpr int FAST_MAXLEN = 12;
 
 constexpr int SM_WS = THREADS * WS_WORDS * 4; // 229376
 constexpr int SM_MISC = SM_WS;
@@ -85,8 +84,7 @@ struct Params {
     int force_slow;          // test hook: route every channel through the general routine
 };
 
-// JPEG.c:12-27 as doubles, and their reciprocals for the fast path (the chroma table is consumed as
-// 8 rows x 4 columns)
+// JPEG.c:12-27 as doubles (the chroma table is consumed as 8 rows x 4 columns)
 __constant__ double kQLum[64] = {
     8.0, 6.0, 6.0, 8.0, 10.0, 14.0, 18.0, 22.0,
     6.0, 6.0, 7.0, 9.0, 12.0, 20.0, 22.0, 20.0,
@@ -97,29 +95,12 @@ __constant__ double kQLum[64] = {
     18.0, 22.0, 26.0, 28.0, 33.0, 40.0, 40.0, 34.0,
     22.0, 26.0, 28.0, 30.0, 36.0, 34.0, 35.0, 33.0,
 };
-__constant__ double kRLum[64] = {
-    1.0 / 8.0, 1.0 / 6.0, 1.0 / 6.0, 1.0 / 8.0, 1.0 / 10.0, 1.0 / 14.0, 1.0 / 18.0, 1.0 / 22.0,
-    1.0 / 6.0, 1.0 / 6.0, 1.0 / 7.0, 1.0 / 9.0, 1.0 / 12.0, 1.0 / 20.0, 1.0 / 22.0, 1.0 / 20.0,
-    1.0 / 6.0, 1.0 / 7.0, 1.0 / 8.0, 1.0 / 10.0, 1.0 / 14.0, 1.0 / 22.0, 1.0 / 25.0, 1.0 / 22.0,
-    1.0 / 8.0, 1.0 / 9.0, 1.0 / 10.0, 1.0 / 14.0, 1.0 / 18.0, 1.0 / 28.0, 1.0 / 27.0, 1.0 / 22.0,
-    1.0 / 10.0, 1.0 / 12.0, 1.0 / 14.0, 1.0 / 18.0, 1.0 / 22.0, 1.0 / 35.0, 1.0 / 33.0, 1.0 / 26.0,
-    1.0 / 14.0, 1.0 / 18.0, 1.0 / 22.0, 1.0 / 22.0, 1.0 / 27.0, 1.0 / 33.0, 1.0 / 36.0, 1.0 / 30.0,
-    1.0 / 18.0, 1.0 / 22.0, 1.0 / 26.0, 1.0 / 28.0, 1.0 / 33.0, 1.0 / 40.0, 1.0 / 40.0, 1.0 / 34.0,
-    1.0 / 22.0, 1.0 / 26.0, 1.0 / 28.0, 1.0 / 30.0, 1.0 / 36.0, 1.0 / 34.0, 1.0 / 35.0, 1.0 / 33.0,
-};
 __constant__ double kQChr[32] = {
     17.0, 18.0, 24.0, 47.0, 18.0, 21.0, 26.0, 66.0,
     24.0, 26.0, 56.0, 99.0, 47.0, 66.0, 99.0, 99.0,
     66.0, 99.0, 99.0, 99.0, 99.0, 99.0, 99.0, 99.0,
     99.0, 99.0, 99.0, 99.0, 99.0, 99.0, 99.0, 99.0,
 };
-__constant__ double kRChr[32] = {
-    1.0 / 17.0, 1.0 / 18.0, 1.0 / 24.0, 1.0 / 47.0, 1.0 / 18.0, 1.0 / 21.0, 1.0 / 26.0, 1.0 / 66.0,
-    1.0 / 24.0, 1.0 / 26.0, 1.0 / 56.0, 1.0 / 99.0, 1.0 / 47.0, 1.0 / 66.0, 1.0 / 99.0, 1.0 / 99.0,
-    1.0 / 66.0, 1.0 / 99.0, 1.0 / 99.0, 1.0 / 99.0, 1.0 / 99.0, 1.0 / 99.0, 1.0 / 99.0, 1.0 / 99.0,
-    1.0 / 99.0, 1.0 / 99.0, 1.0 / 99.0, 1.0 / 99.0, 1.0 / 99.0, 1.0 / 99.0, 1.0 / 99.0, 1.0 / 99.0,
-};
-
 // zig-zag position of row-major index (inverse of the walk in JPEG.c:693-727), evaluated at compile time
 template <int W, int H>
 struct ZigZag {
@@ -228,80 +209,95 @@ __device__ __noinline__ int exact_quant_ws(uint32_t *wl, int byte0, int u, int v
     return (int)__ddiv_rn(ce, (W == 8) ? kQLum[u * W + v] : kQChr[u * W + v]);
 }
 
-// quantise one fast-path coefficient value (already scaled by alpha_u*alpha_v); returns true if the
-// truncation is safe, i.e. the quotient is not within 1e-6 of a non-zero integer
-__device__ __forceinline__ bool quant_fast(double scaled, double recip, int &t)
+// Fast-path quantisation constants: alpha_u * alpha_v / Q[u][v] * 2^20 (the quotient in 12.20 fixed point)
+template <int W>
+struct QuantScale {
+    double m[W * 8];
+    constexpr QuantScale(const int *q) : m()
+    {
+        for (int u = 0; u < 8; ++u)
+            for (int v = 0; v < W; ++v) {
+                const double au = u == 0 ? 0.35355339059327376220 : 0.5;
+                const double av = W == 8 ? (v == 0 ? 0.35355339059327376220 : 0.5) : (v == 0 ? 0.5 : 0.70710678118654752440);
+                m[u * W + v] = au * av * 1048576.0 / (double)q[u * W + v];
+            }
+    }
+};
+constexpr int kQLumI[64] = {8,  6,  6,  8,  10, 14, 18, 22, 6,  6,  7,  9,  12, 20, 22, 20, 6,  7,  8,  10, 14, 22,
+                            25, 22, 8,  9,  10, 14, 18, 28, 27, 22, 10, 12, 14, 18, 22, 35, 33, 26, 14, 18, 22, 22,
+                            27, 33, 36, 30, 18, 22, 26, 28, 33, 40, 40, 34, 22, 26, 28, 30, 36, 34, 35, 33}; // JPEG.c:12-20
+constexpr int kQChrI[32] = {17, 18, 24, 47, 18, 21, 26, 66, 24, 26, 56, 99, 47, 66, 99, 99,
+                            66, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99}; // JPEG.c:22-27 as 8 rows x 4
+__constant__ const QuantScale<8> kMLum = QuantScale<8>(kQLumI);
+__constant__ const QuantScale<4> kMChr = QuantScale<4>(kQChrI);
+
+// Quantise one fast-path coefficient: qs = quotient * 2^20 (accurate to ~1e-11 of the quotient).  Returns false
+// when the quotient lies within 2^-19 of a non-zero integer, where truncation could go either way.
+__device__ __forceinline__ bool quant_fast(double qs, int &t)
 {
-    const double qf = scaled * recip; // within 2 ulp of the quotient
-    t = (int)qf;                      // truncation toward zero, JPEG.c:627
-    return !(fabs(qf) >= 0.999999 && fabs(qf - rint(qf)) < 1e-6);
+    const int fx = __double2int_rz(qs);
+    const unsigned a = (unsigned)abs(fx), ti = a >> 20, fr = a & 0xFFFFFu;
+    t = fx < 0 ? -(int)ti : (int)ti; // truncation toward zero, JPEG.c:627
+    return !((fr >= 0xFFFFEu) || (fr <= 1u && ti >= 1u));
 }
 
-__device__ __forceinline__ void put_i8(uint32_t &reg, int byte, int t)
+// Luma: 8x8 DCT + quantise + zig-zag.  The 64 int8 results go to bytes [0, 64) of the W_PAR words (zig-zag order);
+// returns true if some value is outside int8.  Loops are kept rolled: the code is executed once per group and
+// unrolling it fully (128 coefficient bodies) thrashed the instruction cache.
+template <int PAR>
+__device__ __forceinline__ bool dct_luma_half(uint32_t *wl, uint32_t *wbase, int lane, int16_t *co)
 {
-    reg = (reg & ~(0xFFu << (8 * byte))) | (((uint32_t)t & 0xFFu) << (8 * byte));
-}
-
-// Luma: 8x8 DCT + quantise + zig-zag -> 64 int8 packed in L[16]; returns true if some value is outside int8.
-__device__ __forceinline__ bool dct_luma(uint32_t *wl, uint32_t *wbase, int lane, uint32_t (&L)[16], int16_t *co)
-{
-    constexpr ZigZag<8, 8> zz;
     bool wide = false;
+    // row pass: T[x][vi] = sum_y corr[x][y] * cos8[y][v], v = 2 vi + PAR, using cos8[7-y][v] = (-1)^v cos8[y][v]
+#pragma unroll 1
+    for (int x = 0; x < 8; ++x) {
+        const uint32_t w0 = ws_w(wl, W_SMP + 2 * x), w1 = ws_w(wl, W_SMP + 2 * x + 1);
+        double e[4];
 #pragma unroll
-    for (int par = 0; par < 2; ++par) { // even / odd output columns v
-        // row pass: T[x][vi] = sum_y corr[x][y] * cos8[y][v], v = 2 vi + par, using cos8[7-y][v] = (-1)^v cos8[y][v]
-#pragma unroll
-        for (int x = 0; x < 8; ++x) {
-            const uint32_t w0 = ws_w(wl, W_SMP + 2 * x), w1 = ws_w(wl, W_SMP + 2 * x + 1);
-            double e[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int a = (w0 >> (8 * j)) & 0xFF, b = (w1 >> (8 * (3 - j))) & 0xFF; // y = j and y = 7 - j
-                e[j] = (double)(par == 0 ? a + b - 256 : a - b);
-            }
-#pragma unroll
-            for (int vi = 0; vi < 4; ++vi) {
-                const int v = 2 * vi + par;
-                double acc = e[0] * kCos8[0 * 8 + v];
-#pragma unroll
-                for (int j = 1; j < 4; ++j) acc = fma(e[j], kCos8[j * 8 + v], acc);
-                ws_d(wbase, lane, x * 4 + vi) = acc;
-            }
+        for (int j = 0; j < 4; ++j) {
+            const int a = (w0 >> (8 * j)) & 0xFF, b = (w1 >> (8 * (3 - j))) & 0xFF; // y = j and y = 7 - j
+            e[j] = (double)(PAR == 0 ? a + b - 256 : a - b);
         }
-        // column pass + quantise
 #pragma unroll
         for (int vi = 0; vi < 4; ++vi) {
-            const int v = 2 * vi + par;
-            double s[4], d[4];
+            const int v = 2 * vi + PAR;
+            double acc = e[0] * kCos8[0 * 8 + v];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const double a = ws_d(wbase, lane, j * 4 + vi), b = ws_d(wbase, lane, (7 - j) * 4 + vi);
-                s[j] = a + b;
-                d[j] = a - b;
-            }
+            for (int j = 1; j < 4; ++j) acc = fma(e[j], kCos8[j * 8 + v], acc);
+            ws_d(wbase, lane, x * 4 + vi) = acc;
+        }
+    }
+    // column pass + quantise
+#pragma unroll 1
+    for (int vi = 0; vi < 4; ++vi) {
+        const int v = 2 * vi + PAR;
+        double s[4], d[4];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                double acc = ((u & 1) ? d[0] : s[0]) * kCos8[0 * 8 + u];
+        for (int j = 0; j < 4; ++j) {
+            const double a = ws_d(wbase, lane, j * 4 + vi), b = ws_d(wbase, lane, (7 - j) * 4 + vi);
+            s[j] = a + b;
+            d[j] = a - b;
+        }
 #pragma unroll
-                for (int j = 1; j < 4; ++j) acc = fma((u & 1) ? d[j] : s[j], kCos8[j * 8 + u], acc);
-                const double au = u == 0 ? kAlpha8[0] : kAlpha8[1], av = v == 0 ? kAlpha8[0] : kAlpha8[1];
-                int t;
-                if (!quant_fast((au * av) * acc, kRLum[u * 8 + v], t)) t = exact_quant_ws<8>(wl, 0, u, v);
-                wide |= (t < -128) | (t > 127);
-                put_i8(L[zz.pos[u * 8 + v] >> 2], zz.pos[u * 8 + v] & 3, t);
-                if (co) co[u * 8 + v] = (int16_t)t;
-            }
+        for (int u = 0; u < 8; ++u) {
+            double acc = ((u & 1) ? d[0] : s[0]) * kCos8[0 * 8 + u];
+#pragma unroll
+            for (int j = 1; j < 4; ++j) acc = fma((u & 1) ? d[j] : s[j], kCos8[j * 8 + u], acc);
+            int t;
+            if (!quant_fast(acc * kMLum.m[u * 8 + v], t)) t = exact_quant_ws<8>(wl, 0, u, v);
+            wide |= (t < -128) | (t > 127);
+            ws_b(wl, W_PAR, kZZ8.pos[u * 8 + v]) = (uint8_t)t;
+            if (co) co[u * 8 + v] = (int16_t)t;
         }
     }
     return wide;
 }
 
-// Chroma: 8 rows x 4 columns -> 32 int8 packed in C[8]
-__device__ __forceinline__ bool dct_chroma(uint32_t *wl, uint32_t *wbase, int lane, int byte0, uint32_t (&C)[8], int16_t *co)
+// Chroma: 8 rows x 4 columns; the 32 int8 results go to bytes [out0, out0 + 32) of the W_PAR words
+__device__ __forceinline__ bool dct_chroma(uint32_t *wl, uint32_t *wbase, int lane, int byte0, int out0, int16_t *co)
 {
-    constexpr ZigZag<4, 8> zz;
     bool wide = false;
-#pragma unroll
+#pragma unroll 1
     for (int x = 0; x < 8; ++x) {
         const uint32_t w0 = ws_w(wl, W_SMP + (byte0 >> 2) + x);
         const int c0 = w0 & 0xFF, c1 = (w0 >> 8) & 0xFF, c2 = (w0 >> 16) & 0xFF, c3 = w0 >> 24;
@@ -312,7 +308,7 @@ __device__ __forceinline__ bool dct_chroma(uint32_t *wl, uint32_t *wbase, int la
             ws_d(wbase, lane, x * 4 + v) = fma(b, kCos4[1 * 4 + v], a * kCos4[0 * 4 + v]);
         }
     }
-#pragma unroll
+#pragma unroll 1
     for (int v = 0; v < 4; ++v) {
         double s[4], d[4];
 #pragma unroll
@@ -326,11 +322,10 @@ __device__ __forceinline__ bool dct_chroma(uint32_t *wl, uint32_t *wbase, int la
             double acc = ((u & 1) ? d[0] : s[0]) * kCos8[0 * 8 + u];
 #pragma unroll
             for (int j = 1; j < 4; ++j) acc = fma((u & 1) ? d[j] : s[j], kCos8[j * 8 + u], acc);
-            const double au = u == 0 ? kAlpha8[0] : kAlpha8[1], av = v == 0 ? kAlpha4[0] : kAlpha4[1];
             int t;
-            if (!quant_fast((au * av) * acc, kRChr[u * 4 + v], t)) t = exact_quant_ws<4>(wl, byte0, u, v);
+            if (!quant_fast(acc * kMChr.m[u * 4 + v], t)) t = exact_quant_ws<4>(wl, byte0, u, v);
             wide |= (t < -128) | (t > 127);
-            put_i8(C[zz.pos[u * 4 + v] >> 2], zz.pos[u * 4 + v] & 3, t);
+            ws_b(wl, W_PAR, out0 + kZZ4.pos[u * 4 + v]) = (uint8_t)t;
             if (co) co[u * 4 + v] = (int16_t)t;
         }
     }
@@ -400,7 +395,9 @@ __device__ __noinline__ int slow_channel(const uint8_t *rgba, int w, int h, size
             const double au = u == 0 ? kAlpha8[0] : kAlpha8[1];
             const double av = (W == 8) ? (v == 0 ? kAlpha8[0] : kAlpha8[1]) : (v == 0 ? kAlpha4[0] : kAlpha4[1]);
             int t;
-            if (!quant_fast((au * av) * acc, (W == 8) ? kRLum[u * 8 + v] : kRChr[u * 4 + v], t)) {
+            (void)au;
+            (void)av;
+            if (!quant_fast(acc * ((W == 8) ? kMLum.m[u * 8 + v] : kMChr.m[u * 4 + v]), t)) {
                 const double ce = (W == 8) ? exact_coef_t<8>([&](int i) { return (int)smp[i]; }, u, v)
                                            : exact_coef_t<4>([&](int i) { return (int)smp[i]; }, u, v);
                 t = (int)__ddiv_rn(ce, (W == 8) ? kQLum[u * 8 + v] : kQChr[u * 4 + v]);
@@ -494,52 +491,70 @@ __device__ __noinline__ int slow_channel(const uint8_t *rgba, int w, int h, size
 }
 
 // ---- fast path: symbol table + array heap in the interleaved workspace --------------------------------------
+// Words 64..95 hold, in turn: CNT u32[32] (occurrences per slot, while scanning) -> HEAP u16[1..k] (the 1-based
+// array heap of (count << 8) | node id, built in place from CNT) -> CW u16[63] ((length << 12) | code per node).
+// Words 96..111 hold CHILD u16[31]: left | right << 8 of internal node k + i.
 struct Ent {
-    uint32_t *wl;
+    uint8_t *lb;    // byte address of this lane's word 0
     uint32_t epoch; // pre-shifted: epoch << 5
-    int k;
-    bool over;
+    uint32_t k;
+    uint32_t over;
 };
-__device__ __forceinline__ void sym_count(Ent &E, int sym) // calculate_frequency, JPEG.c:864-885
+__device__ __forceinline__ uint8_t *lut_addr(uint8_t *lb, int sym)
 {
-    uint8_t &l = ws_b(E.wl, W_LUT, sym + 128);
-    const uint32_t e = l;
-    if ((e & 0xE0u) == E.epoch) {
-        ws_h(E.wl, W_HEAP, (e & 31) + 1) += 0x100;
-    } else if (E.k >= FAST_MAXSYM) {
-        E.over = true;
-    } else {
-        l = (uint8_t)(E.epoch | E.k);
-        ws_h(E.wl, W_HEAP, E.k + 1) = (uint16_t)(0x100 | E.k);
-        ++E.k;
-    }
+    const uint32_t idx = (uint32_t)(sym + 128);
+    return lb + ((idx & 0xFCu) << 5) + (idx & 3u); // word idx >> 2 of the lane, byte idx & 3
 }
-__device__ __forceinline__ void sym_emit(const Ent &E, BitWriter &bw, int sym) // generate_encoded_sequence, JPEG.c:993-1007
+__device__ __forceinline__ void sym_count(Ent &E, int sym) // calculate_frequency, JPEG.c:864-885 (branch free)
 {
-    const uint32_t slot = ws_b(E.wl, W_LUT, sym + 128) & 31u;
-    const uint32_t cw = ws_w(E.wl, W_CODE + slot);
-    bw.put(cw & 0x07FFFFFFu, cw >> 27);
+    uint8_t *la = lut_addr(E.lb, sym);
+    const uint32_t e = *la;
+    const bool hit = (e & 0xE0u) == E.epoch;
+    E.over |= (!hit && E.k >= (uint32_t)FAST_MAXSYM) ? 1u : 0u;
+    const uint32_t slot = hit ? (e & 31u) : min(E.k, (uint32_t)FAST_MAXSYM - 1u);
+    *la = (uint8_t)(E.epoch | slot);
+    uint32_t *ca = reinterpret_cast<uint32_t *>(E.lb + (W_CNT * 128) + slot * 128);
+    const uint32_t c = *ca;
+    *ca = hit ? c + 1u : 1u;
+    E.k += hit ? 0u : 1u;
+}
+__device__ __forceinline__ uint32_t sym_code(const Ent &E, int sym)
+{
+    const uint32_t slot = *lut_addr(E.lb, sym) & 31u;
+    return *reinterpret_cast<const uint16_t *>(E.lb + (W_CNT * 128) + ((slot >> 1) << 7) + ((slot & 1u) << 1));
+}
+// generate_encoded_sequence, JPEG.c:993-1007: the codes of one (count, value) pair, at most 12 + 12 bits
+__device__ __forceinline__ void pair_emit(const Ent &E, BitWriter &bw, int c, int v)
+{
+    const uint32_t cc = sym_code(E, c), cv = sym_code(E, v);
+    const uint32_t lv = cv >> 12;
+    bw.put(((cc & 0xFFFu) << lv) | (cv & 0xFFFu), (int)((cc >> 12) + lv));
+}
+// heap entry j (1-based) is the u16 at byte hb + (j >> 1) * 128 + (j & 1) * 2
+__device__ __forceinline__ uint16_t *heap_at(uint8_t *hb, uint32_t j)
+{
+    return reinterpret_cast<uint16_t *>(hb + ((j >> 1) << 7) + ((j & 1u) << 1));
 }
 // sift entry e down from 1-based position j in a heap of n entries (heapify, JPEG.c:894-911)
-__device__ __forceinline__ void sift(uint32_t *wl, int n, int j, uint32_t e)
+__device__ __forceinline__ void sift(uint8_t *hb, uint32_t n, uint32_t j, uint32_t e)
 {
     const uint32_t ec = e >> 8;
+    uint16_t *self = heap_at(hb, j);
     while (2 * j <= n) {
-        const uint32_t pair = ws_w(wl, W_HEAP + j); // children 2j (low half) and 2j+1 (high half)
+        uint8_t *pa = hb + (j << 7);                                   // children 2j (low half) and 2j+1 (high half)
+        const uint32_t pair = *reinterpret_cast<const uint32_t *>(pa);
         const uint32_t lo = pair & 0xFFFFu, hi = pair >> 16;
         const uint32_t lc = lo >> 8, hc = (2 * j + 1 <= n) ? (hi >> 8) : 0x1FFu;
-        uint32_t sc = ec;
-        int s = 0;
-        if (lc < sc) {
-            sc = lc;
-            s = 1;
-        }
-        if (hc < sc) s = 2;
-        if (s == 0) break;
-        ws_h(wl, W_HEAP, j) = (uint16_t)(s == 1 ? lo : hi);
-        j = 2 * j + (s - 1);
+        // smallest = i; if (l.count < smallest.count) smallest = l; if (r.count < smallest.count) smallest = r;
+        const bool tl = lc < ec;
+        const uint32_t sc = tl ? lc : ec;
+        const bool tr = hc < sc;
+        if (!(tl | tr)) break;
+        *self = (uint16_t)(tr ? hi : lo);
+        self = reinterpret_cast<uint16_t *>(pa + (tr ? 2 : 0));
+        j = 2 * j + (tr ? 1u : 0u);
     }
-    ws_h(wl, W_HEAP, j) = (uint16_t)e;
+    *self = (uint16_t)e;
 }
 
 // Scan 32 int8 coefficients (8 registers) for runs; F is called with (count, value) for every finished run.
@@ -567,10 +582,11 @@ __device__ __forceinline__ void scan32(const uint32_t (&r)[8], bool first, int &
 __device__ __forceinline__ int entropy_fast(uint32_t *wl, uint32_t epoch, uint32_t (&cur)[16], int nh, BitWriter &bw)
 {
     Ent E;
-    E.wl = wl;
+    E.lb = reinterpret_cast<uint8_t *>(wl);
     E.epoch = epoch << 5;
     E.k = 0;
-    E.over = false;
+    E.over = 0;
+    uint8_t *hb = E.lb + W_CNT * 128;
     int prev = 0, run = 0;
     uint32_t r[8];
     // pass 1: RLE (JPEG.c:767-809) feeding the symbol table in first-appearance order
@@ -586,42 +602,47 @@ __device__ __forceinline__ int entropy_fast(uint32_t *wl, uint32_t epoch, uint32
     sym_count(E, run);
     sym_count(E, prev);
     if (E.over) return -1;
-    const int k = E.k;
+    const uint32_t k = E.k;
+    // the heap array in the reference's initial (first-appearance) order, in place over CNT: entry j sits in word
+    // j >> 1 <= j - 1, which has been consumed by the time it is overwritten
+    for (uint32_t j = 1; j <= k; ++j) {
+        const uint32_t c = *reinterpret_cast<const uint32_t *>(hb + ((j - 1) << 7));
+        *heap_at(hb, j) = (uint16_t)((c << 8) | (j - 1));
+    }
     // build_heap (JPEG.c:913-934)
-    for (int j = k >> 1; j >= 1; --j) sift(wl, k, j, ws_h(wl, W_HEAP, j));
+    for (uint32_t j = k >> 1; j >= 1; --j) sift(hb, k, j, *heap_at(hb, j));
     // build_huffman_tree (JPEG.c:936-961): pop two, append their parent at the END of the array (no sift-up)
-    int n = k, next = k, bits = 0;
+    uint32_t n = k, next = k;
+    int bits = 0;
+    uint8_t *chb = E.lb + W_PAR * 128;
     while (n > 1) {
-        const uint32_t left = ws_h(wl, W_HEAP, 1);
-        uint32_t e = ws_h(wl, W_HEAP, n);
+        const uint32_t left = *heap_at(hb, 1);
+        uint32_t e = *heap_at(hb, n);
         --n;
-        sift(wl, n, 1, e);
-        const uint32_t right = ws_h(wl, W_HEAP, 1);
-        e = ws_h(wl, W_HEAP, n);
+        sift(hb, n, 1, e);
+        const uint32_t right = *heap_at(hb, 1);
+        e = *heap_at(hb, n);
         --n;
-        if (n >= 1) sift(wl, n, 1, e);
+        if (n >= 1) sift(hb, n, 1, e);
         const uint32_t c = (left >> 8) + (right >> 8);
         bits += (int)c; // total code length = sum of the internal nodes' counts
-        ws_b(wl, W_PAR, left & 0xFF) = (uint8_t)next;
-        ws_b(wl, W_PAR, right & 0xFF) = (uint8_t)(next | 0x80);
+        *heap_at(chb, next - k) = (uint16_t)((left & 0xFFu) | ((right & 0xFFu) << 8));
         ++n;
-        ws_h(wl, W_HEAP, n) = (uint16_t)((c << 8) | next);
+        *heap_at(hb, n) = (uint16_t)((c << 8) | next);
         ++next;
     }
-    const int root = k > 1 ? next - 1 : 0;
-    // assign_codes (JPEG.c:963-982): left = '0', right = '1'; a leaf's code is read off its path to the root
-    bool deep = false;
-    for (int s = 0; s < k; ++s) {
-        uint32_t c = 0;
-        int l = 0, node = s;
-        while (node != root) {
-            const uint32_t b = ws_b(wl, W_PAR, node);
-            c |= (b >> 7) << (l & 31);
-            ++l;
-            node = b & 0x7F;
-        }
-        deep |= l > FAST_MAXLEN;
-        ws_w(wl, W_CODE + s) = ((uint32_t)l << 27) | (c & 0x07FFFFFFu); // the heap is dead: codes reuse its words
+    // assign_codes (JPEG.c:963-982), top down: left = '0', right = '1'.  Children always have smaller ids than
+    // their parent, so one descending sweep over the internal nodes reaches every node after its parent.
+    uint32_t deep = 0;
+    *heap_at(hb, k > 1 ? next - 1 : 0) = 0; // root: empty code (the heap array is dead: CW reuses its words)
+    for (uint32_t t = next; t-- > k;) {
+        const uint32_t cw = *heap_at(hb, t);
+        const uint32_t ch = *heap_at(chb, t - k);
+        const uint32_t len = (cw >> 12) + 1u, code = (cw & 0xFFFu) << 1;
+        deep |= len > (uint32_t)FAST_MAXLEN ? 1u : 0u;
+        const uint32_t down = ((len & 15u) << 12) | (code & 0xFFFu);
+        *heap_at(hb, ch & 0xFFu) = (uint16_t)down;
+        *heap_at(hb, ch >> 8) = (uint16_t)(down | 1u);
     }
     if (deep) return -1;
     // pass 2: generate_encoded_sequence (JPEG.c:993-1007)
@@ -629,13 +650,9 @@ __device__ __forceinline__ int entropy_fast(uint32_t *wl, uint32_t epoch, uint32
     for (int h = 0; h < nh; ++h) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) r[i] = h == 0 ? cur[i] : cur[8 + i];
-        scan32(r, h == 0, prev, run, [&](int c, int v) {
-            sym_emit(E, bw, c);
-            sym_emit(E, bw, v);
-        });
+        scan32(r, h == 0, prev, run, [&](int c, int v) { pair_emit(E, bw, c, v); });
     }
-    sym_emit(E, bw, run);
-    sym_emit(E, bw, prev);
+    pair_emit(E, bw, run, prev);
     return bits;
 }
 
@@ -717,15 +734,20 @@ __global__ void __launch_bounds__(THREADS, 1) jpeg_encode_kernel(Params P)
             }
             // ---- DCT + quantise + zig-zag of the three channels -> int8 coefficients in registers
             uint32_t L[16], R[8], B[8];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) L[i] = 0;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) R[i] = B[i] = 0;
             int16_t *co = P.coefs ? P.coefs + gl * 128 : nullptr;
             unsigned widemask = P.force_slow ? 7u : 0u;
-            if (dct_luma(wl, wbase, lane, L, co)) widemask |= 1u;
-            if (dct_chroma(wl, wbase, lane, 64, R, co ? co + 64 : nullptr)) widemask |= 2u;
-            if (dct_chroma(wl, wbase, lane, 96, B, co ? co + 96 : nullptr)) widemask |= 4u;
+            if (dct_luma_half<0>(wl, wbase, lane, co)) widemask |= 1u;
+            if (dct_luma_half<1>(wl, wbase, lane, co)) widemask |= 1u;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) L[i] = ws_w(wl, W_PAR + i);
+#pragma unroll 1
+            for (int c = 0; c < 2; ++c)
+                if (dct_chroma(wl, wbase, lane, 64 + 32 * c, 32 * c, co ? co + 64 + 32 * c : nullptr)) widemask |= 2u << c;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                R[i] = ws_w(wl, W_PAR + i);
+                B[i] = ws_w(wl, W_PAR + 8 + i);
+            }
             // ---- entropy coding of lum, r, b (reference order JPEG.c:1242, :1284, :1318)
             // The symbol table shares its words with the DCT's row-pass results: clear it once per group; the three
             // channels then tag their entries with epochs 1, 2, 3.
@@ -815,6 +837,16 @@ __global__ void __launch_bounds__(THREADS, 1) jpeg_encode_kernel(Params P)
                 const unsigned int nwords = (rec_bytes - head) >> 2;
                 uint32_t *d4 = reinterpret_cast<uint32_t *>(dst + head);
                 unsigned int j = 0;
+                for (; j + 4 <= nwords; j += 4) { // four staged words in flight per step (they come from L2)
+                    uint32_t wv[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) wv[q] = (j + 1 + q < REC_WORDS) ? stage[(j + 1 + q) * THREADS] : 0u;
+                    d4[j] = __funnelshift_r(w0, wv[0], 8 * head);
+                    d4[j + 1] = __funnelshift_r(wv[0], wv[1], 8 * head);
+                    d4[j + 2] = __funnelshift_r(wv[1], wv[2], 8 * head);
+                    d4[j + 3] = __funnelshift_r(wv[2], wv[3], 8 * head);
+                    w0 = wv[3];
+                }
                 for (; j < nwords; ++j) {
                     const uint32_t w1 = (j + 1 < REC_WORDS) ? stage[(j + 1) * THREADS] : 0u;
                     d4[j] = __funnelshift_r(w0, w1, 8 * head);
