@@ -96,4 +96,42 @@ __device__ __forceinline__ uint64_t ljb_lookback(uint64_t *status, long long idx
     if (lane == 0) ljb_st_volatile(&status[idx], LJB_ST_INC | (excl + mine));
     return excl;
 }
+
+// The same protocol in two steps, for producers that publish a unit's size as soon as it is known and fetch its
+// offset later (after more work), when the predecessors have long been published: the walk then rarely waits.
+__device__ __forceinline__ void ljb_lookback_publish(uint64_t *status, long long idx, uint64_t mine, uint64_t lead)
+{
+    if ((threadIdx.x & 31) == 0) ljb_st_volatile(&status[idx], idx == 0 ? (LJB_ST_INC | (lead + mine)) : (LJB_ST_AGG | mine));
+}
+__device__ __forceinline__ uint64_t ljb_lookback_resolve(uint64_t *status, long long idx, uint64_t mine, uint64_t lead)
+{
+    const unsigned lane = threadIdx.x & 31;
+    if (idx == 0) return lead;
+    uint64_t excl = 0;
+    long long at = idx - 1;
+    for (;;) {
+        long long j = at - (long long)lane;
+        uint64_t w;
+        if (j < 0) {
+            w = LJB_ST_INC | lead;
+        } else {
+            do {
+                w = ljb_ld_volatile(&status[j]);
+            } while ((w & LJB_ST_MASK) == 0);
+        }
+        unsigned inc = __ballot_sync(0xffffffffu, (w & LJB_ST_MASK) == LJB_ST_INC);
+        uint64_t v = w & ~LJB_ST_MASK;
+        if (inc) {
+            int first = __ffs(inc) - 1;
+            if ((int)lane > first) v = 0;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        excl += v;
+        if (inc) break;
+        at -= 32;
+    }
+    if (lane == 0) ljb_st_volatile(&status[idx], LJB_ST_INC | (excl + mine));
+    return excl;
+}
 #endif

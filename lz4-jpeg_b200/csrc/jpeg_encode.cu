@@ -11,8 +11,8 @@
 // the per-group records (device-wide decoupled look-back over record sizes).
 //
 // Work decomposition: the reference spawns one thread per 8x8 group (P-JPG:1297-1302); here one CUDA
-// thread owns one group, 512 groups per CTA tile, one persistent CTA per SM pulling tiles from a ticket
-// counter.  Every per-thread array lives in shared memory WORD-INTERLEAVED across the 32 lanes of its warp
+// thread owns one group; every WARP of the one persistent 512-thread CTA per SM pulls 32-group tiles from a
+// ticket counter on its own (no CTA-wide barrier in the kernel).  Every per-thread array lives in shared memory WORD-INTERLEAVED across the 32 lanes of its warp
 // (word w of lane l at warp_base + (w*32 + l)*4): whatever data-dependent index a lane uses, it stays in
 // its own bank, so the divergent heap / table walks of the Huffman construction are bank-conflict free.
 // 112 words per thread (LUT 64 | heap+codes 32 | parents 16) let 16 warps share the 227 KB of one SM.
@@ -39,7 +39,7 @@ namespace jpgk {
 
 #include "jpeg_tables.inc"
 
-constexpr int THREADS = 512;       // groups per tile
+constexpr int THREADS = 512;       // 16 warps, each working on its own 32-group tile
 constexpr int NWARPS = THREADS / 32;
 constexpr int REC_BYTES = 256;     // max packed record: (1023 + 511 + 511) bits (JPEG.c:1248, :1286, :1320)
 constexpr int REC_WORDS = REC_BYTES / 4;
@@ -56,16 +56,8 @@ constexpr int FAST_MAXSYM = 32;
 constexpr int FAST_MAXLEN = 12;
 
 constexpr int SM_WS = THREADS * WS_WORDS * 4; // 229376
-constexpr int SM_MISC = SM_WS;
-constexpr int SM_TOTAL = SM_MISC + 256;
+constexpr int SM_TOTAL = SM_WS;
 static_assert(SM_TOTAL <= 227 * 1024, "exceeds B200 shared memory per CTA");
-
-struct Misc {
-    unsigned int warp_sum[NWARPS];
-    long long ticket;
-    unsigned long long base;
-    int emit_ok;
-};
 
 struct Params {
     const uint8_t *rgba;
@@ -78,8 +70,8 @@ struct Params {
     uint16_t *group_bits;    // optional, 3 per group
     int16_t *coefs;          // optional, 128 per group
     uint64_t *result;        // [0] length, [1] groups outside the reference's defined behaviour, [2] error flags
-    uint64_t *status;        // [0] ticket, [1..] look-back words (one per tile)
-    uint32_t *scratch;       // per CTA: REC_WORDS x THREADS words of record staging, word-major
+    uint64_t *status;        // [0] ticket, [1..] look-back words (one per 32-group tile)
+    uint32_t *scratch;       // per warp: REC_WORDS x 32 words of record staging, word-major
     uint32_t ntiles;
     int force_slow;          // test hook: route every channel through the general routine
 };
@@ -190,8 +182,10 @@ template <int W, class F>
 __device__ __forceinline__ double exact_coef_t(F smp, int u, int v)
 {
     double sum = 0.0;
+#pragma unroll 1
     for (int x = 0; x < 8; ++x) {
         const double cx = kCos8[x * 8 + u];
+#pragma unroll 1
         for (int y = 0; y < W; ++y) {
             const double cy = (W == 8) ? kCos8[y * 8 + v] : kCos4[y * 4 + v];
             const double corr = (double)(smp(x * W + y) - 128);
@@ -241,62 +235,80 @@ __device__ __forceinline__ bool quant_fast(double qs, int &t)
     return !((fr >= 0xFFFFEu) || (fr <= 1u && ti >= 1u));
 }
 
-// Luma: 8x8 DCT + quantise + zig-zag.  The 64 int8 results go to bytes [0, 64) of the W_PAR words (zig-zag order);
-// returns true if some value is outside int8.  Loops are kept rolled: the code is executed once per group and
-// unrolling it fully (128 coefficient bodies) thrashed the instruction cache.
-template <int PAR>
-__device__ __forceinline__ bool dct_luma_half(uint32_t *wl, uint32_t *wbase, int lane, int16_t *co)
+// Column pass + quantise + zig-zag of ONE column of row-pass results, shared by luma (W = 8) and chroma (W = 4).
+// T holds 8 rows x 4 columns of doubles, this call consumes column vi, which is frequency v of the channel.
+// Results go to byte out0 + zigzag(u, v) of the W_PAR words.  Kept out of line and rolled: the kernel's hot code
+// has to stay well inside the instruction cache because the warps of an SM run desynchronised.
+__device__ __noinline__ unsigned col_pass(uint32_t *wl, uint32_t *wbase, int lane, int vi, int v, int W, int byte0, int out0,
+                                          int16_t *co)
 {
-    bool wide = false;
-    // row pass: T[x][vi] = sum_y corr[x][y] * cos8[y][v], v = 2 vi + PAR, using cos8[7-y][v] = (-1)^v cos8[y][v]
-#pragma unroll 1
-    for (int x = 0; x < 8; ++x) {
-        const uint32_t w0 = ws_w(wl, W_SMP + 2 * x), w1 = ws_w(wl, W_SMP + 2 * x + 1);
-        double e[4];
+    unsigned wide = 0;
+    double s[4], d[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int a = (w0 >> (8 * j)) & 0xFF, b = (w1 >> (8 * (3 - j))) & 0xFF; // y = j and y = 7 - j
-            e[j] = (double)(PAR == 0 ? a + b - 256 : a - b);
-        }
-#pragma unroll
-        for (int vi = 0; vi < 4; ++vi) {
-            const int v = 2 * vi + PAR;
-            double acc = e[0] * kCos8[0 * 8 + v];
-#pragma unroll
-            for (int j = 1; j < 4; ++j) acc = fma(e[j], kCos8[j * 8 + v], acc);
-            ws_d(wbase, lane, x * 4 + vi) = acc;
-        }
+    for (int j = 0; j < 4; ++j) {
+        const double a = ws_d(wbase, lane, j * 4 + vi), b = ws_d(wbase, lane, (7 - j) * 4 + vi);
+        s[j] = a + b; // cos8[7-x][u] = (-1)^u cos8[x][u]
+        d[j] = a - b;
     }
-    // column pass + quantise
 #pragma unroll 1
-    for (int vi = 0; vi < 4; ++vi) {
-        const int v = 2 * vi + PAR;
-        double s[4], d[4];
+    for (int k = 0; k < 4; ++k) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const double a = ws_d(wbase, lane, j * 4 + vi), b = ws_d(wbase, lane, (7 - j) * 4 + vi);
-            s[j] = a + b;
-            d[j] = a - b;
-        }
+        for (int odd = 0; odd < 2; ++odd) {
+            const int u = 2 * k + odd;
+            double acc = (odd ? d[0] : s[0]) * kCos8[0 * 8 + u];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            double acc = ((u & 1) ? d[0] : s[0]) * kCos8[0 * 8 + u];
-#pragma unroll
-            for (int j = 1; j < 4; ++j) acc = fma((u & 1) ? d[j] : s[j], kCos8[j * 8 + u], acc);
+            for (int j = 1; j < 4; ++j) acc = fma(odd ? d[j] : s[j], kCos8[j * 8 + u], acc);
+            const int idx = u * W + v;
             int t;
-            if (!quant_fast(acc * kMLum.m[u * 8 + v], t)) t = exact_quant_ws<8>(wl, 0, u, v);
+            if (!quant_fast(acc * (W == 8 ? kMLum.m[idx] : kMChr.m[idx]), t))
+                t = W == 8 ? exact_quant_ws<8>(wl, byte0, u, v) : exact_quant_ws<4>(wl, byte0, u, v);
             wide |= (t < -128) | (t > 127);
-            ws_b(wl, W_PAR, kZZ8.pos[u * 8 + v]) = (uint8_t)t;
-            if (co) co[u * 8 + v] = (int16_t)t;
+            ws_b(wl, W_PAR, out0 + (W == 8 ? kZZ8.pos[idx] : kZZ4.pos[idx])) = (uint8_t)t;
+            if (co) co[idx] = (int16_t)t;
         }
     }
     return wide;
 }
 
-// Chroma: 8 rows x 4 columns; the 32 int8 results go to bytes [out0, out0 + 32) of the W_PAR words
-__device__ __forceinline__ bool dct_chroma(uint32_t *wl, uint32_t *wbase, int lane, int byte0, int out0, int16_t *co)
+// Luma: 8x8 DCT + quantise + zig-zag.  The 64 int8 results go to bytes [0, 64) of the W_PAR words (zig-zag order);
+// returns non-zero if some value is outside int8.
+__device__ __forceinline__ unsigned dct_luma(uint32_t *wl, uint32_t *wbase, int lane, int16_t *co)
 {
-    bool wide = false;
+    unsigned wide = 0;
+#pragma unroll 1
+    for (int par = 0; par < 2; ++par) { // even / odd output columns v = 2 vi + par
+        double c[4][4];
+#pragma unroll
+        for (int vi = 0; vi < 4; ++vi)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) c[vi][j] = kCos8[j * 8 + 2 * vi + par];
+        // row pass: T[x][vi] = sum_y corr[x][y] * cos8[y][v], using cos8[7-y][v] = (-1)^v cos8[y][v]
+#pragma unroll 1
+        for (int x = 0; x < 8; ++x) {
+            const uint32_t w0 = ws_w(wl, W_SMP + 2 * x), w1 = ws_w(wl, W_SMP + 2 * x + 1);
+            double e[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int a = (w0 >> (8 * j)) & 0xFF, b = (w1 >> (8 * (3 - j))) & 0xFF; // y = j and y = 7 - j
+                e[j] = (double)(par == 0 ? a + b - 256 : a - b);
+            }
+#pragma unroll
+            for (int vi = 0; vi < 4; ++vi) {
+                double acc = e[0] * c[vi][0];
+#pragma unroll
+                for (int j = 1; j < 4; ++j) acc = fma(e[j], c[vi][j], acc);
+                ws_d(wbase, lane, x * 4 + vi) = acc;
+            }
+        }
+#pragma unroll 1
+        for (int vi = 0; vi < 4; ++vi) wide |= col_pass(wl, wbase, lane, vi, 2 * vi + par, 8, 0, 0, co);
+    }
+    return wide;
+}
+
+// Chroma: 8 rows x 4 columns; the 32 int8 results go to bytes [out0, out0 + 32) of the W_PAR words
+__device__ __forceinline__ unsigned dct_chroma(uint32_t *wl, uint32_t *wbase, int lane, int byte0, int out0, int16_t *co)
+{
 #pragma unroll 1
     for (int x = 0; x < 8; ++x) {
         const uint32_t w0 = ws_w(wl, W_SMP + (byte0 >> 2) + x);
@@ -308,27 +320,9 @@ __device__ __forceinline__ bool dct_chroma(uint32_t *wl, uint32_t *wbase, int la
             ws_d(wbase, lane, x * 4 + v) = fma(b, kCos4[1 * 4 + v], a * kCos4[0 * 4 + v]);
         }
     }
+    unsigned wide = 0;
 #pragma unroll 1
-    for (int v = 0; v < 4; ++v) {
-        double s[4], d[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const double a = ws_d(wbase, lane, j * 4 + v), b = ws_d(wbase, lane, (7 - j) * 4 + v);
-            s[j] = a + b;
-            d[j] = a - b;
-        }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            double acc = ((u & 1) ? d[0] : s[0]) * kCos8[0 * 8 + u];
-#pragma unroll
-            for (int j = 1; j < 4; ++j) acc = fma((u & 1) ? d[j] : s[j], kCos8[j * 8 + u], acc);
-            int t;
-            if (!quant_fast(acc * kMChr.m[u * 4 + v], t)) t = exact_quant_ws<4>(wl, byte0, u, v);
-            wide |= (t < -128) | (t > 127);
-            ws_b(wl, W_PAR, out0 + kZZ4.pos[u * 4 + v]) = (uint8_t)t;
-            if (co) co[u * 4 + v] = (int16_t)t;
-        }
-    }
+    for (int v = 0; v < 4; ++v) wide |= col_pass(wl, wbase, lane, v, v, 4, byte0, out0, co);
     return wide;
 }
 
@@ -344,7 +338,7 @@ struct BitWriter {
         nbits += len;
         if (nbits >= 32) {
             const uint32_t wv = (uint32_t)(acc >> (nbits - 32));
-            if (wpos < REC_WORDS) dst[wpos * THREADS] = __byte_perm(wv, 0, 0x0123); // MSB-first bytes
+            if (wpos < REC_WORDS) dst[wpos * 32] = __byte_perm(wv, 0, 0x0123); // MSB-first bytes
             ++wpos;
             nbits -= 32;
         }
@@ -353,7 +347,7 @@ struct BitWriter {
     {
         if (nbits > 0) {
             const uint32_t wv = (uint32_t)(acc << (32 - nbits));
-            if (wpos < REC_WORDS) dst[wpos * THREADS] = __byte_perm(wv, 0, 0x0123);
+            if (wpos < REC_WORDS) dst[wpos * 32] = __byte_perm(wv, 0, 0x0123);
         }
     }
 };
@@ -557,29 +551,33 @@ __device__ __forceinline__ void sift(uint8_t *hb, uint32_t n, uint32_t j, uint32
     *self = (uint16_t)e;
 }
 
-// Scan 32 int8 coefficients (8 registers) for runs; F is called with (count, value) for every finished run.
-template <class F>
-__device__ __forceinline__ void scan32(const uint32_t (&r)[8], bool first, int &prev, int &run, F flush)
+// The 128 int8 coefficients of a group live in 32 registers: luma cz[0..16), Cr cz[16..24), Cb cz[24..32).
+// Registers cannot be indexed dynamically, so the scans below pull 16 coefficients at a time into a 4-register
+// window (a select chain) and shift the window by one byte per step: the loop body exists once.
+__device__ __forceinline__ void window_load(uint32_t (&w)[4], const uint32_t (&cz)[32], int q8)
 {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-        const int v = (int)(int8_t)(r[i >> 2] >> (8 * (i & 3)));
-        if (i == 0 && first) {
-            prev = v;
-            run = 1;
-        } else if (v != prev) {
-            flush(run, prev);
-            prev = v;
-            run = 1;
-        } else {
-            ++run;
-        }
+    for (int i = 0; i < 4; ++i) {
+        uint32_t v = cz[i];
+#pragma unroll
+        for (int q = 1; q < 8; ++q) v = (q8 == q) ? cz[4 * q + i] : v;
+        w[i] = v;
     }
 }
+__device__ __forceinline__ int window_pop(uint32_t (&w)[4])
+{
+    const int v = (int)(int8_t)(w[0] & 0xFFu);
+    w[0] = __funnelshift_r(w[0], w[1], 8);
+    w[1] = __funnelshift_r(w[1], w[2], 8);
+    w[2] = __funnelshift_r(w[2], w[3], 8);
+    w[3] >>= 8;
+    return v;
+}
 
-// One channel through RLE + Huffman + emission.  cur[0..nh*8) hold N = 32*nh int8 coefficients in zig-zag order.
+// One channel through RLE + Huffman + emission.  q0 = index of the channel's first 16-coefficient window
+// (luma 0, Cr 4, Cb 6), nq = number of windows (4 or 2).
 // Returns the number of bits, or -1 if the channel has to go through slow_channel.
-__device__ __forceinline__ int entropy_fast(uint32_t *wl, uint32_t epoch, uint32_t (&cur)[16], int nh, BitWriter &bw)
+__device__ __forceinline__ int entropy_fast(uint32_t *wl, uint32_t epoch, const uint32_t (&cz)[32], int q0, int nq, BitWriter &bw)
 {
     Ent E;
     E.lb = reinterpret_cast<uint8_t *>(wl);
@@ -587,17 +585,23 @@ __device__ __forceinline__ int entropy_fast(uint32_t *wl, uint32_t epoch, uint32
     E.k = 0;
     E.over = 0;
     uint8_t *hb = E.lb + W_CNT * 128;
-    int prev = 0, run = 0;
-    uint32_t r[8];
+    const int n = 16 * nq;
+    uint32_t w[4];
     // pass 1: RLE (JPEG.c:767-809) feeding the symbol table in first-appearance order
+    window_load(w, cz, q0);
+    int prev = (int)(int8_t)(w[0] & 0xFFu), run = 0;
 #pragma unroll 1
-    for (int h = 0; h < nh; ++h) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) r[i] = h == 0 ? cur[i] : cur[8 + i];
-        scan32(r, h == 0, prev, run, [&](int c, int v) {
-            sym_count(E, c);
-            sym_count(E, v);
-        });
+    for (int i = 0; i < n; ++i) {
+        if (i && (i & 15) == 0) window_load(w, cz, q0 + (i >> 4));
+        const int v = window_pop(w);
+        if (v != prev) {
+            sym_count(E, run);
+            sym_count(E, prev);
+            prev = v;
+            run = 1;
+        } else {
+            ++run;
+        }
     }
     sym_count(E, run);
     sym_count(E, prev);
@@ -612,23 +616,23 @@ __device__ __forceinline__ int entropy_fast(uint32_t *wl, uint32_t epoch, uint32
     // build_heap (JPEG.c:913-934)
     for (uint32_t j = k >> 1; j >= 1; --j) sift(hb, k, j, *heap_at(hb, j));
     // build_huffman_tree (JPEG.c:936-961): pop two, append their parent at the END of the array (no sift-up)
-    uint32_t n = k, next = k;
+    uint32_t hn = k, next = k;
     int bits = 0;
     uint8_t *chb = E.lb + W_PAR * 128;
-    while (n > 1) {
-        const uint32_t left = *heap_at(hb, 1);
-        uint32_t e = *heap_at(hb, n);
-        --n;
-        sift(hb, n, 1, e);
-        const uint32_t right = *heap_at(hb, 1);
-        e = *heap_at(hb, n);
-        --n;
-        if (n >= 1) sift(hb, n, 1, e);
-        const uint32_t c = (left >> 8) + (right >> 8);
+    while (hn > 1) {
+        uint32_t pop[2];
+#pragma unroll 1
+        for (int t = 0; t < 2; ++t) { // heap[0] = heap[--size]; heapify(0)
+            pop[t] = *heap_at(hb, 1);
+            const uint32_t e = *heap_at(hb, hn);
+            --hn;
+            if (hn >= 1) sift(hb, hn, 1, e);
+        }
+        const uint32_t c = (pop[0] >> 8) + (pop[1] >> 8);
         bits += (int)c; // total code length = sum of the internal nodes' counts
-        *heap_at(chb, next - k) = (uint16_t)((left & 0xFFu) | ((right & 0xFFu) << 8));
-        ++n;
-        *heap_at(hb, n) = (uint16_t)((c << 8) | next);
+        *heap_at(chb, next - k) = (uint16_t)((pop[0] & 0xFFu) | ((pop[1] & 0xFFu) << 8));
+        ++hn;
+        *heap_at(hb, hn) = (uint16_t)((c << 8) | next);
         ++next;
     }
     // assign_codes (JPEG.c:963-982), top down: left = '0', right = '1'.  Children always have smaller ids than
@@ -646,11 +650,20 @@ __device__ __forceinline__ int entropy_fast(uint32_t *wl, uint32_t epoch, uint32
     }
     if (deep) return -1;
     // pass 2: generate_encoded_sequence (JPEG.c:993-1007)
+    window_load(w, cz, q0);
+    prev = (int)(int8_t)(w[0] & 0xFFu);
+    run = 0;
 #pragma unroll 1
-    for (int h = 0; h < nh; ++h) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) r[i] = h == 0 ? cur[i] : cur[8 + i];
-        scan32(r, h == 0, prev, run, [&](int c, int v) { pair_emit(E, bw, c, v); });
+    for (int i = 0; i < n; ++i) {
+        if (i && (i & 15) == 0) window_load(w, cz, q0 + (i >> 4));
+        const int v = window_pop(w);
+        if (v != prev) {
+            pair_emit(E, bw, run, prev);
+            prev = v;
+            run = 1;
+        } else {
+            ++run;
+        }
     }
     pair_emit(E, bw, run, prev);
     return bits;
@@ -663,18 +676,26 @@ __global__ void __launch_bounds__(THREADS, 1) jpeg_encode_kernel(Params P)
     const int lane = tid & 31, warp = tid >> 5;
     uint32_t *wbase = reinterpret_cast<uint32_t *>(smem) + warp * (WS_WORDS * 32);
     uint32_t *wl = wbase + lane;
-    Misc &M = *reinterpret_cast<Misc *>(smem + SM_MISC);
-    uint32_t *stage = P.scratch + (size_t)blockIdx.x * (REC_WORDS * THREADS) + tid;
+    // each warp is its own producer: 32 groups per tile, no CTA-wide barrier anywhere, so warps drift apart and
+    // their DCT (fp64 pipe), Huffman (integer / shared memory) and copy-out (L2 latency) phases overlap
+    uint32_t *stage2 = P.scratch + ((size_t)blockIdx.x * NWARPS + warp) * (2 * REC_WORDS * 32) + lane; // two staging buffers
     const size_t bpr = ((size_t)P.w + 7) / 8;
     const bool aligned = ((reinterpret_cast<uintptr_t>(P.rgba) | P.stride) & 15) == 0;
+    // the tile computed in the previous iteration: its records wait in the other staging buffer until its offset
+    // is fetched, one tile later, when its predecessors have (almost always) published theirs
+    bool pend = false;
+    long long p_tile = 0;
+    unsigned int p_off = 0, p_bytes = 0, p_total = 0, p_bits = 0;
+    int buf = 0;
 
     for (;;) {
-        if (tid == 0) M.ticket = (long long)atomicAdd((unsigned long long *)&P.status[0], 1ull);
-        __syncthreads();
-        const long long tile = M.ticket;
-        if (tile >= (long long)P.ntiles) break;
-        const size_t gl = (size_t)tile * THREADS + tid; // group index inside this call
-        const bool active = gl < P.ngroups;
+        long long tile = 0;
+        if (lane == 0) tile = (long long)atomicAdd((unsigned long long *)&P.status[0], 1ull);
+        tile = __shfl_sync(0xffffffffu, tile, 0);
+        const bool have = tile < (long long)P.ntiles;
+        uint32_t *stage = stage2 + buf * (REC_WORDS * 32);
+        const size_t gl = (size_t)tile * 32 + lane; // group index inside this call
+        const bool active = have && gl < P.ngroups;
         unsigned int rec_bytes = 0;
         int bl = 0, br = 0, bb = 0;
         if (active) {
@@ -685,25 +706,30 @@ __global__ void __launch_bounds__(THREADS, 1) jpeg_encode_kernel(Params P)
             const bool full = brow * 8 + 8 <= (size_t)P.h && col0 + 8 <= (size_t)P.w;
             if (full && aligned) {
                 const uint8_t *rp = P.rgba + brow * 8 * P.stride + col0 * 4;
-#pragma unroll
+                uint4 na = __ldg(reinterpret_cast<const uint4 *>(rp)), nb = __ldg(reinterpret_cast<const uint4 *>(rp) + 1);
+#pragma unroll 1
                 for (int lr = 0; lr < 8; ++lr) {
-                    const uint4 a = __ldg(reinterpret_cast<const uint4 *>(rp + lr * P.stride));
-                    const uint4 b = __ldg(reinterpret_cast<const uint4 *>(rp + lr * P.stride) + 1);
-                    const uint32_t px[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-                    uint32_t y0 = 0, y1 = 0, cr = 0, cb = 0;
-#pragma unroll
-                    for (int lc = 0; lc < 8; ++lc) {
-                        const int r = px[lc] & 0xFF, gg = (px[lc] >> 8) & 0xFF, bq = (px[lc] >> 16) & 0xFF;
-                        const uint32_t y = (uint32_t)luma_of(r, gg, bq);
-                        if (lc < 4) y0 |= y << (8 * lc);
-                        else y1 |= y << (8 * (lc - 4));
-                        if (lc & 1) { // chroma sample of local column lc-1 is the original chroma at column lc
-                            cr |= (uint32_t)cr_of(r, gg, bq) << (8 * (lc >> 1));
-                            cb |= (uint32_t)cb_of(r, gg, bq) << (8 * (lc >> 1));
-                        }
+                    uint32_t px[8] = {na.x, na.y, na.z, na.w, nb.x, nb.y, nb.z, nb.w};
+                    if (lr < 7) { // next row's pixels are in flight while this row is converted
+                        na = __ldg(reinterpret_cast<const uint4 *>(rp + (lr + 1) * P.stride));
+                        nb = __ldg(reinterpret_cast<const uint4 *>(rp + (lr + 1) * P.stride) + 1);
                     }
-                    ws_w(wl, W_SMP + 2 * lr) = y0;
-                    ws_w(wl, W_SMP + 2 * lr + 1) = y1;
+                    uint32_t yy[2] = {0, 0}, cr = 0, cb = 0;
+#pragma unroll 1
+                    for (int it = 0; it < 4; ++it) { // two pixels per step; the odd one also gives the chroma sample
+                        const int r0 = px[0] & 0xFF, g0 = (px[0] >> 8) & 0xFF, b0 = (px[0] >> 16) & 0xFF;
+                        const int r1 = px[1] & 0xFF, g1 = (px[1] >> 8) & 0xFF, b1 = (px[1] >> 16) & 0xFF;
+                        const uint32_t pair = (uint32_t)luma_of(r0, g0, b0) | ((uint32_t)luma_of(r1, g1, b1) << 8);
+                        const uint32_t sh = pair << (16 * (it & 1));
+                        yy[0] |= it < 2 ? sh : 0u;
+                        yy[1] |= it < 2 ? 0u : sh;
+                        cr |= (uint32_t)cr_of(r1, g1, b1) << (8 * it); // chroma of local column 2 it = original chroma at column 2 it + 1
+                        cb |= (uint32_t)cb_of(r1, g1, b1) << (8 * it);
+#pragma unroll
+                        for (int q = 0; q < 6; ++q) px[q] = px[q + 2];
+                    }
+                    ws_w(wl, W_SMP + 2 * lr) = yy[0];
+                    ws_w(wl, W_SMP + 2 * lr + 1) = yy[1];
                     ws_w(wl, W_SMP + 16 + lr) = cr;
                     ws_w(wl, W_SMP + 24 + lr) = cb;
                 }
@@ -733,21 +759,17 @@ __global__ void __launch_bounds__(THREADS, 1) jpeg_encode_kernel(Params P)
                 }
             }
             // ---- DCT + quantise + zig-zag of the three channels -> int8 coefficients in registers
-            uint32_t L[16], R[8], B[8];
+            uint32_t cz[32]; // luma [0,16), Cr [16,24), Cb [24,32)
             int16_t *co = P.coefs ? P.coefs + gl * 128 : nullptr;
             unsigned widemask = P.force_slow ? 7u : 0u;
-            if (dct_luma_half<0>(wl, wbase, lane, co)) widemask |= 1u;
-            if (dct_luma_half<1>(wl, wbase, lane, co)) widemask |= 1u;
+            if (dct_luma(wl, wbase, lane, co)) widemask |= 1u;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) L[i] = ws_w(wl, W_PAR + i);
+            for (int i = 0; i < 16; ++i) cz[i] = ws_w(wl, W_PAR + i);
 #pragma unroll 1
             for (int c = 0; c < 2; ++c)
                 if (dct_chroma(wl, wbase, lane, 64 + 32 * c, 32 * c, co ? co + 64 + 32 * c : nullptr)) widemask |= 2u << c;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                R[i] = ws_w(wl, W_PAR + i);
-                B[i] = ws_w(wl, W_PAR + 8 + i);
-            }
+            for (int i = 0; i < 16; ++i) cz[16 + i] = ws_w(wl, W_PAR + i);
             // ---- entropy coding of lum, r, b (reference order JPEG.c:1242, :1284, :1318)
             // The symbol table shares its words with the DCT's row-pass results: clear it once per group; the three
             // channels then tag their entries with epochs 1, 2, 3.
@@ -761,15 +783,9 @@ __global__ void __launch_bounds__(THREADS, 1) jpeg_encode_kernel(Params P)
             int bad = 0;
 #pragma unroll 1
             for (int ch = 0; ch < 3; ++ch) {
-                uint32_t cur[16];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    cur[i] = ch == 0 ? L[i] : (ch == 1 ? R[i] : B[i]);
-                    cur[8 + i] = L[8 + i];
-                }
                 const int max_bits = ch == 0 ? 1023 : 511;
                 int bits = -1;
-                if (!((widemask >> ch) & 1u)) bits = entropy_fast(wl, (uint32_t)ch + 1u, cur, ch == 0 ? 2 : 1, bw);
+                if (!((widemask >> ch) & 1u)) bits = entropy_fast(wl, (uint32_t)ch + 1u, cz, ch == 0 ? 0 : 2 + 2 * ch, ch == 0 ? 4 : 2, bw);
                 if (bits < 0) {
                     BitWriter tmp = bw;
                     bits = slow_channel(P.rgba, P.w, P.h, P.stride, g, ch, nullptr, &tmp, max_bits, &bad);
@@ -789,77 +805,77 @@ __global__ void __launch_bounds__(THREADS, 1) jpeg_encode_kernel(Params P)
             const int total_bits = bl + br + bb;
             rec_bytes = (unsigned int)min((total_bits + 7) >> 3, REC_BYTES);
         }
-        // ---- tile-wide exclusive scan of record sizes
+        // ---- warp-wide exclusive scan of record sizes
         unsigned int inc = rec_bytes;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             unsigned int v = __shfl_up_sync(0xffffffffu, inc, o);
             if (lane >= o) inc += v;
         }
-        if (lane == 31) M.warp_sum[warp] = inc;
-        __syncthreads();
-        unsigned int wsum = 0, tile_total = 0;
-#pragma unroll
-        for (int k = 0; k < NWARPS; ++k) {
-            const unsigned int s = M.warp_sum[k];
-            if (k < warp) wsum += s;
-            tile_total += s;
-        }
-        const unsigned int my_off = wsum + inc - rec_bytes;
-        // ---- place the tile in the output stream
-        if (warp == 0) {
-            unsigned long long base = ljb_lookback(P.status + 1, tile, tile_total, 0);
+        const unsigned int tile_total = __shfl_sync(0xffffffffu, inc, 31);
+        const unsigned int my_off = inc - rec_bytes;
+        if (have) ljb_lookback_publish(P.status + 1, tile, tile_total, 0);
+        // ---- place the PREVIOUS tile in the output stream and move its records there
+        if (pend) {
+            const unsigned long long base = ljb_lookback_resolve(P.status + 1, p_tile, p_total, 0);
+            const bool emit_ok = base + p_total <= P.out_cap;
             if (lane == 0) {
-                M.base = base;
-                M.emit_ok = (base + tile_total <= P.out_cap) ? 1 : 0;
-                if (!M.emit_ok) atomicOr((unsigned long long *)&P.result[2], 1ull);
-                if (tile == (long long)P.ntiles - 1) {
-                    P.result[0] = base + tile_total;
-                    P.group_offsets[P.ngroups] = base + tile_total;
+                if (!emit_ok) atomicOr((unsigned long long *)&P.result[2], 1ull);
+                if (p_tile == (long long)P.ntiles - 1) {
+                    P.result[0] = base + p_total;
+                    P.group_offsets[P.ngroups] = base + p_total;
                 }
             }
-        }
-        __syncthreads();
-        const unsigned long long base = M.base;
-        if (active) {
-            P.group_offsets[gl] = base + my_off;
-            if (P.group_bits) {
-                P.group_bits[3 * gl + 0] = (uint16_t)bl;
-                P.group_bits[3 * gl + 1] = (uint16_t)br;
-                P.group_bits[3 * gl + 2] = (uint16_t)bb;
-            }
-            // ---- move the staged record to its place: head bytes, aligned words, tail bytes
-            if (M.emit_ok && rec_bytes) {
-                uint8_t *dst = P.out + base + my_off;
-                const unsigned int head = min((unsigned int)((4 - (reinterpret_cast<uintptr_t>(dst) & 3)) & 3), rec_bytes);
-                uint32_t w0 = stage[0];
-                for (unsigned int i = 0; i < head; ++i) dst[i] = (uint8_t)(w0 >> (8 * i));
-                const unsigned int nwords = (rec_bytes - head) >> 2;
-                uint32_t *d4 = reinterpret_cast<uint32_t *>(dst + head);
-                unsigned int j = 0;
-                for (; j + 4 <= nwords; j += 4) { // four staged words in flight per step (they come from L2)
-                    uint32_t wv[4];
+            const size_t pgl = (size_t)p_tile * 32 + lane;
+            if (pgl < P.ngroups) {
+                P.group_offsets[pgl] = base + p_off;
+                if (P.group_bits) {
+                    P.group_bits[3 * pgl + 0] = (uint16_t)(p_bits & 0x3FFu);
+                    P.group_bits[3 * pgl + 1] = (uint16_t)((p_bits >> 10) & 0x3FFu);
+                    P.group_bits[3 * pgl + 2] = (uint16_t)(p_bits >> 20);
+                }
+                // head bytes, aligned words, tail bytes
+                if (emit_ok && p_bytes) {
+                    const uint32_t *src = stage2 + (buf ^ 1) * (REC_WORDS * 32);
+                    uint8_t *dst = P.out + base + p_off;
+                    const unsigned int head = min((unsigned int)((4 - (reinterpret_cast<uintptr_t>(dst) & 3)) & 3), p_bytes);
+                    uint32_t w0 = src[0];
+                    for (unsigned int i = 0; i < head; ++i) dst[i] = (uint8_t)(w0 >> (8 * i));
+                    const unsigned int nwords = (p_bytes - head) >> 2;
+                    uint32_t *d4 = reinterpret_cast<uint32_t *>(dst + head);
+                    unsigned int j = 0;
+                    for (; j + 4 <= nwords; j += 4) { // four staged words in flight per step (they come from L2)
+                        uint32_t wv[4];
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) wv[q] = (j + 1 + q < REC_WORDS) ? stage[(j + 1 + q) * THREADS] : 0u;
-                    d4[j] = __funnelshift_r(w0, wv[0], 8 * head);
-                    d4[j + 1] = __funnelshift_r(wv[0], wv[1], 8 * head);
-                    d4[j + 2] = __funnelshift_r(wv[1], wv[2], 8 * head);
-                    d4[j + 3] = __funnelshift_r(wv[2], wv[3], 8 * head);
-                    w0 = wv[3];
-                }
-                for (; j < nwords; ++j) {
-                    const uint32_t w1 = (j + 1 < REC_WORDS) ? stage[(j + 1) * THREADS] : 0u;
-                    d4[j] = __funnelshift_r(w0, w1, 8 * head);
-                    w0 = w1;
-                }
-                const unsigned int done = head + 4 * nwords;
-                if (done < rec_bytes) {
-                    const uint32_t w1 = (j + 1 < REC_WORDS) ? stage[(j + 1) * THREADS] : 0u;
-                    const uint32_t t = __funnelshift_r(w0, w1, 8 * head);
-                    for (unsigned int i = 0; done + i < rec_bytes; ++i) dst[done + i] = (uint8_t)(t >> (8 * i));
+                        for (int q = 0; q < 4; ++q) wv[q] = (j + 1 + q < REC_WORDS) ? src[(j + 1 + q) * 32] : 0u;
+                        d4[j] = __funnelshift_r(w0, wv[0], 8 * head);
+                        d4[j + 1] = __funnelshift_r(wv[0], wv[1], 8 * head);
+                        d4[j + 2] = __funnelshift_r(wv[1], wv[2], 8 * head);
+                        d4[j + 3] = __funnelshift_r(wv[2], wv[3], 8 * head);
+                        w0 = wv[3];
+                    }
+                    for (; j < nwords; ++j) {
+                        const uint32_t w1 = (j + 1 < REC_WORDS) ? src[(j + 1) * 32] : 0u;
+                        d4[j] = __funnelshift_r(w0, w1, 8 * head);
+                        w0 = w1;
+                    }
+                    const unsigned int done = head + 4 * nwords;
+                    if (done < p_bytes) {
+                        const uint32_t w1 = (j + 1 < REC_WORDS) ? src[(j + 1) * 32] : 0u;
+                        const uint32_t t = __funnelshift_r(w0, w1, 8 * head);
+                        for (unsigned int i = 0; done + i < p_bytes; ++i) dst[done + i] = (uint8_t)(t >> (8 * i));
+                    }
                 }
             }
         }
+        if (!have) break;
+        pend = true;
+        p_tile = tile;
+        p_off = my_off;
+        p_bytes = rec_bytes;
+        p_total = tile_total;
+        p_bits = (unsigned)bl | ((unsigned)br << 10) | ((unsigned)bb << 20);
+        buf ^= 1;
     }
 }
 
@@ -883,11 +899,12 @@ extern "C" int ljb_jpeg_encode_rgba_dev(ljb_ctx *ctx, const uint8_t *d_rgba, int
     const size_t total = ljb_jpeg_group_count(w, h);
     if (ngroups == 0 || first_group + ngroups > total) return LJB_E_ARG;
     LJB_CUDA(cudaSetDevice(ctx->device));
-    const size_t ntiles = (ngroups + THREADS - 1) / THREADS;
+    const size_t ntiles = (ngroups + 31) / 32;
     if (ntiles > 0x7fffffffull) return LJB_E_ARG;
-    const int grid = (int)((ntiles < (size_t)ctx->num_sms) ? ntiles : (size_t)ctx->num_sms);
+    const size_t want = (ntiles + NWARPS - 1) / NWARPS;
+    const int grid = (int)((want < (size_t)ctx->num_sms) ? want : (size_t)ctx->num_sms);
     int rc;
-    if ((rc = ljb_ensure(&ctx->d_scratch, &ctx->scratch_bytes, (size_t)ctx->num_sms * THREADS * REC_BYTES)) != 0) return rc;
+    if ((rc = ljb_ensure(&ctx->d_scratch, &ctx->scratch_bytes, (size_t)ctx->num_sms * THREADS * REC_BYTES * 2)) != 0) return rc;
     if ((rc = ljb_ensure(&ctx->d_status, &ctx->status_bytes, (ntiles + 2) * sizeof(uint64_t))) != 0) return rc;
     LJB_CUDA(cudaMemsetAsync(ctx->d_status, 0, (ntiles + 2) * sizeof(uint64_t), ctx->stream));
     LJB_CUDA(cudaMemsetAsync(d_result, 0, 3 * sizeof(uint64_t), ctx->stream));
