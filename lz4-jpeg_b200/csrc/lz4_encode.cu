@@ -82,6 +82,8 @@ struct Params {
     uint64_t *result;        // [0] length, [1] phantom, [2] error flags
     uint64_t *status;        // [0] ticket, [1..] look-back words
     uint32_t *scratch;       // per CTA: MAXB u32 match records
+    uint8_t *staging;        // per CTA: two buffers of stage_stride bytes holding the encoded block until its offset is known
+    size_t stage_stride;
     uint32_t lead;           // 1 if this shard writes the frame byte
     uint32_t frame_byte;
     uint16_t *dump_len;      // optional single-block stage dump
@@ -168,6 +170,46 @@ __global__ void __launch_bounds__(THREADS, 1) lz4_encode_kernel(Params P)
     const int lane = tid & 31;
     const int warp = tid >> 5;
     uint32_t *R = P.scratch + (size_t)blockIdx.x * MAXB; // match records, one per position
+    // The encoded block is written to a staging buffer first; its offset in the stream is fetched (decoupled
+    // look-back) only after the NEXT block has been encoded, when the predecessors have long published their
+    // sizes, so the look-back practically never waits.  (Fetching it right away cost 12 % of the kernel in
+    // barrier stalls: every CTA waited for the slowest of the 147 blocks in flight before it.)
+    uint8_t *const stage0 = P.staging + (size_t)blockIdx.x * 2 * P.stage_stride;
+    int buf = 0;
+    bool pend = false;
+    long long pend_b = 0;
+    unsigned long long pend_pay = 0;
+    // moves the pending block from its staging buffer to its place in the stream (all threads)
+    auto flush_pending = [&]() {
+        if (warp == 0) {
+            const unsigned long long base = ljb_lookback_resolve(P.status + 1, pend_b, pend_pay, P.lead);
+            if (lane == 0) {
+                M.base = base;
+                M.emit_ok = (base + pend_pay <= P.out_cap) ? 1 : 0;
+                P.block_offsets[pend_b] = base;
+                if (pend_b == (long long)P.nblocks - 1) {
+                    P.block_offsets[P.nblocks] = base + pend_pay;
+                    P.result[0] = base + pend_pay;
+                }
+                if (!M.emit_ok) atomicOr((unsigned long long *)&P.result[2], 1ull);
+            }
+        }
+        __syncthreads();
+        if (M.emit_ok) {
+            const uint8_t *src = stage0 + (size_t)(buf ^ 1) * P.stage_stride;
+            const uint32_t *srcw = reinterpret_cast<const uint32_t *>(src);
+            uint8_t *dst = P.out + M.base;
+            const uint32_t n = (uint32_t)pend_pay;
+            const uint32_t head = min((uint32_t)((4 - (reinterpret_cast<uintptr_t>(dst) & 3)) & 3), n);
+            if ((uint32_t)tid < head) dst[tid] = src[tid];
+            const uint32_t nwords = (n - head) >> 2;
+            uint32_t *d4 = reinterpret_cast<uint32_t *>(dst + head);
+            for (uint32_t j = tid; j < nwords; j += THREADS) d4[j] = __funnelshift_r(srcw[j], srcw[j + 1], 8 * head);
+            const uint32_t done = head + 4 * nwords;
+            if ((uint32_t)tid < n - done) dst[done + tid] = src[done + tid];
+        }
+        __syncthreads(); // M.base / M.emit_ok are reused
+    };
 
     long long t_prev = clock64();
 #define LJB_PHASE(idx)                                                                      \
@@ -183,7 +225,10 @@ __global__ void __launch_bounds__(THREADS, 1) lz4_encode_kernel(Params P)
         if (tid == 0) M.ticket = (long long)atomicAdd((unsigned long long *)&P.status[0], 1ull);
         __syncthreads();
         const long long b = M.ticket;
-        if (b >= (long long)P.nblocks) break;
+        if (b >= (long long)P.nblocks) {
+            if (pend) flush_pending();
+            break;
+        }
         const size_t boff = (size_t)b * P.block_len;
         const uint32_t nb = (uint32_t)min((size_t)P.block_len, P.n - boff);
         const uint8_t *src = P.in + boff;
@@ -727,6 +772,7 @@ __global__ void __launch_bounds__(THREADS, 1) lz4_encode_kernel(Params P)
         for (int k = 0; k < warp; ++k) start_end = max(start_end, M.warp_last_end[k]);
 
         // sequence pass 2 (sizes) and pass 3 (emit) share one walker
+        uint8_t *const stage = stage0 + (size_t)buf * P.stage_stride;
         auto walk = [&](bool emit, unsigned long long out_base) {
             uint32_t carry_end = start_end;
             unsigned long long bytes = 0, sizes = 0;
@@ -755,7 +801,7 @@ __global__ void __launch_bounds__(THREADS, 1) lz4_encode_kernel(Params P)
                 const uint32_t tot = __shfl_sync(0xffffffffu, inc, 31);
                 if (emit) {
                     unsigned lits_long = __ballot_sync(0xffffffffu, isM && lit > 16);
-                    uint8_t *dst = P.out + out_base + bytes + (inc - sz.payload);
+                    uint8_t *dst = stage + out_base + bytes + (inc - sz.payload);
                     uint32_t lit_dst_off = 0;
                     if (isM) {
                         const uint32_t tok_lit = lit >= 15 ? 15u : lit;
@@ -828,37 +874,23 @@ __global__ void __launch_bounds__(THREADS, 1) lz4_encode_kernel(Params P)
         }
 
         LJB_PHASE(6); // sequence sizing
-        // ---------------- P5: place (decoupled look-back) ----------------
+        // ---------------- P5: publish this block's size; P6: emit into the staging buffer ----------------
         if (warp == 0) {
-            unsigned long long base = ljb_lookback(P.status + 1, b, pay, P.lead);
-            if (lane == 0) {
-                M.base = base;
-                M.emit_ok = (base + pay <= P.out_cap) ? 1 : 0;
-                P.block_offsets[b] = base;
-                if (phantom) atomicAdd((unsigned long long *)&P.result[1], (unsigned long long)phantom);
-                if (b == (long long)P.nblocks - 1) {
-                    P.block_offsets[P.nblocks] = base + pay;
-                    P.result[0] = base + pay;
-                }
-                if (!M.emit_ok) atomicOr((unsigned long long *)&P.result[2], 1ull);
-            }
+            ljb_lookback_publish(P.status + 1, b, pay, P.lead);
+            if (lane == 0 && phantom) atomicAdd((unsigned long long *)&P.result[1], (unsigned long long)phantom);
         }
-        __syncthreads();
-
         LJB_PHASE(7); // look-back
-        // ---------------- P6: emit ----------------
-        if (M.emit_ok) {
-            const unsigned long long base = M.base;
-            walk(true, base + my_prefix);
+        {
+            walk(true, my_prefix);
             if (tid == 0) {
-                uint8_t *hdr = P.out + base;
+                uint8_t *hdr = stage;
                 hdr[0] = (uint8_t)(nseq & 0xFF);          // LZ4.c:615, :417
                 hdr[1] = (uint8_t)(sizes & 0xFF);         // LZ4.c:617, :419 (low 16 bits)
                 hdr[2] = (uint8_t)((sizes >> 8) & 0xFF);
-                if (b == 0 && P.lead) P.out[0] = (uint8_t)P.frame_byte; // LZ4.c:429
+                if (b == 0 && P.lead && P.out_cap) P.out[0] = (uint8_t)P.frame_byte; // LZ4.c:429
             }
             if (tlit) {
-                uint8_t *dst = P.out + base + trail_off;
+                uint8_t *dst = stage + trail_off;
                 uint32_t hdrlen = 3 + lit_ext_count(tlit);
                 if (tid == 0) {
                     uint32_t o = 0;
@@ -878,8 +910,14 @@ __global__ void __launch_bounds__(THREADS, 1) lz4_encode_kernel(Params P)
                 for (uint32_t k = tid; k < tlit; k += THREADS) dst[hdrlen + k] = data[lsrc + k];
             }
         }
-        __syncthreads(); // region B and data are reused by the next block
+        __syncthreads(); // staging writes of this block are complete; region B and data are free
         LJB_PHASE(8); // emit
+        // ---------------- P7: place the PREVIOUS block ----------------
+        if (pend) flush_pending();
+        pend = true;
+        pend_b = b;
+        pend_pay = pay;
+        buf ^= 1;
     }
 #undef LJB_PHASE
 }
@@ -907,7 +945,9 @@ static int lz4_launch(ljb_ctx *ctx, const uint8_t *d_in, size_t n, size_t block_
     LJB_CUDA(cudaSetDevice(ctx->device));
     const int grid = (int)((nblocks < (size_t)ctx->num_sms) ? nblocks : (size_t)ctx->num_sms);
     int rc;
-    if ((rc = ljb_ensure(&ctx->d_scratch, &ctx->scratch_bytes, (size_t)ctx->num_sms * MAXB * sizeof(uint32_t))) != 0) return rc;
+    const size_t rec_bytes = (size_t)ctx->num_sms * MAXB * sizeof(uint32_t);
+    const size_t stage_stride = (ljb_lz4_bound(block_len, block_len) + 16 + 255) & ~(size_t)255; // one encoded block, worst case
+    if ((rc = ljb_ensure(&ctx->d_scratch, &ctx->scratch_bytes, rec_bytes + (size_t)grid * 2 * stage_stride)) != 0) return rc;
     if ((rc = ljb_ensure(&ctx->d_status, &ctx->status_bytes, (nblocks + 2 + 16) * sizeof(uint64_t))) != 0) return rc;
     LJB_CUDA(cudaMemsetAsync(ctx->d_status, 0, (nblocks + 2 + 16) * sizeof(uint64_t), ctx->stream));
     LJB_CUDA(cudaMemsetAsync(d_result, 0, 3 * sizeof(uint64_t), ctx->stream));
@@ -922,6 +962,8 @@ static int lz4_launch(ljb_ctx *ctx, const uint8_t *d_in, size_t n, size_t block_
     P.result = d_result;
     P.status = (uint64_t *)ctx->d_status;
     P.scratch = (uint32_t *)ctx->d_scratch;
+    P.staging = (uint8_t *)ctx->d_scratch + rec_bytes;
+    P.stage_stride = stage_stride;
     P.lead = first_block == 0 ? 1u : 0u;
     P.frame_byte = (uint32_t)(frame_blocks & 0xFF);
     P.dump_len = d_dump_len;
