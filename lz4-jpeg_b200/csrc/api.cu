@@ -2,6 +2,7 @@
 #include "common.cuh"
 
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 static thread_local char g_cuda_err[512] = "";
@@ -24,6 +25,30 @@ int ljb_ensure(void **p, size_t *have, size_t want)
     cudaError_t e = cudaMalloc(p, sz);
     if (e != cudaSuccess) return ljb_set_cuda_error(e, "cudaMalloc(scratch)", __LINE__);
     *have = sz;
+    return LJB_OK;
+}
+
+size_t ljb_pipe_chunk(void)
+{
+    const char *e = getenv("LJB_PIPE_CHUNK_BYTES");
+    if (e) {
+        const unsigned long long v = strtoull(e, nullptr, 10);
+        if (v >= 1) return (size_t)v;
+    }
+    return (size_t)128 << 20;
+}
+
+// pinned host array for the per-chunk kernel results of the pipelined host-buffer entry points
+int ljb_pipe_init(ljb_ctx *ctx, size_t nchunks)
+{
+    if (ctx->h_res_chunks >= nchunks && ctx->h_res) return LJB_OK;
+    if (ctx->h_res) cudaFreeHost(ctx->h_res);
+    ctx->h_res = nullptr;
+    ctx->h_res_chunks = 0;
+    const size_t want = nchunks + 16;
+    cudaError_t e = cudaMallocHost((void **)&ctx->h_res, want * 3 * sizeof(uint64_t));
+    if (e != cudaSuccess) return ljb_set_cuda_error(e, "cudaMallocHost(results)", __LINE__);
+    ctx->h_res_chunks = want;
     return LJB_OK;
 }
 
@@ -64,6 +89,14 @@ extern "C" int ljb_ctx_create(int device, ljb_ctx **out)
     LJB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     LJB_CUDA(cudaEventCreate(&c->ev0));
     LJB_CUDA(cudaEventCreate(&c->ev1));
+    LJB_CUDA(cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
+    LJB_CUDA(cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        LJB_CUDA(cudaEventCreateWithFlags(&c->ev_h2d[i], cudaEventDisableTiming));
+        LJB_CUDA(cudaEventCreateWithFlags(&c->ev_kern[i], cudaEventDisableTiming));
+        LJB_CUDA(cudaEventCreateWithFlags(&c->ev_d2h[i], cudaEventDisableTiming));
+    }
+    LJB_CUDA(cudaEventCreateWithFlags(&c->ev_res, cudaEventDisableTiming));
     *out = c;
     return LJB_OK;
 }
@@ -75,9 +108,20 @@ extern "C" void ljb_ctx_destroy(ljb_ctx *c)
     cudaStreamSynchronize(c->stream);
     cudaFree(c->d_scratch);
     cudaFree(c->d_status);
-    cudaFree(c->d_stage_in);
-    cudaFree(c->d_stage_out);
     cudaFree(c->d_small);
+    cudaStreamSynchronize(c->s_in);
+    cudaStreamSynchronize(c->s_out);
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(c->d_pin[i]);
+        cudaFree(c->d_pout[i]);
+        cudaEventDestroy(c->ev_h2d[i]);
+        cudaEventDestroy(c->ev_kern[i]);
+        cudaEventDestroy(c->ev_d2h[i]);
+    }
+    cudaEventDestroy(c->ev_res);
+    cudaFreeHost(c->h_res);
+    cudaStreamDestroy(c->s_in);
+    cudaStreamDestroy(c->s_out);
     cudaEventDestroy(c->ev0);
     cudaEventDestroy(c->ev1);
     cudaStreamDestroy(c->stream);

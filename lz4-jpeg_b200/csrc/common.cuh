@@ -22,13 +22,23 @@ struct ljb_ctx {
     size_t scratch_bytes;
     void *d_status;       // ticket counter + decoupled look-back status words
     size_t status_bytes;
-    void *d_stage_in;     // device staging for the host-buffer entry points
-    size_t stage_in_bytes;
-    void *d_stage_out;
-    size_t stage_out_bytes;
     void *d_small;        // offsets / results staging
     size_t small_bytes;
+    // host-buffer entry points: chunked H2D -> kernel -> D2H pipeline (two buffers each way, three streams)
+    cudaStream_t s_in, s_out;
+    cudaEvent_t ev_h2d[2], ev_kern[2], ev_d2h[2], ev_res;
+    void *d_pin[2];       // input chunk buffers
+    size_t pin_bytes[2];
+    void *d_pout[2];      // output chunk buffers
+    size_t pout_bytes[2];
+    uint64_t *h_res;      // pinned: per-chunk kernel results (3 x u64 each)
+    size_t h_res_chunks;
 };
+
+// Bytes of input per pipeline chunk of the host-buffer entry points (a multiple of every block / group-row size used).
+// (128 MiB; LJB_PIPE_CHUNK_BYTES overrides it so that tests can drive many chunks through small inputs.)
+size_t ljb_pipe_chunk(void);
+int ljb_pipe_init(ljb_ctx *ctx, size_t nchunks);
 
 int ljb_set_cuda_error(cudaError_t e, const char *what, int line);
 int ljb_ensure(void **p, size_t *have, size_t want);

@@ -73,6 +73,7 @@ struct Params {
     uint64_t *status;        // [0] ticket, [1..] look-back words (one per 32-group tile)
     uint32_t *scratch;       // per warp: REC_WORDS x 32 words of record staging, word-major
     uint32_t ntiles;
+    uint64_t offs_bias;      // added to every group_offsets entry (base of this shard in a larger stream)
     int force_slow;          // test hook: route every channel through the general routine
 };
 
@@ -706,13 +707,13 @@ __global__ void __launch_bounds__(THREADS, 1) jpeg_encode_kernel(Params P)
             const bool full = brow * 8 + 8 <= (size_t)P.h && col0 + 8 <= (size_t)P.w;
             if (full && aligned) {
                 const uint8_t *rp = P.rgba + brow * 8 * P.stride + col0 * 4;
-                uint4 na = __ldg(reinterpret_cast<const uint4 *>(rp)), nb = __ldg(reinterpret_cast<const uint4 *>(rp) + 1);
+                uint4 na = __ldcs(reinterpret_cast<const uint4 *>(rp)), nb = __ldcs(reinterpret_cast<const uint4 *>(rp) + 1); // streamed once
 #pragma unroll 1
                 for (int lr = 0; lr < 8; ++lr) {
                     uint32_t px[8] = {na.x, na.y, na.z, na.w, nb.x, nb.y, nb.z, nb.w};
                     if (lr < 7) { // next row's pixels are in flight while this row is converted
-                        na = __ldg(reinterpret_cast<const uint4 *>(rp + (lr + 1) * P.stride));
-                        nb = __ldg(reinterpret_cast<const uint4 *>(rp + (lr + 1) * P.stride) + 1);
+                        na = __ldcs(reinterpret_cast<const uint4 *>(rp + (lr + 1) * P.stride));
+                        nb = __ldcs(reinterpret_cast<const uint4 *>(rp + (lr + 1) * P.stride) + 1);
                     }
                     uint32_t yy[2] = {0, 0}, cr = 0, cb = 0;
 #pragma unroll 1
@@ -823,12 +824,12 @@ __global__ void __launch_bounds__(THREADS, 1) jpeg_encode_kernel(Params P)
                 if (!emit_ok) atomicOr((unsigned long long *)&P.result[2], 1ull);
                 if (p_tile == (long long)P.ntiles - 1) {
                     P.result[0] = base + p_total;
-                    P.group_offsets[P.ngroups] = base + p_total;
+                    P.group_offsets[P.ngroups] = base + p_total + P.offs_bias;
                 }
             }
             const size_t pgl = (size_t)p_tile * 32 + lane;
             if (pgl < P.ngroups) {
-                P.group_offsets[pgl] = base + p_off;
+                P.group_offsets[pgl] = base + p_off + P.offs_bias;
                 if (P.group_bits) {
                     P.group_bits[3 * pgl + 0] = (uint16_t)(p_bits & 0x3FFu);
                     P.group_bits[3 * pgl + 1] = (uint16_t)((p_bits >> 10) & 0x3FFu);
@@ -889,9 +890,9 @@ extern "C" size_t ljb_jpeg_group_count(int w, int h)
 
 extern "C" size_t ljb_jpeg_bound(size_t ngroups) { return ngroups * (size_t)jpgk::REC_BYTES + 64; }
 
-extern "C" int ljb_jpeg_encode_rgba_dev(ljb_ctx *ctx, const uint8_t *d_rgba, int w, int h, size_t stride, size_t first_group,
-                                        size_t ngroups, uint8_t *d_out, size_t out_cap, uint64_t *d_group_offsets,
-                                        uint16_t *d_group_bits, int16_t *d_coefs, uint64_t *d_result)
+static int jpeg_launch(ljb_ctx *ctx, const uint8_t *d_rgba, int w, int h, size_t stride, size_t first_group, size_t ngroups,
+                       uint8_t *d_out, size_t out_cap, uint64_t *d_group_offsets, uint16_t *d_group_bits, int16_t *d_coefs,
+                       uint64_t *d_result, uint64_t offs_bias)
 {
     using namespace jpgk;
     if (!ctx || !d_rgba || !d_out || !d_group_offsets || !d_result || w <= 0 || h <= 0 || (w & 1) || stride < (size_t)w * 4)
@@ -924,6 +925,7 @@ extern "C" int ljb_jpeg_encode_rgba_dev(ljb_ctx *ctx, const uint8_t *d_rgba, int
     P.status = (uint64_t *)ctx->d_status;
     P.scratch = (uint32_t *)ctx->d_scratch;
     P.ntiles = (uint32_t)ntiles;
+    P.offs_bias = offs_bias;
     P.force_slow = getenv("LJB_JPEG_FORCE_SLOW") ? 1 : 0; // test hook
     static bool attr_done = false;
     if (!attr_done) {
@@ -938,6 +940,16 @@ extern "C" int ljb_jpeg_encode_rgba_dev(ljb_ctx *ctx, const uint8_t *d_rgba, int
     return LJB_OK;
 }
 
+extern "C" int ljb_jpeg_encode_rgba_dev(ljb_ctx *ctx, const uint8_t *d_rgba, int w, int h, size_t stride, size_t first_group,
+                                        size_t ngroups, uint8_t *d_out, size_t out_cap, uint64_t *d_group_offsets,
+                                        uint16_t *d_group_bits, int16_t *d_coefs, uint64_t *d_result)
+{
+    return jpeg_launch(ctx, d_rgba, w, h, stride, first_group, ngroups, d_out, out_cap, d_group_offsets, d_group_bits, d_coefs,
+                       d_result, 0);
+}
+
+// Host-buffer entry point: bands of whole group rows go through a three-stream pipeline (upload of band k+1 and
+// download of band k-1 overlap the kernel of band k), like ljb_lz4_compress.
 extern "C" int ljb_jpeg_encode_rgba(ljb_ctx *ctx, const uint8_t *rgba, int w, int h, size_t stride, size_t first_group,
                                     size_t ngroups, uint8_t *out, size_t out_cap, uint64_t *group_offsets, uint16_t *group_bits,
                                     int16_t *coefs, size_t *out_len)
@@ -947,35 +959,109 @@ extern "C" int ljb_jpeg_encode_rgba(ljb_ctx *ctx, const uint8_t *rgba, int w, in
     if (ngroups == 0 || first_group + ngroups > total) return LJB_E_ARG;
     LJB_CUDA(cudaSetDevice(ctx->device));
     int rc;
-    // device layout of the staging area: image rows packed at a 16-byte aligned stride
+    // device layout of a band: image rows packed at a 16-byte aligned stride
     const size_t dstride = ((size_t)w * 4 + 15) & ~(size_t)15;
-    size_t dcap = ljb_jpeg_bound(ngroups);
-    if (out_cap < dcap) dcap = out_cap;
-    if ((rc = ljb_ensure(&ctx->d_stage_in, &ctx->stage_in_bytes, dstride * (size_t)h + 64)) != 0) return rc;
-    if ((rc = ljb_ensure(&ctx->d_stage_out, &ctx->stage_out_bytes, dcap + 64)) != 0) return rc;
-    const size_t small = (ngroups + 1 + 3) * sizeof(uint64_t) + ngroups * 3 * sizeof(uint16_t) + 64 + (coefs ? ngroups * 128 * sizeof(int16_t) : 0);
+    const size_t bpr = ((size_t)w + 7) / 8;
+    const size_t r_begin = first_group / bpr, r_end = (first_group + ngroups + bpr - 1) / bpr; // group rows touched
+    size_t rows_per_band = ljb_pipe_chunk() / (dstride * 8);
+    if (rows_per_band == 0) rows_per_band = 1;
+    const size_t nbands = (r_end - r_begin + rows_per_band - 1) / rows_per_band;
+    const size_t band_groups = rows_per_band * bpr < ngroups + bpr ? rows_per_band * bpr : ngroups + bpr;
+    size_t bcap = ljb_jpeg_bound(band_groups);
+    if (out_cap < bcap) bcap = out_cap;
+    if ((rc = ljb_pipe_init(ctx, nbands)) != 0) return rc;
+    for (int i = 0; i < (nbands > 1 ? 2 : 1); ++i) {
+        if ((rc = ljb_ensure(&ctx->d_pin[i], &ctx->pin_bytes[i], dstride * 8 * rows_per_band + 64)) != 0) return rc;
+        if ((rc = ljb_ensure(&ctx->d_pout[i], &ctx->pout_bytes[i], bcap + 64)) != 0) return rc;
+    }
+    const size_t offs_words = ngroups + nbands + 4;
+    const size_t small = (offs_words + 3 * nbands + 8) * sizeof(uint64_t) + ngroups * 3 * sizeof(uint16_t) + 64 +
+                         (coefs ? ngroups * 128 * sizeof(int16_t) : 0);
     if ((rc = ljb_ensure(&ctx->d_small, &ctx->small_bytes, small)) != 0) return rc;
-    uint64_t *d_offs = (uint64_t *)ctx->d_small;
-    uint64_t *d_res = d_offs + ngroups + 1;
-    int16_t *d_coefs = coefs ? (int16_t *)(d_res + 3) : nullptr;
-    uint16_t *d_bits = (uint16_t *)((uint8_t *)(d_res + 3) + (coefs ? ngroups * 128 * sizeof(int16_t) : 0));
-    LJB_CUDA(cudaMemcpy2DAsync(ctx->d_stage_in, dstride, rgba, stride, (size_t)w * 4, (size_t)h, cudaMemcpyHostToDevice, ctx->stream));
-    rc = ljb_jpeg_encode_rgba_dev(ctx, (const uint8_t *)ctx->d_stage_in, w, h, dstride, first_group, ngroups,
-                                  (uint8_t *)ctx->d_stage_out, dcap, d_offs, d_bits, d_coefs, d_res);
-    if (rc != 0) return rc;
-    uint64_t res[3];
-    LJB_CUDA(cudaMemcpyAsync(res, d_res, sizeof res, cudaMemcpyDeviceToHost, ctx->stream));
-    LJB_CUDA(cudaStreamSynchronize(ctx->stream));
-    if (out_len) *out_len = (size_t)res[0];
-    if (res[2] & 1) return LJB_E_CAPACITY;
-    LJB_CUDA(cudaMemcpyAsync(out, ctx->d_stage_out, (size_t)res[0], cudaMemcpyDeviceToHost, ctx->stream));
-    if (group_offsets)
-        LJB_CUDA(cudaMemcpyAsync(group_offsets, d_offs, (ngroups + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    uint64_t *d_offs = (uint64_t *)ctx->d_small;              // band k: its groups + 1 entries, at (first group of band - first_group) + k
+    uint64_t *d_res = d_offs + offs_words;                    // 3 per band
+    int16_t *d_coefs = coefs ? (int16_t *)(d_res + 3 * nbands + 4) : nullptr;
+    uint16_t *d_bits = (uint16_t *)((uint8_t *)(d_res + 3 * nbands + 4) + (coefs ? ngroups * 128 * sizeof(int16_t) : 0));
+    uint64_t *h_res = ctx->h_res;
+    // band k covers group rows [r0, r1) and, of those, the requested groups [g0, g1)
+    auto band = [&](size_t k, size_t &r0, size_t &r1, size_t &g0, size_t &g1) {
+        r0 = r_begin + k * rows_per_band;
+        r1 = r0 + rows_per_band < r_end ? r0 + rows_per_band : r_end;
+        g0 = r0 * bpr > first_group ? r0 * bpr : first_group;
+        g1 = r1 * bpr < first_group + ngroups ? r1 * bpr : first_group + ngroups;
+    };
+    auto upload = [&](size_t k, int b) -> cudaError_t {
+        size_t r0, r1, g0, g1;
+        band(k, r0, r1, g0, g1);
+        const size_t y0 = r0 * 8, y1 = r1 * 8 < (size_t)h ? r1 * 8 : (size_t)h;
+        if (y1 <= y0) return cudaSuccess;
+        return cudaMemcpy2DAsync(ctx->d_pin[b], dstride, rgba + y0 * stride, stride, (size_t)w * 4, y1 - y0, cudaMemcpyHostToDevice,
+                                 ctx->s_in);
+    };
+    size_t running = 0;
+    int status = LJB_OK;
+    bool unsupported = false;
+    cudaError_t e;
+#define PIPE(x)                                                                 \
+    do {                                                                        \
+        e = (x);                                                                \
+        if (e != cudaSuccess) {                                                 \
+            status = ljb_set_cuda_error(e, #x, __LINE__);                       \
+            goto done;                                                          \
+        }                                                                       \
+    } while (0)
+    PIPE(upload(0, 0));
+    PIPE(cudaEventRecord(ctx->ev_h2d[0], ctx->s_in));
+    for (size_t k = 0; k < nbands; ++k) {
+        const int b = (int)(k & 1);
+        size_t r0, r1, g0, g1;
+        band(k, r0, r1, g0, g1);
+        const size_t gi = g0 - first_group; // index of the band's first group inside this call
+        PIPE(cudaStreamWaitEvent(ctx->stream, ctx->ev_h2d[b], 0));
+        if (k >= 2) PIPE(cudaStreamWaitEvent(ctx->stream, ctx->ev_d2h[b], 0));
+        const size_t cap_k = out_cap - running < bcap ? out_cap - running : bcap;
+        // the kernel addresses absolute image rows: bias the band buffer so that row r0*8 is its first row
+        const uint8_t *biased = (const uint8_t *)ctx->d_pin[b] - r0 * 8 * dstride;
+        // `running` is known here (band k-1 has been waited for), so the kernel writes stream-global offsets itself
+        rc = jpeg_launch(ctx, biased, w, h, dstride, g0, g1 - g0, (uint8_t *)ctx->d_pout[b], cap_k, d_offs + gi + k, d_bits + 3 * gi,
+                         d_coefs ? d_coefs + 128 * gi : nullptr, d_res + 3 * k, running);
+        if (rc != 0) {
+            status = rc;
+            goto done;
+        }
+        PIPE(cudaMemcpyAsync(h_res + 3 * k, d_res + 3 * k, 3 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+        PIPE(cudaEventRecord(ctx->ev_kern[b], ctx->stream));
+        if (k + 1 < nbands) {
+            if (k >= 1) PIPE(cudaStreamWaitEvent(ctx->s_in, ctx->ev_kern[b ^ 1], 0));
+            PIPE(upload(k + 1, b ^ 1));
+            PIPE(cudaEventRecord(ctx->ev_h2d[b ^ 1], ctx->s_in));
+        }
+        PIPE(cudaEventSynchronize(ctx->ev_kern[b]));
+        const uint64_t len_k = h_res[3 * k + 0];
+        if (h_res[3 * k + 2] & 2) unsupported = true;
+        if (h_res[3 * k + 2] & 1) {
+            running += (size_t)len_k;
+            status = LJB_E_CAPACITY;
+            goto done;
+        }
+        PIPE(cudaStreamWaitEvent(ctx->s_out, ctx->ev_kern[b], 0));
+        PIPE(cudaMemcpyAsync(out + running, ctx->d_pout[b], (size_t)len_k, cudaMemcpyDeviceToHost, ctx->s_out));
+        if (group_offsets) // consecutive bands overlap in one entry (end of k == start of k+1): the values agree
+            PIPE(cudaMemcpyAsync(group_offsets + gi, d_offs + gi + k, (g1 - g0 + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost,
+                                 ctx->s_out));
+        PIPE(cudaEventRecord(ctx->ev_d2h[b], ctx->s_out));
+        running += (size_t)len_k;
+    }
     if (group_bits)
-        LJB_CUDA(cudaMemcpyAsync(group_bits, d_bits, ngroups * 3 * sizeof(uint16_t), cudaMemcpyDeviceToHost, ctx->stream));
-    if (coefs)
-        LJB_CUDA(cudaMemcpyAsync(coefs, d_coefs, ngroups * 128 * sizeof(int16_t), cudaMemcpyDeviceToHost, ctx->stream));
-    LJB_CUDA(cudaStreamSynchronize(ctx->stream));
-    if (res[2] & 2) return LJB_E_UNSUPPORTED;
-    return LJB_OK;
+        PIPE(cudaMemcpyAsync(group_bits, d_bits, ngroups * 3 * sizeof(uint16_t), cudaMemcpyDeviceToHost, ctx->s_out));
+    if (coefs) PIPE(cudaMemcpyAsync(coefs, d_coefs, ngroups * 128 * sizeof(int16_t), cudaMemcpyDeviceToHost, ctx->s_out));
+    PIPE(cudaStreamSynchronize(ctx->s_out));
+done:
+#undef PIPE
+    cudaStreamSynchronize(ctx->s_in);
+    cudaStreamSynchronize(ctx->stream);
+    cudaStreamSynchronize(ctx->s_out);
+    if (out_len) *out_len = running;
+    if (status == LJB_OK && unsupported) return LJB_E_UNSUPPORTED;
+    return status;
 }

@@ -102,22 +102,22 @@ extern "C" int ljb_lz4_decompress(ljb_ctx *ctx, const uint8_t *comp, size_t comp
     int rc;
     const size_t need_out = nblocks * block_len;
     const size_t dcap = need_out < out_cap ? need_out : out_cap;
-    if ((rc = ljb_ensure(&ctx->d_stage_in, &ctx->stage_in_bytes, comp_len + 64)) != 0) return rc;
-    if ((rc = ljb_ensure(&ctx->d_stage_out, &ctx->stage_out_bytes, dcap + 64)) != 0) return rc;
+    if ((rc = ljb_ensure(&ctx->d_pin[0], &ctx->pin_bytes[0], comp_len + 64)) != 0) return rc;
+    if ((rc = ljb_ensure(&ctx->d_pout[0], &ctx->pout_bytes[0], dcap + 64)) != 0) return rc;
     if ((rc = ljb_ensure(&ctx->d_small, &ctx->small_bytes, (nblocks + 1 + 3) * sizeof(uint64_t) + nblocks * sizeof(uint32_t))) != 0)
         return rc;
     uint64_t *d_offs = (uint64_t *)ctx->d_small;
     uint64_t *d_res = d_offs + nblocks + 1;
     uint32_t *d_len = (uint32_t *)(d_res + 3);
-    LJB_CUDA(cudaMemcpyAsync(ctx->d_stage_in, comp, comp_len, cudaMemcpyHostToDevice, ctx->stream));
+    LJB_CUDA(cudaMemcpyAsync(ctx->d_pin[0], comp, comp_len, cudaMemcpyHostToDevice, ctx->stream));
     LJB_CUDA(cudaMemcpyAsync(d_offs, block_offsets, (nblocks + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
     LJB_CUDA(cudaMemsetAsync(d_res, 0, 3 * sizeof(uint64_t), ctx->stream));
     Params P;
-    P.comp = (const uint8_t *)ctx->d_stage_in;
+    P.comp = (const uint8_t *)ctx->d_pin[0];
     P.offs = d_offs;
     P.nblocks = (uint32_t)nblocks;
     P.block_len = (uint32_t)block_len;
-    P.out = (uint8_t *)ctx->d_stage_out;
+    P.out = (uint8_t *)ctx->d_pout[0];
     P.out_cap = dcap;
     P.block_out_len = d_len;
     P.result = d_res;
@@ -137,7 +137,7 @@ extern "C" int ljb_lz4_decompress(ljb_ctx *ctx, const uint8_t *comp, size_t comp
     const size_t total = (nblocks - 1) * block_len + last_len;
     if (out_len) *out_len = total;
     if (total > out_cap) return LJB_E_CAPACITY;
-    LJB_CUDA(cudaMemcpyAsync(out, ctx->d_stage_out, total, cudaMemcpyDeviceToHost, ctx->stream));
+    LJB_CUDA(cudaMemcpyAsync(out, ctx->d_pout[0], total, cudaMemcpyDeviceToHost, ctx->stream));
     LJB_CUDA(cudaStreamSynchronize(ctx->stream));
     return LJB_OK;
 }

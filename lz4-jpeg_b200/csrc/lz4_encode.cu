@@ -84,6 +84,7 @@ struct Params {
     uint32_t *scratch;       // per CTA: MAXB u32 match records
     uint8_t *staging;        // per CTA: two buffers of stage_stride bytes holding the encoded block until its offset is known
     size_t stage_stride;
+    uint64_t offs_bias;      // added to every block_offsets entry (base of this shard in a larger stream)
     uint32_t lead;           // 1 if this shard writes the frame byte
     uint32_t frame_byte;
     uint16_t *dump_len;      // optional single-block stage dump
@@ -186,9 +187,9 @@ __global__ void __launch_bounds__(THREADS, 1) lz4_encode_kernel(Params P)
             if (lane == 0) {
                 M.base = base;
                 M.emit_ok = (base + pend_pay <= P.out_cap) ? 1 : 0;
-                P.block_offsets[pend_b] = base;
+                P.block_offsets[pend_b] = base + P.offs_bias;
                 if (pend_b == (long long)P.nblocks - 1) {
-                    P.block_offsets[P.nblocks] = base + pend_pay;
+                    P.block_offsets[P.nblocks] = base + pend_pay + P.offs_bias;
                     P.result[0] = base + pend_pay;
                 }
                 if (!M.emit_ok) atomicOr((unsigned long long *)&P.result[2], 1ull);
@@ -204,7 +205,7 @@ __global__ void __launch_bounds__(THREADS, 1) lz4_encode_kernel(Params P)
             if ((uint32_t)tid < head) dst[tid] = src[tid];
             const uint32_t nwords = (n - head) >> 2;
             uint32_t *d4 = reinterpret_cast<uint32_t *>(dst + head);
-            for (uint32_t j = tid; j < nwords; j += THREADS) d4[j] = __funnelshift_r(srcw[j], srcw[j + 1], 8 * head);
+            for (uint32_t j = tid; j < nwords; j += THREADS) __stcs(&d4[j], __funnelshift_r(srcw[j], srcw[j + 1], 8 * head)); // streaming store
             const uint32_t done = head + 4 * nwords;
             if ((uint32_t)tid < n - done) dst[done + tid] = src[done + tid];
         }
@@ -240,7 +241,7 @@ __global__ void __launch_bounds__(THREADS, 1) lz4_encode_kernel(Params P)
                 const uint4 *s4 = reinterpret_cast<const uint4 *>(src);
                 uint4 *d4 = reinterpret_cast<uint4 *>(data);
                 const uint32_t n16 = nb >> 4;
-                for (uint32_t i = tid; i < n16; i += THREADS) d4[i] = __ldg(&s4[i]);
+                for (uint32_t i = tid; i < n16; i += THREADS) d4[i] = __ldcs(&s4[i]); // streamed once: do not displace the scratch in L2
                 head = n16 << 4;
             }
             for (uint32_t i = head + tid; i < nb; i += THREADS) data[i] = __ldg(&src[i]);
@@ -355,6 +356,10 @@ __global__ void __launch_bounds__(THREADS, 1) lz4_encode_kernel(Params P)
                     __syncthreads();
                     const uint32_t A = 2654435761u + 0x9E3779B1u * (uint32_t)round * 2u;
                     const uint32_t B = 2246822519u + 0x85EBCA77u * (uint32_t)round * 2u;
+                    if (P.phase_cycles) {
+                        atomicAdd(&P.phase_cycles[21], (unsigned long long)__popcll(ins));
+                        if (tid == 0) atomicAdd(&P.phase_cycles[22], 1ull);
+                    }
                     for (unsigned long long m = ins; m;) {
                         const int i = __ffsll((long long)m) - 1;
                         m &= m - 1;
@@ -440,9 +445,12 @@ __global__ void __launch_bounds__(THREADS, 1) lz4_encode_kernel(Params P)
                 __syncthreads();
                 {
                     const uint32_t nidx = dir16[NBUCKET - 1];
+                    uint32_t d_pos = 0, d_vis = 0, d_eq = 0;
+                    const long long tb1 = clock64();
                     for (uint32_t j = tid; j < nidx; j += THREADS) {
                         const uint32_t p = S[j];
                         if (!((longbits[p >> 5] >> (p & 31)) & 1u)) continue; // a first occurrence: candidate only
+                        ++d_pos;
                         const uint32_t pi = p >> 2, ps = (p & 3) * 8;
                         const uint32_t w0 = dataw[pi], w1 = dataw[pi + 1], w2 = dataw[pi + 2], w3 = dataw[pi + 3], w4 = dataw[pi + 4];
                         const uint32_t P0 = __funnelshift_r(w0, w1, ps), P1 = __funnelshift_r(w1, w2, ps);
@@ -456,12 +464,14 @@ __global__ void __launch_bounds__(THREADS, 1) lz4_encode_kernel(Params P)
                             const uint32_t c = S[i];
                             const uint32_t cch = c >> 10;
                             if (cch > pch) break; // only later positions from here on
+                            ++d_vis;
                             // later positions cannot win a tie; but B2 needs EVERY 16-byte candidate unless it walks the bucket itself
                             if ((best >> 16) == cap16 && (cap16 < 16 || n16 > 2) && cch > ((0xFFFFu - (best & 0xFFFFu)) >> 10)) break;
                             if (c < p) {
                                 const uint32_t ci = c >> 2, cs = (c & 3) * 8;
                                 const uint32_t a0 = dataw[ci], a1 = dataw[ci + 1], a2 = dataw[ci + 2];
                                 if (__funnelshift_r(a0, a1, cs) == P0 && __funnelshift_r(a1, a2, cs) == P1) {
+                                    ++d_eq;
                                     const uint32_t a3 = dataw[ci + 3], a4 = dataw[ci + 4];
                                     const uint32_t x2 = __funnelshift_r(a2, a3, cs) ^ P2, x3 = __funnelshift_r(a3, a4, cs) ^ P3;
                                     uint32_t l = x2 ? 8u + ((uint32_t)(__ffs(x2) - 1) >> 3) : (x3 ? 12u + ((uint32_t)(__ffs(x3) - 1) >> 3) : 16u);
@@ -483,6 +493,13 @@ __global__ void __launch_bounds__(THREADS, 1) lz4_encode_kernel(Params P)
                         } else {
                             R[p] = (bl << 16) | bp; // bl >= 8: the ladder proved an earlier occurrence of the 8-gram
                         }
+                    }
+                    if (P.phase_cycles) {
+                        atomicAdd(&P.phase_cycles[16], (unsigned long long)d_pos);
+                        atomicAdd(&P.phase_cycles[17], (unsigned long long)d_vis);
+                        atomicAdd(&P.phase_cycles[18], (unsigned long long)d_eq);
+                        if (lane == 0) atomicAdd(&P.phase_cycles[19], (unsigned long long)(clock64() - tb1));
+                        if (tid == 0) atomicAdd(&P.phase_cycles[20], (unsigned long long)nidx);
                     }
                 }
                 __syncthreads();
@@ -935,7 +952,7 @@ extern "C" size_t ljb_lz4_bound(size_t n, size_t block_len)
 
 static int lz4_launch(ljb_ctx *ctx, const uint8_t *d_in, size_t n, size_t block_len, uint8_t *d_out, size_t out_cap,
                       uint64_t *d_block_offsets, uint64_t *d_result, size_t first_block, size_t frame_blocks,
-                      uint16_t *d_dump_len, uint16_t *d_dump_dist)
+                      uint16_t *d_dump_len, uint16_t *d_dump_dist, uint64_t offs_bias = 0)
 {
     using namespace lz4k;
     if (!ctx || !d_in || !d_out || !d_block_offsets || !d_result || n == 0 || block_len == 0 || block_len > MAXB)
@@ -948,8 +965,8 @@ static int lz4_launch(ljb_ctx *ctx, const uint8_t *d_in, size_t n, size_t block_
     const size_t rec_bytes = (size_t)ctx->num_sms * MAXB * sizeof(uint32_t);
     const size_t stage_stride = (ljb_lz4_bound(block_len, block_len) + 16 + 255) & ~(size_t)255; // one encoded block, worst case
     if ((rc = ljb_ensure(&ctx->d_scratch, &ctx->scratch_bytes, rec_bytes + (size_t)grid * 2 * stage_stride)) != 0) return rc;
-    if ((rc = ljb_ensure(&ctx->d_status, &ctx->status_bytes, (nblocks + 2 + 16) * sizeof(uint64_t))) != 0) return rc;
-    LJB_CUDA(cudaMemsetAsync(ctx->d_status, 0, (nblocks + 2 + 16) * sizeof(uint64_t), ctx->stream));
+    if ((rc = ljb_ensure(&ctx->d_status, &ctx->status_bytes, (nblocks + 2 + 24) * sizeof(uint64_t))) != 0) return rc;
+    LJB_CUDA(cudaMemsetAsync(ctx->d_status, 0, (nblocks + 2 + 24) * sizeof(uint64_t), ctx->stream));
     LJB_CUDA(cudaMemsetAsync(d_result, 0, 3 * sizeof(uint64_t), ctx->stream));
     Params P;
     P.in = d_in;
@@ -964,6 +981,7 @@ static int lz4_launch(ljb_ctx *ctx, const uint8_t *d_in, size_t n, size_t block_
     P.scratch = (uint32_t *)ctx->d_scratch;
     P.staging = (uint8_t *)ctx->d_scratch + rec_bytes;
     P.stage_stride = stage_stride;
+    P.offs_bias = offs_bias;
     P.lead = first_block == 0 ? 1u : 0u;
     P.frame_byte = (uint32_t)(frame_blocks & 0xFF);
     P.dump_len = d_dump_len;
@@ -983,7 +1001,7 @@ static int lz4_launch(ljb_ctx *ctx, const uint8_t *d_in, size_t n, size_t block_
     LJB_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
     ctx->launches += 1;
     if (P.phase_cycles) {
-        unsigned long long ph[16];
+        unsigned long long ph[24];
         LJB_CUDA(cudaMemcpyAsync(ph, P.phase_cycles, sizeof ph, cudaMemcpyDeviceToHost, ctx->stream));
         LJB_CUDA(cudaStreamSynchronize(ctx->stream));
         static const char *names[9] = {"stage", "phaseB1", "ladderA", "index8", "phaseB", "parse", "sizing", "lookback", "emit"};
@@ -992,6 +1010,9 @@ static int lz4_launch(ljb_ctx *ctx, const uint8_t *d_in, size_t n, size_t block_
         fprintf(stderr, "[ljb lz4 phases] cycles per block:");
         for (int i = 0; i < 9; ++i) fprintf(stderr, " %s=%.0f(%.0f%%)", names[i], (double)ph[i] / (double)nblocks, 100.0 * (double)ph[i] / (double)tot);
         fprintf(stderr, " total=%.0f\n", (double)tot / (double)nblocks);
+        fprintf(stderr, "[ljb lz4 phaseB1] per block: indexed=%.0f positions=%.0f visited=%.0f equal8=%.0f warp-cycles=%.0f | ladder: inserts=%.0f rounds=%.1f\n",
+                (double)ph[20] / nblocks, (double)ph[16] / nblocks, (double)ph[17] / nblocks, (double)ph[18] / nblocks, (double)ph[19] / nblocks,
+                (double)ph[21] / nblocks, (double)ph[22] / nblocks);
         fprintf(stderr, "[ljb lz4 phaseB2] per block: positions=%.0f inherited=%.0f | warp-cycles: rows=%.0f load=%.0f eval=%.0f coop=%.0f fallback=%.0f\n",
                 (double)ph[9] / nblocks, (double)ph[13] / nblocks, (double)ph[14] / nblocks, (double)ph[15] / nblocks, (double)ph[10] / nblocks, (double)ph[11] / nblocks, (double)ph[12] / nblocks);
     }
@@ -1006,6 +1027,10 @@ extern "C" int ljb_lz4_compress_dev(ljb_ctx *ctx, const uint8_t *d_in, size_t n,
                       nullptr);
 }
 
+// Host-buffer entry point.  The input is cut into chunks of whole blocks; chunk k+1 is copied to the device and
+// chunk k-1 is copied back while chunk k is being encoded (three streams, two buffers each way), so that the
+// PCIe transfers hide behind the kernel.  Every chunk is encoded as a shard (first_block / frame_blocks): its
+// stream starts at offset 0 of its own device buffer and lands at the running offset of the host stream.
 extern "C" int ljb_lz4_compress(ljb_ctx *ctx, const uint8_t *in, size_t n, size_t block_len, uint8_t *out, size_t out_cap,
                                 uint64_t *block_offsets, size_t *out_len, uint64_t *phantom)
 {
@@ -1013,30 +1038,90 @@ extern "C" int ljb_lz4_compress(ljb_ctx *ctx, const uint8_t *in, size_t n, size_
     const size_t nblocks = ljb_lz4_block_count(n, block_len);
     LJB_CUDA(cudaSetDevice(ctx->device));
     int rc;
-    // device capacity: never more than the caller can take, never more than the dialect can produce
-    size_t dcap = ljb_lz4_bound(n, block_len);
-    if (out_cap < dcap) dcap = out_cap;
-    if ((rc = ljb_ensure(&ctx->d_stage_in, &ctx->stage_in_bytes, n + 64)) != 0) return rc;
-    if ((rc = ljb_ensure(&ctx->d_stage_out, &ctx->stage_out_bytes, dcap + 64)) != 0) return rc;
-    if ((rc = ljb_ensure(&ctx->d_small, &ctx->small_bytes, (nblocks + 1 + 3) * sizeof(uint64_t))) != 0) return rc;
-    uint64_t *d_offs = (uint64_t *)ctx->d_small;
-    uint64_t *d_res = d_offs + nblocks + 1;
-    LJB_CUDA(cudaMemcpyAsync(ctx->d_stage_in, in, n, cudaMemcpyHostToDevice, ctx->stream));
-    rc = ljb_lz4_compress_dev(ctx, (const uint8_t *)ctx->d_stage_in, n, block_len, (uint8_t *)ctx->d_stage_out, dcap, d_offs,
-                              d_res, 0, nblocks);
-    if (rc != 0) return rc;
-    uint64_t res[3];
-    LJB_CUDA(cudaMemcpyAsync(res, d_res, sizeof(res), cudaMemcpyDeviceToHost, ctx->stream));
-    LJB_CUDA(cudaStreamSynchronize(ctx->stream));
-    LJB_CUDA(cudaEventElapsedTime(&ctx->last_kernel_ms, ctx->ev0, ctx->ev1));
-    if (out_len) *out_len = (size_t)res[0];
-    if (phantom) *phantom = res[1];
-    if (res[2] & 1) return LJB_E_CAPACITY;
-    LJB_CUDA(cudaMemcpyAsync(out, ctx->d_stage_out, (size_t)res[0], cudaMemcpyDeviceToHost, ctx->stream));
-    if (block_offsets)
-        LJB_CUDA(cudaMemcpyAsync(block_offsets, d_offs, (nblocks + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
-    LJB_CUDA(cudaStreamSynchronize(ctx->stream));
-    return LJB_OK;
+    // 4 x the base chunk (512 MiB): every chunk is a kernel launch whose last wave leaves SMs idle (~1.5 ms at 64 KiB
+    // blocks), which at ~10 GB/s outweighs the exposed first upload / last download of a larger chunk
+    size_t cblocks = 4 * ljb_pipe_chunk() / block_len; // blocks per chunk
+    if (cblocks == 0) cblocks = 1;
+    const size_t nchunks = (nblocks + cblocks - 1) / cblocks;
+    const size_t cbytes = cblocks * block_len < n ? cblocks * block_len : n;
+    // device capacity per chunk: never more than the caller can take, never more than the dialect can produce
+    size_t ccap = ljb_lz4_bound(cbytes, block_len);
+    if (out_cap < ccap) ccap = out_cap;
+    if ((rc = ljb_pipe_init(ctx, nchunks)) != 0) return rc;
+    for (int i = 0; i < (nchunks > 1 ? 2 : 1); ++i) {
+        if ((rc = ljb_ensure(&ctx->d_pin[i], &ctx->pin_bytes[i], cbytes + 64)) != 0) return rc;
+        if ((rc = ljb_ensure(&ctx->d_pout[i], &ctx->pout_bytes[i], ccap + 64)) != 0) return rc;
+    }
+    if ((rc = ljb_ensure(&ctx->d_small, &ctx->small_bytes, (nblocks + nchunks + 3 * nchunks + 8) * sizeof(uint64_t))) != 0) return rc;
+    uint64_t *d_offs = (uint64_t *)ctx->d_small;          // per chunk: cblocks + 1 entries at k * (cblocks + 1)
+    uint64_t *d_res = d_offs + nblocks + nchunks + 4;      // per chunk: 3 entries
+    uint64_t *h_res = ctx->h_res;
+    auto chunk_n = [&](size_t k) { return (k + 1 < nchunks) ? cbytes : n - k * cbytes; };
+    size_t running = 0;
+    uint64_t ph_total = 0;
+    int status = LJB_OK;
+    float kernel_ms = 0.f;
+    cudaError_t e;
+#define PIPE(x)                                                                 \
+    do {                                                                        \
+        e = (x);                                                                \
+        if (e != cudaSuccess) {                                                 \
+            status = ljb_set_cuda_error(e, #x, __LINE__);                       \
+            goto done;                                                          \
+        }                                                                       \
+    } while (0)
+    PIPE(cudaMemcpyAsync(ctx->d_pin[0], in, chunk_n(0), cudaMemcpyHostToDevice, ctx->s_in));
+    PIPE(cudaEventRecord(ctx->ev_h2d[0], ctx->s_in));
+    for (size_t k = 0; k < nchunks; ++k) {
+        const int b = (int)(k & 1);
+        const size_t kb = (chunk_n(k) + block_len - 1) / block_len;
+        PIPE(cudaStreamWaitEvent(ctx->stream, ctx->ev_h2d[b], 0));
+        if (k >= 2) PIPE(cudaStreamWaitEvent(ctx->stream, ctx->ev_d2h[b], 0)); // output buffer b is free again
+        size_t cap_k = out_cap - running < ccap ? out_cap - running : ccap;
+        // `running` is known here (chunk k-1 has been waited for), so the kernel writes stream-global offsets itself
+        rc = lz4_launch(ctx, (const uint8_t *)ctx->d_pin[b], chunk_n(k), block_len, (uint8_t *)ctx->d_pout[b], cap_k,
+                        d_offs + k * (cblocks + 1), d_res + 3 * k, k * cblocks, nblocks, nullptr, nullptr, running);
+        if (rc != 0) {
+            status = rc;
+            goto done;
+        }
+        PIPE(cudaMemcpyAsync(h_res + 3 * k, d_res + 3 * k, 3 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+        PIPE(cudaEventRecord(ctx->ev_kern[b], ctx->stream));
+        if (k + 1 < nchunks) { // next chunk's upload overlaps this chunk's kernel; its buffer was read by kernel k-1
+            if (k >= 1) PIPE(cudaStreamWaitEvent(ctx->s_in, ctx->ev_kern[b ^ 1], 0));
+            PIPE(cudaMemcpyAsync(ctx->d_pin[b ^ 1], in + (k + 1) * cbytes, chunk_n(k + 1), cudaMemcpyHostToDevice, ctx->s_in));
+            PIPE(cudaEventRecord(ctx->ev_h2d[b ^ 1], ctx->s_in));
+        }
+        PIPE(cudaEventSynchronize(ctx->ev_kern[b]));
+        {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) kernel_ms += ms;
+        }
+        const uint64_t len_k = h_res[3 * k + 0];
+        ph_total += h_res[3 * k + 1];
+        if (h_res[3 * k + 2] & 1) {
+            running += (size_t)len_k;
+            status = LJB_E_CAPACITY;
+            goto done;
+        }
+        PIPE(cudaStreamWaitEvent(ctx->s_out, ctx->ev_kern[b], 0));
+        PIPE(cudaMemcpyAsync(out + running, ctx->d_pout[b], (size_t)len_k, cudaMemcpyDeviceToHost, ctx->s_out));
+        if (block_offsets) // consecutive chunks overlap in one entry (end of k == start of k+1): the values agree
+            PIPE(cudaMemcpyAsync(block_offsets + k * cblocks, d_offs + k * (cblocks + 1), (kb + 1) * sizeof(uint64_t),
+                                 cudaMemcpyDeviceToHost, ctx->s_out));
+        PIPE(cudaEventRecord(ctx->ev_d2h[b], ctx->s_out));
+        running += (size_t)len_k;
+    }
+    PIPE(cudaStreamSynchronize(ctx->s_out));
+done:
+#undef PIPE
+    cudaStreamSynchronize(ctx->s_in);
+    cudaStreamSynchronize(ctx->stream);
+    cudaStreamSynchronize(ctx->s_out);
+    ctx->last_kernel_ms = kernel_ms;
+    if (out_len) *out_len = running;
+    if (phantom) *phantom = ph_total;
+    return status;
 }
 
 extern "C" int ljb_lz4_block_matches(ljb_ctx *ctx, const uint8_t *in, size_t n, uint16_t *len, uint16_t *dist)
@@ -1045,15 +1130,15 @@ extern "C" int ljb_lz4_block_matches(ljb_ctx *ctx, const uint8_t *in, size_t n, 
     LJB_CUDA(cudaSetDevice(ctx->device));
     int rc;
     const size_t dcap = ljb_lz4_bound(n, n);
-    if ((rc = ljb_ensure(&ctx->d_stage_in, &ctx->stage_in_bytes, n + 64)) != 0) return rc;
-    if ((rc = ljb_ensure(&ctx->d_stage_out, &ctx->stage_out_bytes, dcap + 64)) != 0) return rc;
+    if ((rc = ljb_ensure(&ctx->d_pin[0], &ctx->pin_bytes[0], n + 64)) != 0) return rc;
+    if ((rc = ljb_ensure(&ctx->d_pout[0], &ctx->pout_bytes[0], dcap + 64)) != 0) return rc;
     if ((rc = ljb_ensure(&ctx->d_small, &ctx->small_bytes, 8 * sizeof(uint64_t) + 4 * lz4k::MAXB)) != 0) return rc;
     uint64_t *d_offs = (uint64_t *)ctx->d_small;
     uint64_t *d_res = d_offs + 2;
     uint16_t *d_len = (uint16_t *)(d_offs + 8);
     uint16_t *d_dist = d_len + lz4k::MAXB;
-    LJB_CUDA(cudaMemcpyAsync(ctx->d_stage_in, in, n, cudaMemcpyHostToDevice, ctx->stream));
-    rc = lz4_launch(ctx, (const uint8_t *)ctx->d_stage_in, n, n, (uint8_t *)ctx->d_stage_out, dcap, d_offs, d_res, 0, 1, d_len,
+    LJB_CUDA(cudaMemcpyAsync(ctx->d_pin[0], in, n, cudaMemcpyHostToDevice, ctx->stream));
+    rc = lz4_launch(ctx, (const uint8_t *)ctx->d_pin[0], n, n, (uint8_t *)ctx->d_pout[0], dcap, d_offs, d_res, 0, 1, d_len,
                     d_dist);
     if (rc != 0) return rc;
     LJB_CUDA(cudaMemcpyAsync(len, d_len, n * sizeof(uint16_t), cudaMemcpyDeviceToHost, ctx->stream));

@@ -129,3 +129,22 @@ def test_photo_like_vs_oracle(ljb, ctx, oracle):
     ref = oracle.jpeg_encode(img)
     assert np.array_equal(enc.coefs, ref["coefs"])
     assert np.array_equal(enc.stream, ref["stream"])
+
+
+@pytest.mark.parametrize("chunk", [1, 4096, 20000])
+def test_host_pipeline_many_bands(ljb, ctx, oracle, monkeypatch, chunk):
+    """Bands of group rows through the upload / kernel / download pipeline, including a sub-range of groups that
+    starts and ends in the middle of a group row."""
+    monkeypatch.setenv("LJB_PIPE_CHUNK_BYTES", str(chunk))
+    img = ljb.synth.random_image(72, 52, seed=21)  # 9 groups per row, 7 group rows, last row partial (52 = 6*8 + 4)
+    enc = ljb.jpeg.process(img, ctx=ctx)
+    ref = oracle.jpeg_encode(img)
+    assert np.array_equal(enc.coefs, ref["coefs"])
+    assert np.array_equal(enc.group_bits, ref["bits"])
+    assert np.array_equal(enc.group_offsets, ref["offsets"])
+    assert np.array_equal(enc.stream, ref["stream"])
+    part = ljb.jpeg.process(img, first_group=5, ngroups=40, ctx=ctx)
+    o0, o1 = int(enc.group_offsets[5]), int(enc.group_offsets[45])
+    assert np.array_equal(part.stream, enc.stream[o0:o1])
+    assert np.array_equal(part.group_offsets, enc.group_offsets[5:46] - np.uint64(o0))
+    assert np.array_equal(part.coefs, enc.coefs[5:45])

@@ -140,3 +140,18 @@ def test_roundtrip_full_size_property(ljb, ctx):
         hdr = f.stream[f.block_offsets[:-1].astype(np.int64) + 1].astype(np.int64) | (
             f.stream[f.block_offsets[:-1].astype(np.int64) + 2].astype(np.int64) << 8)
         assert ((hdr - d) % 65536 >= 0).all()
+
+
+@pytest.mark.parametrize("chunk", [65536, 3 * 65536, 1000])
+def test_host_pipeline_many_chunks(ljb, ctx, oracle, monkeypatch, chunk):
+    """The host-buffer entry point cuts the input into chunks that overlap upload, kernel and download; a tiny
+    LJB_PIPE_CHUNK_BYTES drives many chunks (and the per-chunk offset fix-up) through a small input."""
+    monkeypatch.setenv("LJB_PIPE_CHUNK_BYTES", str(chunk))
+    data, bl = ALL["synth_64k_x3"]
+    data = np.concatenate([data, cases.synth_text(4 * 65536 + 777, seed=99)])
+    f = ljb.lz4.lz4_encode(data, bl, ctx=ctx)
+    s, offs, ph = oracle.lz4_compress(data, bl, 1)
+    assert np.array_equal(f.stream, s) and np.array_equal(f.block_offsets, offs) and f.phantom == ph
+    f2 = ljb.lz4.lz4_encode(data[:30000], 300, ctx=ctx)  # 100 blocks of 300 B, chunks of 3 blocks at chunk = 1000
+    s2, offs2, ph2 = oracle.lz4_compress(data[:30000], 300, 1)
+    assert np.array_equal(f2.stream, s2) and np.array_equal(f2.block_offsets, offs2) and f2.phantom == ph2
