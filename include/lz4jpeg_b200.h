@@ -129,6 +129,22 @@ int ljb_jpeg_encode_rgba_dev(ljb_ctx *ctx, const uint8_t *d_rgba, int w, int h, 
                              size_t ngroups, uint8_t *d_out, size_t out_cap, uint64_t *d_group_offsets,
                              uint16_t *d_group_bits, int16_t *d_coefs, uint64_t *d_result);
 
+/* Decode half of the reference's main() (JPEG.c:1408-1428): Inverse_quantize (JPEG.c:631) ->
+ * inverse_discrete_cosine_transform (JPEG.c:399) -> assemble_image (JPEG.c:552, YCbCr -> RGB), bit-exact.
+ *   coefs       128 int16 per group for all ljb_jpeg_group_count(w, h) groups, as ljb_jpeg_encode_rgba returns
+ *               them (the reference's Huffman / RLE / zig-zag stages are a loss-free in-memory round trip,
+ *               JPEG.c:1253-1403, and its code tables are never serialised: a bit stream alone is not decodable)
+ *   orig_rgba   the original image, or NULL.  When w or h is not a multiple of 8 the reference leaves the last
+ *               tiled groups unprocessed (JPEG.c:1131) and its reconstructed.png shows their
+ *               colour-converted original samples; NULL is an error (LJB_E_ARG) for such sizes.
+ *   out_rgba    receives h rows of w RGBA pixels (a = 255) */
+int ljb_jpeg_decode_coefs(ljb_ctx *ctx, const int16_t *coefs, int w, int h, const uint8_t *orig_rgba, size_t orig_stride,
+                          uint8_t *out_rgba, size_t out_stride);
+/* Device-resident form, asynchronous on the context stream.  d_result: 3 device uint64, [2] = error flags
+ * (bit0: unprocessed groups exist and d_orig_rgba is NULL). */
+int ljb_jpeg_decode_coefs_dev(ljb_ctx *ctx, const int16_t *d_coefs, int w, int h, const uint8_t *d_orig_rgba,
+                              size_t orig_stride, uint8_t *d_out_rgba, size_t out_stride, uint64_t *d_result);
+
 /* ------------------------------------------------------------------------------------------------
  * Workload generators (host code): the reference's Experiment/random_extract.c:8-71 and
  * Experiment/random_image.c:58-77 with an explicit seed (the reference uses time() / unseeded rand()).

@@ -42,6 +42,9 @@ SIGNATURES = {
                                        C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, _szp]),
     "ljb_jpeg_encode_rgba_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_size_t, C.c_size_t,
                                            C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ljb_jpeg_decode_coefs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]),
+    "ljb_jpeg_decode_coefs_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p,
+                                            C.c_size_t, C.c_void_p]),
     "ljb_synth_text": (None, [C.c_void_p, C.c_size_t, C.c_uint64, C.c_size_t, C.c_void_p, C.c_size_t]),
     "ljb_synth_image": (None, [C.c_uint64, C.c_int, C.c_int, C.c_void_p]),
 }

@@ -14,7 +14,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "liblz4jpeg_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-CU_SOURCES = ["api.cu", "lz4_encode.cu", "lz4_decode.cu", "jpeg_encode.cu"]
+CU_SOURCES = ["api.cu", "lz4_encode.cu", "lz4_decode.cu", "jpeg_encode.cu", "jpeg_decode.cu"]
 C_SOURCES = ["synth.c"]
 
 
@@ -26,7 +26,7 @@ def _stale() -> bool:
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = sources() + [os.path.join(CSRC, "common.cuh"), os.path.join(os.path.dirname(HERE), "include", "lz4jpeg_b200.h"),
+    deps = sources() + [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "jpeg_colour.cuh"), os.path.join(CSRC, "jpeg_tables.inc"), os.path.join(os.path.dirname(HERE), "include", "lz4jpeg_b200.h"),
                         os.path.abspath(__file__)]
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 

@@ -134,48 +134,7 @@ __device__ __forceinline__ uint16_t &ws_h(uint32_t *wl, int word0, int half)
 // 64-bit interleaved view of words [0, 64): double d of lane l at warp_base + (d*32 + l)*8
 __device__ __forceinline__ double &ws_d(uint32_t *wbase, int lane, int d) { return reinterpret_cast<double *>(wbase)[d * 32 + lane]; }
 
-// ---- colour conversion, JPEG.c:127, :157, :180 ------------------------------------------------------------
-__device__ __noinline__ int luma_exact(int r, int g, int b)
-{
-    double y = __dadd_rn(__dadd_rn(__dmul_rn(0.299, (double)r), __dmul_rn(0.587, (double)g)), __dmul_rn(0.114, (double)b));
-    return (int)y & 0xFF; // implicit double -> uint8_t conversion of a value in [0, 255]
-}
-__device__ __forceinline__ int clamp255(int v) { return v < 0 ? 0 : (v > 255 ? 255 : v); }
-__device__ __noinline__ int cr_exact(int r, int g, int b)
-{
-    double v = __dadd_rn(__dsub_rn(__dsub_rn(__dmul_rn(0.439, (double)r), __dmul_rn(0.368, (double)g)), __dmul_rn(0.071, (double)b)), 128.0);
-    return clamp255((int)v);
-}
-__device__ __noinline__ int cb_exact(int r, int g, int b)
-{
-    double v = __dadd_rn(__dadd_rn(__dsub_rn(__dmul_rn(-0.148, (double)r), __dmul_rn(0.291, (double)g)), __dmul_rn(0.439, (double)b)), 128.0);
-    return clamp255((int)v);
-}
-// floor(s / 1000) for 0 <= s < 2^18, and whether s is a multiple of 1000
-__device__ __forceinline__ int div1000(int s, bool &tie)
-{
-    const int q = (int)__umulhi((unsigned)s, 4294968u); // ceil(2^32 / 1000): exact for s < 2^22
-    tie = (s - q * 1000) == 0;
-    return q;
-}
-__device__ __forceinline__ int luma_of(int r, int g, int b)
-{
-    bool tie;
-    const int q = div1000(299 * r + 587 * g + 114 * b, tie);
-    return tie ? luma_exact(r, g, b) : q;
-}
-__device__ __forceinline__ int cr_of(int r, int g, int b)
-{
-    bool tie; // 439r - 368g - 71b + 128000 lies in [16055, 239945]: positive, so (int) truncation is floor and clamp is idle
-    const int q = div1000(439 * r - 368 * g - 71 * b + 128000, tie);
-    return tie ? cr_exact(r, g, b) : q;
-}
-__device__ __forceinline__ int cb_of(int r, int g, int b)
-{
-    bool tie;
-    const int q = div1000(-148 * r - 291 * g + 439 * b + 128000, tie);
-    return tie ? cb_exact(r, g, b) : q;
-}
+#include "jpeg_colour.cuh"
 
 // ---- the reference's own summation, JPEG.c:471-490, for one coefficient ------------------------------------
 // smp(i) returns sample i of the channel (row-major, W columns)

@@ -7,6 +7,9 @@ reference stages fused in one kernel                                 here
   zigzag_pattern / RLE                                JPEG.c:693 / :767
   encode_huffman / generate_encoded_sequence          JPEG.c:1035 / :993    process(rgba) -> EncodedImage
 (`process` is the reference's fused per-block function, Algorithms/parallel/JPEG/JPEG.c:1103.)
+decode half (JPEG.c:1408-1428)
+  Inverse_quantize / inverse_discrete_cosine_transform / assemble_image   JPEG.c:631 / :399 / :552
+                                                                            assemble_image(coefs, w, h) -> RGBA
 """
 from __future__ import annotations
 
@@ -79,3 +82,24 @@ def encode_device(d_rgba, w: int, h: int, d_out, d_group_offsets, d_group_bits, 
                                           d_group_bits.data_ptr() if d_group_bits is not None else None,
                                           d_coefs.data_ptr() if d_coefs is not None else None, d_result.data_ptr())
     N.check(rc, "ljb_jpeg_encode_rgba_dev")
+
+
+def assemble_image(coefs, w: int, h: int, original=None, ctx: N.Context | None = None) -> np.ndarray:
+    """Quantised coefficients (EncodedImage.coefs of the WHOLE image) -> the reference's reconstructed.png pixels:
+    Inverse_quantize, inverse_discrete_cosine_transform, assemble_image (JPEG.c:631, :399, :552).
+    `original` (H x W x 4) is needed when w or h is not a multiple of 8: the reference leaves the last tiled
+    groups unprocessed (JPEG.c:1131) and shows their colour-converted original samples."""
+    c = np.ascontiguousarray(coefs, dtype=np.int16)
+    if c.size != group_count(w, h) * 128:
+        raise ValueError("coefs must hold 128 values for each of the ceil(w*h/64) groups")
+    o = None
+    if original is not None:
+        o = np.ascontiguousarray(original, dtype=np.uint8)
+        if o.shape != (h, w, 4):
+            raise ValueError("original must be H x W x 4")
+    out = np.empty((h, w, 4), dtype=np.uint8)
+    ctx = ctx or N.default_context()
+    rc = N.lib().ljb_jpeg_decode_coefs(ctx.handle, c.ctypes.data, w, h, o.ctypes.data if o is not None else None, 4 * w,
+                                       out.ctypes.data, 4 * w)
+    N.check(rc, "ljb_jpeg_decode_coefs")
+    return out

@@ -393,6 +393,72 @@ int oracle_jpeg_group_stages(const uint8_t *rgba, int w, int h, size_t stride, s
     return 0;
 }
 
+/* ---- decode half: S-JPG:631-638 Inverse_quantize, S-JPG:399-448 inverse_discrete_cosine_transform ---------- */
+static void orj_idct(const int16_t *q, const unsigned *table, size_t width, size_t height, uint8_t *values)
+{
+    double coef[64];
+    for (size_t i = 0; i < width * height; ++i) {
+        coef[i] = (double)q[i];   /* the reference keeps the quantised integers in doubles (S-JPG:627) */
+        coef[i] *= table[i];      /* S-JPG:636 */
+    }
+    for (size_t x = 0; x < height; ++x)
+        for (size_t y = 0; y < width; ++y) {
+            double sum = 0.0;
+            for (size_t u = 0; u < height; ++u)
+                for (size_t v = 0; v < width; ++v) {
+                    double alpha_u = (u == 0) ? orj_sqrt(1.0 / height) : orj_sqrt(2.0 / height);
+                    double alpha_v = (v == 0) ? orj_sqrt(1.0 / width) : orj_sqrt(2.0 / width);
+                    double cos_x = orj_cos((ORJ_PI * (2 * x + 1) * u) / (2.0 * height));
+                    double cos_y = orj_cos((ORJ_PI * (2 * y + 1) * v) / (2.0 * width));
+                    sum += alpha_u * alpha_v * coef[u * width + v] * cos_x * cos_y; /* S-JPG:430 */
+                }
+            int value = (int)round(sum + 128.0); /* S-JPG:441 */
+            values[x * width + y] = (value < 0) ? 0 : (value > 255) ? 255 : (uint8_t)value;
+        }
+}
+
+/* Decode: coefs (128 int16 per group, groups [0, ceil(w*h/64))) -> RGBA image, following the tail of the
+ * reference's main() (S-JPG:1408-1428) and assemble_image (S-JPG:552-619).  Tiled groups beyond that count are
+ * never processed by the reference (S-JPG:1131): they still hold divide_image's samples of the original, so the
+ * original image is needed for them (orig may be NULL when w and h are multiples of 8).  Returns 0, -1 bad args. */
+int oracle_jpeg_decode(const int16_t *coefs, int w, int h, const uint8_t *orig, size_t orig_stride, uint8_t *out, size_t out_stride)
+{
+    if (w <= 0 || h <= 0 || (w & 1) || !coefs || !out) return -1;
+    size_t bpr = ((size_t)w + 7) / 8, bpc = ((size_t)h + 7) / 8;
+    size_t total = oracle_jpeg_group_count(w, h);
+    for (size_t g = 0; g < bpr * bpc; ++g) {
+        uint8_t lum[64], r[32], b[32];
+        if (g < total) {
+            orj_idct(coefs + 128 * g, orj_qlum, 8, 8, lum);
+            orj_idct(coefs + 128 * g + 96, orj_qchr, 4, 8, b); /* order lum, b, r (S-JPG:1418-1420): irrelevant */
+            orj_idct(coefs + 128 * g + 64, orj_qchr, 4, 8, r);
+        } else {
+            if (!orig) return -1;
+            orj_gather_group(orig, w, h, orig_stride, g, lum, r, b);
+        }
+        size_t brow = g / bpr, bcol = g % bpr;
+        for (size_t lr = 0; lr < 8; ++lr)
+            for (size_t lc = 0; lc < 8; ++lc) {
+                size_t row = brow * 8 + lr, col = bcol * 8 + lc;
+                if (row >= (size_t)h || col >= (size_t)w) continue;
+                uint8_t Y = lum[lr * 8 + lc];
+                uint8_t Cb = b[lr * 4 + lc / 2], Cr = r[lr * 4 + lc / 2];
+                int R = (int)Y + (int)(1.402 * (Cr - 128)); /* S-JPG:598-600 */
+                int G = (int)Y - (int)(0.344136 * (Cb - 128)) - (int)(0.714136 * (Cr - 128));
+                int B = (int)Y + (int)(1.772 * (Cb - 128));
+                R = R < 0 ? 0 : (R > 255 ? 255 : R);
+                G = G < 0 ? 0 : (G > 255 ? 255 : G);
+                B = B < 0 ? 0 : (B > 255 ? 255 : B);
+                uint8_t *p = out + row * out_stride + 4 * col;
+                p[0] = (uint8_t)R;
+                p[1] = (uint8_t)G;
+                p[2] = (uint8_t)B;
+                p[3] = 255;
+            }
+    }
+    return 0;
+}
+
 /* The DCT basis values the reference's cos()/sqrt() calls produce on this libm, for checking the
  * constants embedded in the CUDA source: cos8[x*8+u], cos4[y*4+v], alpha8[2], alpha4[2]. */
 void oracle_jpeg_basis(double *cos8, double *cos4, double *alpha8, double *alpha4)

@@ -77,6 +77,7 @@ class Oracle(_LZ4Mixin):
         L.oracle_jpeg_encode.restype = C.c_int
         L.oracle_jpeg_group_count.restype = C.c_size_t
         L.oracle_jpeg_group_stages.restype = C.c_int
+        L.oracle_jpeg_decode.restype = C.c_int
         L.oracle_synth_text.restype = None
         L.oracle_synth_image.restype = None
         L.oracle_jpeg_planes.restype = None
@@ -124,6 +125,10 @@ class Oracle(_LZ4Mixin):
 
     def jpeg_group_stages(self, rgba: np.ndarray, g: int):
         return _jpeg_stages(self.lib.oracle_jpeg_group_stages, rgba, g)
+
+    def jpeg_decode(self, coefs: np.ndarray, w: int, h: int, orig: np.ndarray | None = None):
+        """Quantised coefficients -> reconstructed RGBA (Inverse_quantize, IDCT, assemble_image)."""
+        return _jpeg_decode(self.lib.oracle_jpeg_decode, coefs, w, h, orig)
 
     def jpeg_basis(self):
         cos8 = np.zeros(64)
@@ -173,6 +178,17 @@ def _jpeg_encode(fn, rgba, g0, g1, want_coefs):
             "max_code_len": int(maxlen.value)}
 
 
+def _jpeg_decode(fn, coefs, w, h, orig):
+    c = np.ascontiguousarray(coefs, dtype=np.int16)
+    out = np.zeros((h, w, 4), dtype=np.uint8)
+    o = _check_rgba(orig) if orig is not None else None
+    rc = fn(_p(c, C.c_int16), C.c_int(w), C.c_int(h), _p(o) if o is not None else None, C.c_size_t(4 * w), _p(out),
+            C.c_size_t(4 * w))
+    if rc != 0:
+        raise RuntimeError(f"jpeg decode rc={rc}")
+    return out
+
+
 def _jpeg_stages(fn, rgba, g):
     a = _check_rgba(rgba)
     h, w, _ = a.shape
@@ -214,6 +230,7 @@ class Ref(_LZ4Mixin):
             self.lib.ref_jpeg_planes.restype = C.c_int
             self.lib.ref_jpeg_group_stages.restype = C.c_int
             self.lib.ref_jpeg_time_groups.restype = C.c_int
+            self.lib.ref_jpeg_decode.restype = C.c_int
 
     def lz4_time_blocks(self, data, block_len: int, nthreads: int):
         a = _as_u8(data)
@@ -230,6 +247,9 @@ class Ref(_LZ4Mixin):
 
     def jpeg_group_stages(self, rgba, g: int):
         return _jpeg_stages(self.lib.ref_jpeg_group_stages, rgba, g)
+
+    def jpeg_decode(self, coefs, w: int, h: int, orig):
+        return _jpeg_decode(self.lib.ref_jpeg_decode, coefs, w, h, orig)
 
     def jpeg_time_groups(self, rgba, nthreads: int):
         a = _check_rgba(rgba)

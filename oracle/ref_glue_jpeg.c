@@ -144,6 +144,56 @@ int ref_jpeg_encode(const uint8_t *rgba, int w, int h, size_t stride, size_t g0,
     return rc;
 }
 
+/* Decode half with the reference's own functions, in the order of its main() (S-JPG:1408-1428): the blocks come
+ * from divide_image of the original (so unprocessed tail groups keep their samples, S-JPG:1131), the quantised
+ * coefficients are planted where Quantize left them, then Inverse_quantize x3, inverse_discrete_cosine_transform
+ * x3 for the first ceil(w*h/64) blocks, assemble_image. */
+int ref_jpeg_decode(const int16_t *coefs, int w, int h, const uint8_t *orig, size_t orig_stride, uint8_t *out, size_t out_stride)
+{
+    ImageData im = ref_make_image(orig, w, h, orig_stride);
+    uint8_t **ym, **rm, **bm;
+    build_luminance_matrix(im, &ym);
+    build_rChrominance_matrix(im, &rm);
+    build_bChrominance_matrix(im, &bm);
+    chroma_subsample(&bm, im);
+    chroma_subsample(&rm, im);
+    PixelGroup *blocks = divide_image(ym, rm, bm, im, 8);
+    size_t total_blocks = (size_t)ceil((double)im.pixel_count / 64); /* S-JPG:1131 */
+    for (size_t i = 0; i < total_blocks; i++) {
+        blocks[i].lum_coefficients = malloc(64 * sizeof(double));
+        blocks[i].r_coefficients = malloc(32 * sizeof(double));
+        blocks[i].b_coefficients = malloc(32 * sizeof(double));
+        for (int j = 0; j < 64; j++) blocks[i].lum_coefficients[j] = (double)coefs[128 * i + j];
+        for (int j = 0; j < 32; j++) blocks[i].r_coefficients[j] = (double)coefs[128 * i + 64 + j];
+        for (int j = 0; j < 32; j++) blocks[i].b_coefficients[j] = (double)coefs[128 * i + 96 + j];
+    }
+    for (size_t i = 0; i < total_blocks; i++) { /* S-JPG:1408-1413 */
+        Inverse_quantize(&(blocks[i].lum_coefficients), LUMINANCE_QUANTIZATION_TABLE, 64);
+        Inverse_quantize(&(blocks[i].b_coefficients), CHROMINANCE_QUANTIZATION_TABLE, 32);
+        Inverse_quantize(&(blocks[i].r_coefficients), CHROMINANCE_QUANTIZATION_TABLE, 32);
+    }
+    for (size_t i = 0; i < total_blocks; i++) { /* S-JPG:1416-1421 */
+        inverse_discrete_cosine_transform(blocks[i].lum_values, 8, 8, blocks[i].lum_coefficients);
+        inverse_discrete_cosine_transform(blocks[i].b_values, 4, 8, blocks[i].b_coefficients);
+        inverse_discrete_cosine_transform(blocks[i].r_values, 4, 8, blocks[i].r_coefficients);
+    }
+    ImageData ni = {0};
+    assemble_image(&ni, im, blocks); /* S-JPG:1425 */
+    for (int y = 0; y < h; y++) memcpy(out + (size_t)y * out_stride, ni.pixels[y], sizeof(Pixel) * (size_t)w);
+    for (size_t i = 0; i < total_blocks; i++) {
+        free(blocks[i].lum_coefficients);
+        free(blocks[i].r_coefficients);
+        free(blocks[i].b_coefficients);
+    }
+    free(blocks);
+    ref_free_planes(ym, h);
+    ref_free_planes(rm, h);
+    ref_free_planes(bm, h);
+    free_pixels(im.pixels, h);
+    free_pixels(ni.pixels, h);
+    return 0;
+}
+
 /* Stage-level outputs of one group for tests (samples, unquantised coefficients, RLE arrays). */
 int ref_jpeg_group_stages(const uint8_t *rgba, int w, int h, size_t stride, size_t g, uint8_t *samples, double *coef,
                           int *rle, size_t *rle_len)

@@ -73,6 +73,9 @@ def main() -> None:
         out[f"{name}__stream"] = r["stream"]
         out[f"{name}__bits"] = r["bits"]
         out[f"{name}__offsets"] = r["offsets"]
+        if name == "og_crop":  # decode half of the reference (Inverse_quantize, IDCT, assemble_image) on a real image crop
+            h, w, _ = rgba.shape
+            out[f"{name}__reconstructed"] = rj.jpeg_decode(r["coefs"], w, h, rgba)
     np.savez_compressed(f"{HERE}/jpeg_ref_vectors.npz", **out)
     print("golden fixtures written:", sorted(os.listdir(HERE)))
 

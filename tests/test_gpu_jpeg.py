@@ -148,3 +148,26 @@ def test_host_pipeline_many_bands(ljb, ctx, oracle, monkeypatch, chunk):
     assert np.array_equal(part.stream, enc.stream[o0:o1])
     assert np.array_equal(part.group_offsets, enc.group_offsets[5:46] - np.uint64(o0))
     assert np.array_equal(part.coefs, enc.coefs[5:45])
+
+
+@pytest.mark.parametrize("name", sorted(ALL))
+def test_decode_matches_oracle(ljb, ctx, oracle, name):
+    """Decode half on the GPU (Inverse_quantize, IDCT, assemble_image) == oracle, bit for bit, for every case."""
+    img = ALL[name]
+    h, w, _ = img.shape
+    enc = ljb.jpeg.process(img, ctx=ctx)
+    rec = ljb.jpeg.assemble_image(enc.coefs, w, h, original=img, ctx=ctx)
+    assert np.array_equal(rec, oracle.jpeg_decode(enc.coefs, w, h, img))
+
+
+def test_decode_golden_and_noise(ljb, ctx, oracle):
+    img = cases.og_crop()
+    h, w, _ = img.shape
+    rec = ljb.jpeg.assemble_image(VEC["og_crop__coefs"], w, h, original=img, ctx=ctx)
+    assert np.array_equal(rec, VEC["og_crop__reconstructed"])  # produced by the reference build
+    noise = ljb.synth.random_image(512, 256, seed=3)
+    enc = ljb.jpeg.process(noise, ctx=ctx)
+    rec = ljb.jpeg.assemble_image(enc.coefs, 512, 256, ctx=ctx)  # multiples of 8: no original needed
+    assert np.array_equal(rec, oracle.jpeg_decode(enc.coefs, 512, 256))
+    with pytest.raises(ljb.LjbError):
+        ljb.jpeg.assemble_image(ljb.jpeg.process(ALL["noise_18x13"], ctx=ctx).coefs, 18, 13, ctx=ctx)

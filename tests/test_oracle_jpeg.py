@@ -110,3 +110,25 @@ def test_partial_tiles_and_group_count(oracle):
 def test_odd_width_rejected(oracle):
     with pytest.raises(RuntimeError):
         oracle.jpeg_encode(cases.synth_image(1, 9, 8))
+
+
+@pytest.mark.parametrize("name", ["og_crop", "noise_64x48", "noise_18x13", "appendix_c", "gradient_24x40", "noise_10x6", "red_24x16"])
+def test_decode_equals_reference_build(oracle, ref_jpeg, name):
+    """Decode half (Inverse_quantize, IDCT, assemble_image): restatement == the reference's own functions, including
+    sizes whose last tiled groups the reference leaves unprocessed."""
+    img = dict(cases.jpeg_cases())[name]
+    h, w, _ = img.shape
+    coefs = oracle.jpeg_encode(img)["coefs"]
+    a = oracle.jpeg_decode(coefs, w, h, img)
+    b = ref_jpeg.jpeg_decode(coefs, w, h, img)
+    assert np.array_equal(a, b)
+    assert (a[..., 3] == 255).all()
+
+
+def test_decode_golden_fixture(oracle):
+    """Committed reconstruction of the og.png crop by the reference build (tests/golden/make_golden.py)."""
+    vec = np.load(os.path.join(cases.GOLDEN, "jpeg_ref_vectors.npz"))
+    img = cases.og_crop()
+    h, w, _ = img.shape
+    out = oracle.jpeg_decode(vec["og_crop__coefs"], w, h, img)
+    assert np.array_equal(out, vec["og_crop__reconstructed"])
