@@ -43,6 +43,8 @@ def main() -> None:
     shutil.copy(f"{REF}/Output-Input/input/input.txt", f"{HERE}/lz4_input.txt")
     shutil.copy(f"{REF}/Output-Input/out/compressed.bin", f"{HERE}/lz4_compressed.bin")
     shutil.copy(f"{REF}/Output-Input/input/Metamorphosis.txt", f"{HERE}/Metamorphosis.txt")
+    shutil.copy(f"{REF}/Output-Input/out/compressed.txt", f"{HERE}/lz4_compressed_hex.txt")    # hex dump of compressed.bin
+    shutil.copy(f"{REF}/Output-Input/out/uncompressed.txt", f"{HERE}/lz4_uncompressed.txt")   # the reference decoder's output
 
     x0, y0, cw, ch = 768, 200, 256, 100
     for src, dst in (("Assets/Images/og.png", "og_crop.png"),
