@@ -82,7 +82,6 @@ struct Params {
     uint64_t *result;        // [0] length, [1] phantom, [2] error flags
     uint64_t *status;        // [0] ticket, [1..] look-back words
     uint32_t *scratch;       // per CTA: MAXB u32 match records
-    uint16_t *lists;         // per CTA: three lists of MAXB positions for the ladder
     uint8_t *staging;        // per CTA: two buffers of stage_stride bytes holding the encoded block until its offset is known
     size_t stage_stride;
     uint64_t offs_bias;      // added to every block_offsets entry (base of this shard in a larger stream)
@@ -329,35 +328,25 @@ __global__ void __launch_bounds__(THREADS, 1) lz4_encode_kernel(Params P)
         // leave the ladder.  Slots owned by a different gram ("losers") are re-hashed in further rounds; all
         // occurrences of a gram win or lose together, which keeps the minimum exact.  Level 8 only flags:
         // matches of 8+ bytes get their true length in phase B.
-        // The still-unresolved positions are kept as compact u16 lists in global scratch (L2-resident, read and
-        // written coalesced), so every round costs exactly its population with all lanes busy.  (Per-thread
-        // bit masks left most lanes idle in the sparse later rounds: 19 rounds ran at ~25 % lane efficiency.)
         {
             uint32_t *T = reinterpret_cast<uint32_t *>(smem + SM_S); // 32768 slots
             constexpr int TBITS = 15;
             constexpr int MAXR = 12;
-            uint16_t *const lists = P.lists + (size_t)blockIdx.x * 3 * MAXB;
-            int li_in = 0, li_retry = 1, li_down = 2;     // roles of the three list buffers
-            uint32_t n_in = nb;                            // level 8, round 0: every position (implicit list)
-            bool implicit = true;
-            unsigned int *const cnt = M.scan_tmp;          // [0] retry count, [1] down count
-            // warp-aggregated append of position p to list `which` if pred
-            auto append = [&](bool pred, uint32_t p, uint16_t *list, unsigned int *counter) {
-                const unsigned mask = __ballot_sync(0xffffffffu, pred);
-                if (mask == 0) return;
-                unsigned base = 0;
-                const int leader = __ffs(mask) - 1;
-                if (lane == leader) base = atomicAdd(counter, (unsigned)__popc(mask));
-                base = __shfl_sync(0xffffffffu, base, leader);
-                if (pred) list[base + __popc(mask & ((1u << lane) - 1u))] = (uint16_t)p;
-            };
+            unsigned long long unres = 0;
+#pragma unroll 1
+            for (int i = 0; i < 64; ++i)
+                if ((uint32_t)tid + 1024u * i < nb) unres |= 1ull << i;
 #pragma unroll 1
             for (int k = 8; k >= 4; --k) {
                 const uint32_t npk = nb >= (uint32_t)k ? nb - k + 1 : 0;
                 const uint32_t m1 = k >= 8 ? 0xFFFFFFFFu : (k == 4 ? 0u : ((1u << (8 * (k - 4))) - 1u));
-                if (tid == 0) cnt[1] = 0;
+                unsigned long long ins = 0;
+                for (unsigned long long m = unres; m;) {
+                    const int i = __ffsll((long long)m) - 1;
+                    m &= m - 1;
+                    if ((uint32_t)tid + 1024u * i < npk) ins |= 1ull << i;
+                }
                 int round = 0;
-                const long long t_level = clock64();
                 for (;;) {
                     {
                         uint4 *T4 = reinterpret_cast<uint4 *>(T);
@@ -365,116 +354,73 @@ __global__ void __launch_bounds__(THREADS, 1) lz4_encode_kernel(Params P)
                         for (int i = tid; i < (1 << TBITS) / 4; i += THREADS) T4[i] = ff;
                     }
                     __syncthreads();
-                    if (tid == 0) cnt[0] = 0; // everyone has read the previous round's count; appends start after the next barrier
-                    const uint16_t *In = lists + (size_t)li_in * MAXB;
-                    uint16_t *Retry = lists + (size_t)li_retry * MAXB, *Down = lists + (size_t)li_down * MAXB;
                     const uint32_t A = 2654435761u + 0x9E3779B1u * (uint32_t)round * 2u;
                     const uint32_t B = 2246822519u + 0x85EBCA77u * (uint32_t)round * 2u;
-                    if (P.phase_cycles && tid == 0) {
-                        atomicAdd(&P.phase_cycles[21], (unsigned long long)n_in);
-                        atomicAdd(&P.phase_cycles[22], 1ull);
+                    if (P.phase_cycles) {
+                        atomicAdd(&P.phase_cycles[21], (unsigned long long)__popcll(ins));
+                        if (tid == 0) atomicAdd(&P.phase_cycles[22], 1ull);
                     }
-                    const uint32_t n_pad = (n_in + 31u) & ~31u; // whole warps stay in the loops (ballots inside)
-                    for (uint32_t j = tid; j < n_pad; j += THREADS) {
-                        if (j < n_in) {
-                            const uint32_t p = implicit ? j : In[j];
-                            if (p < npk) {
-                                const uint32_t P0 = load32u(dataw, p), P1 = load32u(dataw, p + 4) & m1;
-                                uint32_t h = (P0 * A) ^ (P1 * B);
-                                h = ((h ^ (h >> 15)) * 2246822519u) >> (32 - TBITS);
-                                atomicMin(&T[h], p);
-                            }
-                        }
+                    for (unsigned long long m = ins; m;) {
+                        const int i = __ffsll((long long)m) - 1;
+                        m &= m - 1;
+                        const uint32_t p = (uint32_t)tid + 1024u * i;
+                        const uint32_t P0 = load32u(dataw, p), P1 = load32u(dataw, p + 4) & m1;
+                        uint32_t h = (P0 * A) ^ (P1 * B);
+                        h = ((h ^ (h >> 15)) * 2246822519u) >> (32 - TBITS);
+                        atomicMin(&T[h], p);
                     }
                     __syncthreads();
-                    for (uint32_t j = tid; j < n_pad; j += THREADS) {
-                        bool retry = false, down = false;
-                        uint32_t p = 0;
-                        if (j < n_in) {
-                            p = implicit ? j : In[j];
-                            if (p >= npk) {
-                                down = true; // no k-gram inside the block: a shorter gram may still match
+                    unsigned long long next = 0;
+                    for (unsigned long long m = ins; m;) {
+                        const int i = __ffsll((long long)m) - 1;
+                        m &= m - 1;
+                        const uint32_t p = (uint32_t)tid + 1024u * i;
+                        const uint32_t P0 = load32u(dataw, p), P1 = load32u(dataw, p + 4) & m1;
+                        uint32_t h = (P0 * A) ^ (P1 * B);
+                        h = ((h ^ (h >> 15)) * 2246822519u) >> (32 - TBITS);
+                        const uint32_t q = T[h];
+                        if (q != p) { // q < p: the earliest position that hashes here
+                            const uint32_t Q0 = load32u(dataw, q), Q1 = load32u(dataw, q + 4) & m1;
+                            if (Q0 == P0 && Q1 == P1) {
+                                R[p] = ((uint32_t)k << 16) | q;
+                                unres &= ~(1ull << i);
+                                if (k == 8 && nb - p > 8) {
+                                    atomicOr(&longbits[p >> 5], 1u << (p & 31));
+                                    atomicOr(&firstbits[q >> 5], 1u << (q & 31));
+                                }
                             } else {
-                                const uint32_t P0 = load32u(dataw, p), P1 = load32u(dataw, p + 4) & m1;
-                                uint32_t h = (P0 * A) ^ (P1 * B);
-                                h = ((h ^ (h >> 15)) * 2246822519u) >> (32 - TBITS);
-                                const uint32_t q = T[h];
-                                if (q == p) {
-                                    down = true; // first occurrence of its k-gram
-                                } else { // q < p: the earliest position that hashes here
-                                    const uint32_t Q0 = load32u(dataw, q), Q1 = load32u(dataw, q + 4) & m1;
-                                    if (Q0 == P0 && Q1 == P1) {
-                                        R[p] = ((uint32_t)k << 16) | q;
-                                        if (k == 8 && nb - p > 8) {
-                                            atomicOr(&longbits[p >> 5], 1u << (p & 31));
-                                            atomicOr(&firstbits[q >> 5], 1u << (q & 31));
-                                        }
-                                    } else {
-                                        retry = true; // slot owned by another gram: try again with another hash
-                                    }
-                                }
+                                next |= 1ull << i; // slot owned by another gram: try again with another hash
                             }
                         }
-                        append(retry, p, Retry, &cnt[0]);
-                        append(down, p, Down, &cnt[1]);
                     }
-                    __syncthreads();
-                    const uint32_t n_retry = cnt[0];
+                    ins = next;
                     ++round;
-                    if (n_retry == 0) break;
-                    if (round >= MAXR) { // practically unreachable: grams that kept colliding through MAXR independent hashes
-                        for (uint32_t j = tid; j < n_retry; j += THREADS) {
-                            const uint32_t p = Retry[j];
-                            const uint32_t P0 = load32u(dataw, p), P1 = load32u(dataw, p + 4) & m1;
-                            bool found = false;
-                            for (uint32_t q = 0; q < p; ++q) {
-                                if (load32u(dataw, q) == P0 && (load32u(dataw, q + 4) & m1) == P1) {
-                                    R[p] = ((uint32_t)k << 16) | q;
-                                    if (k == 8 && nb - p > 8) {
-                                        atomicOr(&longbits[p >> 5], 1u << (p & 31));
-                                        atomicOr(&firstbits[q >> 5], 1u << (q & 31));
-                                    }
-                                    found = true;
-                                    break;
-                                }
-                            }
-                            if (!found) Down[atomicAdd(&cnt[1], 1u)] = (uint16_t)p;
-                        }
-                        __syncthreads();
-                        break;
-                    }
-                    // next round of this level reads the retry list; the consumed input buffer becomes the new retry buffer
-                    if (implicit) {
-                        implicit = false;
-                        li_in = li_retry;
-                        li_retry = 0; // buffer 0 was never used by the implicit list
-                        if (li_in == 0) li_retry = 1;
-                    } else {
-                        const int t = li_in;
-                        li_in = li_retry;
-                        li_retry = t;
-                    }
-                    n_in = n_retry;
+                    if (!__syncthreads_or(ins != 0)) break;
+                    if (round >= MAXR) break;
                 }
-                if (P.phase_cycles && tid == 0) atomicAdd(&P.phase_cycles[24 + (8 - k)], (unsigned long long)(clock64() - t_level));
-                // next level: everything that is still unresolved
-                n_in = cnt[1];
-                __syncthreads(); // cnt[1] is reset by thread 0 at the top of the next level
-                if (implicit) { // (only when level 8 finished in one round)
-                    implicit = false;
-                    li_in = li_down;
-                    li_down = 0;
-                    li_retry = (li_in == 1) ? 2 : 1;
-                } else {
-                    const int old_in = li_in;
-                    li_in = li_down;
-                    li_down = old_in; // both the old input and the old retry buffers are free
+                // practically unreachable: grams that kept colliding through MAXR independent hashes
+                for (unsigned long long m = ins; m;) {
+                    const int i = __ffsll((long long)m) - 1;
+                    m &= m - 1;
+                    const uint32_t p = (uint32_t)tid + 1024u * i;
+                    const uint32_t P0 = load32u(dataw, p), P1 = load32u(dataw, p + 4) & m1;
+                    for (uint32_t q = 0; q < p; ++q) {
+                        if (load32u(dataw, q) == P0 && (load32u(dataw, q + 4) & m1) == P1) {
+                            R[p] = ((uint32_t)k << 16) | q;
+                            unres &= ~(1ull << i);
+                            if (k == 8 && nb - p > 8) {
+                                atomicOr(&longbits[p >> 5], 1u << (p & 31));
+                                atomicOr(&firstbits[q >> 5], 1u << (q & 31));
+                            }
+                            break;
+                        }
+                    }
                 }
             }
-            // no earlier occurrence of even the 4-gram: literal
-            {
-                const uint16_t *In = lists + (size_t)li_in * MAXB;
-                for (uint32_t j = tid; j < n_in; j += THREADS) R[In[j]] = 0;
+            for (unsigned long long m = unres; m;) { // no earlier occurrence of even the 4-gram: literal
+                const int i = __ffsll((long long)m) - 1;
+                m &= m - 1;
+                R[(uint32_t)tid + 1024u * i] = 0;
             }
         }
         __syncthreads();
@@ -564,15 +510,14 @@ __global__ void __launch_bounds__(THREADS, 1) lz4_encode_kernel(Params P)
                 constexpr uint32_t SHORT = 32; // a lane compares this much on its own; longer runs are compared by the whole warp
                 if (tid == 0) M.scan_tmp[0] = 0;
                 __syncthreads();
-                constexpr uint32_t CH = 8; // positions per lane and row: small rows balance the 32 warps (a row is 32 * CH positions)
-                const uint32_t nrows = (nb + 32 * CH - 1) / (32 * CH);
+                const uint32_t nrows = (nb + 1023) >> 10;
                 for (;;) {
                     uint32_t row = 0;
                     if (lane == 0) row = atomicAdd(&M.scan_tmp[0], 1u);
                     row = __shfl_sync(0xffffffffu, row, 0);
                     if (row >= nrows) break;
                     const uint32_t ch = row * 32 + lane;
-                    const uint32_t bits = (ch * CH < nb) ? ((vlong[(ch * CH) >> 5] >> ((ch * CH) & 31)) & ((1u << CH) - 1u)) : 0u;
+                    const uint32_t bits = (ch * 32 < nb) ? vlong[ch] : 0u;
                     uint32_t pc[KEEP], pl[KEEP]; // candidates of the previous position: position, length | capped << 16
                     uint32_t pn = 0;
                     uint32_t dbg_pos = 0, dbg_vis = 0, dbg_scratch = 0, dbg_bytes = 0, dbg_inh = 0;
@@ -586,7 +531,7 @@ __global__ void __launch_bounds__(THREADS, 1) lz4_encode_kernel(Params P)
                     uint32_t sl_next = 0xFFFFFFFFu;
                     if (steps) {
                         const int i0 = __ffs(steps) - 1;
-                        if ((bits >> i0) & 1u) sl_next = R[ch * CH + i0];
+                        if ((bits >> i0) & 1u) sl_next = R[ch * 32 + i0];
                     }
                     while (steps) {
                         const int i = __ffs(steps) - 1;
@@ -595,10 +540,10 @@ __global__ void __launch_bounds__(THREADS, 1) lz4_encode_kernel(Params P)
                         sl_next = 0xFFFFFFFFu;
                         if (steps) {
                             const int i1 = __ffs(steps) - 1;
-                            if ((bits >> i1) & 1u) sl_next = R[ch * CH + i1];
+                            if ((bits >> i1) & 1u) sl_next = R[ch * 32 + i1];
                         }
                         const bool active = (bits >> i) & 1u;
-                        const uint32_t p = ch * CH + i;
+                        const uint32_t p = ch * 32 + i;
                         const bool chained = active && i > 0 && ((bits >> (i - 1)) & 1u);
                         if (!chained) pn = 0;
                         uint32_t cap = 0, P0 = 0, P1 = 0, bestkey = 0;
@@ -1019,10 +964,9 @@ static int lz4_launch(ljb_ctx *ctx, const uint8_t *d_in, size_t n, size_t block_
     int rc;
     const size_t rec_bytes = (size_t)ctx->num_sms * MAXB * sizeof(uint32_t);
     const size_t stage_stride = (ljb_lz4_bound(block_len, block_len) + 16 + 255) & ~(size_t)255; // one encoded block, worst case
-    const size_t list_bytes = (size_t)ctx->num_sms * 3 * MAXB * sizeof(uint16_t);
-    if ((rc = ljb_ensure(&ctx->d_scratch, &ctx->scratch_bytes, rec_bytes + list_bytes + (size_t)grid * 2 * stage_stride)) != 0) return rc;
-    if ((rc = ljb_ensure(&ctx->d_status, &ctx->status_bytes, (nblocks + 2 + 32) * sizeof(uint64_t))) != 0) return rc;
-    LJB_CUDA(cudaMemsetAsync(ctx->d_status, 0, (nblocks + 2 + 32) * sizeof(uint64_t), ctx->stream));
+    if ((rc = ljb_ensure(&ctx->d_scratch, &ctx->scratch_bytes, rec_bytes + (size_t)grid * 2 * stage_stride)) != 0) return rc;
+    if ((rc = ljb_ensure(&ctx->d_status, &ctx->status_bytes, (nblocks + 2 + 24) * sizeof(uint64_t))) != 0) return rc;
+    LJB_CUDA(cudaMemsetAsync(ctx->d_status, 0, (nblocks + 2 + 24) * sizeof(uint64_t), ctx->stream));
     LJB_CUDA(cudaMemsetAsync(d_result, 0, 3 * sizeof(uint64_t), ctx->stream));
     Params P;
     P.in = d_in;
@@ -1035,8 +979,7 @@ static int lz4_launch(ljb_ctx *ctx, const uint8_t *d_in, size_t n, size_t block_
     P.result = d_result;
     P.status = (uint64_t *)ctx->d_status;
     P.scratch = (uint32_t *)ctx->d_scratch;
-    P.lists = (uint16_t *)((uint8_t *)ctx->d_scratch + rec_bytes);
-    P.staging = (uint8_t *)ctx->d_scratch + rec_bytes + list_bytes;
+    P.staging = (uint8_t *)ctx->d_scratch + rec_bytes;
     P.stage_stride = stage_stride;
     P.offs_bias = offs_bias;
     P.lead = first_block == 0 ? 1u : 0u;
@@ -1058,7 +1001,7 @@ static int lz4_launch(ljb_ctx *ctx, const uint8_t *d_in, size_t n, size_t block_
     LJB_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
     ctx->launches += 1;
     if (P.phase_cycles) {
-        unsigned long long ph[32];
+        unsigned long long ph[24];
         LJB_CUDA(cudaMemcpyAsync(ph, P.phase_cycles, sizeof ph, cudaMemcpyDeviceToHost, ctx->stream));
         LJB_CUDA(cudaStreamSynchronize(ctx->stream));
         static const char *names[9] = {"stage", "phaseB1", "ladderA", "index8", "phaseB", "parse", "sizing", "lookback", "emit"};
@@ -1070,8 +1013,6 @@ static int lz4_launch(ljb_ctx *ctx, const uint8_t *d_in, size_t n, size_t block_
         fprintf(stderr, "[ljb lz4 phaseB1] per block: indexed=%.0f positions=%.0f visited=%.0f equal8=%.0f warp-cycles=%.0f | ladder: inserts=%.0f rounds=%.1f\n",
                 (double)ph[20] / nblocks, (double)ph[16] / nblocks, (double)ph[17] / nblocks, (double)ph[18] / nblocks, (double)ph[19] / nblocks,
                 (double)ph[21] / nblocks, (double)ph[22] / nblocks);
-        fprintf(stderr, "[ljb lz4 ladder] cycles per block at level 8..4: %.0f %.0f %.0f %.0f %.0f\n", (double)ph[24] / nblocks,
-                (double)ph[25] / nblocks, (double)ph[26] / nblocks, (double)ph[27] / nblocks, (double)ph[28] / nblocks);
         fprintf(stderr, "[ljb lz4 phaseB2] per block: positions=%.0f inherited=%.0f | warp-cycles: rows=%.0f load=%.0f eval=%.0f coop=%.0f fallback=%.0f\n",
                 (double)ph[9] / nblocks, (double)ph[13] / nblocks, (double)ph[14] / nblocks, (double)ph[15] / nblocks, (double)ph[10] / nblocks, (double)ph[11] / nblocks, (double)ph[12] / nblocks);
     }
