@@ -36,8 +36,8 @@ BLOCK_LEN = 65536
 LZ4_BYTES = int(os.environ.get("LJB_BENCH_LZ4_BYTES", 4 * GIB))
 JPEG_DIM = int(os.environ.get("LJB_BENCH_JPEG_DIM", 16384))
 # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the ncu pass over this same command committed as
-# profiles/r1/launches_r1b_bench_steps2_warmup1.csv (bytes at the default workload sizes; None for other sizes).
-NCU_TRAFFIC = {"lz4": 6.14e9 + 18.09e9 if LZ4_BYTES == 4 * GIB else None, "jpeg": 1.079e9 + 0.235e9 if JPEG_DIM == 16384 else None}
+# profiles/r1/launches_r1c_bench_steps2_warmup1.csv (bytes at the default workload sizes; None for other sizes).
+NCU_TRAFFIC = {"lz4": 4.83e9 + 16.44e9 if LZ4_BYTES == 4 * GIB else None, "jpeg": 1.077e9 + 0.207e9 if JPEG_DIM == 16384 else None}
 
 
 def measured_peak_gbs():

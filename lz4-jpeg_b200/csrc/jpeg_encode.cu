@@ -210,8 +210,8 @@ __device__ __noinline__ unsigned col_pass(uint32_t *wl, uint32_t *wbase, int lan
         s[j] = a + b; // cos8[7-x][u] = (-1)^u cos8[x][u]
         d[j] = a - b;
     }
-#pragma unroll 1
-    for (int k = 0; k < 4; ++k) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { // unrolled: the 32 cosine operands become immediates instead of indexed constant loads
 #pragma unroll
         for (int odd = 0; odd < 2; ++odd) {
             const int u = 2 * k + odd;
@@ -220,8 +220,13 @@ __device__ __noinline__ unsigned col_pass(uint32_t *wl, uint32_t *wbase, int lan
             for (int j = 1; j < 4; ++j) acc = fma(odd ? d[j] : s[j], kCos8[j * 8 + u], acc);
             const int idx = u * W + v;
             int t;
-            if (!quant_fast(acc * (W == 8 ? kMLum.m[idx] : kMChr.m[idx]), t))
-                t = W == 8 ? exact_quant_ws<8>(wl, byte0, u, v) : exact_quant_ws<4>(wl, byte0, u, v);
+            const double qs = acc * (W == 8 ? kMLum.m[idx] : kMChr.m[idx]);
+            if (!quant_fast(qs, t)) {
+                // Luma DC is sum(corr) / 64 exactly: "near an integer" means it IS that integer n, and the reference's
+                // (alpha0 * alpha0) * sum / 8 with alpha0^2 = 0.125 (1 + 2^-52) never falls below |n|, so it truncates to n.
+                if (W == 8 && u == 0 && v == 0) t = __double2int_rn(qs * (1.0 / 1048576.0));
+                else t = W == 8 ? exact_quant_ws<8>(wl, byte0, u, v) : exact_quant_ws<4>(wl, byte0, u, v);
+            }
             wide |= (t < -128) | (t > 127);
             ws_b(wl, W_PAR, out0 + (W == 8 ? kZZ8.pos[idx] : kZZ4.pos[idx])) = (uint8_t)t;
             if (co) co[idx] = (int16_t)t;

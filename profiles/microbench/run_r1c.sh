@@ -1,0 +1,13 @@
+# round-1 evidence run (final kernels): tests, bench, launch list with DRAM traffic, one ncu --set full capture per kernel
+set -x
+python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+python -c "import __graft_entry__ as g; g.smoke()"
+python bench.py --steps 3 --warmup 3 > gpurun_out/bench_r1c.json 2> gpurun_out/bench_r1c.err; echo bench rc=$?
+python bench.py --impl reference --steps 1 --warmup 0 > gpurun_out/bench_r1c_reference.json 2>> gpurun_out/bench_r1c.err; echo ref rc=$?
+python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/plain_launch.log 2>&1 &&
+ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches_r1c.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_launch.log 2>&1
+python profiles/microbench/quick_lz4.py 268435456 > gpurun_out/lz4_plain.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:lz4_encode -s 1 -c 1 -f -o gpurun_out/lz4_r1c python profiles/microbench/quick_lz4.py 268435456 > gpurun_out/lz4_ncu.log 2>&1
+python profiles/microbench/quick_jpeg.py 16384 > gpurun_out/jpeg_plain.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:jpeg_encode -s 1 -c 1 -f -o gpurun_out/jpeg_r1c python profiles/microbench/quick_jpeg.py 16384 > gpurun_out/jpeg_ncu.log 2>&1
+cat gpurun_out/lz4_plain.log gpurun_out/jpeg_plain.log
