@@ -87,6 +87,16 @@ extern "C" int ljb_ctx_create(int device, ljb_ctx **out)
     c->device = device;
     c->num_sms = prop.multiProcessorCount;
     LJB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    if (!getenv("LJB_NO_L2_PERSIST") && prop.persistingL2CacheMaxSize > 0 && prop.accessPolicyMaxWindowSize > 0) {
+        size_t want = (size_t)64 << 20; // room for the 38 MB of LZ4 match records of 148 CTAs
+        if (want > (size_t)prop.persistingL2CacheMaxSize) want = (size_t)prop.persistingL2CacheMaxSize;
+        if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) {
+            c->l2_persist_bytes = want;
+            c->l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
+        } else {
+            cudaGetLastError();
+        }
+    }
     LJB_CUDA(cudaEventCreate(&c->ev0));
     LJB_CUDA(cudaEventCreate(&c->ev1));
     LJB_CUDA(cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));

@@ -17,6 +17,8 @@ struct ljb_ctx {
     cudaEvent_t ev0, ev1;
     uint64_t launches;
     float last_kernel_ms;
+    size_t l2_persist_bytes; // L2 set aside for persisting accesses (0 = unsupported / disabled by LJB_NO_L2_PERSIST)
+    size_t l2_window_max;    // largest access-policy window the device accepts
     // persistent scratch (grown on demand, never shrunk)
     void *d_scratch;      // per-CTA match records etc.
     size_t scratch_bytes;

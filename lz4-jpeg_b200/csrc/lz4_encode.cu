@@ -28,6 +28,7 @@
 
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 #include <type_traits>
 
 namespace lz4k {
@@ -995,11 +996,27 @@ static int lz4_launch(ljb_ctx *ctx, const uint8_t *d_in, size_t n, size_t block_
         LJB_CUDA(cudaFuncSetAttribute(lz4_encode_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
         attr_done = true;
     }
+    // The per-CTA match records (256 KiB each, rewritten for every block) are the only data the kernel re-reads: pin
+    // them in L2 for the duration of the launch so that the input / output streams cannot push them out to HBM.
+    cudaStreamAttrValue win;
+    memset(&win, 0, sizeof win);
+    if (ctx->l2_persist_bytes) {
+        win.accessPolicyWindow.base_ptr = ctx->d_scratch;
+        win.accessPolicyWindow.num_bytes = rec_bytes < ctx->l2_window_max ? rec_bytes : ctx->l2_window_max;
+        win.accessPolicyWindow.hitRatio = 1.0f;
+        win.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        win.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        LJB_CUDA(cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &win));
+    }
     LJB_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
     lz4_encode_kernel<8><<<grid, THREADS, SM_TOTAL, ctx->stream>>>(P);
     LJB_CUDA(cudaGetLastError());
     LJB_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
     ctx->launches += 1;
+    if (ctx->l2_persist_bytes) {
+        win.accessPolicyWindow.num_bytes = 0; // later launches on this stream (JPEG, copies) run without a window
+        LJB_CUDA(cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &win));
+    }
     if (P.phase_cycles) {
         unsigned long long ph[24];
         LJB_CUDA(cudaMemcpyAsync(ph, P.phase_cycles, sizeof ph, cudaMemcpyDeviceToHost, ctx->stream));
