@@ -461,8 +461,10 @@ __global__ void __launch_bounds__(THREADS, 1) lz4_encode_kernel(Params P)
                         const uint32_t cap16 = min(16u, nb - p);
                         const uint32_t pch = p >> 10;
                         uint32_t best = 0, n16 = 0, cand = 0xFFFFFFFFu;
+                        uint32_t c_next = lo < hi ? S[lo] : 0u;
                         for (uint32_t i = lo; i < hi; ++i) {
-                            const uint32_t c = S[i];
+                            const uint32_t c = c_next;
+                            c_next = S[i + 1]; // one entry ahead (S has slack past the last bucket): shortens the dependent chain
                             const uint32_t cch = c >> 10;
                             if (cch > pch) break; // only later positions from here on
                             ++d_vis;
@@ -528,20 +530,28 @@ __global__ void __launch_bounds__(THREADS, 1) lz4_encode_kernel(Params P)
                     // all lanes step through the 32 positions of their chunks together (warp-uniform control flow),
                     // so that long compares can be done by the whole warp
                     uint32_t steps = __reduce_or_sync(0xffffffffu, bits);
-                    // the candidates of the next step are fetched (one L2 round trip) while this step is processed
-                    uint32_t sl_next = 0xFFFFFFFFu;
-                    if (steps) {
-                        const int i0 = __ffs(steps) - 1;
-                        if ((bits >> i0) & 1u) sl_next = R[ch * 32 + i0];
+                    // the candidates of the next three steps are in flight (L2 round trips) while this step is processed
+                    auto fetch = [&](uint32_t m) -> uint32_t {
+                        if (!m) return 0xFFFFFFFFu;
+                        const int i = __ffs(m) - 1;
+                        return ((bits >> i) & 1u) ? R[ch * 32 + i] : 0xFFFFFFFFu;
+                    };
+                    uint32_t sl_a, sl_b, sl_c;
+                    {
+                        const uint32_t m2 = steps & (steps - 1), m3 = m2 & (m2 - 1);
+                        sl_a = fetch(steps);
+                        sl_b = fetch(m2);
+                        sl_c = fetch(m3);
                     }
                     while (steps) {
                         const int i = __ffs(steps) - 1;
                         steps &= steps - 1;
-                        const uint32_t sl = sl_next;
-                        sl_next = 0xFFFFFFFFu;
-                        if (steps) {
-                            const int i1 = __ffs(steps) - 1;
-                            if ((bits >> i1) & 1u) sl_next = R[ch * 32 + i1];
+                        const uint32_t sl = sl_a;
+                        sl_a = sl_b;
+                        sl_b = sl_c;
+                        {
+                            const uint32_t m2 = steps & (steps - 1);
+                            sl_c = fetch(m2 & (m2 - 1));
                         }
                         const bool active = (bits >> i) & 1u;
                         const uint32_t p = ch * 32 + i;
