@@ -150,7 +150,7 @@ def run_reference(args):
         return 0
     threads = os.cpu_count() or 1
     sample_blocks = max(threads, 16)
-    jw, jh = 1024, 512
+    jw, jh = 4096, 2048  # ~25 CPU-seconds of the reference's per-group stages
     lz, jp = [], []
     kind = "reference"
     for i in range(args.warmup + args.steps):
@@ -361,9 +361,9 @@ def run_gpu(args):
         v, kind, sec = _cpu_lz4(sb, threads)
         cpu_lz = {"value": v, "unit": "GB/s", "cores": threads, "kind": kind,
                   "sample": f"{sb} blocks of 64 KiB of the same seed-42 text, reference block_encode on {threads} threads, {sec:.1f} s"}
-        vj, kindj, secj = _cpu_jpeg(1024, 512, threads)
+        vj, kindj, secj = _cpu_jpeg(4096, 2048, threads)
         cpu_jp = {"value": vj, "unit": "MPix/s", "cores": threads, "kind": kindj,
-                  "sample": f"1024x512 seed-42 noise image, reference per-group encode stages on {threads} threads, {secj:.1f} s"}
+                  "sample": f"4096x2048 seed-42 noise image, reference per-group encode stages on {threads} threads, {secj:.1f} s"}
 
     if rank == 0:
         line = {
