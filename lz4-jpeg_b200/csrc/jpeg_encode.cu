@@ -15,7 +15,7 @@
 // ticket counter on its own (no CTA-wide barrier in the kernel).  Every per-thread array lives in shared memory WORD-INTERLEAVED across the 32 lanes of its warp
 // (word w of lane l at warp_base + (w*32 + l)*4): whatever data-dependent index a lane uses, it stays in
 // its own bank, so the divergent heap / table walks of the Huffman construction are bank-conflict free.
-// 112 words per thread (LUT 64 | heap+codes 32 | parents 16) let 16 warps share the 227 KB of one SM.
+// 81 words per thread (symbol table 33 | counts / heap / codes 32 | child links 16) let 22 warps share the 227 KB of one SM.
 //
 // Exactness (results are bit-identical to the reference built with gcc x86-64 SSE2 -O2 -ffp-contract=off):
 //   colour   the reference evaluates 0.299*r+0.587*g+0.114*b (etc.) in double and truncates.  The exact
@@ -39,23 +39,24 @@ namespace jpgk {
 
 #include "jpeg_tables.inc"
 
-constexpr int THREADS = 512;       // 16 warps, each working on its own 32-group tile
+constexpr int THREADS = 704;       // 22 warps, each working on its own 32-group tile
 constexpr int NWARPS = THREADS / 32;
 constexpr int REC_BYTES = 256;     // max packed record: (1023 + 511 + 511) bits (JPEG.c:1248, :1286, :1320)
 constexpr int REC_WORDS = REC_BYTES / 4;
 
 // per-thread workspace, in 32-bit words (interleaved across the warp)
-constexpr int W_LUT = 0;           // u8[256]: symbol+128 -> (epoch << 5) | slot
-constexpr int W_CNT = 64;          // u32[32] counts -> u16 heap -> u16[63] code words (see entropy_fast)
-constexpr int W_PAR = 96;          // u16[31]: children of the internal nodes; int8 coefficients while the DCT runs
-constexpr int WS_WORDS = 112;
+constexpr int W_LUT = 0;           // u8[129]: symbol + 64 -> (epoch << 5) | slot, symbols -64 .. 64 (33 words)
+constexpr int W_CNT = 33;          // u32[32] counts -> u16 heap -> u16[63] code words (see entropy_fast)
+constexpr int W_PAR = 65;          // u16[31]: children of the internal nodes; int8 coefficients while the DCT runs
+constexpr int WS_WORDS = 81;
+constexpr int SYM_MIN = -64, SYM_MAX = 64; // table range; a DC value outside it is carried in a register (see entropy_fast)
 // DCT phase view of the same words
-constexpr int W_T = 0;             // double[32]: row-pass results (8 rows x 4 columns), 64-bit interleaved
-constexpr int W_SMP = 64;          // u8[128]: samples lum[64] | Cr[32] | Cb[32]
+constexpr int W_T = 0;             // double[16]: row-pass results (8 rows x 2 columns), 64-bit interleaved = words 0..31
+constexpr int W_SMP = 33;          // u8[128]: samples lum[64] | Cr[32] | Cb[32]
 constexpr int FAST_MAXSYM = 32;
 constexpr int FAST_MAXLEN = 12;
 
-constexpr int SM_WS = THREADS * WS_WORDS * 4; // 229376
+constexpr int SM_WS = THREADS * WS_WORDS * 4; // 228096
 constexpr int SM_TOTAL = SM_WS;
 static_assert(SM_TOTAL <= 227 * 1024, "exceeds B200 shared memory per CTA");
 
@@ -196,7 +197,7 @@ __device__ __forceinline__ bool quant_fast(double qs, int &t)
 }
 
 // Column pass + quantise + zig-zag of ONE column of row-pass results, shared by luma (W = 8) and chroma (W = 4).
-// T holds 8 rows x 4 columns of doubles, this call consumes column vi, which is frequency v of the channel.
+// T holds 8 rows x 2 columns of doubles, this call consumes column vi (0 or 1), which is frequency v of the channel.
 // Results go to byte out0 + zigzag(u, v) of the W_PAR words.  Kept out of line and rolled: the kernel's hot code
 // has to stay well inside the instruction cache because the warps of an SM run desynchronised.
 __device__ __noinline__ unsigned col_pass(uint32_t *wl, uint32_t *wbase, int lane, int vi, int v, int W, int byte0, int out0,
@@ -206,7 +207,7 @@ __device__ __noinline__ unsigned col_pass(uint32_t *wl, uint32_t *wbase, int lan
     double s[4], d[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        const double a = ws_d(wbase, lane, j * 4 + vi), b = ws_d(wbase, lane, (7 - j) * 4 + vi);
+        const double a = ws_d(wbase, lane, j * 2 + vi), b = ws_d(wbase, lane, (7 - j) * 2 + vi);
         s[j] = a + b; // cos8[7-x][u] = (-1)^u cos8[x][u]
         d[j] = a - b;
     }
@@ -227,7 +228,8 @@ __device__ __noinline__ unsigned col_pass(uint32_t *wl, uint32_t *wbase, int lan
                 if (W == 8 && u == 0 && v == 0) t = __double2int_rn(qs * (1.0 / 1048576.0));
                 else t = W == 8 ? exact_quant_ws<8>(wl, byte0, u, v) : exact_quant_ws<4>(wl, byte0, u, v);
             }
-            wide |= (t < -128) | (t > 127);
+            // the DC may be any int8 (it gets a register-held table slot), the others have to fit the symbol table
+            wide |= (u == 0 && v == 0) ? ((t < -128) | (t > 127)) : ((t < SYM_MIN) | (t > SYM_MAX));
             ws_b(wl, W_PAR, out0 + (W == 8 ? kZZ8.pos[idx] : kZZ4.pos[idx])) = (uint8_t)t;
             if (co) co[idx] = (int16_t)t;
         }
@@ -236,18 +238,20 @@ __device__ __noinline__ unsigned col_pass(uint32_t *wl, uint32_t *wbase, int lan
 }
 
 // Luma: 8x8 DCT + quantise + zig-zag.  The 64 int8 results go to bytes [0, 64) of the W_PAR words (zig-zag order);
-// returns non-zero if some value is outside int8.
+// returns non-zero if some value does not fit the fast path.  Two output columns per pass: the row-pass results of
+// a pass (8 x 2 doubles) are all that fits beside the samples in the 81-word workspace.
 __device__ __forceinline__ unsigned dct_luma(uint32_t *wl, uint32_t *wbase, int lane, int16_t *co)
 {
     unsigned wide = 0;
 #pragma unroll 1
-    for (int par = 0; par < 2; ++par) { // even / odd output columns v = 2 vi + par
-        double c[4][4];
+    for (int pass = 0; pass < 4; ++pass) { // columns v = 2 vi + par, vi = 2 (pass >> 1) + {0, 1}, par = pass & 1
+        const int par = pass & 1, vi0 = 2 * (pass >> 1);
+        double c[2][4];
 #pragma unroll
-        for (int vi = 0; vi < 4; ++vi)
+        for (int q = 0; q < 2; ++q)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) c[vi][j] = kCos8[j * 8 + 2 * vi + par];
-        // row pass: T[x][vi] = sum_y corr[x][y] * cos8[y][v], using cos8[7-y][v] = (-1)^v cos8[y][v]
+            for (int j = 0; j < 4; ++j) c[q][j] = kCos8[j * 8 + 2 * (vi0 + q) + par];
+        // row pass: T[x][q] = sum_y corr[x][y] * cos8[y][v], using cos8[7-y][v] = (-1)^v cos8[y][v]
 #pragma unroll 1
         for (int x = 0; x < 8; ++x) {
             const uint32_t w0 = ws_w(wl, W_SMP + 2 * x), w1 = ws_w(wl, W_SMP + 2 * x + 1);
@@ -258,15 +262,15 @@ __device__ __forceinline__ unsigned dct_luma(uint32_t *wl, uint32_t *wbase, int 
                 e[j] = (double)(par == 0 ? a + b - 256 : a - b);
             }
 #pragma unroll
-            for (int vi = 0; vi < 4; ++vi) {
-                double acc = e[0] * c[vi][0];
+            for (int q = 0; q < 2; ++q) {
+                double acc = e[0] * c[q][0];
 #pragma unroll
-                for (int j = 1; j < 4; ++j) acc = fma(e[j], c[vi][j], acc);
-                ws_d(wbase, lane, x * 4 + vi) = acc;
+                for (int j = 1; j < 4; ++j) acc = fma(e[j], c[q][j], acc);
+                ws_d(wbase, lane, x * 2 + q) = acc;
             }
         }
 #pragma unroll 1
-        for (int vi = 0; vi < 4; ++vi) wide |= col_pass(wl, wbase, lane, vi, 2 * vi + par, 8, 0, 0, co);
+        for (int q = 0; q < 2; ++q) wide |= col_pass(wl, wbase, lane, q, 2 * (vi0 + q) + par, 8, 0, 0, co);
     }
     return wide;
 }
@@ -274,20 +278,21 @@ __device__ __forceinline__ unsigned dct_luma(uint32_t *wl, uint32_t *wbase, int 
 // Chroma: 8 rows x 4 columns; the 32 int8 results go to bytes [out0, out0 + 32) of the W_PAR words
 __device__ __forceinline__ unsigned dct_chroma(uint32_t *wl, uint32_t *wbase, int lane, int byte0, int out0, int16_t *co)
 {
-#pragma unroll 1
-    for (int x = 0; x < 8; ++x) {
-        const uint32_t w0 = ws_w(wl, W_SMP + (byte0 >> 2) + x);
-        const int c0 = w0 & 0xFF, c1 = (w0 >> 8) & 0xFF, c2 = (w0 >> 16) & 0xFF, c3 = w0 >> 24;
-        const double s0 = (double)(c0 + c3 - 256), s1 = (double)(c1 + c2 - 256), d0 = (double)(c0 - c3), d1 = (double)(c1 - c2);
-#pragma unroll
-        for (int v = 0; v < 4; ++v) {
-            const double a = (v & 1) ? d0 : s0, b = (v & 1) ? d1 : s1;
-            ws_d(wbase, lane, x * 4 + v) = fma(b, kCos4[1 * 4 + v], a * kCos4[0 * 4 + v]);
-        }
-    }
     unsigned wide = 0;
 #pragma unroll 1
-    for (int v = 0; v < 4; ++v) wide |= col_pass(wl, wbase, lane, v, v, 4, byte0, out0, co);
+    for (int half = 0; half < 2; ++half) { // columns v = 2 half + {0, 1}
+#pragma unroll 1
+        for (int x = 0; x < 8; ++x) {
+            const uint32_t w0 = ws_w(wl, W_SMP + (byte0 >> 2) + x);
+            const int c0 = w0 & 0xFF, c1 = (w0 >> 8) & 0xFF, c2 = (w0 >> 16) & 0xFF, c3 = w0 >> 24;
+            const double s0 = (double)(c0 + c3 - 256), s1 = (double)(c1 + c2 - 256), d0 = (double)(c0 - c3), d1 = (double)(c1 - c2);
+            // v even uses the sums, v odd the differences (cos4[3-y][v] = (-1)^v cos4[y][v])
+            ws_d(wbase, lane, x * 2 + 0) = fma(s1, kCos4[1 * 4 + 2 * half], s0 * kCos4[0 * 4 + 2 * half]);
+            ws_d(wbase, lane, x * 2 + 1) = fma(d1, kCos4[1 * 4 + 2 * half + 1], d0 * kCos4[0 * 4 + 2 * half + 1]);
+        }
+#pragma unroll 1
+        for (int q = 0; q < 2; ++q) wide |= col_pass(wl, wbase, lane, q, 2 * half + q, 4, byte0, out0, co);
+    }
     return wide;
 }
 
@@ -458,10 +463,12 @@ struct Ent {
     uint32_t epoch; // pre-shifted: epoch << 5
     uint32_t k;
     uint32_t over;
+    uint32_t dc_slot; // slot of a DC value outside the table range (it can only be the value of the channel's first run)
 };
+__device__ __forceinline__ bool in_table(int sym) { return (unsigned)(sym - SYM_MIN) <= (unsigned)(SYM_MAX - SYM_MIN); }
 __device__ __forceinline__ uint8_t *lut_addr(uint8_t *lb, int sym)
 {
-    const uint32_t idx = (uint32_t)(sym + 128);
+    const uint32_t idx = (uint32_t)(sym - SYM_MIN);
     return lb + ((idx & 0xFCu) << 5) + (idx & 3u); // word idx >> 2 of the lane, byte idx & 3
 }
 __device__ __forceinline__ void sym_count(Ent &E, int sym) // calculate_frequency, JPEG.c:864-885 (branch free)
@@ -482,10 +489,26 @@ __device__ __forceinline__ uint32_t sym_code(const Ent &E, int sym)
     const uint32_t slot = *lut_addr(E.lb, sym) & 31u;
     return *reinterpret_cast<const uint16_t *>(E.lb + (W_CNT * 128) + ((slot >> 1) << 7) + ((slot & 1u) << 1));
 }
+// one finished run (count, value) for calculate_frequency; `first` = it is the channel's first run
+__device__ __forceinline__ void pair_count(Ent &E, int c, int v, bool first)
+{
+    sym_count(E, c);
+    if (in_table(v)) {
+        sym_count(E, v);
+    } else if (first && E.k < (uint32_t)FAST_MAXSYM) { // the DC: a symbol of its own, next slot in first-appearance order
+        E.dc_slot = E.k;
+        *reinterpret_cast<uint32_t *>(E.lb + (W_CNT * 128) + E.k * 128) = 1u;
+        ++E.k;
+    } else {
+        E.over = 1;
+    }
+}
 // generate_encoded_sequence, JPEG.c:993-1007: the codes of one (count, value) pair, at most 12 + 12 bits
 __device__ __forceinline__ void pair_emit(const Ent &E, BitWriter &bw, int c, int v)
 {
-    const uint32_t cc = sym_code(E, c), cv = sym_code(E, v);
+    const uint32_t cc = sym_code(E, c);
+    const uint32_t cv = in_table(v) ? sym_code(E, v)
+                                    : *reinterpret_cast<const uint16_t *>(E.lb + (W_CNT * 128) + ((E.dc_slot >> 1) << 7) + ((E.dc_slot & 1u) << 1));
     const uint32_t lv = cv >> 12;
     bw.put(((cc & 0xFFFu) << lv) | (cv & 0xFFFu), (int)((cc >> 12) + lv));
 }
@@ -549,27 +572,28 @@ __device__ __forceinline__ int entropy_fast(uint32_t *wl, uint32_t epoch, const 
     E.epoch = epoch << 5;
     E.k = 0;
     E.over = 0;
+    E.dc_slot = 0;
     uint8_t *hb = E.lb + W_CNT * 128;
     const int n = 16 * nq;
     uint32_t w[4];
     // pass 1: RLE (JPEG.c:767-809) feeding the symbol table in first-appearance order
     window_load(w, cz, q0);
     int prev = (int)(int8_t)(w[0] & 0xFFu), run = 0;
+    bool first = true;
 #pragma unroll 1
     for (int i = 0; i < n; ++i) {
         if (i && (i & 15) == 0) window_load(w, cz, q0 + (i >> 4));
         const int v = window_pop(w);
         if (v != prev) {
-            sym_count(E, run);
-            sym_count(E, prev);
+            pair_count(E, run, prev, first);
+            first = false;
             prev = v;
             run = 1;
         } else {
             ++run;
         }
     }
-    sym_count(E, run);
-    sym_count(E, prev);
+    pair_count(E, run, prev, first);
     if (E.over) return -1;
     const uint32_t k = E.k;
     // the heap array in the reference's initial (first-appearance) order, in place over CNT: entry j sits in word
@@ -739,7 +763,7 @@ __global__ void __launch_bounds__(THREADS, 1) jpeg_encode_kernel(Params P)
             // The symbol table shares its words with the DCT's row-pass results: clear it once per group; the three
             // channels then tag their entries with epochs 1, 2, 3.
 #pragma unroll 8
-            for (int i = 0; i < 64; ++i) ws_w(wl, W_LUT + i) = 0;
+            for (int i = 0; i < W_CNT - W_LUT; ++i) ws_w(wl, W_LUT + i) = 0;
             BitWriter bw;
             bw.acc = 0;
             bw.nbits = 0;
