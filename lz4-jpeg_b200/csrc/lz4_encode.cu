@@ -357,8 +357,9 @@ __global__ void __launch_bounds__(THREADS, 1) lz4_encode_kernel(Params P)
                     __syncthreads();
                     const uint32_t A = 2654435761u + 0x9E3779B1u * (uint32_t)round * 2u;
                     const uint32_t B = 2246822519u + 0x85EBCA77u * (uint32_t)round * 2u;
-                    if (P.phase_cycles) {
-                        atomicAdd(&P.phase_cycles[21], (unsigned long long)__popcll(ins));
+                    if (P.phase_cycles) { // (one atomic per warp: per-thread atomics here tripled the ladder's time)
+                        const unsigned tot = __reduce_add_sync(0xffffffffu, (unsigned)__popcll(ins));
+                        if (lane == 0) atomicAdd(&P.phase_cycles[21], (unsigned long long)tot);
                         if (tid == 0) atomicAdd(&P.phase_cycles[22], 1ull);
                     }
                     for (unsigned long long m = ins; m;) {
@@ -460,6 +461,9 @@ __global__ void __launch_bounds__(THREADS, 1) lz4_encode_kernel(Params P)
                         const uint32_t lo = h ? dir16[h - 1] : 0u, hi = dir16[h];
                         const uint32_t cap16 = min(16u, nb - p);
                         const uint32_t pch = p >> 10;
+                        // a chain = consecutive flagged positions inside one 32-position chunk (B2's unit of sequential work)
+                        const bool chain_start = (p & 31u) == 0u || !((longbits[(p - 1) >> 5] >> ((p - 1) & 31)) & 1u);
+                        const uint32_t prev_byte = p ? data[p - 1] : 0u;
                         uint32_t best = 0, n16 = 0, cand = 0xFFFFFFFFu;
                         uint32_t c_next = lo < hi ? S[lo] : 0u;
                         for (uint32_t i = lo; i < hi; ++i) {
@@ -474,6 +478,9 @@ __global__ void __launch_bounds__(THREADS, 1) lz4_encode_kernel(Params P)
                                 const uint32_t ci = c >> 2, cs = (c & 3) * 8;
                                 const uint32_t a0 = dataw[ci], a1 = dataw[ci + 1], a2 = dataw[ci + 2];
                                 if (__funnelshift_r(a0, a1, cs) == P0 && __funnelshift_r(a1, a2, cs) == P1) {
+                                    // inside a chain B2 carries the pairs that continue a diagonal: only pairs that START one here
+                                    // (different byte in front, or nothing in front) are measured
+                                    if (!chain_start && c != 0u && data[c - 1] == prev_byte) continue;
                                     ++d_eq;
                                     const uint32_t a3 = dataw[ci + 3], a4 = dataw[ci + 4];
                                     const uint32_t x2 = __funnelshift_r(a2, a3, cs) ^ P2, x3 = __funnelshift_r(a3, a4, cs) ^ P3;
@@ -494,21 +501,32 @@ __global__ void __launch_bounds__(THREADS, 1) lz4_encode_kernel(Params P)
                             if (n16 > 2) cand = (cand & 0xFFFFu) | 0xFFFE0000u; // overflow: B2 walks the bucket itself
                             R[p] = cand; // provisional: the two candidates, in place of (length, position)
                         } else {
-                            R[p] = (bl << 16) | bp; // bl >= 8: the ladder proved an earlier occurrence of the 8-gram
+                            R[p] = best ? ((bl << 16) | bp) : 0u; // 0: no pair starts here (the match continues a diagonal)
                         }
                     }
                     if (P.phase_cycles) {
-                        atomicAdd(&P.phase_cycles[16], (unsigned long long)d_pos);
-                        atomicAdd(&P.phase_cycles[17], (unsigned long long)d_vis);
-                        atomicAdd(&P.phase_cycles[18], (unsigned long long)d_eq);
+                        const unsigned t_pos = __reduce_add_sync(0xffffffffu, d_pos), t_vis = __reduce_add_sync(0xffffffffu, d_vis);
+                        const unsigned t_eq = __reduce_add_sync(0xffffffffu, d_eq);
+                        if (lane == 0) {
+                            atomicAdd(&P.phase_cycles[16], (unsigned long long)t_pos);
+                            atomicAdd(&P.phase_cycles[17], (unsigned long long)t_vis);
+                            atomicAdd(&P.phase_cycles[18], (unsigned long long)t_eq);
+                        }
                         if (lane == 0) atomicAdd(&P.phase_cycles[19], (unsigned long long)(clock64() - tb1));
                         if (tid == 0) atomicAdd(&P.phase_cycles[20], (unsigned long long)nidx);
                     }
                 }
                 __syncthreads();
                 LJB_PHASE(1); // search phase B1
-                // ---- B2: very long matches, in position order.
-                // Each thread walks one 32-position chunk (one word of vlong) in position order and keeps
+                // ---- B2: every position with an >= 8 byte match, in position order.
+                // Lemma (order preservation): if (c, p) and (c', p) both match >= 9 bytes, then (c+1, p+1) and (c'+1, p+1)
+                // match one byte less each, so the best pair of p stays the best among all pairs that CONTINUE a diagonal
+                // into p+1.  A pair that starts a new diagonal at p+1 is "left-maximal" (data[c-1] != data[p], or c == 0),
+                // and only those were measured by B1 for positions inside a chain.  Hence
+                //     best(p+1) = better of { best(p) moved along its diagonal, B1's best over the left-maximal pairs of p+1 }.
+                // The lemma needs true lengths: pairs cut by the cap (1024 or the block end) tie there and may separate
+                // later, so ALL pairs that reach the cap are carried along (up to KEEP; beyond that, and whenever a bucket
+                // walk stopped early, the next position walks its bucket again).
                 constexpr int KEEP = 4;
                 constexpr uint32_t SHORT = 32; // a lane compares this much on its own; longer runs are compared by the whole warp
                 if (tid == 0) M.scan_tmp[0] = 0;
@@ -520,21 +538,21 @@ __global__ void __launch_bounds__(THREADS, 1) lz4_encode_kernel(Params P)
                     row = __shfl_sync(0xffffffffu, row, 0);
                     if (row >= nrows) break;
                     const uint32_t ch = row * 32 + lane;
-                    const uint32_t bits = (ch * 32 < nb) ? vlong[ch] : 0u;
-                    uint32_t pc[KEEP], pl[KEEP]; // candidates of the previous position: position, length | capped << 16
+                    const uint32_t bits = (ch * 32 < nb) ? longbits[ch] : 0u; // positions of this lane's chunk with an >= 8 byte match
+                    const uint32_t vbits = (ch * 32 < nb) ? vlong[ch] : 0u;   // ... whose record holds 16-byte candidates
+                    uint32_t pc[KEEP], pl[KEEP]; // pairs carried from the previous position: candidate position, length | capped << 16
                     uint32_t pn = 0;
-                    uint32_t dbg_pos = 0, dbg_vis = 0, dbg_scratch = 0, dbg_bytes = 0, dbg_inh = 0;
-                    long long tA = 0, tB = 0, tC = 0, tD = 0, tcur = clock64();
-                    const long long trow0 = tcur;
-#define LJB_T(acc) do { long long tn = clock64(); acc += tn - tcur; tcur = tn; } while (0)
+                    bool pinc = false;           // the carried set may be incomplete: walk the bucket
+                    uint32_t dbg_pos = 0, dbg_inh = 0, dbg_walk = 0;
+                    const long long trow0 = clock64();
                     // all lanes step through the 32 positions of their chunks together (warp-uniform control flow),
                     // so that long compares can be done by the whole warp
                     uint32_t steps = __reduce_or_sync(0xffffffffu, bits);
-                    // the candidates of the next three steps are in flight (L2 round trips) while this step is processed
+                    // the records of the next three steps are in flight (L2 round trips) while this step is processed
                     auto fetch = [&](uint32_t m) -> uint32_t {
-                        if (!m) return 0xFFFFFFFFu;
+                        if (!m) return 0u;
                         const int i = __ffs(m) - 1;
-                        return ((bits >> i) & 1u) ? R[ch * 32 + i] : 0xFFFFFFFFu;
+                        return ((bits >> i) & 1u) ? R[ch * 32 + i] : 0u;
                     };
                     uint32_t sl_a, sl_b, sl_c;
                     {
@@ -556,48 +574,69 @@ __global__ void __launch_bounds__(THREADS, 1) lz4_encode_kernel(Params P)
                         const bool active = (bits >> i) & 1u;
                         const uint32_t p = ch * 32 + i;
                         const bool chained = active && i > 0 && ((bits >> (i - 1)) & 1u);
-                        if (!chained) pn = 0;
-                        uint32_t cap = 0, P0 = 0, P1 = 0, bestkey = 0;
-                        bool overflow = false;
+                        if (!chained) {
+                            pn = 0;
+                            pinc = false;
+                        }
+                        uint32_t cap = 0, P0 = 0, P1 = 0;
                         if (active) {
                             ++dbg_pos;
                             cap = min((uint32_t)MAX_MATCH, nb - p);
                             P0 = load32u(dataw, p);
                             P1 = load32u(dataw, p + 4);
-                            overflow = (sl >> 16) == 0xFFFEu;
                         }
+                        const bool isv = active && ((vbits >> i) & 1u);
+                        bool walk = active && (pinc || (isv && (sl >> 16) == 0xFFFEu));
+                        // this position's pairs: the capped ones (all of them matter later) and the best uncapped one
                         uint32_t nc[KEEP], nl[KEEP], nn = 0;
-                        if (__shfl_sync(0xffffffffu, sl, 0) == 0x12345u) tA += 1; // keep the loads before the timer
-                        LJB_T(tA);
-                        // the (at most 2) candidates B1 found with >= 16 matching bytes: measure each, reusing the
-                        // previous position's result when the pair continues that diagonal
+                        uint32_t bestkey = 0; // (length << 16) | (0xFFFF - position): longest, then earliest
+                        bool ninc = false;
+                        auto take = [&](uint32_t l, uint32_t c) {
+                            bestkey = max(bestkey, (l << 16) | (0xFFFFu - c));
+                            if (l == cap) {
+                                if (nn < KEEP) {
+#pragma unroll
+                                    for (int u = 0; u < KEEP; ++u)
+                                        if ((uint32_t)u == nn) {
+                                            nc[u] = c;
+                                            nl[u] = l | 0x10000u;
+                                        }
+                                    ++nn;
+                                } else {
+                                    ninc = true;
+                                }
+                            }
+                        };
+                        // 1. pairs carried along their diagonals
+#pragma unroll
+                        for (int t = 0; t < KEEP; ++t) {
+                            if (active && (uint32_t)t < pn) {
+                                const uint32_t c = pc[t] + 1;
+                                uint32_t l = (pl[t] & 0xFFFF) - 1;
+                                if (pl[t] >> 16) // the length was cut by the cap, not by a mismatch: it may go on
+                                    while (l < cap && data[c + l] == data[p + l]) ++l;
+                                l = min(l, cap);
+                                pc[t] = c; // now this position's candidate (duplicate test below)
+                                take(l, c);
+                                ++dbg_inh;
+                            }
+                        }
+                        // 2. what B1 measured: either the best pair below 16 bytes, or up to two 16-byte candidates
+                        if (active && !isv && sl != 0u && !walk) take(sl >> 16, sl & 0xFFFFu);
 #pragma unroll
                         for (int q = 0; q < 2; ++q) {
                             const uint32_t c = (sl >> (q * 16)) & 0xFFFFu;
-                            const bool eval = active && !overflow && c != 0xFFFFu && (bestkey >> 16) != (uint32_t)MAX_MATCH;
-                            uint32_t l = 0xFFFFFFFFu;
-                            bool fresh = false;
-                            if (eval) {
-#pragma unroll
-                                for (int t = 0; t < KEEP; ++t) {
-                                    if ((uint32_t)t < pn && pc[t] + 1 == c) {
-                                        l = (pl[t] & 0xFFFF) - 1;
-                                        if (pl[t] >> 16) // previous length was cut by the cap, not by a mismatch: it may go on
-                                            while (l < cap && data[c + l] == data[p + l]) ++l;
-                                        l = min(l, cap);
-                                        ++dbg_inh;
-                                    }
-                                }
-                                if (l == 0xFFFFFFFFu) {
-                                    l = lcp_from(dataw, c, p, P0, P1, min(cap, SHORT));
-                                    fresh = true;
-                                    ++dbg_scratch;
-                                }
+                            bool eval = isv && !walk && c != 0xFFFFu;
+                            if (eval && (bestkey >> 16) == (uint32_t)MAX_MATCH) { // a carried pair already gives 1024: not measured now,
+                                eval = false;                                     // but it may be the one that lasts longest
+                                ninc = true;
                             }
+#pragma unroll
+                            for (int t = 0; t < KEEP; ++t) eval = eval && !((uint32_t)t < pn && pc[t] == c); // already carried
+                            uint32_t l = 0;
+                            if (eval) l = lcp_from(dataw, c, p, P0, P1, min(cap, SHORT));
                             // runs that are still matching after SHORT bytes: the warp compares 256 bytes per step
-                            LJB_T(tB);
-                            // (inherited lengths are exact or already extended; only from-scratch results can be cut at SHORT)
-                            unsigned pend = __ballot_sync(0xffffffffu, fresh && l == SHORT && cap > SHORT);
+                            unsigned pend = __ballot_sync(0xffffffffu, eval && l == SHORT && cap > SHORT);
                             while (pend) {
                                 const int src = __ffs(pend) - 1;
                                 pend &= pend - 1;
@@ -623,110 +662,77 @@ __global__ void __launch_bounds__(THREADS, 1) lz4_encode_kernel(Params P)
                                         break;
                                     }
                                 }
-                                if (lane == src) {
-                                    l = res;
-                                    dbg_bytes += res;
-                                }
+                                if (lane == src) l = res;
                             }
-                            LJB_T(tC);
-                            if (eval) {
-                                bestkey = max(bestkey, (l << 16) | (0xFFFFu - c));
-#pragma unroll
-                                for (int u = 0; u < KEEP; ++u)
-                                    if ((uint32_t)u == nn) {
-                                        nc[u] = c;
-                                        nl[u] = l | ((l == cap) ? 0x10000u : 0u);
-                                    }
-                                ++nn;
-                            }
+                            if (eval) take(l, c);
                         }
-                        LJB_T(tB);
-                        if (active && overflow) {
-                            // more than 4 long candidates (highly repetitive data): walk the bucket with pruning
-                            // 1. candidates inherited along the diagonals of the previous position's long matches
-#pragma unroll
-                            for (int t = 0; t < KEEP; ++t) {
-                                if ((uint32_t)t < pn) {
-                                    const uint32_t c = pc[t] + 1;
-                                    uint32_t l = (pl[t] & 0xFFFF) - 1;
-                                    if (pl[t] >> 16)
-                                        while (l < cap && data[c + l] == data[p + l]) ++l;
-                                    l = min(l, cap);
-                                    bestkey = max(bestkey, (l << 16) | (0xFFFFu - c));
-                                    pc[t] = c; // now holds this position's candidate (used for the duplicate test below)
-                                    if (l >= 16) {
-#pragma unroll
-                                        for (int u = 0; u < KEEP; ++u)
-                                            if ((uint32_t)u == nn) {
-                                                nc[u] = c;
-                                                nl[u] = l | ((l == cap) ? 0x10000u : 0u);
-                                            }
-                                        ++nn;
-                                    }
-                                }
-                            }
-                            // 2. the rest of the bucket; a capped 1024 match becomes a literal step ((uint8_t)1024 == 0,
-                            //    LZ4.c:317) whose distance is never used, so nothing else needs to be looked at
-                            if ((bestkey >> 16) != (uint32_t)MAX_MATCH) {
+                        // 3. too many candidates, or an incomplete carried set: walk the bucket with pruning.  A capped 1024
+                        //    match becomes a literal step ((uint8_t)1024 == 0, LZ4.c:317) whose distance is never used, so
+                        //    then nothing else needs to be looked at here (but the set stays marked incomplete).
+                        if (walk) {
+                            ++dbg_walk;
+                            if ((bestkey >> 16) == (uint32_t)MAX_MATCH) {
+                                ninc = true;
+                            } else {
                                 const uint32_t h = hash8(P0, P1);
                                 const uint32_t lo = h ? dir16[h - 1] : 0u, hi = dir16[h];
                                 const uint32_t pch = p >> 10;
                                 for (uint32_t k = lo; k < hi; ++k) {
                                     const uint32_t c = S[k];
                                     if ((c >> 10) > pch) break; // only later positions from here on
-                                    ++dbg_vis;
                                     if (c >= p) continue;
                                     const uint32_t bl = bestkey >> 16, bp = 0xFFFFu - (bestkey & 0xFFFFu);
-                                    if (bl == cap && (c >> 10) > (bp >> 10)) break; // later positions cannot win a tie
+                                    if (bl == cap && (c >> 10) > (bp >> 10)) { // later positions cannot win a tie ...
+                                        ninc = true;                            // ... but may reach the cap as well
+                                        break;
+                                    }
                                     // a candidate matters only if it beats the best length, or ties it from an earlier position
-                                    const uint32_t need = bl < 16 ? 16u : (c < bp ? bl : bl + 1); // B1 proved a 16-byte match exists
+                                    const uint32_t need = max(8u, bl == 0 ? 8u : (c < bp ? bl : bl + 1));
                                     if (need > cap) continue;
                                     bool dup = false;
 #pragma unroll
                                     for (int t = 0; t < KEEP; ++t) dup |= ((uint32_t)t < pn && pc[t] == c);
-                                    if (dup) continue; // already evaluated as an inherited candidate
+                                    if (dup) continue; // already measured as a carried pair
                                     if (data[c + need - 1] != data[p + need - 1]) continue;
                                     const uint32_t l = lcp_from(dataw, c, p, P0, P1, cap);
-                                    if (l < 16) continue; // cannot be the answer: a 16-byte match exists
-                                    bestkey = max(bestkey, (l << 16) | (0xFFFFu - c));
-                                    if (nn < KEEP) {
-#pragma unroll
-                                        for (int u = 0; u < KEEP; ++u)
-                                            if ((uint32_t)u == nn) {
-                                                nc[u] = c;
-                                                nl[u] = l | ((l == cap) ? 0x10000u : 0u);
-                                            }
-                                        ++nn;
+                                    if (l < 8) continue; // a different 8-gram in the same bucket
+                                    take(l, c);
+                                    if (l == (uint32_t)MAX_MATCH) {
+                                        ninc = true;
+                                        break;
                                     }
-                                    if (l == (uint32_t)MAX_MATCH) break;
                                 }
                             }
                         }
-                        LJB_T(tD);
                         if (active) {
-#pragma unroll
-                            for (int t = 0; t < KEEP; ++t) {
-                                pc[t] = nc[t];
-                                pl[t] = nl[t];
-                            }
-                            pn = nn;
                             const uint32_t bl = bestkey >> 16, bp = 0xFFFFu - (bestkey & 0xFFFFu);
-                            R[p] = (bl << 16) | bp; // bl >= 16 here
+                            R[p] = (bl << 16) | bp;
+                            if (bl == cap) { // carry every pair that reached the cap
+#pragma unroll
+                                for (int t = 0; t < KEEP; ++t) {
+                                    pc[t] = nc[t];
+                                    pl[t] = nl[t];
+                                }
+                                pn = nn;
+                            } else { // carry the best pair only (order preservation)
+                                pc[0] = bp;
+                                pl[0] = bl;
+                                pn = bl >= 9 ? 1u : 0u;
+                                ninc = false; // pairs below the best never matter again
+                            }
+                            pinc = ninc;
                         }
                     }
                     if (P.phase_cycles) {
-                        atomicAdd(&P.phase_cycles[9], (unsigned long long)dbg_pos);
-                        (void)dbg_vis; (void)dbg_scratch; (void)dbg_bytes;
-                        atomicAdd(&P.phase_cycles[13], (unsigned long long)dbg_inh);
+                        const unsigned t_pos = __reduce_add_sync(0xffffffffu, dbg_pos), t_inh = __reduce_add_sync(0xffffffffu, dbg_inh);
+                        const unsigned t_walk = __reduce_add_sync(0xffffffffu, dbg_walk);
                         if (lane == 0) {
+                            atomicAdd(&P.phase_cycles[9], (unsigned long long)t_pos);
+                            atomicAdd(&P.phase_cycles[13], (unsigned long long)t_inh);
+                            atomicAdd(&P.phase_cycles[12], (unsigned long long)t_walk);
                             atomicAdd(&P.phase_cycles[14], (unsigned long long)(clock64() - trow0));
-                            atomicAdd(&P.phase_cycles[15], (unsigned long long)tA);
-                            atomicAdd(&P.phase_cycles[10], (unsigned long long)tB);
-                            atomicAdd(&P.phase_cycles[11], (unsigned long long)tC);
-                            atomicAdd(&P.phase_cycles[12], (unsigned long long)tD);
                         }
                     }
-#undef LJB_T
                 }
             }
         }
@@ -1040,8 +1046,8 @@ static int lz4_launch(ljb_ctx *ctx, const uint8_t *d_in, size_t n, size_t block_
         fprintf(stderr, "[ljb lz4 phaseB1] per block: indexed=%.0f positions=%.0f visited=%.0f equal8=%.0f warp-cycles=%.0f | ladder: inserts=%.0f rounds=%.1f\n",
                 (double)ph[20] / nblocks, (double)ph[16] / nblocks, (double)ph[17] / nblocks, (double)ph[18] / nblocks, (double)ph[19] / nblocks,
                 (double)ph[21] / nblocks, (double)ph[22] / nblocks);
-        fprintf(stderr, "[ljb lz4 phaseB2] per block: positions=%.0f inherited=%.0f | warp-cycles: rows=%.0f load=%.0f eval=%.0f coop=%.0f fallback=%.0f\n",
-                (double)ph[9] / nblocks, (double)ph[13] / nblocks, (double)ph[14] / nblocks, (double)ph[15] / nblocks, (double)ph[10] / nblocks, (double)ph[11] / nblocks, (double)ph[12] / nblocks);
+        fprintf(stderr, "[ljb lz4 phaseB2] per block: positions=%.0f carried=%.0f bucket walks=%.0f | warp-cycles in rows=%.0f\n",
+                (double)ph[9] / nblocks, (double)ph[13] / nblocks, (double)ph[12] / nblocks, (double)ph[14] / nblocks);
     }
     return LJB_OK;
 }
