@@ -146,6 +146,33 @@ int ljb_jpeg_decode_coefs_dev(ljb_ctx *ctx, const int16_t *d_coefs, int w, int h
                               size_t orig_stride, uint8_t *d_out_rgba, size_t out_stride, uint64_t *d_result);
 
 /* ------------------------------------------------------------------------------------------------
+ * Baseline JPEG / JFIF
+ *
+ * ljb_jfif_encode replaces stbi_write_jpg_to_func / stbi_write_jpg_core of the stb_image_write.h the reference
+ * vendors (Algorithms/sequential/JPEG/stb_image_write.h:1607, :1398-1605; the reference programs never call it):
+ * a complete .jpg file — SOI, JFIF APP0, DQT, SOF0, DHT, SOS, entropy-coded segment with 0xFF stuffing, EOI —
+ * byte-identical to what stb writes for the same pixels and quality.
+ *
+ *   pixels, w, h, comp, stride  8-bit samples, comp = 1 (grey), 2 (grey + alpha), 3 (RGB) or 4 (RGBA), as stb's
+ *                       `comp`; stride is the row pitch in bytes (stb: w * comp)
+ *   quality             1..100, 0 = 90 (stb_image_write.h:1479)
+ *   subsample           -1 = stb's rule: 4:2:0 (16x16 MCUs) when quality <= 90, else 4:4:4 (:1480);
+ *                       0 / 1 force 4:4:4 / 4:2:0 (BASELINE.json words its workload as "quality 75, 4:4:4")
+ *   out, out_cap        receives the file; ljb_jfif_bound(w, h) is always enough, far less usually is
+ *   out_len             receives the file length (on LJB_E_CAPACITY: a lower bound of the size needed)
+ * ------------------------------------------------------------------------------------------------ */
+size_t ljb_jfif_bound(int w, int h);
+
+int ljb_jfif_encode(ljb_ctx *ctx, const uint8_t *pixels, int w, int h, int comp, size_t stride, int quality, int subsample,
+                    uint8_t *out, size_t out_cap, size_t *out_len);
+
+/* Device-resident form, asynchronous on the context stream.  d_result: 3 device uint64: [0] file length,
+ * [1] unused, [2] error flags (bit0 = out_cap exceeded, bit1 = internal scratch exceeded — both mean a larger
+ * out_cap is needed).  d_coefs (optional, for tests): 64 int16 per data unit in stream order, zig-zag order. */
+int ljb_jfif_encode_dev(ljb_ctx *ctx, const uint8_t *d_pixels, int w, int h, int comp, size_t stride, int quality,
+                        int subsample, uint8_t *d_out, size_t out_cap, uint64_t *d_result, int16_t *d_coefs);
+
+/* ------------------------------------------------------------------------------------------------
  * Workload generators (host code): the reference's Experiment/random_extract.c:8-71 and
  * Experiment/random_image.c:58-77 with an explicit seed (the reference uses time() / unseeded rand()).
  * ------------------------------------------------------------------------------------------------ */

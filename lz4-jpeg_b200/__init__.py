@@ -8,7 +8,8 @@ from . import _native  # noqa: F401
 from ._native import Context, LjbError, default_context  # noqa: F401
 from . import lz4  # noqa: F401
 from . import jpeg  # noqa: F401
+from . import jfif  # noqa: F401
 from . import synth  # noqa: F401
 from . import sharding  # noqa: F401
 
-__all__ = ["Context", "LjbError", "default_context", "lz4", "jpeg", "synth", "sharding"]
+__all__ = ["Context", "LjbError", "default_context", "lz4", "jpeg", "jfif", "synth", "sharding"]

@@ -45,6 +45,11 @@ SIGNATURES = {
     "ljb_jpeg_decode_coefs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]),
     "ljb_jpeg_decode_coefs_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p,
                                             C.c_size_t, C.c_void_p]),
+    "ljb_jfif_bound": (C.c_size_t, [C.c_int, C.c_int]),
+    "ljb_jfif_encode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_int, C.c_void_p,
+                                  C.c_size_t, _szp]),
+    "ljb_jfif_encode_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_int, C.c_void_p,
+                                      C.c_size_t, C.c_void_p, C.c_void_p]),
     "ljb_synth_text": (None, [C.c_void_p, C.c_size_t, C.c_uint64, C.c_size_t, C.c_void_p, C.c_size_t]),
     "ljb_synth_image": (None, [C.c_uint64, C.c_int, C.c_int, C.c_void_p]),
 }

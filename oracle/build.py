@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """oracle/build.py — build the CPU checkers (TEST INFRASTRUCTURE, not product code).
 
-* ``oracle/liboracle.so``      : this repo's C restatement (lz4_oracle.c + jpeg_oracle.c).
+* ``oracle/liboracle.so``      : this repo's C restatement (lz4_oracle.c + jpeg_oracle.c + jfif_oracle.c).
 * ``oracle/_ref/libref_*.so``  : the REFERENCE's own C sources, compiled from where they lie under
   /root/reference (never copied into the repo), with ref_glue_*.c as a buffer-level driver.
   Built only where /root/reference exists (this container); the GPU box uses the prebuilt files
@@ -12,6 +12,10 @@ Variants of the reference LZ4 build:
                           past the block: undefined behaviour).
   libref_lz4.so           "bounded" parity target: three textual edits applied to a temporary copy
                           (deleted after compilation) that stop the extension at the block end.
+
+The reference's vendored baseline-JPEG writer (stb_image_write.h, never called by the reference programs):
+  libref_jfif.so          stbi_write_jpg_to_func, compiled from a temporary copy of the header in which the
+                          chroma-subsampling rule (`quality <= 90`) reads an override first (default: stb's rule).
 
 Flags follow SURVEY.md Appendix E: gcc -O2 -ffp-contract=off, x86-64 SSE2, no -march=native.
 """
@@ -45,7 +49,7 @@ def _newer(target: str, sources: list[str]) -> bool:
 
 def build_restatement(force: bool = False) -> str:
     out = os.path.join(HERE, "liboracle.so")
-    srcs = [os.path.join(HERE, "lz4_oracle.c"), os.path.join(HERE, "jpeg_oracle.c")]
+    srcs = [os.path.join(HERE, "lz4_oracle.c"), os.path.join(HERE, "jpeg_oracle.c"), os.path.join(HERE, "jfif_oracle.c")]
     if force or not _newer(out, srcs + [os.path.abspath(__file__)]):
         _run(["gcc", *CFLAGS, "-Wall", "-o", out, *srcs, "-lm"])
     return out
@@ -65,12 +69,21 @@ def _patch_bounded(src_text: str) -> str:
     return src_text
 
 
+def _patch_subsample(src_text: str) -> str:
+    """One edit: let the caller force 4:4:4 or 4:2:0 (BASELINE.json's "quality 75, 4:4:4"); -1 keeps stb's rule."""
+    a = "subsample = quality <= 90 ? 1 : 0;"
+    if src_text.count(a) != 1:
+        raise RuntimeError(f"reference stb_image_write.h changed: anchor not unique: {a!r}")
+    return src_text.replace(a, "subsample = ljb_force_subsample >= 0 ? (ljb_force_subsample != 0) : (quality <= 90 ? 1 : 0);")
+
+
 def build_reference(force: bool = False) -> dict[str, str]:
     """Compile the reference where it lies; returns {name: path} of what exists afterwards."""
     names = {
         "lz4": os.path.join(REF_OUT, "libref_lz4.so"),
         "lz4_verbatim": os.path.join(REF_OUT, "libref_lz4_verbatim.so"),
         "jpeg": os.path.join(REF_OUT, "libref_jpeg.so"),
+        "jfif": os.path.join(REF_OUT, "libref_jfif.so"),
     }
     lz4_src = os.path.join(REF, "Algorithms/sequential/LZ4/LZ4.c")
     jpg_dir = os.path.join(REF, "Algorithms/sequential/JPEG")
@@ -97,6 +110,19 @@ def build_reference(force: bool = False) -> dict[str, str]:
             shutil.rmtree(tmp, ignore_errors=True)
     if force or not _newer(names["jpeg"], [glue_jpg, jpg_src, me]):
         _run(["gcc", *CFLAGS, f"-I{jpg_dir}", f'-DREF_SRC="{jpg_src}"', "-o", names["jpeg"], glue_jpg, "-lm", "-lpthread"])
+    stbw = os.path.join(jpg_dir, "stb_image_write.h")
+    glue_jfif = os.path.join(HERE, "ref_glue_jfif.c")
+    if os.path.exists(stbw) and (force or not _newer(names["jfif"], [glue_jfif, stbw, me])):
+        tmp = tempfile.mkdtemp(prefix="ljb_ref_")
+        try:
+            patched = os.path.join(tmp, "stbw_subsample.h")
+            with open(stbw, "r", encoding="latin-1") as f:
+                text = f.read()
+            with open(patched, "w", encoding="latin-1") as f:
+                f.write(_patch_subsample(text))
+            _run(["gcc", *CFLAGS, f'-DREF_STBW="{patched}"', "-o", names["jfif"], glue_jfif, "-lm", "-lpthread"])
+        finally:
+            shutil.rmtree(tmp, ignore_errors=True)
     return {k: v for k, v in names.items() if os.path.exists(v)}
 
 

@@ -82,6 +82,10 @@ class Oracle(_LZ4Mixin):
         L.oracle_synth_image.restype = None
         L.oracle_jpeg_planes.restype = None
         L.oracle_jpeg_basis.restype = None
+        L.oracle_jfif_encode.restype = C.c_int
+        L.oracle_jfif_unit_count.restype = C.c_size_t
+        L.oracle_jfif_tables.restype = None
+        L.oracle_jfif_huffman.restype = None
 
     # ---- LZ4 -------------------------------------------------------------------------------
     def lz4_matches(self, block, mode: int = 0):
@@ -130,6 +134,37 @@ class Oracle(_LZ4Mixin):
         """Quantised coefficients -> reconstructed RGBA (Inverse_quantize, IDCT, assemble_image)."""
         return _jpeg_decode(self.lib.oracle_jpeg_decode, coefs, w, h, orig)
 
+    # ---- baseline JFIF (stb_image_write's encoder) -------------------------------------------
+    def jfif_encode(self, px: np.ndarray, quality: int, force_subsample: int = -1, want_coefs: bool = False):
+        """px: H x W (grey), H x W x 2/3/4 uint8.  Returns the .jpg bytes (and the quantised data units, zig-zag order)."""
+        a, h, w, comp = _check_pixels(px)
+        cap = jfif_bound(w, h)
+        out = np.empty(cap, dtype=np.uint8)
+        n = C.c_size_t(0)
+        units = int(self.lib.oracle_jfif_unit_count(C.c_int(w), C.c_int(h), C.c_int(quality), C.c_int(force_subsample)))
+        coefs = np.zeros((units, 64), dtype=np.int16) if want_coefs else None
+        rc = self.lib.oracle_jfif_encode(_p(a), C.c_int(w), C.c_int(h), C.c_int(comp), C.c_size_t(w * comp), C.c_int(quality),
+                                         C.c_int(force_subsample), _p(out), C.c_size_t(cap), C.byref(n),
+                                         _p(coefs, C.c_int16) if want_coefs else None)
+        if rc != 0:
+            raise RuntimeError(f"oracle_jfif_encode rc={rc}")
+        return (out[: n.value].copy(), coefs) if want_coefs else out[: n.value].copy()
+
+    def jfif_tables(self, quality: int):
+        qy = np.zeros(64, np.uint8)
+        quv = np.zeros(64, np.uint8)
+        dy = np.zeros(64, np.float32)
+        duv = np.zeros(64, np.float32)
+        rank = np.zeros(64, np.uint8)
+        self.lib.oracle_jfif_tables(C.c_int(quality), _p(qy), _p(quv), _p(dy, C.c_float), _p(duv, C.c_float), _p(rank))
+        return qy, quv, dy, duv, rank
+
+    def jfif_huffman(self, which: int):
+        code = np.zeros(256, np.uint16)
+        ln = np.zeros(256, np.uint8)
+        self.lib.oracle_jfif_huffman(C.c_int(which), _p(code, C.c_uint16), _p(ln))
+        return code, ln
+
     def jpeg_basis(self):
         cos8 = np.zeros(64)
         cos4 = np.zeros(16)
@@ -137,6 +172,20 @@ class Oracle(_LZ4Mixin):
         a4 = np.zeros(2)
         self.lib.oracle_jpeg_basis(_p(cos8, C.c_double), _p(cos4, C.c_double), _p(a8, C.c_double), _p(a4, C.c_double))
         return cos8, cos4, a8, a4
+
+
+def jfif_bound(w: int, h: int) -> int:
+    """Worst case of the baseline stream: 27 bits per coefficient, every byte stuffed, three full-size components."""
+    units = ((w + 7) // 8) * ((h + 7) // 8) * 3
+    return 607 + 2 + units * 64 * 27 // 8 * 2 + 64
+
+
+def _check_pixels(px: np.ndarray):
+    a = np.ascontiguousarray(px, dtype=np.uint8)
+    if a.ndim == 2:
+        a = a[:, :, None]
+    assert a.ndim == 3 and 1 <= a.shape[2] <= 4, "expect H x W [x comp] uint8"
+    return a, a.shape[0], a.shape[1], a.shape[2]
 
 
 def _check_rgba(rgba: np.ndarray) -> np.ndarray:
@@ -213,7 +262,8 @@ class Ref(_LZ4Mixin):
     def paths() -> dict[str, str]:
         d = os.path.join(HERE, "_ref")
         return {k: os.path.join(d, f) for k, f in
-                (("lz4", "libref_lz4.so"), ("lz4_verbatim", "libref_lz4_verbatim.so"), ("jpeg", "libref_jpeg.so"))}
+                (("lz4", "libref_lz4.so"), ("lz4_verbatim", "libref_lz4_verbatim.so"), ("jpeg", "libref_jpeg.so"),
+                 ("jfif", "libref_jfif.so"))}
 
     @staticmethod
     def available(which: str = "lz4") -> bool:
@@ -225,6 +275,9 @@ class Ref(_LZ4Mixin):
         if which.startswith("lz4"):
             self.lib.ref_lz4_compress.restype = C.c_int
             self.lib.ref_lz4_time_blocks.restype = C.c_int
+        elif which == "jfif":
+            self.lib.ref_jfif_encode.restype = C.c_int
+            self.lib.ref_jfif_time_mt.restype = C.c_double
         else:
             self.lib.ref_jpeg_encode.restype = C.c_int
             self.lib.ref_jpeg_planes.restype = C.c_int
@@ -238,6 +291,25 @@ class Ref(_LZ4Mixin):
         nb = C.c_uint64(0)
         self.lib.ref_lz4_time_blocks(_p(a), C.c_size_t(a.size), C.c_size_t(block_len), C.c_int(nthreads), C.byref(sec), C.byref(nb))
         return sec.value, int(nb.value)
+
+    def jfif_encode(self, px: np.ndarray, quality: int, force_subsample: int = -1) -> np.ndarray:
+        """stbi_write_jpg_to_func of the reference's vendored stb_image_write.h on tightly packed pixels."""
+        a, h, w, comp = _check_pixels(px)
+        cap = jfif_bound(w, h)
+        out = np.empty(cap, dtype=np.uint8)
+        n = C.c_size_t(0)
+        rc = self.lib.ref_jfif_encode(_p(a), C.c_int(w), C.c_int(h), C.c_int(comp), C.c_int(quality), C.c_int(force_subsample),
+                                      _p(out), C.c_size_t(cap), C.byref(n))
+        if rc != 0:
+            raise RuntimeError(f"ref_jfif_encode rc={rc}")
+        return out[: n.value].copy()
+
+    def jfif_time_mt(self, px: np.ndarray, quality: int, force_subsample: int, nthreads: int, reps: int = 1):
+        a, h, w, comp = _check_pixels(px)
+        nb = C.c_size_t(0)
+        sec = self.lib.ref_jfif_time_mt(_p(a), C.c_int(w), C.c_int(h), C.c_int(comp), C.c_int(quality), C.c_int(force_subsample),
+                                        C.c_int(nthreads), C.c_int(reps), C.byref(nb))
+        return float(sec), int(nb.value)
 
     def jpeg_planes(self, rgba):
         return _jpeg_planes(self.lib.ref_jpeg_planes, rgba)

@@ -155,3 +155,51 @@ def jpeg_cases():
     g128[..., :3] = 128
     out.append(("grey128_8x8", g128[:8, :8]))
     return out
+
+
+def jfif_cases():
+    """Yields (name, pixels uint8[h,w(,comp)], quality, subsample) for the baseline-JPEG writer (stb_image_write.h:1398).
+    subsample: -1 = stb's own rule (4:2:0 when quality <= 90), 0 / 1 = forced 4:4:4 / 4:2:0."""
+    rng = np.random.default_rng(2024)
+    out = []
+    crop = og_crop()  # 256 x 100: the height is not a multiple of 8 or 16 (edge MCUs repeat the last row)
+    out.append(("og_crop_q75", crop, 75, -1))
+    out.append(("og_crop_q75_444", crop, 75, 0))
+    out.append(("og_crop_q95", crop, 95, -1))
+    out.append(("og_crop_rgb_q50", crop[:, :, :3].copy(), 50, -1))
+    out.append(("og_crop_q0_default", crop, 0, -1))
+    out.append(("noise_64x48_q75", synth_image(42, 64, 48), 75, -1))
+    out.append(("noise_64x48_q75_444", synth_image(42, 64, 48), 75, 0))
+    out.append(("noise_160x96_q100", synth_image(3, 160, 96), 100, -1))       # longest codes, 4:4:4 by stb's rule
+    out.append(("noise_160x96_q100_420", synth_image(3, 160, 96), 100, 1))
+    out.append(("noise_96x80_q1", synth_image(4, 96, 80), 1, -1))             # quantisers clamp to 255: runs of zeros, ZRL
+    out.append(("noise_33x70_q90", synth_image(5, 33, 70), 90, -1))           # ragged in both directions
+    out.append(("noise_17x23_rgb_q91", synth_image(6, 17, 23)[:, :, :3].copy(), 91, -1))
+    out.append(("noise_1x1_q75", synth_image(8, 1, 1), 75, -1))
+    out.append(("noise_1x1_q95", synth_image(8, 1, 1), 95, -1))
+    out.append(("noise_8x8_q75_444", synth_image(9, 8, 8), 75, 0))
+    out.append(("noise_16x16_q75", synth_image(10, 16, 16), 75, -1))
+    out.append(("noise_400x8_q75", synth_image(11, 400, 8), 75, -1))          # one MCU row, several rounds
+    out.append(("noise_8x400_q75_444", synth_image(12, 8, 400), 75, 0))      # one MCU column
+    out.append(("grey_100x37_q80", rng.integers(0, 256, size=(37, 100), dtype=np.uint8), 80, -1))       # comp 1
+    out.append(("greyalpha_64x48_q60", rng.integers(0, 256, size=(48, 64, 2), dtype=np.uint8), 60, -1))  # comp 2: alpha ignored
+    yy, xx = np.mgrid[0:200, 0:300]
+    grad = np.stack([(xx * 255) // 300, (yy * 255) // 200, (xx + yy) % 256, np.full_like(xx, 255)], axis=2).astype(np.uint8)
+    out.append(("gradient_300x200_q30", grad, 30, -1))
+    out.append(("gradient_300x200_q75", grad, 75, -1))
+    out.append(("gradient_300x200_q95", grad, 95, -1))
+    flat = np.zeros((64, 64, 4), np.uint8)
+    flat[..., 3] = 255
+    out.append(("black_64x64_q75", flat.copy(), 75, -1))
+    w = flat.copy()
+    w[..., :3] = 255
+    out.append(("white_64x64_q75_444", w, 75, 0))
+    sparse = flat.copy()
+    sparse[::16, ::16, :3] = 255   # isolated bright pixels: long zero runs between a few large coefficients
+    out.append(("sparse_64x64_q50", sparse, 50, -1))
+    chk = flat.copy()
+    chk[(np.indices((64, 64)).sum(0) & 1) == 1, :3] = 255  # checkerboard: extreme high-frequency coefficient
+    out.append(("checker_64x64_q100", chk, 100, -1))
+    out.append(("noise_640x360_q75", synth_image(13, 640, 360), 75, -1))      # many tiles, ragged bottom (360 = 22.5 MCUs)
+    out.append(("noise_640x360_q75_444", synth_image(13, 640, 360), 75, 0))
+    return out
