@@ -6,19 +6,22 @@
 // round-to-nearest mul/add, never fused), same Annex-K Huffman codes, one continuous bit stream with 0xFF stuffing.
 //
 // The sequential program is one bit stream whose every data unit depends on its predecessor twice (DC prediction,
-// bit position).  Here it is three kernels on one stream:
+// bit position).  Here it is two kernels on one stream:
 //
-//   jfif_encode_kernel   persistent; every WARP pulls tiles of 4 "rounds" from a ticket counter.  A round is 30 data
-//                        units = 5 MCUs of 4:2:0 (4 Y + Cb + Cr) or 10 MCUs of 4:4:4, one data unit per lane:
-//                          fetch + colour conversion (Y lanes of 4:2:0 also produce the 2x2 chroma means for the chroma
-//                          lanes of their MCU, through shared memory) -> AAN DCT rows/columns in registers -> quantise
-//                          into zig-zag order -> DC predictor from the neighbouring lane (the data unit before the tile
-//                          is recomputed, DC only) -> branch-free bit-length pass -> warp scan -> emit pass that writes
-//                          code + extra bits at the exact bit offset into the warp's bit buffer in shared memory.
-//                        At the end of the tile a decoupled look-back over per-round bit counts gives the global bit
+//   jfif_encode_kernel   persistent; every WARP pulls tiles of R "rounds" from a ticket counter.  A round is 30 data
+//                        units = 5 MCUs of 4:2:0 (4 Y + Cb + Cr) or 10 MCUs of 4:4:4.
+//                          transform, one data unit per lane: pixels (prefetched into registers during the previous
+//                            round's entropy phase) -> float YCbCr (the Y lanes of 4:2:0 also produce the 2x2 chroma
+//                            means for the chroma lanes of their MCU, through shared memory) -> AAN DCT rows/columns in
+//                            registers -> quantise -> DC difference against the neighbouring lane's DC (the data unit
+//                            before the tile is recomputed, DC only) -> 64 int16 in zig-zag order to shared memory;
+//                          entropy, one data unit per iteration, TWO coefficients per lane: zero runs from ballots,
+//                            (run, size) code + extra bits per lane, warp scan of the lengths, every lane ORs its bits at
+//                            its exact offset into the warp's bit buffer in shared memory.  No divergence, no unrolling.
+//                        At the end of the tile a decoupled look-back over per-tile bit counts gives the global bit
 //                        offset; the buffer is funnel-shifted to it and written to the unstuffed stream as aligned
-//                        32-bit words.  A byte shared by two tiles is left to the patch kernel.
-//   jfif_patch_kernel    one thread per round: OR the two halves of every byte that straddles a tile boundary.
+//                        32-bit words.  The byte two tiles share is completed by the later one (the earlier tile
+//                        publishes its trailing bits).
 //   jfif_stuff_kernel    persistent; 4 KiB chunks of the unstuffed stream: count 0xFF, block scan, look-back for the
 //                        output offset, expand in shared memory, coalesced copy-out; the first chunk also writes the
 //                        607-byte header (passed by value), the last one the EOI marker and the length.
@@ -33,26 +36,31 @@ namespace jfk {
 
 constexpr int THREADS = 256;
 constexpr int NWARPS = THREADS / 32;
-constexpr int ROUNDS_PER_TILE = 4;
+constexpr int MAX_ROUNDS_PER_TILE = 8;
 constexpr int UNITS_PER_ROUND = 30;
-constexpr int CAP_WORDS = 2560; // per-warp bit buffer: 10 KB; one round is at most 30 * 64 * 27 bits = 6480 bytes
+constexpr int CAP_WORDS = 1024; // per-warp bit buffer: 4 KB
 constexpr int CAP_BITS = CAP_WORDS * 32;
-static_assert(UNITS_PER_ROUND * 64 * 27 + 7 <= CAP_BITS, "a single round must fit the bit buffer");
-constexpr int CHROMA_SLOT = 65;                 // 64 floats + 1: the chroma lanes read conflict-free
-constexpr int CHROMA_WORDS = 10 * CHROMA_SLOT + 2; // 5 MCUs x (Cb, Cr)
-constexpr int WARP_WORDS = CAP_WORDS + CHROMA_WORDS;
+constexpr int UNIT_MAX_BITS = 64 * 27; // 16-bit code + 11 extra bits per coefficient
+constexpr int COEF_STRIDE = 33;       // 32 words (64 int16) per data unit + 1: lane j writes unit j conflict-free
+constexpr int COEF_WORDS = UNITS_PER_ROUND * COEF_STRIDE + 2;
+constexpr int CHROMA_SLOT = 65;       // 64 floats + 1: the chroma lanes read conflict-free
+static_assert(10 * CHROMA_SLOT <= COEF_WORDS, "the chroma exchange aliases the coefficient buffer");
+// pixel staging (cp.async): 4:2:0 5 MCUs x 16 rows x 64 B, 4:4:4 10 MCUs x 8 rows x 32 B; each MCU padded by 16 B so
+// that the 128-bit reads of the lanes spread over the banks
+constexpr int PIX_MCU_WORDS_420 = 16 * 16 + 4, PIX_MCU_WORDS_444 = 8 * 8 + 4;
+constexpr int PIX_WORDS = 5 * PIX_MCU_WORDS_420;
+static_assert(10 * PIX_MCU_WORDS_444 <= PIX_WORDS, "4:4:4 staging fits the 4:2:0 buffer");
+constexpr int WARP_WORDS = CAP_WORDS + COEF_WORDS + PIX_WORDS;
 
-// table block (32-bit words): built on the host once per context, copied to shared memory by every CTA
+// table block (32-bit words): built on the host, copied to shared memory by every CTA
 constexpr int T_AC_Y = 0;      // 256 x ((code << 8) | len), index run*16 + size
 constexpr int T_AC_C = 256;
 constexpr int T_DC_Y = 512;    // 16
 constexpr int T_DC_C = 528;
-constexpr int T_LEN_Y = 544;   // 1024 bytes: [run 0..63][size 0..15] -> ZRLs + code + extra bits of one AC symbol
-constexpr int T_LEN_C = 800;
-constexpr int T_WORDS = 1056;
+constexpr int T_WORDS = 544;
 constexpr int S_MULT = T_WORDS;       // 64 floats luminance multipliers, natural order
 constexpr int S_MULT_C = S_MULT + 65; // chroma table one bank further, so that mixed warps do not conflict
-constexpr int S_FIXED = S_MULT_C + 64 + 3; // 1188 words
+constexpr int S_FIXED = S_MULT_C + 64 + 3;
 constexpr int SM_BYTES = (S_FIXED + NWARPS * WARP_WORDS) * 4;
 static_assert(SM_BYTES * 2 <= 227 * 1024, "two CTAs per SM must fit");
 
@@ -60,20 +68,23 @@ constexpr int HEADER_BYTES = 607;
 constexpr int STUFF_THREADS = 256;
 constexpr int STUFF_CHUNK = STUFF_THREADS * 16;
 
+// tail word of a tile: bit 8 = published, bits 7..0 = its last, partial byte (high bits valid, rest zero)
+constexpr uint32_t TAIL_VALID = 0x100u;
+
 struct Params {
     const uint8_t *px;
     int w, h, comp;
     size_t stride;
     int fast_ok;        // comp == 4, base and stride 16-byte aligned: interior units use two 128-bit loads per row
     int mcux;           // MCUs per row
+    int rounds_per_tile;
     uint32_t nmcu, nrounds, ntiles;
     uint8_t *ustream;   // unstuffed entropy-coded bytes
     size_t ucap;
-    uint64_t *status;   // [0] ticket, [1 + r] look-back word of round r (bits)
-    uint64_t *gstart;   // [r] = 1<<63 | global bit offset, for rounds that start a flushed group
-    uint8_t *head, *tail; // partial first / last byte of a flushed group, indexed by its first / last round
+    uint64_t *status;   // [0] ticket, [1 + t] look-back word of tile t (bits)
+    uint32_t *tailw;    // [t]
     uint64_t *total_bits;
-    uint64_t *result;   // [0] length, [1] unused, [2] flags (bit1: scratch capacity exceeded)
+    uint64_t *result;   // [0] length, [1] tiles that had to flush early, [2] flags (bit1: scratch capacity exceeded)
     int16_t *coefs;     // optional: 64 per data unit, zig-zag order
     const uint32_t *tables;
     float mult[128];    // [0..63] luminance, [64..127] chrominance
@@ -146,56 +157,72 @@ __device__ __forceinline__ float to_y(float r, float g, float b) { return FS(FA(
 __device__ __forceinline__ float to_u(float r, float g, float b) { return FA(FS(FM(-0.16874f, r), FM(0.33126f, g)), FM(0.50000f, b)); }
 __device__ __forceinline__ float to_v(float r, float g, float b) { return FS(FS(FM(0.50000f, r), FM(0.41869f, g)), FM(0.08131f, b)); }
 
-// 8 pixels of one row starting at column x0 as r | g << 8 | b << 16; coordinates beyond the image repeat the edge
-__device__ __forceinline__ void load_row(const Params &P, int x0, int y, bool fast, uint32_t (&p)[8])
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
 {
-    const int yy = y < P.h ? y : P.h - 1;
-    const uint8_t *row = P.px + (size_t)yy * P.stride;
-    if (fast) {
-        const uint4 a = __ldg(reinterpret_cast<const uint4 *>(row + (size_t)x0 * 4));
-        const uint4 b = __ldg(reinterpret_cast<const uint4 *>(row + (size_t)x0 * 4 + 16));
-        p[0] = a.x; p[1] = a.y; p[2] = a.z; p[3] = a.w;
-        p[4] = b.x; p[5] = b.y; p[6] = b.z; p[7] = b.w;
-    } else {
-        const int og = P.comp > 2 ? 1 : 0, ob = P.comp > 2 ? 2 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory"); }
+
+// Stage the pixels of `count` consecutive MCUs starting at MCU m0 into the warp's pixel buffer, 4 pixels (16 B) per
+// chunk, as words r | g << 8 | b << 16 (| a << 24).  MCUs that lie inside the image horizontally, of 16-byte aligned RGBA
+// rows, are copied with cp.async; all others pixel by pixel, coordinates beyond the image repeating the last row /
+// column (stb_image_write.h:1533-1540).
+template <bool SUB>
+__device__ __forceinline__ void stage_pixels(const Params &P, uint32_t *pix, uint32_t m0, int count, int lane)
+{
+    constexpr int MSZ = SUB ? 16 : 8;                 // MCU edge in pixels
+    constexpr int CPR = MSZ / 4;                      // chunks per MCU row
+    constexpr int CPM = MSZ * CPR;                    // chunks per MCU: 64 / 16
+    constexpr int MCU_WORDS = SUB ? PIX_MCU_WORDS_420 : PIX_MCU_WORDS_444;
+    int mx = (int)(m0 % (uint32_t)P.mcux), my = (int)(m0 / (uint32_t)P.mcux);
+    int cur = 0; // MCU (within this call) that (mx, my) refers to
+    const int nchunks = count * CPM;
+    for (int c = lane; c < nchunks; c += 32) {
+        const int mcu = c / CPM, within = c % CPM;
+        while (cur < mcu) {
+            ++cur;
+            if (++mx == P.mcux) {
+                mx = 0;
+                ++my;
+            }
+        }
+        const int row = within / CPR, part = within % CPR;
+        const int x = mx * MSZ + part * 4, y = my * MSZ + row;
+        const int yy = y < P.h ? y : P.h - 1;
+        uint32_t *dst = pix + mcu * MCU_WORDS + within * 4;
+        const uint8_t *rowp = P.px + (size_t)yy * P.stride;
+        if (P.fast_ok && x + 4 <= P.w) {
+            cp_async16(dst, rowp + (size_t)x * 4);
+        } else {
+            const int og = P.comp > 2 ? 1 : 0, ob = P.comp > 2 ? 2 : 0;
+            uint32_t t[4];
 #pragma unroll
-        for (int x = 0; x < 8; ++x) {
-            const int xx = x0 + x < P.w ? x0 + x : P.w - 1;
-            const uint8_t *q = row + (size_t)xx * (size_t)P.comp;
-            p[x] = (uint32_t)q[0] | ((uint32_t)q[og] << 8) | ((uint32_t)q[ob] << 16);
+            for (int i = 0; i < 4; ++i) {
+                const int xx = x + i < P.w ? x + i : P.w - 1;
+                const uint8_t *q = rowp + (size_t)xx * (size_t)P.comp;
+                t[i] = (uint32_t)q[0] | ((uint32_t)q[og] << 8) | ((uint32_t)q[ob] << 16);
+            }
+            *reinterpret_cast<uint4 *>(dst) = make_uint4(t[0], t[1], t[2], t[3]);
         }
     }
 }
 
-// ---- bit buffer ------------------------------------------------------------------------------------------------
-struct BitWriter {
-    uint32_t *buf;
-    uint64_t acc;
-    int fill, wp;
-    __device__ __forceinline__ void start(uint32_t *b, uint32_t bitoff)
-    {
-        buf = b;
-        acc = 0;
-        wp = (int)(bitoff >> 5);
-        fill = (int)(bitoff & 31);
-    }
-    __device__ __forceinline__ void put(uint32_t val, int len) // len <= 32 - with fill < 32 the accumulator never overflows
-    {
-        acc = (acc << len) | val;
-        fill += len;
-        if (fill >= 32) {
-            fill -= 32;
-            atomicOr(&buf[wp++], (uint32_t)(acc >> fill));
-        }
-    }
-    __device__ __forceinline__ void finish()
-    {
-        if (fill > 0) atomicOr(&buf[wp], (uint32_t)(acc << (32 - fill)));
-    }
-};
-
 __device__ __forceinline__ int bitlen(int v) { return 32 - __clz(v < 0 ? -v : v); }
 __device__ __forceinline__ uint32_t extra_bits(int v, int n) { return (uint32_t)(v + (v >> 31)) & ((1u << n) - 1u); }
+
+// OR the low `len` bits of `val` (len <= 64 - 31) into the big-endian bit buffer at bit offset `off`.
+__device__ __forceinline__ void or_bits(uint32_t *buf, uint32_t off, uint64_t val, int len)
+{
+    if (len == 0) return;
+    const uint64_t x = val << (64 - len); // left aligned
+    const int sh = (int)(off & 31);
+    uint32_t *w = buf + (off >> 5);
+    const uint32_t w0 = (uint32_t)(x >> (32 + sh)), w1 = (uint32_t)(x >> sh);
+    const uint32_t w2 = (uint32_t)(((x & 0xffffffffull) << 32) >> sh);
+    if (w0) atomicOr(w, w0);
+    if (w1) atomicOr(w + 1, w1);
+    if (w2) atomicOr(w + 2, w2);
+}
 
 template <bool SUB>
 __global__ void __launch_bounds__(THREADS, 2) jfif_encode_kernel(const __grid_constant__ Params P)
@@ -210,75 +237,101 @@ __global__ void __launch_bounds__(THREADS, 2) jfif_encode_kernel(const __grid_co
         sm[S_MULT_C + i] = __float_as_uint(P.mult[64 + i]);
     }
     uint32_t *buf = sm + S_FIXED + warp * WARP_WORDS;
-    float *chroma = reinterpret_cast<float *>(buf + CAP_WORDS);
+    uint32_t *coef = buf + CAP_WORDS;
+    uint32_t *pix = coef + COEF_WORDS;
+    float *chroma = reinterpret_cast<float *>(coef); // 4:2:0 exchange of the 2x2 means; dead before the coefficients are stored
     for (int i = lane; i < CAP_WORDS; i += 32) buf[i] = 0;
     __syncthreads();
 
     const int mi = lane / DPM, d = lane - mi * DPM; // MCU within the round, data unit within the MCU
     const bool lane_used = lane < UNITS_PER_ROUND;
     const bool is_luma = SUB ? d < 4 : d == 0;
-    const uint32_t *tab_ac = sm + (is_luma ? T_AC_Y : T_AC_C);
-    const uint32_t *tab_dc = sm + (is_luma ? T_DC_Y : T_DC_C);
-    const uint8_t *tab_len = reinterpret_cast<const uint8_t *>(sm + (is_luma ? T_LEN_Y : T_LEN_C));
     const float *mult = reinterpret_cast<const float *>(sm + (is_luma ? S_MULT : S_MULT_C));
+    const uint32_t below = (1u << lane) - 1u;
+    const int R = P.rounds_per_tile;
 
     for (;;) {
         uint32_t tile = 0;
         if (lane == 0) tile = (uint32_t)atomicAdd((unsigned long long *)&P.status[0], 1ull);
         tile = __shfl_sync(0xffffffffu, tile, 0);
         if (tile >= P.ntiles) break;
-        const uint32_t r0 = tile * ROUNDS_PER_TILE;
-        const uint32_t r1 = r0 + ROUNDS_PER_TILE < P.nrounds ? r0 + ROUNDS_PER_TILE : P.nrounds;
+        const uint32_t r0 = tile * (uint32_t)R;
+        const uint32_t r1 = r0 + (uint32_t)R < P.nrounds ? r0 + (uint32_t)R : P.nrounds;
         int carry_y = 0, carry_u = 0, carry_v = 0; // DC of the last Y / Cb / Cr data unit before the current round
         uint32_t running = 0;                      // bits in the buffer
-        uint32_t rf = r0;                          // first round of the group in the buffer
+        bool resolved = false;                     // global bit offset of the tile known (an early flush happened)
+        uint64_t g_tile = 0, flushed = 0;          // bit offset of the tile; bits of the tile already written
+        uint32_t prev_tail = 0;                    // partial byte left by the previous group (high bits)
 
-        // flush rounds [rf, rend): look back for the global bit offset, shift, write words, record the shared bytes
-        auto flush = [&](uint32_t rend) {
+        // Write the buffer to the unstuffed stream.  final: this is the tile's last group.
+        auto flush = [&](bool final) {
             __syncwarp();
-            uint64_t G = 0;
-            if (rf > 0) { // exclusive prefix of the per-round bit counts (every round < rf is claimed by a running warp)
-                long long at = (long long)rf - 1;
-                for (;;) {
-                    const long long j = at - lane;
-                    uint64_t wd;
-                    if (j < 0) {
-                        wd = LJB_ST_INC;
-                    } else {
-                        do {
-                            wd = ljb_ld_volatile(&P.status[1 + j]);
-                        } while ((wd & LJB_ST_MASK) == 0);
-                    }
-                    const unsigned inc = __ballot_sync(0xffffffffu, (wd & LJB_ST_MASK) == LJB_ST_INC);
-                    uint64_t v = wd & ~LJB_ST_MASK;
-                    if (inc) {
-                        const int first = __ffs(inc) - 1;
-                        if (lane > first) v = 0;
-                    }
+            if (!resolved) {
+                if (final && lane == 0 && tile > 0) ljb_st_volatile(&P.status[1 + tile], LJB_ST_AGG | (uint64_t)running);
+                if (tile > 0) { // exclusive prefix over the tiles before this one (all claimed by running warps)
+                    long long at = (long long)tile - 1;
+                    for (;;) {
+                        const long long j = at - lane;
+                        uint64_t wd;
+                        if (j < 0) {
+                            wd = LJB_ST_INC;
+                        } else {
+                            while (((wd = ljb_ld_volatile(&P.status[1 + j])) & LJB_ST_MASK) == 0) __nanosleep(200);
+                        }
+                        const unsigned inc = __ballot_sync(0xffffffffu, (wd & LJB_ST_MASK) == LJB_ST_INC);
+                        uint64_t v = wd & ~LJB_ST_MASK;
+                        if (inc) {
+                            const int first = __ffs(inc) - 1;
+                            if (lane > first) v = 0;
+                        }
 #pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                    G += v;
-                    if (inc) break;
-                    at -= 32;
+                        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                        g_tile += v;
+                        if (inc) break;
+                        at -= 32;
+                    }
                 }
+                resolved = true;
+                if (!final && lane == 0) atomicAdd((unsigned long long *)&P.result[1], 1ull);
             }
-            const uint64_t E = G + running; // end bit
-            if (lane == 0) {
-                ljb_st_volatile(&P.status[1 + rend - 1], LJB_ST_INC | E);
-                P.gstart[rf] = (1ull << 63) | G;
-                if (rend == P.nrounds) *P.total_bits = E;
+            const uint64_t G = g_tile + flushed, E = G + running;
+            if (final && lane == 0) {
+                ljb_st_volatile(&P.status[1 + tile], LJB_ST_INC | E);
+                if (tile + 1 == P.ntiles) *P.total_bits = E;
+                // The tile's trailing partial byte depends only on its own bits and offset (a tile has at least 12 bits):
+                // publish it before waiting for the predecessor's, so that tiles never wait in a chain.
+                uint32_t tb = 0;
+                const int k = (int)(E & 7);
+                if (k && running >= (uint32_t)k) { // the last k bits of the buffer, as the high bits of a byte
+                    const uint32_t pos = running - (uint32_t)k;
+                    const uint32_t wi = pos >> 5;
+                    const uint64_t two = ((uint64_t)buf[wi] << 32) | (wi + 1 < (uint32_t)CAP_WORDS ? buf[wi + 1] : 0u);
+                    tb = (uint32_t)(two >> (56 - (pos & 31))) & (0xff00u >> k) & 0xffu;
+                } else if (k) { // a last group shorter than that (only after an early flush): it continues this warp's own byte
+                    tb = (prev_tail | ((buf[0] >> 24) >> (int)(G & 7))) & (0xff00u >> k) & 0xffu;
+                }
+                *(volatile uint32_t *)&P.tailw[tile] = TAIL_VALID | tb;
             }
-            const uint64_t blo = (G + 7) >> 3, bhi = E >> 3; // bytes this group owns completely
+            if (flushed == 0 && tile > 0 && (G & 7)) { // first group of the tile: the byte shared with the previous tile
+                uint32_t tw = 0;
+                if (lane == 0) {
+                    while (((tw = *(volatile uint32_t *)&P.tailw[tile - 1]) & TAIL_VALID) == 0) __nanosleep(200);
+                }
+                prev_tail = __shfl_sync(0xffffffffu, tw, 0) & 0xffu;
+            }
+            const uint64_t blo = G >> 3, bhi = E >> 3; // bytes completed by this group (the first may start in the previous one)
             const bool fits = ((E + 7) >> 3) <= P.ucap;
             if (!fits && lane == 0) atomicOr((unsigned long long *)&P.result[2], 2ull);
             const int sh = (int)(G & 31);
             const uint64_t w0 = G >> 5;
             const int nw = (int)((sh + running + 31) >> 5); // output words touched
+            uint32_t tail_here = 0;
             for (int j = lane; j < nw; j += 32) {
                 const uint32_t cur = j < CAP_WORDS ? buf[j] : 0u; // sh + running can reach one word past the buffer
                 const uint32_t prev = j > 0 ? buf[j - 1] : 0u;
-                const uint32_t be = sh ? __funnelshift_r(cur, prev, sh) : cur; // big-endian bit order
-                const uint64_t b0 = (w0 + (uint64_t)j) << 2;                   // first global byte of this word
+                uint32_t be = sh ? __funnelshift_r(cur, prev, sh) : cur; // big-endian bit order
+                if (j == 0 && (G & 7)) be |= prev_tail << (24 - 8 * (int)((G >> 3) & 3)); // complete the shared byte
+                const uint64_t b0 = (w0 + (uint64_t)j) << 2;                             // first global byte of this word
                 if (fits) {
                     if (b0 >= blo && b0 + 4 <= bhi) {
                         reinterpret_cast<uint32_t *>(P.ustream)[w0 + j] = __byte_perm(be, 0, 0x0123);
@@ -286,48 +339,67 @@ __global__ void __launch_bounds__(THREADS, 2) jfif_encode_kernel(const __grid_co
 #pragma unroll
                         for (int b = 0; b < 4; ++b) {
                             const uint64_t gb = b0 + b;
-                            const uint8_t val = (uint8_t)(be >> (24 - 8 * b));
-                            if (gb >= blo && gb < bhi) P.ustream[gb] = val;
-                            if ((G & 7) && gb == (G >> 3)) P.head[rf] = val;
-                            if ((E & 7) && gb == (E >> 3)) P.tail[rend - 1] = val;
+                            if (gb >= blo && gb < bhi) P.ustream[gb] = (uint8_t)(be >> (24 - 8 * b));
                         }
                     }
                 }
+                if ((E & 7) && b0 <= bhi && bhi < b0 + 4) tail_here = 0x100u | ((be >> (24 - 8 * (int)(bhi & 3))) & 0xffu);
             }
+            // after an early flush the trailing partial byte is completed by this warp's next group
+            const unsigned who = __ballot_sync(0xffffffffu, tail_here != 0);
+            prev_tail = who ? (__shfl_sync(0xffffffffu, tail_here, __ffs(who) - 1) & 0xffu) : 0u;
             __syncwarp();
             const int used = (int)((running + 31) >> 5) + 1;
             for (int j = lane; j < used && j < CAP_WORDS; j += 32) buf[j] = 0;
             __syncwarp();
+            flushed += running;
             running = 0;
-            rf = rend;
+        };
+        // lane's data unit in round `rr` (rr == r0 - 1: the halo MCU just before the tile, DC values only)
+        auto unit_of = [&](long long rr, uint32_t &m, bool &valid) {
+            const bool halo = rr < (long long)r0;
+            m = halo ? r0 * MPR - 1 : (uint32_t)rr * MPR + mi;
+            valid = lane_used && m < P.nmcu && (!halo || mi == 0);
+        };
+        // asynchronous copy of the round's pixels into shared memory
+        auto fetch = [&](long long rr) {
+            if (rr < (long long)r0) {
+                stage_pixels<SUB>(P, pix, r0 * MPR - 1, 1, lane);
+            } else {
+                const uint32_t m0 = (uint32_t)rr * MPR, left = P.nmcu - m0;
+                stage_pixels<SUB>(P, pix, m0, left < (uint32_t)MPR ? (int)left : MPR, lane);
+            }
         };
 
-        for (long long rr = (r0 == 0 ? 0 : (long long)r0 - 1); rr < (long long)r1; ++rr) {
-            // rr == r0 - 1 is the halo pass: only the MCU just before the tile, DC values only
+        const long long first = r0 == 0 ? 0 : (long long)r0 - 1;
+        fetch(first);
+        for (long long rr = first; rr < (long long)r1; ++rr) {
             const bool halo = rr < (long long)r0;
-            const uint32_t m = halo ? r0 * MPR - 1 : (uint32_t)rr * MPR + mi;
-            const bool valid = lane_used && m < P.nmcu && (!halo || mi == 0);
-            const int mx = (int)(m % (uint32_t)P.mcux), my = (int)(m / (uint32_t)P.mcux);
+            uint32_t m;
+            bool valid;
+            unit_of(rr, m, valid);
+            cp_async_wait_all();
+            __syncwarp();
             float s[64];
 #pragma unroll
             for (int i = 0; i < 64; ++i) s[i] = 0.f;
 
-            // ---- fetch + colour conversion ----
+            // ---- colour conversion ----
             if (SUB) {
                 float *slot = chroma + (mi * 2) * CHROMA_SLOT;
                 if (valid && d < 4) {
                     const int qx = d & 1, qy = d >> 1;
-                    const int x0 = mx * 16 + qx * 8, y0 = my * 16 + qy * 8;
-                    const bool fast = P.fast_ok && x0 + 8 <= P.w;
+                    const uint32_t *blk = pix + mi * PIX_MCU_WORDS_420 + qy * 128 + qx * 8;
                     float pu[8], pv[8];
 #pragma unroll
                     for (int y = 0; y < 8; ++y) {
-                        uint32_t p[8];
-                        load_row(P, x0, y0 + y, fast, p);
                         float cu[8], cv[8];
+                        const uint4 pa = *reinterpret_cast<const uint4 *>(blk + y * 16), pb = *reinterpret_cast<const uint4 *>(blk + y * 16 + 4);
+                        const uint32_t pw[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};
 #pragma unroll
                         for (int x = 0; x < 8; ++x) {
-                            const float r = (float)(p[x] & 255u), g = (float)((p[x] >> 8) & 255u), b = (float)((p[x] >> 16) & 255u);
+                            const uint32_t p = pw[x];
+                            const float r = (float)(p & 255u), g = (float)((p >> 8) & 255u), b = (float)((p >> 16) & 255u);
                             s[y * 8 + x] = to_y(r, g, b);
                             cu[x] = to_u(r, g, b);
                             cv[x] = to_v(r, g, b);
@@ -357,15 +429,15 @@ __global__ void __launch_bounds__(THREADS, 2) jfif_encode_kernel(const __grid_co
                 __syncwarp();
             } else {
                 if (valid) {
-                    const int x0 = mx * 8, y0 = my * 8;
-                    const bool fast = P.fast_ok && x0 + 8 <= P.w;
+                    const uint32_t *blk = pix + mi * PIX_MCU_WORDS_444;
 #pragma unroll
                     for (int y = 0; y < 8; ++y) {
-                        uint32_t p[8];
-                        load_row(P, x0, y0 + y, fast, p);
+                        const uint4 pa = *reinterpret_cast<const uint4 *>(blk + y * 8), pb = *reinterpret_cast<const uint4 *>(blk + y * 8 + 4);
+                        const uint32_t pw[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};
 #pragma unroll
                         for (int x = 0; x < 8; ++x) {
-                            const float r = (float)(p[x] & 255u), g = (float)((p[x] >> 8) & 255u), b = (float)((p[x] >> 16) & 255u);
+                            const uint32_t p = pw[x];
+                            const float r = (float)(p & 255u), g = (float)((p >> 8) & 255u), b = (float)((p >> 16) & 255u);
                             s[y * 8 + x] = d == 0 ? to_y(r, g, b) : d == 1 ? to_u(r, g, b) : to_v(r, g, b);
                         }
                     }
@@ -381,130 +453,138 @@ __global__ void __launch_bounds__(THREADS, 2) jfif_encode_kernel(const __grid_co
                 carry_y = __shfl_sync(0xffffffffu, dc, SUB ? 3 : 0);
                 carry_u = __shfl_sync(0xffffffffu, dc, SUB ? 4 : 1);
                 carry_v = __shfl_sync(0xffffffffu, dc, SUB ? 5 : 2);
+                __syncwarp();
+                fetch(rr + 1);
                 continue;
             }
             const uint32_t r = (uint32_t)rr;
 
-            // ---- DCT + quantisation into zig-zag order ----
-            int q[64];
+            // ---- DCT, quantisation, DC difference; 64 int16 in zig-zag order to shared memory ----
+            int dc = 0;
             if (valid) {
 #pragma unroll
                 for (int y = 0; y < 8; ++y)
                     aan8(s[y * 8], s[y * 8 + 1], s[y * 8 + 2], s[y * 8 + 3], s[y * 8 + 4], s[y * 8 + 5], s[y * 8 + 6], s[y * 8 + 7]);
 #pragma unroll
                 for (int x = 0; x < 8; ++x) aan8(s[x], s[8 + x], s[16 + x], s[24 + x], s[32 + x], s[40 + x], s[48 + x], s[56 + x]);
-#pragma unroll
-                for (int k = 0; k < 64; ++k) q[k] = quantise(s[kZZ.nat[k]], mult[kZZ.nat[k]]);
-            } else {
-#pragma unroll
-                for (int k = 0; k < 64; ++k) q[k] = 0;
+                dc = quantise(s[0], mult[0]);
             }
-            if (P.coefs && valid) {
-                int16_t *dst = P.coefs + ((size_t)m * DPM + d) * 64;
-#pragma unroll
-                for (int k = 0; k < 64; ++k) dst[k] = (int16_t)q[k];
-            }
-
-            // ---- DC predictor: the previous data unit of the same component ----
             int pred;
             {
                 const int back = SUB ? (d == 0 ? 3 : d < 4 ? 1 : 6) : 3;
                 const bool from_carry = SUB ? (mi == 0 && (d == 0 || d >= 4)) : mi == 0;
                 const int src = lane - back;
-                const int up = __shfl_sync(0xffffffffu, q[0], src < 0 ? 0 : src);
+                const int up = __shfl_sync(0xffffffffu, dc, src < 0 ? 0 : src);
                 const int cy = SUB ? (d == 0 ? carry_y : d == 4 ? carry_u : carry_v) : (d == 0 ? carry_y : d == 1 ? carry_u : carry_v);
                 pred = from_carry ? cy : up;
             }
-            const int diff = q[0] - pred;
-
-            // ---- bit length of this data unit (branch free) ----
-            uint32_t len = 0;
             if (valid) {
-                const int n0 = bitlen(diff);
-                len = (tab_dc[n0] & 255u) + n0;
-                int run = 0;
+                uint32_t *dst = coef + lane * COEF_STRIDE;
+                int16_t *gdst = P.coefs ? P.coefs + ((size_t)m * DPM + d) * 64 : nullptr;
 #pragma unroll
-                for (int k = 1; k < 64; ++k) {
-                    const int n = bitlen(q[k]);
-                    len += tab_len[run * 16 + n];
-                    run = q[k] ? 0 : run + 1;
-                }
-                if (run) len += tab_ac[0] & 255u; // EOB unless the last coefficient is non-zero
-            }
-            uint32_t incl = len;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += t;
-            }
-            uint32_t round_bits = __shfl_sync(0xffffffffu, incl, 31);
-            const bool last_round = r + 1 == P.nrounds;
-            if (last_round) round_bits += 7; // padding of the EOI marker: seven one-bits (stb :1586)
-            if (running + round_bits > (uint32_t)CAP_BITS) flush(r);
-            if (lane == 0) ljb_st_volatile(&P.status[1 + r], LJB_ST_AGG | (uint64_t)round_bits);
-
-            // ---- emit ----
-            if (valid) {
-                BitWriter bw;
-                bw.start(buf, running + incl - len);
-                {
-                    const int n0 = bitlen(diff);
-                    const uint32_t e = tab_dc[n0];
-                    bw.put(((e >> 8) << n0) | (n0 ? extra_bits(diff, n0) : 0u), (int)(e & 255u) + n0);
-                }
-                int run = 0;
-                const uint32_t zrl = tab_ac[0xF0];
-#pragma unroll
-                for (int k = 1; k < 64; ++k) {
-                    const int c = q[k];
-                    if (c == 0) {
-                        ++run;
-                    } else {
-                        while (run >= 16) {
-                            bw.put(zrl >> 8, (int)(zrl & 255u));
-                            run -= 16;
-                        }
-                        const int n = bitlen(c);
-                        const uint32_t e = tab_ac[run * 16 + n];
-                        bw.put(((e >> 8) << n) | extra_bits(c, n), (int)(e & 255u) + n);
-                        run = 0;
+                for (int k = 0; k < 64; k += 2) {
+                    const int a = k == 0 ? dc : quantise(s[kZZ.nat[k]], mult[kZZ.nat[k]]);
+                    const int b = quantise(s[kZZ.nat[k + 1]], mult[kZZ.nat[k + 1]]);
+                    if (gdst) {
+                        gdst[k] = (int16_t)a;
+                        gdst[k + 1] = (int16_t)b;
                     }
+                    // position 0 carries the DC DIFFERENCE: that is what gets coded
+                    dst[k >> 1] = (uint32_t)((k == 0 ? dc - pred : a) & 0xffff) | ((uint32_t)b << 16);
                 }
-                if (run) bw.put(tab_ac[0] >> 8, (int)(tab_ac[0] & 255u));
-                bw.finish();
             }
-            if (last_round && lane == 0) {
-                BitWriter bw;
-                bw.start(buf, running + round_bits - 7);
-                bw.put(0x7Fu, 7);
-                bw.finish();
-            }
-            running += round_bits;
-
-            // ---- carry the last DC values into the next round ----
             {
                 const uint32_t left = P.nmcu - r * MPR;
                 const int nv = left < (uint32_t)MPR ? (int)left : MPR;
                 const int base = (nv - 1) * DPM;
-                carry_y = __shfl_sync(0xffffffffu, q[0], base + (SUB ? 3 : 0));
-                carry_u = __shfl_sync(0xffffffffu, q[0], base + (SUB ? 4 : 1));
-                carry_v = __shfl_sync(0xffffffffu, q[0], base + (SUB ? 5 : 2));
+                carry_y = __shfl_sync(0xffffffffu, dc, base + (SUB ? 3 : 0));
+                carry_u = __shfl_sync(0xffffffffu, dc, base + (SUB ? 4 : 1));
+                carry_v = __shfl_sync(0xffffffffu, dc, base + (SUB ? 5 : 2));
             }
-        }
-        flush(r1);
-    }
-}
+            __syncwarp();
+            if (rr + 1 < (long long)r1) fetch(rr + 1); // in flight during the entropy phase
 
-// A byte that holds the last bits of one flushed group and the first bits of the next was written by neither.
-__global__ void jfif_patch_kernel(const uint64_t *gstart, const uint8_t *head, const uint8_t *tail, uint8_t *ustream, size_t ucap,
-                                  uint32_t nrounds)
-{
-    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r == 0 || r >= nrounds) return;
-    const uint64_t g = gstart[r];
-    if (!(g >> 63)) return;
-    const uint64_t G = g & ~(1ull << 63);
-    if ((G & 7) && (G >> 3) < ucap) ustream[G >> 3] = tail[r - 1] | head[r];
+            // ---- entropy coding: one data unit per iteration, lane l codes zig-zag positions 2l and 2l+1 ----
+            {
+                const uint32_t left = P.nmcu - r * MPR;
+                const int nunits = (left < (uint32_t)MPR ? (int)left : MPR) * DPM;
+                int dd = 0; // data unit within its MCU
+                for (int j = 0; j < nunits; ++j) {
+                    const bool luma = SUB ? dd < 4 : dd == 0;
+                    dd = dd + 1 == DPM ? 0 : dd + 1;
+                    const uint32_t *tab_ac = sm + (luma ? T_AC_Y : T_AC_C);
+                    const uint32_t *tab_dc = sm + (luma ? T_DC_Y : T_DC_C);
+                    const uint32_t wd = coef[j * COEF_STRIDE + lane];
+                    const int c0 = (int)(short)(wd & 0xffffu), c1 = (int)wd >> 16;
+                    const uint32_t nz_e = __ballot_sync(0xffffffffu, c0 != 0) | 1u; // position 0 (DC) always bounds a run
+                    const uint32_t nz_o = __ballot_sync(0xffffffffu, c1 != 0);
+                    // nearest coded position before 2l: even ones are 2*i, odd ones 2*i+1
+                    const uint32_t pe = nz_e & below, po = nz_o & below;
+                    const int prev_e = max(62 - 2 * __clz(pe), 63 - 2 * __clz(po)); // -2 / -1 when empty (lane 0 only)
+                    const int run0 = 2 * lane - 1 - prev_e;
+                    const int run1 = (c0 != 0 || lane == 0) ? 0 : run0 + 1;
+                    uint64_t v0 = 0, v1 = 0;
+                    int l0 = 0, l1 = 0;
+                    const int n0 = bitlen(c0), n1 = bitlen(c1);
+                    if (lane == 0) {
+                        const uint32_t e = tab_dc[n0];
+                        v0 = ((uint64_t)(e >> 8) << n0) | (n0 ? extra_bits(c0, n0) : 0u);
+                        l0 = (int)(e & 255u) + n0;
+                    } else if (c0 != 0) {
+                        const uint32_t e = tab_ac[(run0 & 15) * 16 + n0];
+                        v0 = ((uint64_t)(e >> 8) << n0) | extra_bits(c0, n0);
+                        l0 = (int)(e & 255u) + n0;
+                    }
+                    if (c1 != 0) {
+                        const uint32_t e = tab_ac[(run1 & 15) * 16 + n1];
+                        v1 = ((uint64_t)(e >> 8) << n1) | extra_bits(c1, n1);
+                        l1 = (int)(e & 255u) + n1;
+                    } else if (lane == 31) { // position 63 is zero: end of block
+                        v1 = tab_ac[0] >> 8;
+                        l1 = (int)(tab_ac[0] & 255u);
+                    }
+                    // runs of 16 or more zeros: ZRL codes in front (rare; at most 3 per symbol)
+                    const bool z0 = lane != 0 && c0 != 0 && run0 >= 16, z1 = c1 != 0 && run1 >= 16;
+                    const bool any_zrl = __any_sync(0xffffffffu, z0 || z1);
+                    if (any_zrl) {
+                        const uint32_t zrl = tab_ac[0xF0];
+                        const int zl = (int)(zrl & 255u);
+                        if (z0) {
+                            for (int i = 0; i < (run0 >> 4); ++i) v0 |= (uint64_t)(zrl >> 8) << (l0 + i * zl);
+                            l0 += (run0 >> 4) * zl;
+                        }
+                        if (z1) {
+                            for (int i = 0; i < (run1 >> 4); ++i) v1 |= (uint64_t)(zrl >> 8) << (l1 + i * zl);
+                            l1 += (run1 >> 4) * zl;
+                        }
+                    }
+                    const uint32_t len = (uint32_t)(l0 + l1);
+                    uint32_t incl = len;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+                        if (lane >= o) incl += t;
+                    }
+                    const uint32_t unit_bits = __shfl_sync(0xffffffffu, incl, 31);
+                    if (running + unit_bits + 7 > (uint32_t)CAP_BITS) flush(false);
+                    const uint32_t off = running + incl - len;
+                    if (any_zrl) { // up to 59 bits each
+                        or_bits(buf, off, v0, l0);
+                        or_bits(buf, off + (uint32_t)l0, v1, l1);
+                    } else { // at most 2 x 27 bits: one string
+                        or_bits(buf, off, (v0 << l1) | v1, (int)len);
+                    }
+                    running += unit_bits;
+                }
+            }
+            __syncwarp();
+        }
+        if (r1 == P.nrounds) { // padding of the EOI marker: seven one-bits (stb :1586)
+            if (lane == 0) or_bits(buf, running, 0x7Fu, 7);
+            running += 7;
+        }
+        flush(true);
+    }
 }
 
 struct Header {
@@ -680,13 +760,6 @@ static void build_tables(uint32_t *t)
     memcpy(t + T_DC_Y, dc, 16 * sizeof(uint32_t));
     canonical(kDcChromaBits, kDcVals, dc, 256);
     memcpy(t + T_DC_C, dc, 16 * sizeof(uint32_t));
-    for (int c = 0; c < 2; ++c) {
-        const uint32_t *ac = t + (c ? T_AC_C : T_AC_Y);
-        uint8_t *len = reinterpret_cast<uint8_t *>(t + (c ? T_LEN_C : T_LEN_Y));
-        for (int run = 0; run < 64; ++run)
-            for (int n = 0; n < 16; ++n)
-                len[run * 16 + n] = n == 0 ? 0 : (uint8_t)((run >> 4) * (ac[0xF0] & 255u) + (ac[(run & 15) * 16 + n] & 255u) + (unsigned)n);
-    }
 }
 
 struct Plan {
@@ -809,22 +882,28 @@ extern "C" int ljb_jfif_encode_dev(ljb_ctx *ctx, const uint8_t *d_pixels, int w,
     const uint32_t nmcu = (uint32_t)nmcu64;
     const uint32_t mpr = pl.subsample ? 5 : 10;
     const uint32_t nrounds = (nmcu + mpr - 1) / mpr;
-    const uint32_t ntiles = (nrounds + ROUNDS_PER_TILE - 1) / ROUNDS_PER_TILE;
+    // rounds per tile: as many as fit the 4 KB bit buffer on uniform noise (the densest realistic input) at this quality;
+    // denser tiles still encode correctly through early flushes, only slower
+    const int q0 = quality ? quality : 90;
+    int R = q0 <= 60 ? 6 : q0 <= 80 ? 4 : q0 <= 90 ? 3 : q0 <= 95 ? 2 : 1;
+    if (const char *e = getenv("LJB_JFIF_ROUNDS")) { // test / tuning hook
+        const int v = atoi(e);
+        if (v >= 1 && v <= MAX_ROUNDS_PER_TILE) R = v;
+    }
+    const uint32_t ntiles = (nrounds + (uint32_t)R - 1) / (uint32_t)R;
     // unstuffed stream: never longer than the worst case, nor (usefully) than the caller's output buffer
     size_t ucap = jfif_units(w, h, pl.subsample) * 216 + 8;
     if (ucap > out_cap) ucap = out_cap;
     const size_t nchunks_max = (ucap + STUFF_CHUNK - 1) / STUFF_CHUNK + 1;
     int rc;
     if ((rc = ljb_ensure(&ctx->d_scratch, &ctx->scratch_bytes, ucap + STUFF_CHUNK + 64)) != 0) return rc;
-    // status block: tables | total_bits | ticket+round status | gstart | ticket+chunk status | head | tail
+    // status block: tables | total_bits | ticket + tile status | ticket + chunk status | tile tail words
     const size_t o_tab = 0;
     const size_t o_total = o_tab + T_WORDS * 4;
     const size_t o_st1 = o_total + 8;
-    const size_t o_gs = o_st1 + ((size_t)nrounds + 1) * 8;
-    const size_t o_st2 = o_gs + (size_t)nrounds * 8;
-    const size_t o_head = o_st2 + (nchunks_max + 1) * 8;
-    const size_t o_tail = o_head + (((size_t)nrounds + 7) & ~(size_t)7);
-    const size_t o_end = o_tail + (((size_t)nrounds + 7) & ~(size_t)7);
+    const size_t o_st2 = o_st1 + ((size_t)ntiles + 1) * 8;
+    const size_t o_tailw = o_st2 + (nchunks_max + 1) * 8;
+    const size_t o_end = o_tailw + (size_t)ntiles * 4;
     if ((rc = ljb_ensure(&ctx->d_status, &ctx->status_bytes, o_end)) != 0) return rc;
     uint8_t *sb = (uint8_t *)ctx->d_status;
     uint32_t tables[T_WORDS];
@@ -848,9 +927,8 @@ extern "C" int ljb_jfif_encode_dev(ljb_ctx *ctx, const uint8_t *d_pixels, int w,
     P.ustream = (uint8_t *)ctx->d_scratch;
     P.ucap = ucap;
     P.status = (uint64_t *)(sb + o_st1);
-    P.gstart = (uint64_t *)(sb + o_gs);
-    P.head = sb + o_head;
-    P.tail = sb + o_tail;
+    P.tailw = (uint32_t *)(sb + o_tailw);
+    P.rounds_per_tile = R;
     P.total_bits = (uint64_t *)(sb + o_total);
     P.result = d_result;
     P.coefs = d_coefs;
@@ -871,8 +949,6 @@ extern "C" int ljb_jfif_encode_dev(ljb_ctx *ctx, const uint8_t *d_pixels, int w,
     else jfif_encode_kernel<false><<<grid, THREADS, SM_BYTES, ctx->stream>>>(P);
     LJB_CUDA(cudaGetLastError());
     LJB_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
-    jfif_patch_kernel<<<(nrounds + 255) / 256, 256, 0, ctx->stream>>>(P.gstart, P.head, P.tail, P.ustream, ucap, nrounds);
-    LJB_CUDA(cudaGetLastError());
     StuffParams S;
     S.ustream = P.ustream;
     S.ucap = ucap;
@@ -886,7 +962,7 @@ extern "C" int ljb_jfif_encode_dev(ljb_ctx *ctx, const uint8_t *d_pixels, int w,
     const int sgrid = (int)(nchunks_max < sfull ? nchunks_max : sfull);
     jfif_stuff_kernel<<<sgrid, STUFF_THREADS, 0, ctx->stream>>>(S);
     LJB_CUDA(cudaGetLastError());
-    ctx->launches += 3;
+    ctx->launches += 2;
     return LJB_OK;
 }
 
