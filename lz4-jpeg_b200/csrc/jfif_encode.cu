@@ -9,22 +9,27 @@
 // bit position).  Here it is two kernels on one stream:
 //
 //   jfif_encode_kernel   persistent; every WARP pulls tiles of R "rounds" from a ticket counter.  A round is 30 data
-//                        units = 5 MCUs of 4:2:0 (4 Y + Cb + Cr) or 10 MCUs of 4:4:4.
-//                          transform, one data unit per lane: pixels (prefetched into registers during the previous
-//                            round's entropy phase) -> float YCbCr (the Y lanes of 4:2:0 also produce the 2x2 chroma
-//                            means for the chroma lanes of their MCU, through shared memory) -> AAN DCT rows/columns in
-//                            registers -> quantise -> DC difference against the neighbouring lane's DC (the data unit
-//                            before the tile is recomputed, DC only) -> 64 int16 in zig-zag order to shared memory;
-//                          entropy, one data unit per iteration, TWO coefficients per lane: zero runs from ballots,
-//                            (run, size) code + extra bits per lane, warp scan of the lengths, every lane ORs its bits at
-//                            its exact offset into the warp's bit buffer in shared memory.  No divergence, no unrolling.
-//                        At the end of the tile a decoupled look-back over per-tile bit counts gives the global bit
-//                        offset; the buffer is funnel-shifted to it and written to the unstuffed stream as aligned
-//                        32-bit words.  The byte two tiles share is completed by the later one (the earlier tile
-//                        publishes its trailing bits).
+//                        units = 5 MCUs of 4:2:0 (4 Y + Cb + Cr) or 10 MCUs of 4:4:4; each data unit owns a 64-word block
+//                        of the warp's shared memory that holds, in turn, its pixels, its samples and its coefficients.
+//                          stage      cp.async of the round's pixels into the blocks (16 B per lane and instruction)
+//                          convert    float YCbCr in place, a rolled loop over rows (the Y lanes of 4:2:0 also write the
+//                                     2x2 chroma means into the blocks of the chroma lanes of their MCU)
+//                          transform  one data unit per lane: 64 samples to registers, AAN DCT rows/columns, quantise,
+//                                     DC difference against the neighbouring lane's DC (the data unit before the tile is
+//                                     recomputed, DC only), 64 int32 back into the block
+//                          entropy    two data units per iteration, two coefficients per lane: zero runs from ballots,
+//                                     (run, size) code + extra bits per lane, one warp scan for both units, every lane
+//                                     ORs its bits at its exact offset into the warp's bit buffer.  No divergence.
+//                        A finished tile publishes its bit count and its last seven bits and keeps its bits in one of two
+//                        bit buffers; one tile later (every predecessor has published by then) the warp resolves the
+//                        decoupled look-back, funnel-shifts the buffer to the global bit offset and writes aligned 32-bit
+//                        words to the unstuffed stream.  The byte two tiles share is completed by the later one.
 //   jfif_stuff_kernel    persistent; 4 KiB chunks of the unstuffed stream: count 0xFF, block scan, look-back for the
 //                        output offset, expand in shared memory, coalesced copy-out; the first chunk also writes the
 //                        607-byte header (passed by value), the last one the EOI marker and the length.
+//
+// Code size matters here: the B200 instruction cache holds 32 KB per SM and sixteen warps run in different phases, so
+// only the 8x8 transform is unrolled (it must be: its 64 values live in registers).
 //
 // Algorithmic bytes: comp*W*H read + N_out written; the unstuffed stream is one extra write + read of ~N_out.
 #include "common.cuh"
@@ -38,19 +43,16 @@ constexpr int THREADS = 256;
 constexpr int NWARPS = THREADS / 32;
 constexpr int MAX_ROUNDS_PER_TILE = 8;
 constexpr int UNITS_PER_ROUND = 30;
-constexpr int CAP_WORDS = 1024; // per-warp bit buffer: 4 KB
+constexpr int CAP_WORDS = 640; // one bit buffer: 2.5 KB; a warp has two
 constexpr int CAP_BITS = CAP_WORDS * 32;
-constexpr int UNIT_MAX_BITS = 64 * 27; // 16-bit code + 11 extra bits per coefficient
-constexpr int COEF_STRIDE = 33;       // 32 words (64 int16) per data unit + 1: lane j writes unit j conflict-free
-constexpr int COEF_WORDS = UNITS_PER_ROUND * COEF_STRIDE + 2;
-constexpr int CHROMA_SLOT = 65;       // 64 floats + 1: the chroma lanes read conflict-free
-static_assert(10 * CHROMA_SLOT <= COEF_WORDS, "the chroma exchange aliases the coefficient buffer");
-// pixel staging (cp.async): 4:2:0 5 MCUs x 16 rows x 64 B, 4:4:4 10 MCUs x 8 rows x 32 B; each MCU padded by 16 B so
-// that the 128-bit reads of the lanes spread over the banks
-constexpr int PIX_MCU_WORDS_420 = 16 * 16 + 4, PIX_MCU_WORDS_444 = 8 * 8 + 4;
-constexpr int PIX_WORDS = 5 * PIX_MCU_WORDS_420;
-static_assert(10 * PIX_MCU_WORDS_444 <= PIX_WORDS, "4:4:4 staging fits the 4:2:0 buffer");
-constexpr int WARP_WORDS = CAP_WORDS + COEF_WORDS + PIX_WORDS;
+constexpr int SPILL_WORDS = CAP_WORDS + 4; // a spilled buffer + its bit count
+// data-unit blocks of one round.  4:2:0, per MCU: a 16 x 16 luminance area (row stride 16 words, the four Y units are its
+// quadrants) + one 8 x 8 block each for Cb and Cr (row stride 8) + 4 words so that MCUs start in different banks.
+// 4:4:4, per MCU: three 8 x 8 blocks (Y, Cb, Cr; the pixels are staged into the first) + 4 words.
+constexpr int MCU_WORDS_420 = 256 + 128 + 4, MCU_WORDS_444 = 192 + 4;
+constexpr int BLOCK_WORDS = 10 * MCU_WORDS_444;
+static_assert(5 * MCU_WORDS_420 <= BLOCK_WORDS, "4:2:0 blocks fit the 4:4:4 area");
+constexpr int WARP_WORDS = 2 * CAP_WORDS + BLOCK_WORDS;
 
 // table block (32-bit words): built on the host, copied to shared memory by every CTA
 constexpr int T_AC_Y = 0;      // 256 x ((code << 8) | len), index run*16 + size
@@ -61,21 +63,22 @@ constexpr int T_WORDS = 544;
 constexpr int S_MULT = T_WORDS;       // 64 floats luminance multipliers, natural order
 constexpr int S_MULT_C = S_MULT + 65; // chroma table one bank further, so that mixed warps do not conflict
 constexpr int S_FIXED = S_MULT_C + 64 + 3;
+static_assert(S_FIXED % 4 == 0 && WARP_WORDS % 4 == 0 && CAP_WORDS % 4 == 0, "16-byte alignment of the blocks");
 constexpr int SM_BYTES = (S_FIXED + NWARPS * WARP_WORDS) * 4;
-static_assert(SM_BYTES * 2 <= 227 * 1024, "two CTAs per SM must fit");
+static_assert((SM_BYTES + 1024) * 2 <= 228 * 1024, "two CTAs per SM must fit");
 
 constexpr int HEADER_BYTES = 607;
 constexpr int STUFF_THREADS = 256;
 constexpr int STUFF_CHUNK = STUFF_THREADS * 16;
 
-// tail word of a tile: bit 8 = published, bits 7..0 = its last, partial byte (high bits valid, rest zero)
+// tail word of a tile: bit 8 = published, bits 6..0 = the last seven bits of the tile's bit string
 constexpr uint32_t TAIL_VALID = 0x100u;
 
 struct Params {
     const uint8_t *px;
     int w, h, comp;
     size_t stride;
-    int fast_ok;        // comp == 4, base and stride 16-byte aligned: interior units use two 128-bit loads per row
+    int fast_ok;        // comp == 4, base and stride 16-byte aligned: cp.async straight from the image
     int mcux;           // MCUs per row
     int rounds_per_tile;
     uint32_t nmcu, nrounds, ntiles;
@@ -83,8 +86,10 @@ struct Params {
     size_t ucap;
     uint64_t *status;   // [0] ticket, [1 + t] look-back word of tile t (bits)
     uint32_t *tailw;    // [t]
+    uint32_t *spill;    // per warp of the grid: spill_slots x SPILL_WORDS words, for tiles denser than the bit buffer
+    int spill_slots;
     uint64_t *total_bits;
-    uint64_t *result;   // [0] length, [1] tiles that had to flush early, [2] flags (bit1: scratch capacity exceeded)
+    uint64_t *result;   // [0] length, [1] tiles that spilled, [2] flags (bit1: scratch capacity exceeded)
     int16_t *coefs;     // optional: 64 per data unit, zig-zag order
     const uint32_t *tables;
     float mult[128];    // [0..63] luminance, [64..127] chrominance
@@ -112,6 +117,7 @@ constexpr ZigZag make_zigzag()
     return z;
 }
 __device__ constexpr ZigZag kZZ = make_zigzag();
+__constant__ ZigZag cZZ = make_zigzag(); // the same table for run-time indices
 
 // ---- arithmetic with the reference's rounding: one IEEE operation per C operator, no contraction ---------------
 #define FA(a, b) __fadd_rn((a), (b))
@@ -152,10 +158,22 @@ __device__ __forceinline__ int quantise(float coef, float mult)
     return __float2int_rz(v < 0.f ? FS(v, 0.5f) : FA(v, 0.5f));
 }
 
-// stb_image_write.h:1541-1543
-__device__ __forceinline__ float to_y(float r, float g, float b) { return FS(FA(FA(FM(0.29900f, r), FM(0.58700f, g)), FM(0.11400f, b)), 128.f); }
-__device__ __forceinline__ float to_u(float r, float g, float b) { return FA(FS(FM(-0.16874f, r), FM(0.33126f, g)), FM(0.50000f, b)); }
-__device__ __forceinline__ float to_v(float r, float g, float b) { return FS(FS(FM(0.50000f, r), FM(0.41869f, g)), FM(0.08131f, b)); }
+// stb_image_write.h:1541-1543; p = r | g << 8 | b << 16
+__device__ __forceinline__ float to_y(uint32_t p)
+{
+    const float r = (float)(p & 255u), g = (float)((p >> 8) & 255u), b = (float)((p >> 16) & 255u);
+    return FS(FA(FA(FM(0.29900f, r), FM(0.58700f, g)), FM(0.11400f, b)), 128.f);
+}
+__device__ __forceinline__ float to_u(uint32_t p)
+{
+    const float r = (float)(p & 255u), g = (float)((p >> 8) & 255u), b = (float)((p >> 16) & 255u);
+    return FA(FS(FM(-0.16874f, r), FM(0.33126f, g)), FM(0.50000f, b));
+}
+__device__ __forceinline__ float to_v(uint32_t p)
+{
+    const float r = (float)(p & 255u), g = (float)((p >> 8) & 255u), b = (float)((p >> 16) & 255u);
+    return FS(FS(FM(0.50000f, r), FM(0.41869f, g)), FM(0.08131f, b));
+}
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
 {
@@ -163,17 +181,18 @@ __device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory"); }
 
-// Stage the pixels of `count` consecutive MCUs starting at MCU m0 into the warp's pixel buffer, 4 pixels (16 B) per
-// chunk, as words r | g << 8 | b << 16 (| a << 24).  MCUs that lie inside the image horizontally, of 16-byte aligned RGBA
-// rows, are copied with cp.async; all others pixel by pixel, coordinates beyond the image repeating the last row /
-// column (stb_image_write.h:1533-1540).
+// Stage the pixels of `count` consecutive MCUs starting at MCU m0 into the warp's blocks, 4 pixels (16 B) per chunk, as
+// words r | g << 8 | b << 16 (| a << 24).  Chunks that lie inside the image horizontally, of 16-byte aligned RGBA rows,
+// are copied with cp.async; all others pixel by pixel, coordinates beyond the image repeating the last row / column
+// (stb_image_write.h:1533-1540).
 template <bool SUB>
-__device__ __forceinline__ void stage_pixels(const Params &P, uint32_t *pix, uint32_t m0, int count, int lane)
+__device__ __noinline__ void stage_pixels(const Params &P, uint32_t *blocks, uint32_t m0, int count)
 {
-    constexpr int MSZ = SUB ? 16 : 8;                 // MCU edge in pixels
-    constexpr int CPR = MSZ / 4;                      // chunks per MCU row
-    constexpr int CPM = MSZ * CPR;                    // chunks per MCU: 64 / 16
-    constexpr int MCU_WORDS = SUB ? PIX_MCU_WORDS_420 : PIX_MCU_WORDS_444;
+    constexpr int MSZ = SUB ? 16 : 8;  // MCU edge in pixels
+    constexpr int CPR = MSZ / 4;       // chunks per MCU row (also: words per row / 4)
+    constexpr int CPM = MSZ * CPR;     // chunks per MCU: 64 / 16
+    constexpr int MCU_WORDS = SUB ? MCU_WORDS_420 : MCU_WORDS_444;
+    const int lane = threadIdx.x & 31;
     int mx = (int)(m0 % (uint32_t)P.mcux), my = (int)(m0 / (uint32_t)P.mcux);
     int cur = 0; // MCU (within this call) that (mx, my) refers to
     const int nchunks = count * CPM;
@@ -189,7 +208,7 @@ __device__ __forceinline__ void stage_pixels(const Params &P, uint32_t *pix, uin
         const int row = within / CPR, part = within % CPR;
         const int x = mx * MSZ + part * 4, y = my * MSZ + row;
         const int yy = y < P.h ? y : P.h - 1;
-        uint32_t *dst = pix + mcu * MCU_WORDS + within * 4;
+        uint32_t *dst = blocks + mcu * MCU_WORDS + within * 4; // row stride = MSZ words in both layouts
         const uint8_t *rowp = P.px + (size_t)yy * P.stride;
         if (P.fast_ok && x + 4 <= P.w) {
             cp_async16(dst, rowp + (size_t)x * 4);
@@ -210,18 +229,171 @@ __device__ __forceinline__ void stage_pixels(const Params &P, uint32_t *pix, uin
 __device__ __forceinline__ int bitlen(int v) { return 32 - __clz(v < 0 ? -v : v); }
 __device__ __forceinline__ uint32_t extra_bits(int v, int n) { return (uint32_t)(v + (v >> 31)) & ((1u << n) - 1u); }
 
-// OR the low `len` bits of `val` (len <= 64 - 31) into the big-endian bit buffer at bit offset `off`.
-__device__ __forceinline__ void or_bits(uint32_t *buf, uint32_t off, uint64_t val, int len)
+// OR a left-aligned 64-bit string (hi:lo, bits beyond its length zero) into the big-endian bit buffer at bit offset `off`.
+__device__ __forceinline__ void or_left64(uint32_t *buf, uint32_t off, uint32_t hi, uint32_t lo)
 {
-    if (len == 0) return;
-    const uint64_t x = val << (64 - len); // left aligned
     const int sh = (int)(off & 31);
     uint32_t *w = buf + (off >> 5);
-    const uint32_t w0 = (uint32_t)(x >> (32 + sh)), w1 = (uint32_t)(x >> sh);
-    const uint32_t w2 = (uint32_t)(((x & 0xffffffffull) << 32) >> sh);
+    const uint32_t w0 = hi >> sh, w1 = __funnelshift_r(lo, hi, sh), w2 = __funnelshift_lc(0u, lo, 32 - sh);
     if (w0) atomicOr(w, w0);
     if (w1) atomicOr(w + 1, w1);
     if (w2) atomicOr(w + 2, w2);
+}
+// the low `len` (<= 32) bits of `val`
+__device__ __forceinline__ void or_bits(uint32_t *buf, uint32_t off, uint32_t val, int len)
+{
+    or_left64(buf, off, __funnelshift_lc(0u, val, 32 - len), 0u);
+}
+// two strings of at most 27 bits back to back (either may be empty)
+__device__ __forceinline__ void or_pair(uint32_t *buf, uint32_t off, uint32_t v0, int l0, uint32_t v1, int l1)
+{
+    const uint32_t a0 = __funnelshift_lc(0u, v0, 32 - l0), a1 = __funnelshift_lc(0u, v1, 32 - l1); // left aligned; 0 when empty
+    or_left64(buf, off, a0 | (a1 >> l0), __funnelshift_lc(0u, a1, 32 - l0));
+}
+
+// What one lane contributes to one data unit: the code + extra bits of zig-zag positions 2l and 2l+1 (v, length l; 0 when
+// the coefficient is zero) and how many ZRL codes precede each (k: run / 16).
+struct UnitBits {
+    uint32_t v0, v1;
+    int l0, l1, k0, k1;
+};
+// c0, c1: the lane's two coefficients (position 0 holds the DC difference).  Lane 0's even symbol is the DC category
+// (always coded); lane 31's odd position is 63: a zero there codes EOB.  (stb_image_write.h:1357-1395)
+__device__ __forceinline__ void unit_symbols(int c0, int c1, bool active, const uint32_t *tab_ac, const uint32_t *tab_dc, int lane,
+                                             uint32_t below, UnitBits &u)
+{
+    const uint32_t nz_e = __ballot_sync(0xffffffffu, c0 != 0) | 1u; // position 0 (DC) always bounds a run
+    const uint32_t nz_o = __ballot_sync(0xffffffffu, c1 != 0);
+    // nearest coded position before 2l: even positions are 2*i, odd ones 2*i+1
+    const int prev_e = max(62 - 2 * __clz(nz_e & below), 63 - 2 * __clz(nz_o & below)); // lane 0: -1 (unused)
+    const int run0 = 2 * lane - 1 - prev_e;
+    const int run1 = (c0 != 0 || lane == 0) ? 0 : run0 + 1;
+    const int n0 = bitlen(c0), n1 = bitlen(c1);
+    const bool first = lane == 0;
+    const bool emit0 = active && (first || c0 != 0), emit1 = active && (c1 != 0 || lane == 31);
+    const uint32_t e0 = first ? tab_dc[n0] : tab_ac[(run0 & 15) * 16 + n0];
+    const uint32_t e1 = tab_ac[c1 != 0 ? (run1 & 15) * 16 + n1 : 0]; // index 0 = EOB
+    u.v0 = emit0 ? ((e0 >> 8) << n0) | extra_bits(c0, n0) : 0u;
+    u.l0 = emit0 ? (int)(e0 & 255u) + n0 : 0;
+    u.v1 = emit1 ? ((e1 >> 8) << n1) | extra_bits(c1, n1) : 0u;
+    u.l1 = emit1 ? (int)(e1 & 255u) + n1 : 0;
+    u.k0 = (emit0 && !first) ? run0 >> 4 : 0;
+    u.k1 = (emit1 && c1 != 0) ? run1 >> 4 : 0;
+}
+// slow path of a data unit that holds a run of 16 or more zeros somewhere: [ZRL x k0][symbol 0][ZRL x k1][symbol 1]
+__device__ __forceinline__ void or_pair_zrl(uint32_t *buf, uint32_t off, const UnitBits &u, uint32_t zrl, int zl)
+{
+    for (int i = 0; i < u.k0; ++i, off += zl) or_bits(buf, off, zrl, zl);
+    or_bits(buf, off, u.v0, u.l0);
+    off += (uint32_t)u.l0;
+    for (int i = 0; i < u.k1; ++i, off += zl) or_bits(buf, off, zrl, zl);
+    or_bits(buf, off, u.v1, u.l1);
+}
+
+// the last min(7, nbits) bits of a big-endian bit buffer holding nbits bits
+__device__ __forceinline__ uint32_t last_bits(const uint32_t *buf, uint32_t nbits, int &count)
+{
+    count = nbits < 7 ? (int)nbits : 7;
+    if (count == 0) return 0;
+    const uint32_t pos = nbits - (uint32_t)count, wi = pos >> 5;
+    const uint64_t two = ((uint64_t)buf[wi] << 32) | ((wi + 1) * 32 < nbits ? buf[wi + 1] : 0u);
+    return (uint32_t)(two >> (64 - (pos & 31) - count)) & ((1u << count) - 1u);
+}
+
+// What a warp remembers about the tile it is writing out (one group normally; several when the tile spilled).
+struct TileOut {
+    uint64_t g_tile;    // global bit offset of the tile, valid once `resolved`
+    uint64_t flushed;   // bits of the tile already placed
+    uint32_t last7;     // the last seven bits placed so far
+    uint32_t resolved;
+};
+
+// Write `nbits` bits of the big-endian bit buffer `src` (shared memory; cleared afterwards) to the unstuffed stream as the
+// next group of tile `tile`: decoupled look-back over the per-tile bit counts the first time, then the buffer
+// funnel-shifted to the global bit offset and stored as aligned 32-bit words.  The byte two groups share is completed by
+// the later one from the earlier one's last bits.  final: the tile's last group (the tile has published its size and its
+// last bits itself, as soon as it was finished; here it publishes its inclusive prefix).
+__device__ __noinline__ void place_group(const Params &P, uint32_t *src, uint32_t tile, uint32_t nbits, bool final, TileOut &t)
+{
+    const int lane = threadIdx.x & 31;
+    __syncwarp();
+    if (!t.resolved) {
+        uint64_t g = 0;
+        if (tile > 0) { // exclusive prefix over the tiles before this one (all claimed by running warps)
+            long long at = (long long)tile - 1;
+            for (;;) {
+                const long long j = at - lane;
+                uint64_t wd;
+                if (j < 0) {
+                    wd = LJB_ST_INC;
+                } else {
+                    for (unsigned ns = 100; ((wd = ljb_ld_volatile(&P.status[1 + j])) & LJB_ST_MASK) == 0; ns = ns < 1600 ? ns * 2 : ns)
+                        __nanosleep(ns);
+                }
+                const unsigned inc = __ballot_sync(0xffffffffu, (wd & LJB_ST_MASK) == LJB_ST_INC);
+                uint64_t v = wd & ~LJB_ST_MASK;
+                if (inc) {
+                    const int first = __ffs(inc) - 1;
+                    if (lane > first) v = 0;
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                g += v;
+                if (inc) break;
+                at -= 32;
+            }
+        }
+        t.g_tile = g;
+        t.resolved = 1;
+        if ((g & 7) && tile > 0) { // the byte shared with the previous tile: its last bits were published with its size
+            uint32_t tw = 0;
+            if (lane == 0) {
+                for (unsigned ns = 100; ((tw = *(volatile uint32_t *)&P.tailw[tile - 1]) & TAIL_VALID) == 0; ns = ns < 1600 ? ns * 2 : ns)
+                    __nanosleep(ns);
+            }
+            t.last7 = __shfl_sync(0xffffffffu, tw, 0) & 0x7fu;
+        }
+    }
+    const uint64_t G = t.g_tile + t.flushed, E = G + nbits;
+    const int k = (int)(G & 7);
+    const uint32_t prev_tail = k ? (t.last7 & ((1u << k) - 1u)) << (8 - k) : 0u; // the k bits before G, as the high bits of a byte
+    int cnt;
+    const uint32_t lb = last_bits(src, nbits, cnt);
+    const uint32_t last7 = ((t.last7 << cnt) | lb) & 0x7fu;
+    if (final && lane == 0) {
+        ljb_st_volatile(&P.status[1 + tile], LJB_ST_INC | E); // walkers stop here
+        if (tile + 1 == P.ntiles) *P.total_bits = E;
+    }
+    const uint64_t blo = G >> 3, bhi = E >> 3; // bytes completed by this group (the first may start in the previous one)
+    const bool fits = ((E + 7) >> 3) <= P.ucap;
+    if (!fits && lane == 0) atomicOr((unsigned long long *)&P.result[2], 2ull);
+    const int sh = (int)(G & 31);
+    const uint64_t w0 = G >> 5;
+    const int nsrc = (int)((nbits + 31) >> 5);
+    const int nw = (int)((sh + nbits + 31) >> 5); // output words touched
+    for (int j = lane; j < nw; j += 32) {
+        const uint32_t cur = j < nsrc ? src[j] : 0u;
+        const uint32_t prev = j > 0 ? src[j - 1] : 0u;
+        uint32_t be = sh ? __funnelshift_r(cur, prev, sh) : cur;            // big-endian bit order
+        if (j == 0 && k) be |= prev_tail << (24 - 8 * (int)((G >> 3) & 3)); // complete the shared byte
+        const uint64_t b0 = (w0 + (uint64_t)j) << 2;                       // first global byte of this word
+        if (fits) {
+            if (b0 >= blo && b0 + 4 <= bhi) {
+                reinterpret_cast<uint32_t *>(P.ustream)[w0 + j] = __byte_perm(be, 0, 0x0123);
+            } else {
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    const uint64_t gb = b0 + b;
+                    if (gb >= blo && gb < bhi) P.ustream[gb] = (uint8_t)(be >> (24 - 8 * b));
+                }
+            }
+        }
+    }
+    __syncwarp();
+    for (int j = lane; j < nsrc; j += 32) src[j] = 0;
+    t.last7 = last7;
+    t.flushed += nbits;
+    __syncwarp();
 }
 
 template <bool SUB>
@@ -229,18 +401,18 @@ __global__ void __launch_bounds__(THREADS, 2) jfif_encode_kernel(const __grid_co
 {
     constexpr int DPM = SUB ? 6 : 3;  // data units per MCU
     constexpr int MPR = SUB ? 5 : 10; // MCUs per round
-    extern __shared__ uint32_t sm[];
+    constexpr int MCU_WORDS = SUB ? MCU_WORDS_420 : MCU_WORDS_444;
+    extern __shared__ __align__(16) uint32_t sm[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < T_WORDS; i += THREADS) sm[i] = P.tables[i];
     for (int i = threadIdx.x; i < 64; i += THREADS) {
         sm[S_MULT + i] = __float_as_uint(P.mult[i]);
         sm[S_MULT_C + i] = __float_as_uint(P.mult[64 + i]);
     }
-    uint32_t *buf = sm + S_FIXED + warp * WARP_WORDS;
-    uint32_t *coef = buf + CAP_WORDS;
-    uint32_t *pix = coef + COEF_WORDS;
-    float *chroma = reinterpret_cast<float *>(coef); // 4:2:0 exchange of the 2x2 means; dead before the coefficients are stored
-    for (int i = lane; i < CAP_WORDS; i += 32) buf[i] = 0;
+    uint32_t *buf = sm + S_FIXED + warp * WARP_WORDS; // the bit buffer being filled
+    uint32_t *pend = buf + CAP_WORDS;                 // the other one: the previous tile's bits, until placed
+    uint32_t *blocks = buf + 2 * CAP_WORDS;
+    for (int i = lane; i < 2 * CAP_WORDS; i += 32) buf[i] = 0;
     __syncthreads();
 
     const int mi = lane / DPM, d = lane - mi * DPM; // MCU within the round, data unit within the MCU
@@ -249,199 +421,125 @@ __global__ void __launch_bounds__(THREADS, 2) jfif_encode_kernel(const __grid_co
     const float *mult = reinterpret_cast<const float *>(sm + (is_luma ? S_MULT : S_MULT_C));
     const uint32_t below = (1u << lane) - 1u;
     const int R = P.rounds_per_tile;
+    // this lane's data-unit block and its row stride
+    const int my_rs = (SUB && d < 4) ? 16 : 8;
+    uint32_t *my_blk = blocks + mi * MCU_WORDS + (SUB ? (d < 4 ? (d >> 1) * 128 + (d & 1) * 8 : 256 + (d - 4) * 64) : d * 64);
+    // entropy phase: offsets of zig-zag positions 2l and 2l+1 inside a block of row stride 8; stride 16 adds 8 per row
+    const int nat0 = cZZ.nat[2 * lane], nat1 = cZZ.nat[2 * lane + 1];
+    const int off0_8 = nat0, off1_8 = nat1, off0_16 = nat0 + (nat0 >> 3) * 8, off1_16 = nat1 + (nat1 >> 3) * 8;
 
+    uint32_t pend_tile = 0, pend_bits = 0; // finished tile waiting in `pend` for its offset
     for (;;) {
         uint32_t tile = 0;
         if (lane == 0) tile = (uint32_t)atomicAdd((unsigned long long *)&P.status[0], 1ull);
         tile = __shfl_sync(0xffffffffu, tile, 0);
-        if (tile >= P.ntiles) break;
+        const bool have = tile < P.ntiles;
         const uint32_t r0 = tile * (uint32_t)R;
-        const uint32_t r1 = r0 + (uint32_t)R < P.nrounds ? r0 + (uint32_t)R : P.nrounds;
+        const uint32_t r1 = !have ? r0 : r0 + (uint32_t)R < P.nrounds ? r0 + (uint32_t)R : P.nrounds;
         int carry_y = 0, carry_u = 0, carry_v = 0; // DC of the last Y / Cb / Cr data unit before the current round
         uint32_t running = 0;                      // bits in the buffer
-        bool resolved = false;                     // global bit offset of the tile known (an early flush happened)
-        uint64_t g_tile = 0, flushed = 0;          // bit offset of the tile; bits of the tile already written
-        uint32_t prev_tail = 0;                    // partial byte left by the previous group (high bits)
-
-        // Write the buffer to the unstuffed stream.  final: this is the tile's last group.
-        auto flush = [&](bool final) {
+        auto place_pending = [&]() {
+            if (pend_bits) {
+                TileOut po = {0, 0, 0, 0};
+                place_group(P, pend, pend_tile, pend_bits, true, po);
+                pend_bits = 0;
+            }
+        };
+        // The buffer is full in the middle of a tile (denser data than the rounds-per-tile choice expects): move it to this
+        // warp's spill area in global memory and go on; the tile is then written out from there when it is finished.
+        uint32_t *spill = P.spill + (size_t)(blockIdx.x * NWARPS + warp) * (size_t)P.spill_slots * SPILL_WORDS;
+        int nspill = 0;
+        auto spill_buffer = [&]() {
             __syncwarp();
-            if (!resolved) {
-                if (final && lane == 0 && tile > 0) ljb_st_volatile(&P.status[1 + tile], LJB_ST_AGG | (uint64_t)running);
-                if (tile > 0) { // exclusive prefix over the tiles before this one (all claimed by running warps)
-                    long long at = (long long)tile - 1;
-                    for (;;) {
-                        const long long j = at - lane;
-                        uint64_t wd;
-                        if (j < 0) {
-                            wd = LJB_ST_INC;
-                        } else {
-                            while (((wd = ljb_ld_volatile(&P.status[1 + j])) & LJB_ST_MASK) == 0) __nanosleep(200);
-                        }
-                        const unsigned inc = __ballot_sync(0xffffffffu, (wd & LJB_ST_MASK) == LJB_ST_INC);
-                        uint64_t v = wd & ~LJB_ST_MASK;
-                        if (inc) {
-                            const int first = __ffs(inc) - 1;
-                            if (lane > first) v = 0;
-                        }
-#pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                        g_tile += v;
-                        if (inc) break;
-                        at -= 32;
-                    }
-                }
-                resolved = true;
-                if (!final && lane == 0) atomicAdd((unsigned long long *)&P.result[1], 1ull);
+            uint32_t *slot = spill + (size_t)nspill * SPILL_WORDS;
+            const int used = (int)((running + 31) >> 5);
+            for (int j = lane; j < used; j += 32) {
+                slot[j] = buf[j];
+                buf[j] = 0;
             }
-            const uint64_t G = g_tile + flushed, E = G + running;
-            if (final && lane == 0) {
-                ljb_st_volatile(&P.status[1 + tile], LJB_ST_INC | E);
-                if (tile + 1 == P.ntiles) *P.total_bits = E;
-                // The tile's trailing partial byte depends only on its own bits and offset (a tile has at least 12 bits):
-                // publish it before waiting for the predecessor's, so that tiles never wait in a chain.
-                uint32_t tb = 0;
-                const int k = (int)(E & 7);
-                if (k && running >= (uint32_t)k) { // the last k bits of the buffer, as the high bits of a byte
-                    const uint32_t pos = running - (uint32_t)k;
-                    const uint32_t wi = pos >> 5;
-                    const uint64_t two = ((uint64_t)buf[wi] << 32) | (wi + 1 < (uint32_t)CAP_WORDS ? buf[wi + 1] : 0u);
-                    tb = (uint32_t)(two >> (56 - (pos & 31))) & (0xff00u >> k) & 0xffu;
-                } else if (k) { // a last group shorter than that (only after an early flush): it continues this warp's own byte
-                    tb = (prev_tail | ((buf[0] >> 24) >> (int)(G & 7))) & (0xff00u >> k) & 0xffu;
-                }
-                *(volatile uint32_t *)&P.tailw[tile] = TAIL_VALID | tb;
-            }
-            if (flushed == 0 && tile > 0 && (G & 7)) { // first group of the tile: the byte shared with the previous tile
-                uint32_t tw = 0;
-                if (lane == 0) {
-                    while (((tw = *(volatile uint32_t *)&P.tailw[tile - 1]) & TAIL_VALID) == 0) __nanosleep(200);
-                }
-                prev_tail = __shfl_sync(0xffffffffu, tw, 0) & 0xffu;
-            }
-            const uint64_t blo = G >> 3, bhi = E >> 3; // bytes completed by this group (the first may start in the previous one)
-            const bool fits = ((E + 7) >> 3) <= P.ucap;
-            if (!fits && lane == 0) atomicOr((unsigned long long *)&P.result[2], 2ull);
-            const int sh = (int)(G & 31);
-            const uint64_t w0 = G >> 5;
-            const int nw = (int)((sh + running + 31) >> 5); // output words touched
-            uint32_t tail_here = 0;
-            for (int j = lane; j < nw; j += 32) {
-                const uint32_t cur = j < CAP_WORDS ? buf[j] : 0u; // sh + running can reach one word past the buffer
-                const uint32_t prev = j > 0 ? buf[j - 1] : 0u;
-                uint32_t be = sh ? __funnelshift_r(cur, prev, sh) : cur; // big-endian bit order
-                if (j == 0 && (G & 7)) be |= prev_tail << (24 - 8 * (int)((G >> 3) & 3)); // complete the shared byte
-                const uint64_t b0 = (w0 + (uint64_t)j) << 2;                             // first global byte of this word
-                if (fits) {
-                    if (b0 >= blo && b0 + 4 <= bhi) {
-                        reinterpret_cast<uint32_t *>(P.ustream)[w0 + j] = __byte_perm(be, 0, 0x0123);
-                    } else {
-#pragma unroll
-                        for (int b = 0; b < 4; ++b) {
-                            const uint64_t gb = b0 + b;
-                            if (gb >= blo && gb < bhi) P.ustream[gb] = (uint8_t)(be >> (24 - 8 * b));
-                        }
-                    }
-                }
-                if ((E & 7) && b0 <= bhi && bhi < b0 + 4) tail_here = 0x100u | ((be >> (24 - 8 * (int)(bhi & 3))) & 0xffu);
-            }
-            // after an early flush the trailing partial byte is completed by this warp's next group
-            const unsigned who = __ballot_sync(0xffffffffu, tail_here != 0);
-            prev_tail = who ? (__shfl_sync(0xffffffffu, tail_here, __ffs(who) - 1) & 0xffu) : 0u;
-            __syncwarp();
-            const int used = (int)((running + 31) >> 5) + 1;
-            for (int j = lane; j < used && j < CAP_WORDS; j += 32) buf[j] = 0;
-            __syncwarp();
-            flushed += running;
+            if (lane == 0) slot[CAP_WORDS] = running;
+            ++nspill;
             running = 0;
-        };
-        // lane's data unit in round `rr` (rr == r0 - 1: the halo MCU just before the tile, DC values only)
-        auto unit_of = [&](long long rr, uint32_t &m, bool &valid) {
-            const bool halo = rr < (long long)r0;
-            m = halo ? r0 * MPR - 1 : (uint32_t)rr * MPR + mi;
-            valid = lane_used && m < P.nmcu && (!halo || mi == 0);
-        };
-        // asynchronous copy of the round's pixels into shared memory
-        auto fetch = [&](long long rr) {
-            if (rr < (long long)r0) {
-                stage_pixels<SUB>(P, pix, r0 * MPR - 1, 1, lane);
-            } else {
-                const uint32_t m0 = (uint32_t)rr * MPR, left = P.nmcu - m0;
-                stage_pixels<SUB>(P, pix, m0, left < (uint32_t)MPR ? (int)left : MPR, lane);
-            }
+            __syncwarp();
         };
 
         const long long first = r0 == 0 ? 0 : (long long)r0 - 1;
-        fetch(first);
         for (long long rr = first; rr < (long long)r1; ++rr) {
+            // rr == r0 - 1 is the halo pass: only the MCU just before the tile, DC values only
             const bool halo = rr < (long long)r0;
-            uint32_t m;
-            bool valid;
-            unit_of(rr, m, valid);
+            const uint32_t m0 = halo ? r0 * MPR - 1 : (uint32_t)rr * MPR;
+            const uint32_t left = P.nmcu - m0;
+            const int nmcus = halo ? 1 : (left < (uint32_t)MPR ? (int)left : MPR);
+            const bool valid = lane_used && mi < nmcus;
+            const uint32_t m = m0 + (uint32_t)mi;
+            stage_pixels<SUB>(P, blocks, m0, nmcus);
             cp_async_wait_all();
             __syncwarp();
-            float s[64];
-#pragma unroll
-            for (int i = 0; i < 64; ++i) s[i] = 0.f;
 
-            // ---- colour conversion ----
+            // ---- colour conversion, in place ----
             if (SUB) {
-                float *slot = chroma + (mi * 2) * CHROMA_SLOT;
                 if (valid && d < 4) {
-                    const int qx = d & 1, qy = d >> 1;
-                    const uint32_t *blk = pix + mi * PIX_MCU_WORDS_420 + qy * 128 + qx * 8;
-                    float pu[8], pv[8];
-#pragma unroll
-                    for (int y = 0; y < 8; ++y) {
-                        float cu[8], cv[8];
-                        const uint4 pa = *reinterpret_cast<const uint4 *>(blk + y * 16), pb = *reinterpret_cast<const uint4 *>(blk + y * 16 + 4);
-                        const uint32_t pw[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};
+                    float *cu = reinterpret_cast<float *>(blocks + mi * MCU_WORDS + 256 + ((d >> 1) * 4) * 8 + (d & 1) * 4);
+#pragma unroll 1
+                    for (int yp = 0; yp < 4; ++yp) { // two pixel rows -> 16 Y samples + one row of 4 chroma means each
+                        uint4 *row0 = reinterpret_cast<uint4 *>(my_blk + (2 * yp) * 16), *row1 = reinterpret_cast<uint4 *>(my_blk + (2 * yp + 1) * 16);
+                        const uint4 a0 = row0[0], a1 = row0[1], b0 = row1[0], b1 = row1[1];
+                        const uint32_t t[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+                        const uint32_t bt[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                        float y0[8], y1[8], u[4], v[4];
 #pragma unroll
                         for (int x = 0; x < 8; ++x) {
-                            const uint32_t p = pw[x];
-                            const float r = (float)(p & 255u), g = (float)((p >> 8) & 255u), b = (float)((p >> 16) & 255u);
-                            s[y * 8 + x] = to_y(r, g, b);
-                            cu[x] = to_u(r, g, b);
-                            cv[x] = to_v(r, g, b);
+                            y0[x] = to_y(t[x]);
+                            y1[x] = to_y(bt[x]);
                         }
-                        if (y & 1) { // (top-left + top-right + bottom-left + bottom-right) * 0.25f  (stb :1557-1558)
 #pragma unroll
-                            for (int x = 0; x < 4; ++x) {
-                                const int at = (qy * 4 + (y >> 1)) * 8 + qx * 4 + x;
-                                slot[at] = FM(FA(FA(FA(pu[2 * x], pu[2 * x + 1]), cu[2 * x]), cu[2 * x + 1]), 0.25f);
-                                slot[CHROMA_SLOT + at] = FM(FA(FA(FA(pv[2 * x], pv[2 * x + 1]), cv[2 * x]), cv[2 * x + 1]), 0.25f);
-                            }
-                        } else {
-#pragma unroll
-                            for (int x = 0; x < 8; ++x) {
-                                pu[x] = cu[x];
-                                pv[x] = cv[x];
-                            }
+                        for (int x = 0; x < 4; ++x) { // (top-left + top-right + bottom-left + bottom-right) * 0.25f  (stb :1557-1558)
+                            u[x] = FM(FA(FA(FA(to_u(t[2 * x]), to_u(t[2 * x + 1])), to_u(bt[2 * x])), to_u(bt[2 * x + 1])), 0.25f);
+                            v[x] = FM(FA(FA(FA(to_v(t[2 * x]), to_v(t[2 * x + 1])), to_v(bt[2 * x])), to_v(bt[2 * x + 1])), 0.25f);
                         }
+                        reinterpret_cast<float4 *>(row0)[0] = make_float4(y0[0], y0[1], y0[2], y0[3]);
+                        reinterpret_cast<float4 *>(row0)[1] = make_float4(y0[4], y0[5], y0[6], y0[7]);
+                        reinterpret_cast<float4 *>(row1)[0] = make_float4(y1[0], y1[1], y1[2], y1[3]);
+                        reinterpret_cast<float4 *>(row1)[1] = make_float4(y1[4], y1[5], y1[6], y1[7]);
+                        *reinterpret_cast<float4 *>(cu + yp * 8) = make_float4(u[0], u[1], u[2], u[3]);
+                        *reinterpret_cast<float4 *>(cu + 64 + yp * 8) = make_float4(v[0], v[1], v[2], v[3]);
                     }
-                }
-                __syncwarp();
-                if (valid && d >= 4) {
-                    const float *src = slot + (d - 4) * CHROMA_SLOT;
-#pragma unroll
-                    for (int i = 0; i < 64; ++i) s[i] = src[i];
                 }
                 __syncwarp();
             } else {
-                if (valid) {
-                    const uint32_t *blk = pix + mi * PIX_MCU_WORDS_444;
+                const uint4 *src = reinterpret_cast<const uint4 *>(blocks + mi * MCU_WORDS);
+#pragma unroll 1
+                for (int y = 0; y < 8; ++y) { // the three lanes of an MCU read the same pixel row, then each writes its own
+                    uint4 a0 = make_uint4(0, 0, 0, 0), a1 = a0;
+                    if (valid) {
+                        a0 = src[2 * y];
+                        a1 = src[2 * y + 1];
+                    }
+                    __syncwarp();
+                    if (valid) {
+                        const uint32_t t[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+                        float o[8];
 #pragma unroll
-                    for (int y = 0; y < 8; ++y) {
-                        const uint4 pa = *reinterpret_cast<const uint4 *>(blk + y * 8), pb = *reinterpret_cast<const uint4 *>(blk + y * 8 + 4);
-                        const uint32_t pw[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};
-#pragma unroll
-                        for (int x = 0; x < 8; ++x) {
-                            const uint32_t p = pw[x];
-                            const float r = (float)(p & 255u), g = (float)((p >> 8) & 255u), b = (float)((p >> 16) & 255u);
-                            s[y * 8 + x] = d == 0 ? to_y(r, g, b) : d == 1 ? to_u(r, g, b) : to_v(r, g, b);
-                        }
+                        for (int x = 0; x < 8; ++x) o[x] = d == 0 ? to_y(t[x]) : d == 1 ? to_u(t[x]) : to_v(t[x]);
+                        float4 *dst = reinterpret_cast<float4 *>(my_blk + y * 8);
+                        dst[0] = make_float4(o[0], o[1], o[2], o[3]);
+                        dst[1] = make_float4(o[4], o[5], o[6], o[7]);
                     }
                 }
+                __syncwarp();
+            }
+
+            // ---- the lane's 64 samples to registers ----
+            float s[64];
+#pragma unroll
+            for (int y = 0; y < 8; ++y) {
+                float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+                if (valid) {
+                    a = *reinterpret_cast<const float4 *>(my_blk + y * my_rs);
+                    b = *reinterpret_cast<const float4 *>(my_blk + y * my_rs + 4);
+                }
+                s[y * 8 + 0] = a.x; s[y * 8 + 1] = a.y; s[y * 8 + 2] = a.z; s[y * 8 + 3] = a.w;
+                s[y * 8 + 4] = b.x; s[y * 8 + 5] = b.y; s[y * 8 + 6] = b.z; s[y * 8 + 7] = b.w;
             }
 
             if (halo) { // DC only: output 0 of the row passes, then of the column pass over them
@@ -454,136 +552,161 @@ __global__ void __launch_bounds__(THREADS, 2) jfif_encode_kernel(const __grid_co
                 carry_u = __shfl_sync(0xffffffffu, dc, SUB ? 4 : 1);
                 carry_v = __shfl_sync(0xffffffffu, dc, SUB ? 5 : 2);
                 __syncwarp();
-                fetch(rr + 1);
                 continue;
             }
-            const uint32_t r = (uint32_t)rr;
 
-            // ---- DCT, quantisation, DC difference; 64 int16 in zig-zag order to shared memory ----
-            int dc = 0;
-            if (valid) {
+            // ---- DCT, quantisation, DC difference; 64 int32 back into the block ----
 #pragma unroll
-                for (int y = 0; y < 8; ++y)
-                    aan8(s[y * 8], s[y * 8 + 1], s[y * 8 + 2], s[y * 8 + 3], s[y * 8 + 4], s[y * 8 + 5], s[y * 8 + 6], s[y * 8 + 7]);
+            for (int y = 0; y < 8; ++y)
+                aan8(s[y * 8], s[y * 8 + 1], s[y * 8 + 2], s[y * 8 + 3], s[y * 8 + 4], s[y * 8 + 5], s[y * 8 + 6], s[y * 8 + 7]);
 #pragma unroll
-                for (int x = 0; x < 8; ++x) aan8(s[x], s[8 + x], s[16 + x], s[24 + x], s[32 + x], s[40 + x], s[48 + x], s[56 + x]);
-                dc = quantise(s[0], mult[0]);
-            }
+            for (int x = 0; x < 8; ++x) aan8(s[x], s[8 + x], s[16 + x], s[24 + x], s[32 + x], s[40 + x], s[48 + x], s[56 + x]);
+            int q[64];
+#pragma unroll
+            for (int i = 0; i < 64; ++i) q[i] = quantise(s[i], mult[i]);
+            const int dc = valid ? q[0] : 0;
             int pred;
             {
                 const int back = SUB ? (d == 0 ? 3 : d < 4 ? 1 : 6) : 3;
                 const bool from_carry = SUB ? (mi == 0 && (d == 0 || d >= 4)) : mi == 0;
-                const int src = lane - back;
-                const int up = __shfl_sync(0xffffffffu, dc, src < 0 ? 0 : src);
+                const int srcl = lane - back;
+                const int up = __shfl_sync(0xffffffffu, dc, srcl < 0 ? 0 : srcl);
                 const int cy = SUB ? (d == 0 ? carry_y : d == 4 ? carry_u : carry_v) : (d == 0 ? carry_y : d == 1 ? carry_u : carry_v);
                 pred = from_carry ? cy : up;
             }
             if (valid) {
-                uint32_t *dst = coef + lane * COEF_STRIDE;
-                int16_t *gdst = P.coefs ? P.coefs + ((size_t)m * DPM + d) * 64 : nullptr;
+                if (P.coefs) {
+                    int16_t *gdst = P.coefs + ((size_t)m * DPM + d) * 64;
 #pragma unroll
-                for (int k = 0; k < 64; k += 2) {
-                    const int a = k == 0 ? dc : quantise(s[kZZ.nat[k]], mult[kZZ.nat[k]]);
-                    const int b = quantise(s[kZZ.nat[k + 1]], mult[kZZ.nat[k + 1]]);
-                    if (gdst) {
-                        gdst[k] = (int16_t)a;
-                        gdst[k + 1] = (int16_t)b;
-                    }
-                    // position 0 carries the DC DIFFERENCE: that is what gets coded
-                    dst[k >> 1] = (uint32_t)((k == 0 ? dc - pred : a) & 0xffff) | ((uint32_t)b << 16);
+                    for (int kk = 0; kk < 64; ++kk) gdst[kk] = (int16_t)q[kZZ.nat[kk]];
+                }
+                q[0] = dc - pred; // position 0 carries the DC DIFFERENCE: that is what gets coded
+#pragma unroll
+                for (int y = 0; y < 8; ++y) {
+                    *reinterpret_cast<int4 *>(my_blk + y * my_rs) = make_int4(q[y * 8], q[y * 8 + 1], q[y * 8 + 2], q[y * 8 + 3]);
+                    *reinterpret_cast<int4 *>(my_blk + y * my_rs + 4) = make_int4(q[y * 8 + 4], q[y * 8 + 5], q[y * 8 + 6], q[y * 8 + 7]);
                 }
             }
             {
-                const uint32_t left = P.nmcu - r * MPR;
-                const int nv = left < (uint32_t)MPR ? (int)left : MPR;
-                const int base = (nv - 1) * DPM;
+                const int base = (nmcus - 1) * DPM;
                 carry_y = __shfl_sync(0xffffffffu, dc, base + (SUB ? 3 : 0));
                 carry_u = __shfl_sync(0xffffffffu, dc, base + (SUB ? 4 : 1));
                 carry_v = __shfl_sync(0xffffffffu, dc, base + (SUB ? 5 : 2));
             }
             __syncwarp();
-            if (rr + 1 < (long long)r1) fetch(rr + 1); // in flight during the entropy phase
 
-            // ---- entropy coding: one data unit per iteration, lane l codes zig-zag positions 2l and 2l+1 ----
+            // ---- entropy coding: two data units per iteration, lane l codes zig-zag positions 2l and 2l+1 of each ----
             {
-                const uint32_t left = P.nmcu - r * MPR;
-                const int nunits = (left < (uint32_t)MPR ? (int)left : MPR) * DPM;
-                int dd = 0; // data unit within its MCU
-                for (int j = 0; j < nunits; ++j) {
-                    const bool luma = SUB ? dd < 4 : dd == 0;
-                    dd = dd + 1 == DPM ? 0 : dd + 1;
-                    const uint32_t *tab_ac = sm + (luma ? T_AC_Y : T_AC_C);
-                    const uint32_t *tab_dc = sm + (luma ? T_DC_Y : T_DC_C);
-                    const uint32_t wd = coef[j * COEF_STRIDE + lane];
-                    const int c0 = (int)(short)(wd & 0xffffu), c1 = (int)wd >> 16;
-                    const uint32_t nz_e = __ballot_sync(0xffffffffu, c0 != 0) | 1u; // position 0 (DC) always bounds a run
-                    const uint32_t nz_o = __ballot_sync(0xffffffffu, c1 != 0);
-                    // nearest coded position before 2l: even ones are 2*i, odd ones 2*i+1
-                    const uint32_t pe = nz_e & below, po = nz_o & below;
-                    const int prev_e = max(62 - 2 * __clz(pe), 63 - 2 * __clz(po)); // -2 / -1 when empty (lane 0 only)
-                    const int run0 = 2 * lane - 1 - prev_e;
-                    const int run1 = (c0 != 0 || lane == 0) ? 0 : run0 + 1;
-                    uint64_t v0 = 0, v1 = 0;
-                    int l0 = 0, l1 = 0;
-                    const int n0 = bitlen(c0), n1 = bitlen(c1);
-                    if (lane == 0) {
-                        const uint32_t e = tab_dc[n0];
-                        v0 = ((uint64_t)(e >> 8) << n0) | (n0 ? extra_bits(c0, n0) : 0u);
-                        l0 = (int)(e & 255u) + n0;
-                    } else if (c0 != 0) {
-                        const uint32_t e = tab_ac[(run0 & 15) * 16 + n0];
-                        v0 = ((uint64_t)(e >> 8) << n0) | extra_bits(c0, n0);
-                        l0 = (int)(e & 255u) + n0;
+                const int nunits = nmcus * DPM;
+                int mA = 0, dA = 0; // MCU and data unit within it of unit j
+#pragma unroll 1
+                for (int j = 0; j < nunits; j += 2) {
+                    const bool haveB = j + 1 < nunits;
+                    int mB = mA, dB = dA + 1;
+                    if (dB == DPM) {
+                        dB = 0;
+                        ++mB;
                     }
-                    if (c1 != 0) {
-                        const uint32_t e = tab_ac[(run1 & 15) * 16 + n1];
-                        v1 = ((uint64_t)(e >> 8) << n1) | extra_bits(c1, n1);
-                        l1 = (int)(e & 255u) + n1;
-                    } else if (lane == 31) { // position 63 is zero: end of block
-                        v1 = tab_ac[0] >> 8;
-                        l1 = (int)(tab_ac[0] & 255u);
+                    const bool lumaA = SUB ? dA < 4 : dA == 0, lumaB = SUB ? dB < 4 : dB == 0;
+                    const int *blkA = reinterpret_cast<const int *>(blocks) + mA * MCU_WORDS +
+                                      (SUB ? (dA < 4 ? (dA >> 1) * 128 + (dA & 1) * 8 : 256 + (dA - 4) * 64) : dA * 64);
+                    const int *blkB = reinterpret_cast<const int *>(blocks) + mB * MCU_WORDS +
+                                      (SUB ? (dB < 4 ? (dB >> 1) * 128 + (dB & 1) * 8 : 256 + (dB - 4) * 64) : dB * 64);
+                    const bool wideA = SUB && dA < 4, wideB = SUB && dB < 4;
+                    const int a0 = blkA[wideA ? off0_16 : off0_8], a1 = blkA[wideA ? off1_16 : off1_8];
+                    int b0 = 0, b1 = 0;
+                    if (haveB) {
+                        b0 = blkB[wideB ? off0_16 : off0_8];
+                        b1 = blkB[wideB ? off1_16 : off1_8];
                     }
-                    // runs of 16 or more zeros: ZRL codes in front (rare; at most 3 per symbol)
-                    const bool z0 = lane != 0 && c0 != 0 && run0 >= 16, z1 = c1 != 0 && run1 >= 16;
-                    const bool any_zrl = __any_sync(0xffffffffu, z0 || z1);
+                    UnitBits A, B;
+                    unit_symbols(a0, a1, true, sm + (lumaA ? T_AC_Y : T_AC_C), sm + (lumaA ? T_DC_Y : T_DC_C), lane, below, A);
+                    unit_symbols(b0, b1, haveB, sm + (lumaB ? T_AC_Y : T_AC_C), sm + (lumaB ? T_DC_Y : T_DC_C), lane, below, B);
+                    // runs of 16 or more zeros need ZRL codes in front of the symbol (rare on dense data): lengths first
+                    const bool any_zrl = __any_sync(0xffffffffu, A.k0 | A.k1 | B.k0 | B.k1);
+                    uint32_t lenA = (uint32_t)(A.l0 + A.l1), lenB = (uint32_t)(B.l0 + B.l1);
+                    int zlA = 0, zlB = 0;
                     if (any_zrl) {
-                        const uint32_t zrl = tab_ac[0xF0];
-                        const int zl = (int)(zrl & 255u);
-                        if (z0) {
-                            for (int i = 0; i < (run0 >> 4); ++i) v0 |= (uint64_t)(zrl >> 8) << (l0 + i * zl);
-                            l0 += (run0 >> 4) * zl;
-                        }
-                        if (z1) {
-                            for (int i = 0; i < (run1 >> 4); ++i) v1 |= (uint64_t)(zrl >> 8) << (l1 + i * zl);
-                            l1 += (run1 >> 4) * zl;
-                        }
+                        zlA = (int)(sm[(lumaA ? T_AC_Y : T_AC_C) + 0xF0] & 255u);
+                        zlB = (int)(sm[(lumaB ? T_AC_Y : T_AC_C) + 0xF0] & 255u);
+                        lenA += (uint32_t)((A.k0 + A.k1) * zlA);
+                        lenB += (uint32_t)((B.k0 + B.k1) * zlB);
                     }
-                    const uint32_t len = (uint32_t)(l0 + l1);
-                    uint32_t incl = len;
+                    uint32_t incl = lenA | (lenB << 16); // both prefix sums in one scan (a data unit has < 2^16 bits)
 #pragma unroll
                     for (int o = 1; o < 32; o <<= 1) {
-                        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-                        if (lane >= o) incl += t;
+                        const uint32_t tt = __shfl_up_sync(0xffffffffu, incl, o);
+                        if (lane >= o) incl += tt;
                     }
-                    const uint32_t unit_bits = __shfl_sync(0xffffffffu, incl, 31);
-                    if (running + unit_bits + 7 > (uint32_t)CAP_BITS) flush(false);
-                    const uint32_t off = running + incl - len;
-                    if (any_zrl) { // up to 59 bits each
-                        or_bits(buf, off, v0, l0);
-                        or_bits(buf, off + (uint32_t)l0, v1, l1);
-                    } else { // at most 2 x 27 bits: one string
-                        or_bits(buf, off, (v0 << l1) | v1, (int)len);
+                    const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
+                    const uint32_t totA = tot & 0xffffu, totB = tot >> 16;
+                    if (running + totA + totB + 7 > (uint32_t)CAP_BITS) spill_buffer();
+                    const uint32_t offA = running + (incl & 0xffffu) - lenA, offB = running + totA + (incl >> 16) - lenB;
+                    if (!any_zrl) {
+                        or_pair(buf, offA, A.v0, A.l0, A.v1, A.l1);
+                        or_pair(buf, offB, B.v0, B.l0, B.v1, B.l1);
+                    } else {
+                        or_pair_zrl(buf, offA, A, sm[(lumaA ? T_AC_Y : T_AC_C) + 0xF0] >> 8, zlA);
+                        or_pair_zrl(buf, offB, B, sm[(lumaB ? T_AC_Y : T_AC_C) + 0xF0] >> 8, zlB);
                     }
-                    running += unit_bits;
+                    running += totA + totB;
+                    mA = mB;
+                    dA = dB + 1;
+                    if (dA == DPM) {
+                        dA = 0;
+                        ++mA;
+                    }
                 }
             }
             __syncwarp();
         }
+        // the previous tile: another tile's worth of time has passed, its predecessors have long published
+        place_pending();
+        if (!have) break;
         if (r1 == P.nrounds) { // padding of the EOI marker: seven one-bits (stb :1586)
             if (lane == 0) or_bits(buf, running, 0x7Fu, 7);
             running += 7;
+            __syncwarp();
         }
-        flush(true);
+        if (nspill == 0) { // publish size and last bits now; the offset is fetched after the next tile
+            if (lane == 0) {
+                int cnt;
+                const uint32_t lb = last_bits(buf, running, cnt); // a tile has at least 12 bits: cnt == 7
+                *(volatile uint32_t *)&P.tailw[tile] = TAIL_VALID | lb;
+                ljb_st_volatile(&P.status[1 + tile], (tile == 0 ? LJB_ST_INC : LJB_ST_AGG) | (uint64_t)running);
+            }
+            uint32_t *t2 = buf;
+            buf = pend;
+            pend = t2;
+            pend_tile = tile;
+            pend_bits = running;
+        } else { // a spilled tile: publish, then write it out at once, group by group
+            uint64_t total = running;
+            uint32_t last7 = 0;
+            for (int i = 0; i < nspill; ++i) {
+                const uint32_t *slot = spill + (size_t)i * SPILL_WORDS;
+                int cnt;
+                const uint32_t nb = slot[CAP_WORDS], lb = last_bits(slot, nb, cnt);
+                last7 = ((last7 << cnt) | lb) & 0x7fu;
+                total += nb;
+            }
+            {
+                int cnt;
+                const uint32_t lb = last_bits(buf, running, cnt);
+                last7 = ((last7 << cnt) | lb) & 0x7fu;
+            }
+            if (lane == 0) {
+                atomicAdd((unsigned long long *)&P.result[1], 1ull);
+                *(volatile uint32_t *)&P.tailw[tile] = TAIL_VALID | last7;
+                ljb_st_volatile(&P.status[1 + tile], (tile == 0 ? LJB_ST_INC : LJB_ST_AGG) | total);
+            }
+            TileOut tout = {0, 0, 0, 0};
+            for (int i = 0; i < nspill; ++i) {
+                uint32_t *slot = spill + (size_t)i * SPILL_WORDS;
+                place_group(P, slot, tile, slot[CAP_WORDS], false, tout);
+            }
+            place_group(P, buf, tile, running, true, tout);
+        }
     }
 }
 
@@ -882,10 +1005,10 @@ extern "C" int ljb_jfif_encode_dev(ljb_ctx *ctx, const uint8_t *d_pixels, int w,
     const uint32_t nmcu = (uint32_t)nmcu64;
     const uint32_t mpr = pl.subsample ? 5 : 10;
     const uint32_t nrounds = (nmcu + mpr - 1) / mpr;
-    // rounds per tile: as many as fit the 4 KB bit buffer on uniform noise (the densest realistic input) at this quality;
-    // denser tiles still encode correctly through early flushes, only slower
+    // rounds per tile: as many as fit the 2.5 KB bit buffer on uniform noise (the densest realistic input) at this quality;
+    // denser tiles spill their bit buffer to global memory and are written out from there: correct, only slower
     const int q0 = quality ? quality : 90;
-    int R = q0 <= 60 ? 6 : q0 <= 80 ? 4 : q0 <= 90 ? 3 : q0 <= 95 ? 2 : 1;
+    int R = q0 <= 50 ? 4 : q0 <= 80 ? 3 : q0 <= 90 ? 2 : 1;
     if (const char *e = getenv("LJB_JFIF_ROUNDS")) { // test / tuning hook
         const int v = atoi(e);
         if (v >= 1 && v <= MAX_ROUNDS_PER_TILE) R = v;
@@ -904,7 +1027,11 @@ extern "C" int ljb_jfif_encode_dev(ljb_ctx *ctx, const uint8_t *d_pixels, int w,
     const size_t o_st2 = o_st1 + ((size_t)ntiles + 1) * 8;
     const size_t o_tailw = o_st2 + (nchunks_max + 1) * 8;
     const size_t o_end = o_tailw + (size_t)ntiles * 4;
-    if ((rc = ljb_ensure(&ctx->d_status, &ctx->status_bytes, o_end)) != 0) return rc;
+    // spill area: a tile is at most R rounds of 30 data units of 216 bytes
+    const int spill_slots = (R * UNITS_PER_ROUND * 216 * 8) / (CAP_BITS - UNITS_PER_ROUND * 216 * 8 / 15) + 2;
+    const size_t o_spill = (o_end + 15) & ~(size_t)15;
+    const size_t spill_bytes = (size_t)ctx->num_sms * 2 * NWARPS * (size_t)spill_slots * SPILL_WORDS * 4;
+    if ((rc = ljb_ensure(&ctx->d_status, &ctx->status_bytes, o_spill + spill_bytes)) != 0) return rc;
     uint8_t *sb = (uint8_t *)ctx->d_status;
     uint32_t tables[T_WORDS];
     build_tables(tables);
@@ -929,6 +1056,8 @@ extern "C" int ljb_jfif_encode_dev(ljb_ctx *ctx, const uint8_t *d_pixels, int w,
     P.status = (uint64_t *)(sb + o_st1);
     P.tailw = (uint32_t *)(sb + o_tailw);
     P.rounds_per_tile = R;
+    P.spill = (uint32_t *)(sb + o_spill);
+    P.spill_slots = spill_slots;
     P.total_bits = (uint64_t *)(sb + o_total);
     P.result = d_result;
     P.coefs = d_coefs;

@@ -94,6 +94,15 @@ def test_noise_512_other_qualities(ljb, ctx, oracle, quality, sub):
     assert np.array_equal(ljb.jfif.write_jpg(img, quality, sub, ctx=ctx), oracle.jfif_encode(img, quality, sub))
 
 
+def test_spilled_tiles(ljb, ctx, oracle, monkeypatch):
+    """Eight rounds per tile at quality 75 (the library would choose three): every tile overflows the 2.5 KB bit buffer
+    several times and goes through the spill area in global memory; the file does not change."""
+    monkeypatch.setenv("LJB_JFIF_ROUNDS", "8")
+    img = ljb.synth.random_image(640, 480, seed=21)
+    for q, sub in ((75, -1), (75, 0), (100, 1)):
+        assert np.array_equal(ljb.jfif.write_jpg(img, q, sub, ctx=ctx), oracle.jfif_encode(img, q, sub)), (q, sub)
+
+
 def test_natural_image_tiles(ljb, ctx, oracle):
     """The og.png crop tiled to 2048 x 1500: smooth content, most coefficients zero, long runs, many tiles."""
     crop = cases.og_crop()
