@@ -10,6 +10,8 @@ collective, ONE all-gather of the per-rank compressed byte totals per step (SURV
 A "step" is one pass of the hot path over one batch of synthetic input:
   LZ4  (headline `value`): BASELINE.json configs[2] — 4 GiB random_extract-style text, 64 KiB blocks, per GPU
   JPEG (`jpeg` object)   : BASELINE.json configs[3] — one 16384 x 16384 random_image-style RGBA image, per GPU
+  JFIF (`jfif` object)   : the same image through the true baseline-JPEG encoder (byte-identical to the stb_image_write.h
+                           the reference vendors) at quality 75: 4:4:4 as BASELINE.json words it, and stb's own 4:2:0
 `value` is measured with inputs resident in HBM (CUDA events, max over ranks); `e2e` is the same work
 through the C ABI's host-buffer entry point with pinned host buffers, H2D and D2H inside the timed region.
 Inputs are far larger than the 126 MB L2, so no explicit L2 flush is needed between iterations.
@@ -37,7 +39,9 @@ LZ4_BYTES = int(os.environ.get("LJB_BENCH_LZ4_BYTES", 4 * GIB))
 JPEG_DIM = int(os.environ.get("LJB_BENCH_JPEG_DIM", 16384))
 # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the ncu pass over this same command committed as
 # profiles/r1/launches_r1c_bench_steps2_warmup1.csv (bytes at the default workload sizes; None for other sizes).
-NCU_TRAFFIC = {"lz4": 4.83e9 + 16.44e9 if LZ4_BYTES == 4 * GIB else None, "jpeg": 1.077e9 + 0.207e9 if JPEG_DIM == 16384 else None}
+NCU_TRAFFIC = {"lz4": 4.83e9 + 16.44e9 if LZ4_BYTES == 4 * GIB else None, "jpeg": 1.077e9 + 0.207e9 if JPEG_DIM == 16384 else None,
+               "jfif": None}
+JFIF_QUALITY = 75
 
 
 def measured_peak_gbs():
@@ -144,6 +148,26 @@ def _cpu_jpeg(w: int, h: int, threads: int):
     return w * h / sec / 1e6, kind, sec
 
 
+def _cpu_jfif(w: int, h: int, threads: int, subsample: int):
+    """The reference's vendored stbi_write_jpg (oracle/_ref) on `threads` host threads, one whole image each; falls back
+    to this repo's C restatement of it."""
+    from oracle.pyoracle import Oracle, Ref
+
+    orc = Oracle()
+    img = orc.synth_image(42, w, h)
+    if Ref.available("jfif"):
+        reps = max(1, (64 << 20) // (w * h))  # ~5-10 s of stb on every thread
+        sec, _ = Ref("jfif").jfif_time_mt(img, JFIF_QUALITY, subsample, threads, reps)
+        return reps * threads * w * h / sec / 1e6, "reference", sec
+    from concurrent.futures import ThreadPoolExecutor
+
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(threads) as ex:
+        list(ex.map(lambda i: orc.jfif_encode(img, JFIF_QUALITY, subsample), range(threads)))
+    sec = time.perf_counter() - t0
+    return threads * w * h / sec / 1e6, "port", sec
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -151,16 +175,21 @@ def run_reference(args):
     threads = os.cpu_count() or 1
     sample_blocks = max(threads, 16)
     jw, jh = 4096, 2048  # ~25 CPU-seconds of the reference's per-group stages
-    lz, jp = [], []
+    lz, jp, jf4, jf2 = [], [], [], []
     kind = "reference"
     for i in range(args.warmup + args.steps):
         v, kind, _ = _cpu_lz4(sample_blocks, threads)
         vj, kindj, _ = _cpu_jpeg(jw, jh, threads)
+        v4, kindf, _ = _cpu_jfif(2048, 2048, threads, 0)
+        v2, _, _ = _cpu_jfif(2048, 2048, threads, -1)
         if i >= args.warmup:
             lz.append(v)
             jp.append(vj)
+            jf4.append(v4)
+            jf2.append(v2)
     value = sum(lz) / len(lz)
     jvalue = sum(jp) / len(jp)
+    f4value, f2value = sum(jf4) / len(jf4), sum(jf2) / len(jf2)
     sample = f"{sample_blocks} blocks of 64 KiB of the seed-42 random_extract text, block_encode on {threads} threads"
     line = {
         "impl": "reference", "metric": "LZ4 compress GB/s (headline) & JPEG encode MPix/s (jpeg)", "value": value, "unit": "GB/s",
@@ -175,6 +204,11 @@ def run_reference(args):
                  "cpu_baseline": {"value": jvalue, "unit": "MPix/s", "cores": threads, "kind": kindj,
                                   "sample": f"{jw}x{jh} seed-42 noise image, per-group encode stages on {threads} threads"},
                  "e2e": {"value": jvalue, "unit": "MPix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}},
+        "jfif": {"metric": "baseline JPEG (JFIF) encode MPix/s, quality 75, 4:4:4", "value": f4value, "unit": "MPix/s",
+                 "cpu_baseline": {"value": f4value, "unit": "MPix/s", "cores": threads, "kind": kindf,
+                                  "sample": f"2048x2048 seed-42 noise image, stbi_write_jpg quality {JFIF_QUALITY}, 16 images per thread on {threads} threads"},
+                 "e2e": {"value": f4value, "unit": "MPix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                 "stb_rule_420": {"value": f2value, "unit": "MPix/s"}},
     }
     print(json.dumps(line))
     return 0
@@ -351,6 +385,46 @@ def run_gpu(args):
     jp_e2e_value = total_px / (jp_e2e_ms * 1e-3) / 1e6
     jp_achieved = (4.0 * W * H + jp_out_bytes) / (jp_kernel_ms * 1e-3) / 1e9
 
+    # ------------------------------- JFIF (true baseline JPEG) ------------------------------------------
+    del hj_out, dj_out, dj_offs, dj_bits
+    torch.cuda.empty_cache()
+    fcap = 607 + 2 + 2 * W * H + 4096  # noise at quality 75 needs ~1.26 B/px (4:4:4); LJB_E_CAPACITY is reported if exceeded
+    df_out = torch.empty(fcap, dtype=torch.uint8, device=dev)
+    df_res = torch.zeros(3, dtype=torch.int64, device=dev)
+    hf_out = torch.empty(fcap, dtype=torch.uint8, pin_memory=True)
+    fout_len = C.c_size_t(0)
+    jfif = {}
+    for name, sub in (("444", 0), ("420", -1)):
+        def jfif_step_device():
+            ljb.jfif.encode_device(dj_in, W, H, 4, JFIF_QUALITY, sub, df_out, df_res, ctx)
+            if world > 1:
+                with torch.cuda.stream(ext_stream):
+                    ljb.sharding.gather_totals_device(df_res[0:1])
+
+        def jfif_step_e2e():
+            rc = lib.ljb_jfif_encode(ctx.handle, hj_in.data_ptr(), W, H, 4, 4 * W, JFIF_QUALITY, sub, hf_out.data_ptr(), fcap,
+                                     C.byref(fout_len))
+            N.check(rc, "ljb_jfif_encode")
+            if world > 1:
+                ljb.sharding.gather_totals(int(fout_len.value), device=dev)
+
+        f_ms, _, f_launches = timed(jfif_step_device, args.steps, args.warmup)
+        ks = []
+        for _ in range(min(3, args.steps)):
+            ljb.jfif.encode_device(dj_in, W, H, 4, JFIF_QUALITY, sub, df_out, df_res, ctx)
+            ks.append(ctx.last_kernel_ms())
+        f_kernel_ms = sum(ks) / len(ks)
+        torch.cuda.synchronize()
+        f_out_bytes = int(df_res[0].item())
+        if int(df_res[2].item()):
+            raise SystemExit(f"JFIF kernels reported error flags {int(df_res[2].item())}")
+        _, fe2e_wall, _ = timed(jfif_step_e2e, e2e_steps, 1, use_events=False)
+        f_e2e_ms = max_over_ranks(fe2e_wall * 1e3 / e2e_steps)
+        assert int(fout_len.value) == f_out_bytes, "host-buffer path and device path disagree on the file length"
+        jfif[name] = {"value": total_px / (f_ms / args.steps * 1e-3) / 1e6, "ms_per_step": f_ms / args.steps, "kernel_ms": f_kernel_ms,
+                      "out_bytes": f_out_bytes, "e2e_value": total_px / (f_e2e_ms * 1e-3) / 1e6, "e2e_ms": f_e2e_ms,
+                      "achieved": (4.0 * W * H + f_out_bytes) / (f_kernel_ms * 1e-3) / 1e9, "launches": f_launches}
+
     clocks = sampler.stop()
 
     # ------------------------------- CPU baseline (rank 0, N = 1 only) ----------------------------------
@@ -364,6 +438,11 @@ def run_gpu(args):
         vj, kindj, secj = _cpu_jpeg(4096, 2048, threads)
         cpu_jp = {"value": vj, "unit": "MPix/s", "cores": threads, "kind": kindj,
                   "sample": f"4096x2048 seed-42 noise image, reference per-group encode stages on {threads} threads, {secj:.1f} s"}
+        cpu_jf = {}
+        for name, sub in (("444", 0), ("420", -1)):
+            vf, kindf, secf = _cpu_jfif(4096, 4096, threads, sub)
+            cpu_jf[name] = {"value": vf, "unit": "MPix/s", "cores": threads, "kind": kindf,
+                            "sample": f"4096x4096 seed-42 noise image, stbi_write_jpg quality {JFIF_QUALITY}, 4 images per thread on {threads} threads, {secf:.1f} s"}
 
     if rank == 0:
         line = {
@@ -380,7 +459,7 @@ def run_gpu(args):
             "e2e": {"value": lz_e2e_value, "unit": "GB/s", "h2d_bytes_per_step": n,
                     "d2h_bytes_per_step": lz_out_bytes + 8 * (nblocks + 1) + 24, "ms_per_step": lz_e2e_ms,
                     "api": "ljb_lz4_compress (host buffers, pinned)"},
-            "gpu_launches": lz_launches + jp_launches,
+            "gpu_launches": lz_launches + jp_launches + sum(v["launches"] for v in jfif.values()),
             "clocks": clocks,
             "jpeg": {
                 "metric": "JPEG encode MPix/s", "value": jp_value, "unit": "MPix/s", "ms_per_step": jp_ms / args.steps,
@@ -394,9 +473,27 @@ def run_gpu(args):
                         "api": "ljb_jpeg_encode_rgba (host buffers, pinned)"},
             },
         }
+        def jfif_obj(name, label):
+            v = jfif[name]
+            return {"metric": f"baseline JPEG (JFIF) encode MPix/s, quality {JFIF_QUALITY}, {label}", "value": v["value"], "unit": "MPix/s",
+                    "ms_per_step": v["ms_per_step"],
+                    "config": {"workload": f"stbi_write_jpg-identical .jpg of one {W}x{H} random_image-style RGBA image per GPU, quality "
+                                           f"{JFIF_QUALITY}, {label}", "file_bytes_rank0": v["out_bytes"],
+                               "kernels_per_step": "jfk::jfif_encode_kernel + jfk::jfif_stuff_kernel"},
+                    "roofline": {"bound": "hbm", "achieved": v["achieved"], "peak": peak, "unit": "GB/s", "frac": v["achieved"] / peak,
+                                 "traffic": NCU_TRAFFIC["jfif"], "peak_source": peak_src, "kernel": "jfk::jfif_encode_kernel",
+                                 "kernel_ms": v["kernel_ms"], "algorithmic_bytes": 4 * W * H + v["out_bytes"]},
+                    "e2e": {"value": v["e2e_value"], "unit": "MPix/s", "h2d_bytes_per_step": 4 * W * H,
+                            "d2h_bytes_per_step": v["out_bytes"] + 24, "ms_per_step": v["e2e_ms"],
+                            "api": "ljb_jfif_encode (host buffers, pinned)"}}
+
+        line["jfif"] = jfif_obj("444", "4:4:4 (BASELINE.json's wording)")
+        line["jfif"]["stb_rule_420"] = jfif_obj("420", "4:2:0 (what stbi_write_jpg itself does at quality <= 90)")
         if cpu_lz:
             line["cpu_baseline"] = cpu_lz
             line["jpeg"]["cpu_baseline"] = cpu_jp
+            line["jfif"]["cpu_baseline"] = cpu_jf["444"]
+            line["jfif"]["stb_rule_420"]["cpu_baseline"] = cpu_jf["420"]
         print(json.dumps(line))
     ctx.close()
     if world > 1:

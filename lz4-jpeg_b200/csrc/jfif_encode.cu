@@ -472,7 +472,31 @@ __global__ void __launch_bounds__(THREADS, 2) jfif_encode_kernel(const __grid_co
             const int nmcus = halo ? 1 : (left < (uint32_t)MPR ? (int)left : MPR);
             const bool valid = lane_used && mi < nmcus;
             const uint32_t m = m0 + (uint32_t)mi;
-            stage_pixels<SUB>(P, blocks, m0, nmcus);
+            {
+                // common case: the round's MCUs lie in one MCU row, completely inside an aligned RGBA image: every lane has a
+                // fixed (row, 16-byte part) of the MCU and copies it for one MCU after the other
+                const int mx0 = (int)(m0 % (uint32_t)P.mcux), my0 = (int)(m0 / (uint32_t)P.mcux);
+                constexpr int MSZ = SUB ? 16 : 8;
+                if (P.fast_ok && mx0 + nmcus <= P.mcux && (mx0 + nmcus) * MSZ <= P.w) {
+                    if (SUB) {
+                        const int part = lane & 3;
+#pragma unroll
+                        for (int hb = 0; hb < 2; ++hb) {
+                            const int row = (lane >> 2) + 8 * hb, y = my0 * 16 + row;
+                            const uint8_t *src = P.px + (size_t)(y < P.h ? y : P.h - 1) * P.stride + (size_t)mx0 * 64 + part * 16;
+                            uint32_t *dst = blocks + row * 16 + part * 4;
+                            for (int i = 0; i < nmcus; ++i) cp_async16(dst + i * MCU_WORDS, src + i * 64);
+                        }
+                    } else {
+                        const int row = (lane & 15) >> 1, part = lane & 1, y = my0 * 8 + row;
+                        const uint8_t *src = P.px + (size_t)(y < P.h ? y : P.h - 1) * P.stride + (size_t)mx0 * 32 + part * 16;
+                        uint32_t *dst = blocks + row * 8 + part * 4;
+                        for (int i = lane >> 4; i < nmcus; i += 2) cp_async16(dst + i * MCU_WORDS, src + i * 32);
+                    }
+                } else {
+                    stage_pixels<SUB>(P, blocks, m0, nmcus);
+                }
+            }
             cp_async_wait_all();
             __syncwarp();
 

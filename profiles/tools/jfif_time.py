@@ -50,7 +50,8 @@ for i in range(a.iters + 2):
         ker.append(ctx.last_kernel_ms())
 n = int(d_res[0].item())
 flags = int(d_res[2].item())
+spilled = int(d_res[1].item())
 t, k = float(np.median(tot)), float(np.median(ker))
-print(f"dim {W} q{a.quality} sub {a.sub} {'natural' if a.natural else 'noise'}: file {n} B ({n / (W * H):.3f} B/px) flags {flags} | "
+print(f"dim {W} q{a.quality} sub {a.sub} {'natural' if a.natural else 'noise'}: file {n} B ({n / (W * H):.3f} B/px) flags {flags} spilled tiles {spilled} | "
       f"whole {t:.3f} ms ({W * H / t / 1e6:.1f} GPix/s) | encode kernel {k:.3f} ms | "
       f"algorithmic {(4 * W * H + n) / t / 1e6:.1f} GB/s")
