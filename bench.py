@@ -38,9 +38,10 @@ BLOCK_LEN = 65536
 LZ4_BYTES = int(os.environ.get("LJB_BENCH_LZ4_BYTES", 4 * GIB))
 JPEG_DIM = int(os.environ.get("LJB_BENCH_JPEG_DIM", 16384))
 # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the ncu pass over this same command committed as
-# profiles/r1/launches_r1c_bench_steps2_warmup1.csv (bytes at the default workload sizes; None for other sizes).
+# profiles/r1/launches_r1c_bench_steps2_warmup1.csv / launches_r1e_bench_steps2_warmup1.csv (bytes at the default workload
+# sizes; None for other sizes).
 NCU_TRAFFIC = {"lz4": 4.83e9 + 16.44e9 if LZ4_BYTES == 4 * GIB else None, "jpeg": 1.077e9 + 0.207e9 if JPEG_DIM == 16384 else None,
-               "jfif": None}
+               "jfif444": 1.0746e9 + 0.3176e9 if JPEG_DIM == 16384 else None, "jfif420": 1.0740e9 + 0.1446e9 if JPEG_DIM == 16384 else None}
 JFIF_QUALITY = 75
 
 
@@ -481,7 +482,7 @@ def run_gpu(args):
                                            f"{JFIF_QUALITY}, {label}", "file_bytes_rank0": v["out_bytes"],
                                "kernels_per_step": "jfk::jfif_encode_kernel + jfk::jfif_stuff_kernel"},
                     "roofline": {"bound": "hbm", "achieved": v["achieved"], "peak": peak, "unit": "GB/s", "frac": v["achieved"] / peak,
-                                 "traffic": NCU_TRAFFIC["jfif"], "peak_source": peak_src, "kernel": "jfk::jfif_encode_kernel",
+                                 "traffic": NCU_TRAFFIC["jfif" + name], "peak_source": peak_src, "kernel": "jfk::jfif_encode_kernel",
                                  "kernel_ms": v["kernel_ms"], "algorithmic_bytes": 4 * W * H + v["out_bytes"]},
                     "e2e": {"value": v["e2e_value"], "unit": "MPix/s", "h2d_bytes_per_step": 4 * W * H,
                             "d2h_bytes_per_step": v["out_bytes"] + 24, "ms_per_step": v["e2e_ms"],
