@@ -38,10 +38,10 @@ constexpr int NWARPS = THREADS / 32;
 constexpr int MAXB = 65536;          // LJB_LZ4_MAX_BLOCK
 constexpr int HASH_BITS = 13;
 constexpr int NBUCKET = 1 << HASH_BITS;
-constexpr int SEG = 68;              // parse segment: 17 words, so per-thread segment walks are bank-conflict free
-constexpr int MAXSEG = (MAXB + SEG - 1) / SEG; // 964
+constexpr int SEG = 132;             // parse segment: 33 words, so per-thread segment walks are bank-conflict free
+constexpr int MAXSEG = (MAXB + SEG - 1) / SEG; // 497
+constexpr int SLOTS = 26;            // match distances a segment parks in shared memory (13 words: conflict free); more are re-read from the records
 constexpr int MAX_MATCH = 1024;      // LZ4.c:20
-constexpr int REGION = MAXB / NWARPS; // 2048 positions per warp in the sequence passes
 
 // ---- shared memory map (bytes) ---------------------------------------------------------------------
 constexpr int SM_DATA = 0;                         // 65536 + 64 pad
@@ -51,26 +51,29 @@ constexpr int SM_S = SM_B;                         // u16 S[65536]          sort
 constexpr int SM_DIR = SM_S + 2 * MAXB;            // u32 dirw[4096 + 1]    packed u16 bucket ends
 // parse view of region B
 constexpr int SM_STEP = SM_B;                      // u8 step[65536 + 64]
-constexpr int SM_FLAG = SM_STEP + MAXB + 64;       // u8 x1/flag[65536 + 64]
-constexpr int SM_ENTRY = SM_FLAG + MAXB + 64;      // u8 entry[1024]
+constexpr int SM_ENTRY = SM_STEP + MAXB + 64;      // u8 entry[1024]
+constexpr int SM_FLAG = SM_ENTRY + 1024;           // u8 exit table[65536 + 64]; dead once the chain's segment entries are known, then:
+constexpr int SM_SLOT = SM_FLAG;                   // u16 slots[MAXSEG * SLOTS]     distances of the segment's first matches
+constexpr int SM_OUT = (SM_SLOT + 2 * MAXSEG * SLOTS + 15) & ~15; // the encoded block, up to SOUT_CAP bytes (to the end of region B)
 constexpr int SM_LONG = SM_DIR + 4 * (NBUCKET / 2 + 4); // u32 longbits[2048]: positions that have an >= 8 byte match
 constexpr int SM_FIRST = SM_LONG + MAXB / 8;             // u32 firstbits[2048]: first occurrences of a repeated 8-gram
 constexpr int SM_MISC = SM_FIRST + MAXB / 8;
 constexpr int SM_TOTAL = SM_MISC + 1024;
-static_assert(SM_ENTRY + 1024 <= SM_LONG, "parse view must fit inside region B");
+constexpr int SOUT_CAP = ((SM_MISC - SM_OUT) & ~15) - 16; // larger blocks are encoded straight into the global staging buffer
+static_assert(SM_FLAG + MAXB + 64 <= SM_MISC, "parse view must fit inside region B");
+static_assert(SOUT_CAP >= 56 * 1024, "the shared staging area should hold a typical encoded block");
+static_assert(SEG <= 254 && MAXSEG <= 512, "entry offsets are bytes; one segment per thread");
 static_assert(SM_TOTAL <= 227 * 1024, "exceeds B200 shared memory per CTA");
 
 struct Misc {
-    unsigned long long warp_bytes[NWARPS];   // payload bytes per warp region
-    unsigned long long warp_sizes[NWARPS];   // sum of byte_size fields per warp region (header arithmetic)
-    unsigned int warp_nseq[NWARPS];
-    unsigned int warp_phantom[NWARPS];
-    unsigned int warp_last_end[NWARPS];      // end of the last match in the region (0 = none)
+    unsigned long long warp_x[NWARPS];       // per warp of segments: payload bytes | sum of byte_size fields << 32
+    unsigned long long warp_y[NWARPS];       // per warp of segments: sequences | phantom sequences << 32
     unsigned int scan_tmp[NWARPS];
     long long ticket;
     unsigned long long base;                 // output offset of this block
     int emit_ok;
 };
+static_assert(sizeof(Misc) <= 1024, "Misc must fit its area");
 
 struct Params {
     const uint8_t *in;
@@ -751,13 +754,27 @@ __global__ void __launch_bounds__(THREADS, 1) lz4_encode_kernel(Params P)
 
         // ---------------- P4: parse ----------------
         // step[p] = (uint8_t) best if best >= 4 else 0 (LZ4.c:314-321): 0 means "literal step"
-        for (uint32_t p = tid; p < nb; p += THREADS) step[p] = (uint8_t)(R[p] >> 16);
+        // (eight records in flight per thread: the loop is bound by the L2 round trip, not by bandwidth)
+#pragma unroll 1
+        for (uint32_t base = 0; base < nb; base += 8 * THREADS) {
+            uint32_t r[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const uint32_t p = base + j * THREADS + tid;
+                r[j] = p < nb ? R[p] : 0u;
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const uint32_t p = base + j * THREADS + tid;
+                if (p < nb) step[p] = (uint8_t)(r[j] >> 16);
+            }
+        }
         for (int i = tid; i < 1024; i += THREADS) entry[i] = 0xFF;
         __syncthreads();
         const uint32_t nseg = (nb + SEG - 1) / SEG;
+        const uint32_t s0 = (uint32_t)tid * SEG, s1 = min(s0 + SEG, nb); // this thread's segment (tid < nseg)
         // pass A: x1[p] = (first chain position >= segment end) - segment end, for every p (walk descending)
         if ((uint32_t)tid < nseg) {
-            const uint32_t s0 = tid * SEG, s1 = min(s0 + SEG, nb);
             for (uint32_t p = s1; p-- > s0;) {
                 uint32_t st = step[p];
                 uint32_t t = p + (st ? st : 1u);
@@ -765,136 +782,127 @@ __global__ void __launch_bounds__(THREADS, 1) lz4_encode_kernel(Params P)
             }
         }
         __syncthreads();
+        LJB_PHASE(15); // (probe) step extraction + pass A
         // pass C: one thread hops segment to segment and records where the chain enters each one
         if (tid == 0) {
             uint32_t pos = 0;
             while (pos < nb) {
-                uint32_t s = pos / SEG;
+                const uint32_t x = flag[pos]; // issued first: the only dependent load of the hop
+                const uint32_t s = pos / SEG;
                 entry[s] = (uint8_t)(pos - s * SEG);
-                uint32_t s1 = min((s + 1) * SEG, nb);
-                pos = s1 + flag[pos];
+                pos = min((s + 1) * SEG, nb) + x;
             }
         }
-        __syncthreads();
-        // pass E: mark the chain inside each segment: 0 not visited, 1 literal step, 2 match start
-        if ((uint32_t)tid < nseg) {
-            const uint32_t s0 = tid * SEG, s1 = min(s0 + SEG, nb);
-            for (uint32_t p = s0; p < s1; ++p) flag[p] = 0;
-            if (entry[tid] != 0xFF) {
-                uint32_t p = s0 + entry[tid];
-                while (p < s1) {
-                    uint32_t st = step[p];
-                    flag[p] = st ? 2 : 1;
-                    p += st ? st : 1u;
-                }
-            }
-        }
-        __syncthreads();
-
+        __syncthreads(); // the exit table is dead from here on: its memory becomes the slots and the output area
         LJB_PHASE(5); // parse: chain resolution
-        // sequence pass 1: last match end per warp region
-        const uint32_t r0 = warp * REGION;
-        {
-            uint32_t le = 0;
-            for (uint32_t p = r0 + lane; p < min(r0 + REGION, nb); p += 32)
-                if (flag[p] == 2) le = max(le, p + step[p]);
-            le = __reduce_max_sync(0xffffffffu, le);
-            if (lane == 0) M.warp_last_end[warp] = le;
+
+        // ---------------- sizing: every thread walks the chain inside its segment ----------------
+        // A sequence = the literals since the previous match + one match (LZ4.c:516-583).  Inside a segment only the first
+        // sequence depends on other segments (through the end of the last match before it): two block scans give every
+        // segment that end and the byte offset of its first sequence.
+        uint16_t *const myslots = reinterpret_cast<uint16_t *>(smem + SM_SLOT) + tid * SLOTS;
+        const bool has_seg = (uint32_t)tid < nseg && entry[tid] != 0xFF;
+        uint32_t cnt = 0, seg_last_end = 0, first_p = 0, first_ml = 0;
+        uint32_t rest_pay = 0, rest_sizes = 0, rest_ph = 0;
+        if (has_seg) {
+            uint32_t p = s0 + entry[tid], pe = 0;
+            while (p < s1) {
+                const uint32_t st = step[p];
+                if (st) {
+                    if (cnt < (uint32_t)SLOTS) myslots[cnt] = (uint16_t)p; // becomes the match distance below
+                    if (cnt == 0) {
+                        first_p = p;
+                        first_ml = st;
+                    } else {
+                        const SeqSize z = seq_size(p - pe, st);
+                        rest_pay += z.payload;
+                        rest_sizes += z.byte_size;
+                        rest_ph += (z.payload != z.byte_size) ? 1u : 0u;
+                    }
+                    pe = p + st;
+                    ++cnt;
+                    p += st;
+                } else {
+                    ++p;
+                }
+            }
+            seg_last_end = pe;
         }
-        __syncthreads();
-        uint32_t start_end = 0; // end of the last match before this warp's region
-        for (int k = 0; k < warp; ++k) start_end = max(start_end, M.warp_last_end[k]);
-
-        // sequence pass 2 (sizes) and pass 3 (emit) share one walker
-        uint8_t *const stage = stage0 + (size_t)buf * P.stage_stride;
-        auto walk = [&](bool emit, unsigned long long out_base) {
-            uint32_t carry_end = start_end;
-            unsigned long long bytes = 0, sizes = 0;
-            uint32_t nseq = 0, phantom = 0;
-            const uint32_t rend = min(r0 + REGION, nb);
-            for (uint32_t q = r0; q < rend; q += 32) {
-                const uint32_t p = q + lane;
-                const bool isM = (p < rend) && flag[p] == 2;
-                const unsigned m = __ballot_sync(0xffffffffu, isM);
-                if (m == 0) continue;
-                const uint32_t ml = isM ? step[p] : 0;
-                const uint32_t end = p + ml;
-                const unsigned lower = m & ((1u << lane) - 1u);
-                const int srcl = lower ? 31 - __clz(lower) : 0;
-                const uint32_t pe = __shfl_sync(0xffffffffu, end, srcl);
-                const uint32_t prev_end = lower ? pe : carry_end;
-                const uint32_t lit = isM ? p - prev_end : 0;
-                SeqSize sz = {0, 0};
-                if (isM) sz = seq_size(lit, ml);
-                uint32_t inc = sz.payload;
+        // match distances of the parked matches, for the emit pass: gathered from the records six at a time (the walk above
+        // would otherwise wait for one L2 round trip per match)
+        {
+            const uint32_t m = min(cnt, (uint32_t)SLOTS);
+#pragma unroll 1
+            for (uint32_t i = 0; i < m; i += 6) {
+                uint32_t q[6], r[6];
 #pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
-                    if (lane >= o) inc += v;
-                }
-                const uint32_t tot = __shfl_sync(0xffffffffu, inc, 31);
-                if (emit) {
-                    unsigned lits_long = __ballot_sync(0xffffffffu, isM && lit > 16);
-                    uint8_t *dst = stage + out_base + bytes + (inc - sz.payload);
-                    uint32_t lit_dst_off = 0;
-                    if (isM) {
-                        const uint32_t tok_lit = lit >= 15 ? 15u : lit;
-                        const uint32_t tok_m = ml >= 19 ? 15u : ((ml - 4) & 0xFF);
-                        uint32_t o = 0;
-                        dst[o++] = (uint8_t)((tok_lit << 4) | tok_m);
-                        dst[o++] = (uint8_t)(sz.byte_size & 0xFF);
-                        dst[o++] = (uint8_t)((sz.byte_size >> 8) & 0xFF);
-                        if (lit >= 15) {
-                            uint32_t rem = (lit - 15) & 0xFF;
-                            if (rem == 255) { dst[o++] = 255; rem = 0; }
-                            dst[o++] = (uint8_t)rem;
-                        }
-                        lit_dst_off = o;
-                        if (lit <= 16)
-                            for (uint32_t k = 0; k < lit; ++k) dst[o + k] = data[prev_end + k];
-                        o += lit;
-                        const uint32_t dist = p - (R[p] & 0xFFFF);
-                        dst[o++] = (uint8_t)(dist & 0xFF);
-                        dst[o++] = (uint8_t)(dist >> 8);
-                        if (ml >= 19) dst[o++] = (uint8_t)(ml - 19);
-                    }
-                    while (lits_long) { // long literal runs: the whole warp copies them
-                        const int L = __ffs(lits_long) - 1;
-                        lits_long &= lits_long - 1;
-                        const uint32_t n_l = __shfl_sync(0xffffffffu, lit, L);
-                        const uint32_t s_l = __shfl_sync(0xffffffffu, prev_end, L);
-                        const unsigned long long d_l =
-                            __shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)(dst + lit_dst_off), L);
-                        uint8_t *dp = reinterpret_cast<uint8_t *>((uintptr_t)d_l);
-                        for (uint32_t k = lane; k < n_l; k += 32) dp[k] = data[s_l + k];
-                    }
-                }
-                bytes += tot;
-                sizes += __reduce_add_sync(0xffffffffu, sz.byte_size);
-                nseq += __popc(m);
-                phantom += __popc(__ballot_sync(0xffffffffu, isM && sz.byte_size != sz.payload));
-                carry_end = __shfl_sync(0xffffffffu, end, 31 - __clz(m));
+                for (int j = 0; j < 6; ++j) q[j] = i + j < m ? (uint32_t)myslots[i + j] : 0u;
+#pragma unroll
+                for (int j = 0; j < 6; ++j) r[j] = i + j < m ? R[q[j]] : 0u;
+#pragma unroll
+                for (int j = 0; j < 6; ++j)
+                    if (i + j < m) myslots[i + j] = (uint16_t)(q[j] - (r[j] & 0xFFFF));
             }
-            if (!emit && lane == 0) {
-                M.warp_bytes[warp] = bytes;
-                M.warp_sizes[warp] = sizes;
-                M.warp_nseq[warp] = nseq;
-                M.warp_phantom[warp] = phantom;
+        }
+        LJB_PHASE(10); // (probe) E1 walk
+        // scan 1: end of the last match before this segment (exclusive max; ends grow along the chain)
+        uint32_t prev_end_in;
+        {
+            uint32_t inc = seg_last_end;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc = max(inc, v);
             }
-        };
-        walk(false, 0);
-        __syncthreads();
-
-        // block totals (every thread computes them redundantly from 32 warp entries)
-        unsigned long long pay = 3, sizes = 3, my_prefix = 3;
-        uint32_t nseq = 0, phantom = 0, last_end = 0;
-        for (int k = 0; k < NWARPS; ++k) {
-            if (k == warp) my_prefix = pay;
-            pay += M.warp_bytes[k];
-            sizes += M.warp_sizes[k];
-            nseq += M.warp_nseq[k];
-            phantom += M.warp_phantom[k];
-            last_end = max(last_end, M.warp_last_end[k]);
+            if (lane == 31) M.scan_tmp[warp] = inc;
+            uint32_t ex = __shfl_up_sync(0xffffffffu, inc, 1);
+            if (lane == 0) ex = 0;
+            __syncthreads();
+            uint32_t wmax = 0;
+            for (int k = 0; k < warp; ++k) wmax = max(wmax, M.scan_tmp[k]);
+            prev_end_in = max(wmax, ex);
+        }
+        uint32_t last_end = 0; // end of the last match of the block
+        for (int k = 0; k < NWARPS; ++k) last_end = max(last_end, M.scan_tmp[k]);
+        // scan 2: bytes, size-field sums, sequence and phantom counts before this segment
+        unsigned long long my_prefix; // offset of this segment's first sequence in the encoded block
+        unsigned long long pay = 3, sizes = 3;
+        uint32_t nseq = 0, phantom = 0;
+        {
+            uint32_t seg_pay = rest_pay, seg_sizes = rest_sizes, seg_ph = rest_ph;
+            if (cnt) {
+                const SeqSize z = seq_size(first_p - prev_end_in, first_ml);
+                seg_pay += z.payload;
+                seg_sizes += z.byte_size;
+                seg_ph += (z.payload != z.byte_size) ? 1u : 0u;
+            }
+            unsigned long long x = (unsigned long long)seg_pay | ((unsigned long long)seg_sizes << 32);
+            unsigned long long y = (unsigned long long)cnt | ((unsigned long long)seg_ph << 32);
+            const unsigned long long own = x;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned long long vx = __shfl_up_sync(0xffffffffu, x, o), vy = __shfl_up_sync(0xffffffffu, y, o);
+                if (lane >= o) {
+                    x += vx;
+                    y += vy;
+                }
+            }
+            if (lane == 31) {
+                M.warp_x[warp] = x;
+                M.warp_y[warp] = y;
+            }
+            __syncthreads();
+            unsigned long long bx = 0, tx = 0, ty = 0;
+            for (int k = 0; k < NWARPS; ++k) {
+                if (k == warp) bx = tx;
+                tx += M.warp_x[k];
+                ty += M.warp_y[k];
+            }
+            my_prefix = 3 + ((bx + x - own) & 0xFFFFFFFFull);
+            pay += tx & 0xFFFFFFFFull;
+            sizes += tx >> 32;
+            nseq = (uint32_t)(ty & 0xFFFFFFFFull);
+            phantom = (uint32_t)(ty >> 32);
         }
         // trailing literals (LZ4.c:585-613); literal_counter is uint16_t (LZ4.c:514) so 65536 wraps to "none"
         const uint32_t tlit = (nb - last_end) & 0xFFFF;
@@ -908,23 +916,85 @@ __global__ void __launch_bounds__(THREADS, 1) lz4_encode_kernel(Params P)
         }
 
         LJB_PHASE(6); // sequence sizing
-        // ---------------- P5: publish this block's size; P6: emit into the staging buffer ----------------
+        // ---------------- P5: publish this block's size; P6: emit ----------------
         if (warp == 0) {
             ljb_lookback_publish(P.status + 1, b, pay, P.lead);
             if (lane == 0 && phantom) atomicAdd((unsigned long long *)&P.result[1], (unsigned long long)phantom);
         }
         LJB_PHASE(7); // look-back
+        // The block is encoded in shared memory and copied to its staging buffer with 16-byte stores; a block too large for
+        // that (it expanded by more than ~10 %) is encoded straight into the staging buffer through the same generic pointer.
+        uint8_t *const stage = stage0 + (size_t)buf * P.stage_stride;
+        const bool in_shared = pay <= (unsigned long long)SOUT_CAP;
+        uint8_t *const obase = in_shared ? smem + SM_OUT : stage;
         {
-            walk(true, my_prefix);
+            // every lane serialises the sequences of its own segment; the warp stays converged so that long literal runs can
+            // be copied by all its lanes
+            uint32_t p = has_seg ? s0 + entry[tid] : 0u, pe = prev_end_in, idx = 0;
+            unsigned long long off = my_prefix;
+            bool done = !has_seg;
+            for (;;) {
+                uint32_t st = 0;
+                if (!done) {
+                    while (p < s1 && (st = step[p]) == 0) ++p; // literal steps
+                    if (p >= s1) done = true;
+                }
+                const bool found = !done;
+                if (!__any_sync(0xffffffffu, found)) break;
+                uint32_t lit = 0, lit_dst_off = 0;
+                uint8_t *dst = obase + off;
+                if (found) {
+                    const uint32_t ml = st;
+                    lit = p - pe;
+                    const SeqSize sz = seq_size(lit, ml);
+                    const uint32_t dist = idx < (uint32_t)SLOTS ? (uint32_t)myslots[idx] : ((p - (R[p] & 0xFFFF)) & 0xFFFFu);
+                    const uint32_t tok_lit = lit >= 15 ? 15u : lit;
+                    const uint32_t tok_m = ml >= 19 ? 15u : ((ml - 4) & 0xFF);
+                    uint32_t o = 0;
+                    dst[o++] = (uint8_t)((tok_lit << 4) | tok_m);
+                    dst[o++] = (uint8_t)(sz.byte_size & 0xFF);
+                    dst[o++] = (uint8_t)((sz.byte_size >> 8) & 0xFF);
+                    if (lit >= 15) {
+                        uint32_t rem = (lit - 15) & 0xFF;
+                        if (rem == 255) { dst[o++] = 255; rem = 0; }
+                        dst[o++] = (uint8_t)rem;
+                    }
+                    lit_dst_off = o;
+                    if (lit <= 16)
+                        for (uint32_t k = 0; k < lit; ++k) dst[o + k] = data[pe + k];
+                    o += lit;
+                    dst[o++] = (uint8_t)(dist & 0xFF);
+                    dst[o++] = (uint8_t)(dist >> 8);
+                    if (ml >= 19) dst[o++] = (uint8_t)(ml - 19);
+                    off += sz.payload;
+                }
+                unsigned lits_long = __ballot_sync(0xffffffffu, found && lit > 16);
+                while (lits_long) { // long literal runs: the whole warp copies them
+                    const int L = __ffs(lits_long) - 1;
+                    lits_long &= lits_long - 1;
+                    const uint32_t n_l = __shfl_sync(0xffffffffu, lit, L);
+                    const uint32_t s_l = __shfl_sync(0xffffffffu, pe, L);
+                    const unsigned long long d_l =
+                        __shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)(dst + lit_dst_off), L);
+                    uint8_t *dp = reinterpret_cast<uint8_t *>((uintptr_t)d_l);
+                    for (uint32_t k = lane; k < n_l; k += 32) dp[k] = data[s_l + k];
+                }
+                if (found) {
+                    pe = p + st;
+                    p += st;
+                    ++idx;
+                }
+            }
+            LJB_PHASE(11); // (probe) E2 walk
             if (tid == 0) {
-                uint8_t *hdr = stage;
+                uint8_t *hdr = obase;
                 hdr[0] = (uint8_t)(nseq & 0xFF);          // LZ4.c:615, :417
                 hdr[1] = (uint8_t)(sizes & 0xFF);         // LZ4.c:617, :419 (low 16 bits)
                 hdr[2] = (uint8_t)((sizes >> 8) & 0xFF);
                 if (b == 0 && P.lead && P.out_cap) P.out[0] = (uint8_t)P.frame_byte; // LZ4.c:429
             }
             if (tlit) {
-                uint8_t *dst = stage + trail_off;
+                uint8_t *dst = obase + trail_off;
                 uint32_t hdrlen = 3 + lit_ext_count(tlit);
                 if (tid == 0) {
                     uint32_t o = 0;
@@ -942,6 +1012,13 @@ __global__ void __launch_bounds__(THREADS, 1) lz4_encode_kernel(Params P)
                 // literals start where the counter was last reset; after a uint16 wrap that is the wrap point
                 const uint32_t lsrc = nb - tlit;
                 for (uint32_t k = tid; k < tlit; k += THREADS) dst[hdrlen + k] = data[lsrc + k];
+            }
+            if (in_shared) {
+                __syncthreads();
+                const uint4 *s4 = reinterpret_cast<const uint4 *>(smem + SM_OUT);
+                uint4 *d4 = reinterpret_cast<uint4 *>(stage);
+                const uint32_t n16 = (uint32_t)((pay + 15) >> 4);
+                for (uint32_t i = tid; i < n16; i += THREADS) d4[i] = s4[i];
             }
         }
         __syncthreads(); // staging writes of this block are complete; region B and data are free
@@ -1043,6 +1120,7 @@ static int lz4_launch(ljb_ctx *ctx, const uint8_t *d_in, size_t n, size_t block_
         fprintf(stderr, "[ljb lz4 phases] cycles per block:");
         for (int i = 0; i < 9; ++i) fprintf(stderr, " %s=%.0f(%.0f%%)", names[i], (double)ph[i] / (double)nblocks, 100.0 * (double)ph[i] / (double)tot);
         fprintf(stderr, " total=%.0f\n", (double)tot / (double)nblocks);
+        fprintf(stderr, "[ljb lz4 probes] per block: T1+passA=%.0f E1=%.0f E2=%.0f\n", (double)ph[15] / nblocks, (double)ph[10] / nblocks, (double)ph[11] / nblocks);
         fprintf(stderr, "[ljb lz4 phaseB1] per block: indexed=%.0f positions=%.0f visited=%.0f equal8=%.0f warp-cycles=%.0f | ladder: inserts=%.0f rounds=%.1f\n",
                 (double)ph[20] / nblocks, (double)ph[16] / nblocks, (double)ph[17] / nblocks, (double)ph[18] / nblocks, (double)ph[19] / nblocks,
                 (double)ph[21] / nblocks, (double)ph[22] / nblocks);
