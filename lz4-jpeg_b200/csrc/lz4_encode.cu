@@ -58,6 +58,8 @@ constexpr int SM_OUT = (SM_SLOT + 2 * MAXSEG * SLOTS + 15) & ~15; // the encoded
 constexpr int SM_LONG = SM_DIR + 4 * (NBUCKET / 2 + 4); // u32 longbits[2048]: positions that have an >= 8 byte match
 constexpr int SM_FIRST = SM_LONG + MAXB / 8;             // u32 firstbits[2048]: first occurrences of a repeated 8-gram
 constexpr int SM_MISC = SM_FIRST + MAXB / 8;
+constexpr int SM_PREF = SM_LONG - (2 * (MAXB / 32) + 16); // u16 pref[2048]: first occurrences before each 32-position word
+constexpr int GIDX_BYTES = SM_PREF - SM_S;             // what S and the group directory share
 constexpr int SM_TOTAL = SM_MISC + 1024;
 constexpr int SOUT_CAP = ((SM_MISC - SM_OUT) & ~15) - 16; // larger blocks are encoded straight into the global staging buffer
 static_assert(SM_FLAG + MAXB + 64 <= SM_MISC, "parse view must fit inside region B");
@@ -86,6 +88,7 @@ struct Params {
     uint64_t *result;        // [0] length, [1] phantom, [2] error flags
     uint64_t *status;        // [0] ticket, [1..] look-back words
     uint32_t *scratch;       // per CTA: MAXB u32 match records
+    uint16_t *gids;          // per CTA: MAXB u16 group ids (dense rank of the 8-gram's first occurrence)
     uint8_t *staging;        // per CTA: two buffers of stage_stride bytes holding the encoded block until its offset is known
     size_t stage_stride;
     uint64_t offs_bias;      // added to every block_offsets entry (base of this shard in a larger stream)
@@ -164,8 +167,6 @@ __global__ void __launch_bounds__(THREADS, 1) lz4_encode_kernel(Params P)
     uint8_t *data = smem + SM_DATA;
     const uint32_t *dataw = reinterpret_cast<const uint32_t *>(data);
     uint16_t *S = reinterpret_cast<uint16_t *>(smem + SM_S);
-    uint32_t *dirw = reinterpret_cast<uint32_t *>(smem + SM_DIR);
-    const uint16_t *dir16 = reinterpret_cast<const uint16_t *>(dirw);
     uint8_t *step = smem + SM_STEP;
     uint8_t *flag = smem + SM_FLAG;
     uint8_t *entry = smem + SM_ENTRY;
@@ -250,7 +251,6 @@ __global__ void __launch_bounds__(THREADS, 1) lz4_encode_kernel(Params P)
             }
             for (uint32_t i = head + tid; i < nb; i += THREADS) data[i] = __ldg(&src[i]);
             for (uint32_t i = nb + tid; i < ((nb + 63) & ~15u) + 16; i += THREADS) data[i] = 0; // defined bytes past the end
-            for (int i = tid; i < NBUCKET / 2 + 1; i += THREADS) dirw[i] = 0;
         }
         __syncthreads();
         LJB_PHASE(0); // stage
@@ -264,63 +264,6 @@ __global__ void __launch_bounds__(THREADS, 1) lz4_encode_kernel(Params P)
             longbits[i] = 0;
             firstbits[i] = 0;
         }
-
-        // index = counting sort of positions [0, cnt) by the hash of their GRAM-gram.  Afterwards
-        // dir16[h] = end of bucket h = start of bucket h+1; inside a bucket, entries of an earlier
-        // 1024-position chunk come first (the scatter runs in position-ordered rounds).
-        // Only positions whose 8-gram occurs more than once are indexed (flagged ones and the first occurrences
-        // they point at): everything else can never be a candidate.
-        auto build_index = [&](auto gram_tag, uint32_t cnt) {
-            constexpr int GRAM = decltype(gram_tag)::value;
-            for (uint32_t p = tid; p < cnt; p += THREADS) {
-                if (!(((longbits[p >> 5] | firstbits[p >> 5]) >> (p & 31)) & 1u)) continue;
-                uint32_t h = hash_at<GRAM>(dataw, p);
-                atomicAdd(&dirw[h >> 1], (h & 1) ? 0x10000u : 1u);
-            }
-            __syncthreads();
-            {
-                // exclusive scan of 8192 u16 counts; thread t owns buckets 8t .. 8t+7 (4 packed words)
-                uint32_t c[8], sum = 0;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    uint32_t wv = dirw[tid * 4 + k];
-                    c[2 * k] = wv & 0xFFFF;
-                    c[2 * k + 1] = wv >> 16;
-                }
-#pragma unroll
-                for (int k = 0; k < 8; ++k) sum += c[k];
-                uint32_t inc = sum;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
-                    if (lane >= o) inc += v;
-                }
-                if (lane == 31) M.scan_tmp[warp] = inc;
-                __syncthreads();
-                uint32_t wbase = 0;
-                for (int k = 0; k < warp; ++k) wbase += M.scan_tmp[k];
-                uint32_t run = wbase + inc - sum;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    uint32_t lo = run;
-                    run += c[2 * k];
-                    uint32_t hi = run;
-                    run += c[2 * k + 1];
-                    dirw[tid * 4 + k] = (lo & 0xFFFF) | (hi << 16);
-                }
-            }
-            __syncthreads();
-            for (uint32_t base = 0; base < cnt; base += THREADS) {
-                uint32_t p = base + tid;
-                if (p < cnt && ((((longbits[p >> 5] | firstbits[p >> 5]) >> (p & 31)) & 1u))) {
-                    uint32_t h = hash_at<GRAM>(dataw, p);
-                    uint32_t old = atomicAdd(&dirw[h >> 1], (h & 1) ? 0x10000u : 1u);
-                    uint32_t slot = (h & 1) ? (old >> 16) : (old & 0xFFFF);
-                    S[slot] = (uint16_t)p;
-                }
-                __syncthreads();
-            }
-        };
 
         // ---- phase A: first-occurrence ladder, k = 8, 7, 6, 5, 4
         // Level k puts every still-unresolved position into a table keyed by a hash of its k-gram that keeps
@@ -437,11 +380,146 @@ __global__ void __launch_bounds__(THREADS, 1) lz4_encode_kernel(Params P)
             for (int i = tid; i < MAXB / 32; i += THREADS) any |= longbits[i];
             any = __syncthreads_or(any != 0);
             if (any) {
-                for (int i = tid; i < NBUCKET / 2 + 1; i += THREADS) dirw[i] = 0;
-                __syncthreads();
+                // ---- group index.  Level 8 of the ladder left, for every flagged position, the FIRST occurrence q of its
+                // 8-gram (R[p] & 0xFFFF) and a bit for every such q: the rank of q among the set bits is an exact, dense id
+                // of the 8-gram ("group").  Counting sort of the flagged positions and the first occurrences by group id:
+                // afterwards S holds every group contiguously (entries of an earlier 1024-position chunk first) and
+                // gdir16[g] = end of group g = start of group g+1.  A position then visits only true occurrences of its
+                // own 8-gram — no hash collisions, no 8-byte compare.  Layout inside the S/dir area: S (2 bytes x entries),
+                // the directory right behind it (2 bytes x groups), the rank table at the end.  Should the directory not
+                // fit (only when nearly every position is flagged), neighbouring groups share a bucket (gid >> shift)
+                // and candidates are filtered by comparing the 8 bytes, as a hashed index would.
                 const uint32_t npos8 = nb >= 8 ? nb - 7 : 0;
-                build_index(std::integral_constant<int, 8>{}, npos8);
-                LJB_PHASE(3); // index (8-gram)
+                uint16_t *const pref = reinterpret_cast<uint16_t *>(smem + SM_PREF);
+                uint16_t *const gids = P.gids + (size_t)blockIdx.x * MAXB;
+                uint32_t ngroups, nidx;
+                {
+                    const uint32_t f0 = firstbits[2 * tid], f1 = firstbits[2 * tid + 1];
+                    const uint32_t cf = __popc(f0) + __popc(f1);
+                    const uint32_t cl = __popc(longbits[2 * tid]) + __popc(longbits[2 * tid + 1]);
+                    uint32_t inc = cf;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
+                        if (lane >= o) inc += v;
+                    }
+                    const uint32_t wl = __reduce_add_sync(0xffffffffu, cl);
+                    if (lane == 31) {
+                        M.scan_tmp[warp] = inc;
+                        M.warp_y[warp] = wl;
+                    }
+                    __syncthreads();
+                    uint32_t before = 0, tot_f = 0, tot_l = 0;
+                    for (int k = 0; k < NWARPS; ++k) {
+                        if (k == warp) before = tot_f;
+                        tot_f += M.scan_tmp[k];
+                        tot_l += (uint32_t)M.warp_y[k];
+                    }
+                    pref[2 * tid] = (uint16_t)(before + inc - cf);
+                    pref[2 * tid + 1] = (uint16_t)(before + inc - cf + __popc(f0));
+                    ngroups = tot_f;
+                    nidx = tot_f + tot_l;
+                }
+                const uint32_t sbytes = (2 * nidx + 4 + 3) & ~3u; // S, with slack for the one-ahead reads
+                uint32_t shift = 0;
+                while (sbytes + 4 * (((ngroups >> shift) + 1) / 2 + 2) > (uint32_t)GIDX_BYTES) ++shift;
+                const bool exact = shift == 0;
+                uint32_t *const gdirw = reinterpret_cast<uint32_t *>(smem + SM_S + sbytes);
+                const uint16_t *const gdir16 = reinterpret_cast<const uint16_t *>(gdirw);
+                const uint32_t dwords = ((ngroups >> shift) + 1) / 2 + 1;
+                for (uint32_t i = tid; i < dwords; i += THREADS) gdirw[i] = 0;
+                __syncthreads();
+                auto rank_of = [&](uint32_t q) -> uint32_t { return (uint32_t)pref[q >> 5] + __popc(firstbits[q >> 5] & ((1u << (q & 31)) - 1u)); };
+                // histogram; the group id of a flagged position is kept in a per-CTA array (it is needed three more times)
+#pragma unroll 1
+                for (uint32_t base = 0; base < npos8; base += 8 * THREADS) {
+                    uint32_t r[8];
+                    bool lb[8], fb[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const uint32_t q = base + j * THREADS + tid;
+                        lb[j] = q < npos8 && ((longbits[q >> 5] >> (q & 31)) & 1u);
+                        fb[j] = q < npos8 && ((firstbits[q >> 5] >> (q & 31)) & 1u);
+                        r[j] = lb[j] ? R[q] : 0u;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const uint32_t q = base + j * THREADS + tid;
+                        if (lb[j] || fb[j]) {
+                            const uint32_t g = rank_of(lb[j] ? (r[j] & 0xFFFFu) : q);
+                            if (lb[j]) gids[q] = (uint16_t)g;
+                            const uint32_t bk = g >> shift;
+                            atomicAdd(&gdirw[bk >> 1], (bk & 1) ? 0x10000u : 1u);
+                        }
+                    }
+                }
+                __syncthreads();
+                {
+                    // exclusive scan of the u16 counts; every thread owns `cw` consecutive packed words
+                    const uint32_t cw = (dwords + THREADS - 1) / THREADS;
+                    const uint32_t w0 = min((uint32_t)tid * cw, dwords), w1 = min(w0 + cw, dwords);
+                    uint32_t sum = 0;
+                    for (uint32_t k = w0; k < w1; ++k) {
+                        const uint32_t wv = gdirw[k];
+                        sum += (wv & 0xFFFF) + (wv >> 16);
+                    }
+                    uint32_t inc = sum;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
+                        if (lane >= o) inc += v;
+                    }
+                    if (lane == 31) M.scan_tmp[warp] = inc; // (last read before the barrier that follows the histogram)
+                    __syncthreads();
+                    uint32_t run = inc - sum;
+                    for (int k = 0; k < warp; ++k) run += M.scan_tmp[k];
+                    for (uint32_t k = w0; k < w1; ++k) {
+                        const uint32_t wv = gdirw[k];
+                        const uint32_t lo = run;
+                        run += wv & 0xFFFF;
+                        const uint32_t hi = run;
+                        run += wv >> 16;
+                        gdirw[k] = (lo & 0xFFFF) | (hi << 16);
+                    }
+                }
+                __syncthreads();
+                {
+                    // scatter in position-ordered rounds; the group ids of four rounds are fetched four rounds ahead (a round is
+                    // much shorter than the L2 round trip)
+                    uint32_t gn[4];
+                    bool ln[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const uint32_t q = j * THREADS + tid;
+                        ln[j] = q < npos8 && ((longbits[q >> 5] >> (q & 31)) & 1u);
+                        gn[j] = ln[j] ? (uint32_t)gids[q] : 0u;
+                    }
+#pragma unroll 1
+                    for (uint32_t base = 0; base < npos8; base += 4 * THREADS) {
+                        uint32_t gc[4];
+                        bool lc[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            gc[j] = gn[j];
+                            lc[j] = ln[j];
+                            const uint32_t q = base + (4 + j) * THREADS + tid;
+                            ln[j] = q < npos8 && ((longbits[q >> 5] >> (q & 31)) & 1u);
+                            gn[j] = ln[j] ? (uint32_t)gids[q] : 0u;
+                        }
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const uint32_t q = base + j * THREADS + tid;
+                            const bool fbq = q < npos8 && ((firstbits[q >> 5] >> (q & 31)) & 1u);
+                            if (lc[j] || fbq) {
+                                const uint32_t bk = (lc[j] ? gc[j] : rank_of(q)) >> shift;
+                                const uint32_t old = atomicAdd(&gdirw[bk >> 1], (bk & 1) ? 0x10000u : 1u);
+                                S[(bk & 1) ? (old >> 16) : (old & 0xFFFF)] = (uint16_t)q;
+                            }
+                            __syncthreads();
+                        }
+                    }
+                }
+                LJB_PHASE(3); // index (8-gram groups)
                 // ---- B1: sorted-order walk of the 8-gram index, first 16 bytes only.  The lanes of a warp sit in
                 // the same bucket (equal trip counts, broadcast loads).  A position whose best candidate is
                 // shorter than 16 bytes is final here; the others ("very long") go to B2.
@@ -449,19 +527,29 @@ __global__ void __launch_bounds__(THREADS, 1) lz4_encode_kernel(Params P)
                 for (int i = tid; i < MAXB / 32; i += THREADS) vlong[i] = 0;
                 __syncthreads();
                 {
-                    const uint32_t nidx = dir16[NBUCKET - 1];
                     uint32_t d_pos = 0, d_vis = 0, d_eq = 0;
                     const long long tb1 = clock64();
+                    // (the group id of the next entry is fetched while this one is processed)
+                    uint32_t p_n = (uint32_t)tid < nidx ? (uint32_t)S[tid] : 0u;
+                    bool l_n = (uint32_t)tid < nidx && ((longbits[p_n >> 5] >> (p_n & 31)) & 1u);
+                    uint32_t g_n = l_n ? (uint32_t)gids[p_n] : 0u;
                     for (uint32_t j = tid; j < nidx; j += THREADS) {
-                        const uint32_t p = S[j];
-                        if (!((longbits[p >> 5] >> (p & 31)) & 1u)) continue; // a first occurrence: candidate only
+                        const uint32_t p = p_n, gp = g_n;
+                        const bool lp = l_n;
+                        {
+                            const uint32_t jn = j + THREADS;
+                            p_n = jn < nidx ? (uint32_t)S[jn] : 0u;
+                            l_n = jn < nidx && ((longbits[p_n >> 5] >> (p_n & 31)) & 1u);
+                            g_n = l_n ? (uint32_t)gids[p_n] : 0u;
+                        }
+                        if (!lp) continue; // a first occurrence: candidate only
                         ++d_pos;
                         const uint32_t pi = p >> 2, ps = (p & 3) * 8;
                         const uint32_t w0 = dataw[pi], w1 = dataw[pi + 1], w2 = dataw[pi + 2], w3 = dataw[pi + 3], w4 = dataw[pi + 4];
                         const uint32_t P0 = __funnelshift_r(w0, w1, ps), P1 = __funnelshift_r(w1, w2, ps);
                         const uint32_t P2 = __funnelshift_r(w2, w3, ps), P3 = __funnelshift_r(w3, w4, ps);
-                        const uint32_t h = hash8(P0, P1);
-                        const uint32_t lo = h ? dir16[h - 1] : 0u, hi = dir16[h];
+                        const uint32_t bk = gp >> shift;
+                        const uint32_t lo = bk ? gdir16[bk - 1] : 0u, hi = gdir16[bk];
                         const uint32_t cap16 = min(16u, nb - p);
                         const uint32_t pch = p >> 10;
                         // a chain = consecutive flagged positions inside one 32-position chunk (B2's unit of sequential work)
@@ -479,13 +567,13 @@ __global__ void __launch_bounds__(THREADS, 1) lz4_encode_kernel(Params P)
                             if ((best >> 16) == cap16 && (cap16 < 16 || n16 > 2) && cch > ((0xFFFFu - (best & 0xFFFFu)) >> 10)) break;
                             if (c < p) {
                                 const uint32_t ci = c >> 2, cs = (c & 3) * 8;
-                                const uint32_t a0 = dataw[ci], a1 = dataw[ci + 1], a2 = dataw[ci + 2];
-                                if (__funnelshift_r(a0, a1, cs) == P0 && __funnelshift_r(a1, a2, cs) == P1) {
+                                // an entry of the same group has the same 8 bytes; shared buckets need the comparison
+                                if (exact || (__funnelshift_r(dataw[ci], dataw[ci + 1], cs) == P0 && __funnelshift_r(dataw[ci + 1], dataw[ci + 2], cs) == P1)) {
                                     // inside a chain B2 carries the pairs that continue a diagonal: only pairs that START one here
                                     // (different byte in front, or nothing in front) are measured
                                     if (!chain_start && c != 0u && data[c - 1] == prev_byte) continue;
                                     ++d_eq;
-                                    const uint32_t a3 = dataw[ci + 3], a4 = dataw[ci + 4];
+                                    const uint32_t a2 = dataw[ci + 2], a3 = dataw[ci + 3], a4 = dataw[ci + 4];
                                     const uint32_t x2 = __funnelshift_r(a2, a3, cs) ^ P2, x3 = __funnelshift_r(a3, a4, cs) ^ P3;
                                     uint32_t l = x2 ? 8u + ((uint32_t)(__ffs(x2) - 1) >> 3) : (x3 ? 12u + ((uint32_t)(__ffs(x3) - 1) >> 3) : 16u);
                                     l = min(l, cap16);
@@ -677,8 +765,8 @@ __global__ void __launch_bounds__(THREADS, 1) lz4_encode_kernel(Params P)
                             if ((bestkey >> 16) == (uint32_t)MAX_MATCH) {
                                 ninc = true;
                             } else {
-                                const uint32_t h = hash8(P0, P1);
-                                const uint32_t lo = h ? dir16[h - 1] : 0u, hi = dir16[h];
+                                const uint32_t bk = (uint32_t)gids[p] >> shift;
+                                const uint32_t lo = bk ? gdir16[bk - 1] : 0u, hi = gdir16[bk];
                                 const uint32_t pch = p >> 10;
                                 for (uint32_t k = lo; k < hi; ++k) {
                                     const uint32_t c = S[k];
@@ -1056,7 +1144,8 @@ static int lz4_launch(ljb_ctx *ctx, const uint8_t *d_in, size_t n, size_t block_
     LJB_CUDA(cudaSetDevice(ctx->device));
     const int grid = (int)((nblocks < (size_t)ctx->num_sms) ? nblocks : (size_t)ctx->num_sms);
     int rc;
-    const size_t rec_bytes = (size_t)ctx->num_sms * MAXB * sizeof(uint32_t);
+    const size_t rec32_bytes = (size_t)ctx->num_sms * MAXB * sizeof(uint32_t);
+    const size_t rec_bytes = rec32_bytes + (size_t)ctx->num_sms * MAXB * sizeof(uint16_t); // match records + group ids
     const size_t stage_stride = (ljb_lz4_bound(block_len, block_len) + 16 + 255) & ~(size_t)255; // one encoded block, worst case
     if ((rc = ljb_ensure(&ctx->d_scratch, &ctx->scratch_bytes, rec_bytes + (size_t)grid * 2 * stage_stride)) != 0) return rc;
     if ((rc = ljb_ensure(&ctx->d_status, &ctx->status_bytes, (nblocks + 2 + 24) * sizeof(uint64_t))) != 0) return rc;
@@ -1073,6 +1162,7 @@ static int lz4_launch(ljb_ctx *ctx, const uint8_t *d_in, size_t n, size_t block_
     P.result = d_result;
     P.status = (uint64_t *)ctx->d_status;
     P.scratch = (uint32_t *)ctx->d_scratch;
+    P.gids = (uint16_t *)((uint8_t *)ctx->d_scratch + rec32_bytes);
     P.staging = (uint8_t *)ctx->d_scratch + rec_bytes;
     P.stage_stride = stage_stride;
     P.offs_bias = offs_bias;
