@@ -525,6 +525,7 @@ __global__ void __launch_bounds__(THREADS, 1) lz4_encode_kernel(Params P)
                 // shorter than 16 bytes is final here; the others ("very long") go to B2.
                 uint32_t *vlong = firstbits; // the first-occurrence bits are dead once the index is built
                 for (int i = tid; i < MAXB / 32; i += THREADS) vlong[i] = 0;
+                if (tid < 64) reinterpret_cast<uint32_t *>(M.warp_x)[tid] = 0; // per 1024-position row: candidates overflows (B2's schedule)
                 __syncthreads();
                 {
                     uint32_t d_pos = 0, d_vis = 0, d_eq = 0;
@@ -589,7 +590,10 @@ __global__ void __launch_bounds__(THREADS, 1) lz4_encode_kernel(Params P)
                         const uint32_t bl = best >> 16, bp = 0xFFFFu - (best & 0xFFFFu);
                         if (bl == 16 && nb - p > 16) { // may be longer: B2 decides
                             atomicOr(&vlong[p >> 5], 1u << (p & 31));
-                            if (n16 > 2) cand = (cand & 0xFFFFu) | 0xFFFE0000u; // overflow: B2 walks the bucket itself
+                            if (n16 > 2) { // overflow: B2 walks the group itself
+                                cand = (cand & 0xFFFFu) | 0xFFFE0000u;
+                                atomicAdd(&reinterpret_cast<uint32_t *>(M.warp_x)[p >> 10], 1u);
+                            }
                             R[p] = cand; // provisional: the two candidates, in place of (length, position)
                         } else {
                             R[p] = best ? ((bl << 16) | bp) : 0u; // 0: no pair starts here (the match continues a diagonal)
@@ -620,14 +624,42 @@ __global__ void __launch_bounds__(THREADS, 1) lz4_encode_kernel(Params P)
                 // walk stopped early, the next position walks its bucket again).
                 constexpr int KEEP = 4;
                 constexpr uint32_t SHORT = 32; // a lane compares this much on its own; longer runs are compared by the whole warp
-                if (tid == 0) M.scan_tmp[0] = 0;
-                __syncthreads();
                 const uint32_t nrows = (nb + 1023) >> 10;
+                // rows are handed out heaviest first (longest-processing-time rule): with two rows per warp on average, the
+                // last rows to finish decide how long the other warps wait at the barrier
+                {
+                    const uint32_t *rheavy = reinterpret_cast<const uint32_t *>(M.warp_x); // positions per row that will walk their group
+                    uint16_t *rcost = reinterpret_cast<uint16_t *>(M.warp_y);       // 64 costs
+                    uint8_t *rorder = reinterpret_cast<uint8_t *>(M.warp_y) + 128;  // 64 row numbers
+                    for (int r = warp; r < 64; r += NWARPS) {
+                        const uint32_t c = __popc(longbits[r * 32 + lane]) + 3u * __popc(vlong[r * 32 + lane]);
+                        const uint32_t t = __reduce_add_sync(0xffffffffu, c) + 24u * rheavy[r];
+                        if (lane == 0) rcost[r] = (uint16_t)min(t, 65535u);
+                    }
+                    if (tid == 0) M.scan_tmp[0] = 0;
+                    __syncthreads();
+                    if (tid < 64) {
+                        const uint32_t mine = rcost[tid];
+                        uint32_t rank = 0;
+                        for (int r = 0; r < 64; ++r) {
+                            const uint32_t o = rcost[r];
+                            rank += (o > mine || (o == mine && r < tid)) ? 1u : 0u;
+                        }
+                        rorder[rank] = (uint8_t)tid;
+                    }
+                    __syncthreads();
+                }
                 for (;;) {
                     uint32_t row = 0;
-                    if (lane == 0) row = atomicAdd(&M.scan_tmp[0], 1u);
+                    if (lane == 0) {
+                        row = atomicAdd(&M.scan_tmp[0], 1u);
+                        row = row < 64u ? (uint32_t)(reinterpret_cast<const uint8_t *>(M.warp_y) + 128)[row] : 64u;
+                    }
                     row = __shfl_sync(0xffffffffu, row, 0);
-                    if (row >= nrows) break;
+                    if (row >= nrows) { // (rows beyond the block sort last: nothing is left)
+                        if (row >= 64u) break;
+                        continue;
+                    }
                     const uint32_t ch = row * 32 + lane;
                     const uint32_t bits = (ch * 32 < nb) ? longbits[ch] : 0u; // positions of this lane's chunk with an >= 8 byte match
                     const uint32_t vbits = (ch * 32 < nb) ? vlong[ch] : 0u;   // ... whose record holds 16-byte candidates
