@@ -42,6 +42,7 @@ constexpr int SEG = 132;             // parse segment: 33 words, so per-thread s
 constexpr int MAXSEG = (MAXB + SEG - 1) / SEG; // 497
 constexpr int SLOTS = 26;            // match distances a segment parks in shared memory (13 words: conflict free); more are re-read from the records
 constexpr int MAX_MATCH = 1024;      // LZ4.c:20
+constexpr int B1_BUDGET = 512;       // group entries a position inside a chain looks at before B2 takes over
 
 // ---- shared memory map (bytes) ---------------------------------------------------------------------
 constexpr int SM_DATA = 0;                         // 65536 + 64 pad
@@ -557,13 +558,20 @@ __global__ void __launch_bounds__(THREADS, 1) lz4_encode_kernel(Params P)
                         const bool chain_start = (p & 31u) == 0u || !((longbits[(p - 1) >> 5] >> ((p - 1) & 31)) & 1u);
                         const uint32_t prev_byte = p ? data[p - 1] : 0u;
                         uint32_t best = 0, n16 = 0, cand = 0xFFFFFFFFu;
+                        const bool budgeted = !chain_start && nb - p > 16 && hi - lo > (uint32_t)B1_BUDGET;
+                        const uint32_t hi_w = budgeted ? lo + (uint32_t)B1_BUDGET : hi;
                         uint32_t c_next = lo < hi ? S[lo] : 0u;
-                        for (uint32_t i = lo; i < hi; ++i) {
+                        uint32_t i = lo;
+                        for (; i < hi_w; ++i) {
                             const uint32_t c = c_next;
                             c_next = S[i + 1]; // one entry ahead (S has slack past the last bucket): shortens the dependent chain
                             const uint32_t cch = c >> 10;
                             if (cch > pch) break; // only later positions from here on
                             ++d_vis;
+                            // Inside a chain only the (few) pairs that start a diagonal count, so nothing ends the walk of a huge
+                            // group early (runs of one byte, short periods: every position is in one group): after B1_BUDGET
+                            // entries the position is handed to B2, whose own walk is pruned by the pairs it carries.
+                            // (the budget is the loop bound: hi_w)
                             // later positions cannot win a tie; but B2 needs EVERY 16-byte candidate unless it walks the bucket itself
                             if ((best >> 16) == cap16 && (cap16 < 16 || n16 > 2) && cch > ((0xFFFFu - (best & 0xFFFFu)) >> 10)) break;
                             if (c < p) {
@@ -587,10 +595,11 @@ __global__ void __launch_bounds__(THREADS, 1) lz4_encode_kernel(Params P)
                                 }
                             }
                         }
+                        const bool forced = budgeted && i == hi_w; // the walk ran into its budget
                         const uint32_t bl = best >> 16, bp = 0xFFFFu - (best & 0xFFFFu);
-                        if (bl == 16 && nb - p > 16) { // may be longer: B2 decides
+                        if ((bl == 16 && nb - p > 16) || forced) { // may be longer: B2 decides
                             atomicOr(&vlong[p >> 5], 1u << (p & 31));
-                            if (n16 > 2) { // overflow: B2 walks the group itself
+                            if (n16 > 2 || forced) { // overflow: B2 walks the group itself
                                 cand = (cand & 0xFFFFu) | 0xFFFE0000u;
                                 atomicAdd(&reinterpret_cast<uint32_t *>(M.warp_x)[p >> 10], 1u);
                             }

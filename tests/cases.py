@@ -114,6 +114,17 @@ def lz4_cases():
     out.append(("random_65536", rng.integers(0, 256, size=65536, dtype=np.uint8), 65536))
     out.append(("random_65535", rng.integers(0, 256, size=65535, dtype=np.uint8), 65536))
     out.append(("random_65536_plus", rng.integers(0, 256, size=65536 + 100, dtype=np.uint8), 65536))
+    # huge 8-gram groups (> 512 occurrences of one 8-gram inside a block): the search's budgeted walks and group walks
+    unit = np.frombuffer(b"ABCDEFGHI", dtype=np.uint8)
+    big = np.concatenate([np.concatenate([unit, rng.integers(0, 256, size=5, dtype=np.uint8)]) for _ in range(1400)])
+    out.append(("big_group_19600", big, big.size))
+    out.append(("zeros_4096", np.zeros(4096, np.uint8), 4096))
+    out.append(("period2_4096", np.tile(np.array([97, 98], np.uint8), 2048), 4096))
+    out.append(("period7_6000", np.tile(np.frombuffer(b"abcdefg", dtype=np.uint8), 858)[:6000].copy(), 6000))
+    mixed = synth_text(16384, seed=21)
+    mixed[3000:9000] = 0
+    mixed[11000:13000] = np.tile(np.array([1, 2, 3], np.uint8), 667)[:2000]
+    out.append(("text_with_runs_16384", mixed, 16384))
     return out
 
 

@@ -102,7 +102,12 @@ def test_full_size_blocks_parity(ljb, ctx, oracle):
 def test_pathological_blocks_terminate(ljb, ctx, oracle):
     """All-equal and two-symbol 64 KiB blocks: worst cases for the candidate search, still exact."""
     rng = np.random.default_rng(3)
-    for data in (np.zeros(65536, np.uint8), rng.integers(0, 2, 65536, dtype=np.uint8) + 65):
+    mixed = cases.synth_text(2 * 65536, seed=33)
+    mixed[10000:50000] = 0
+    mixed[70000:90000] = np.tile(np.array([7, 8, 9], np.uint8), 6667)[:20000]
+    for data in (np.zeros(65536, np.uint8), rng.integers(0, 2, 65536, dtype=np.uint8) + 65,
+                 np.tile(np.array([97, 98], np.uint8), 32768), np.tile(rng.integers(0, 256, 1000, dtype=np.uint8), 66)[:65536].copy(),
+                 np.tile(np.frombuffer(b"abcdefg", dtype=np.uint8), 9363)[:65536].copy(), mixed):
         f = ljb.lz4.lz4_encode(data, 65536, ctx=ctx)
         s, offs, ph = oracle.lz4_compress(data, 65536, 1)
         assert np.array_equal(f.stream, s) and f.phantom == ph
