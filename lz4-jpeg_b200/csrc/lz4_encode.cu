@@ -40,7 +40,7 @@ constexpr int HASH_BITS = 13;
 constexpr int NBUCKET = 1 << HASH_BITS;
 constexpr int SEG = 132;             // parse segment: 33 words, so per-thread segment walks are bank-conflict free
 constexpr int MAXSEG = (MAXB + SEG - 1) / SEG; // 497
-constexpr int SLOTS = 26;            // match distances a segment parks in shared memory (13 words: conflict free); more are re-read from the records
+constexpr int SLOTS = 27;            // match positions a segment parks in shared memory for the eight-lane passes (the rest: its own thread)
 constexpr int MAX_MATCH = 1024;      // LZ4.c:20
 constexpr int B1_BUDGET = 512;       // group entries a position inside a chain looks at before B2 takes over
 
@@ -54,8 +54,10 @@ constexpr int SM_DIR = SM_S + 2 * MAXB;            // u32 dirw[4096 + 1]    pack
 constexpr int SM_STEP = SM_B;                      // u8 step[65536 + 64]
 constexpr int SM_ENTRY = SM_STEP + MAXB + 64;      // u8 entry[1024]
 constexpr int SM_FLAG = SM_ENTRY + 1024;           // u8 exit table[65536 + 64]; dead once the chain's segment entries are known, then:
-constexpr int SM_SLOT = SM_FLAG;                   // u16 slots[MAXSEG * SLOTS]     distances of the segment's first matches
-constexpr int SM_OUT = (SM_SLOT + 2 * MAXSEG * SLOTS + 15) & ~15; // the encoded block, up to SOUT_CAP bytes (to the end of region B)
+constexpr int SM_SEGINFO = SM_FLAG;                // uint4 seginfo[512]            per segment: previous match end, byte offset, payload, size sum
+constexpr int SM_SEGCNT = SM_SEGINFO + 16 * 512;   // u8 segcnt[512], u8 segph[512]
+constexpr int SM_SLOT = SM_SEGCNT + 1024;          // u16 slots[MAXSEG * SLOTS]     positions of the segment's first matches
+constexpr int SM_OUT = (SM_SLOT + 2 * 512 * SLOTS + 15) & ~15; // the encoded block, up to SOUT_CAP bytes (to the end of region B)
 constexpr int SM_LONG = SM_DIR + 4 * (NBUCKET / 2 + 4); // u32 longbits[2048]: positions that have an >= 8 byte match
 constexpr int SM_FIRST = SM_LONG + MAXB / 8;             // u32 firstbits[2048]: first occurrences of a repeated 8-gram
 constexpr int SM_MISC = SM_FIRST + MAXB / 8;
@@ -65,6 +67,7 @@ constexpr int SM_TOTAL = SM_MISC + 1024;
 constexpr int SOUT_CAP = ((SM_MISC - SM_OUT) & ~15) - 16; // larger blocks are encoded straight into the global staging buffer
 static_assert(SM_FLAG + MAXB + 64 <= SM_MISC, "parse view must fit inside region B");
 static_assert(SOUT_CAP >= 56 * 1024, "the shared staging area should hold a typical encoded block");
+static_assert(SM_SEGINFO % 16 == 0, "seginfo is a uint4 array");
 static_assert(SEG <= 254 && MAXSEG <= 512, "entry offsets are bytes; one segment per thread");
 static_assert(SM_TOTAL <= 227 * 1024, "exceeds B200 shared memory per CTA");
 
@@ -938,28 +941,32 @@ __global__ void __launch_bounds__(THREADS, 1) lz4_encode_kernel(Params P)
         __syncthreads(); // the exit table is dead from here on: its memory becomes the slots and the output area
         LJB_PHASE(5); // parse: chain resolution
 
-        // ---------------- sizing: every thread walks the chain inside its segment ----------------
-        // A sequence = the literals since the previous match + one match (LZ4.c:516-583).  Inside a segment only the first
-        // sequence depends on other segments (through the end of the last match before it): two block scans give every
-        // segment that end and the byte offset of its first sequence.
-        uint16_t *const myslots = reinterpret_cast<uint16_t *>(smem + SM_SLOT) + tid * SLOTS;
+        // ---------------- sizing and emission ----------------
+        // A sequence = the literals since the previous match + one match (LZ4.c:516-583).
+        //   E1  one thread per segment walks the chain inside its segment and parks the match positions (the first SLOTS of
+        //       them; more than that needs runs of one- to three-byte phantom matches) in shared memory
+        //   S   eight lanes per segment size the parked sequences (a sequence needs its own match, the match before it, and
+        //       for the first one of a segment the end of the last match before the segment: block scan 1)
+        //   scan 2 gives every segment the byte offset of its first sequence
+        //   E2  eight lanes per segment serialise the parked sequences; whatever a segment could not park is sized and
+        //       serialised by the segment's own thread
+        uint16_t *const slots = reinterpret_cast<uint16_t *>(smem + SM_SLOT);
+        uint4 *const seginfo = reinterpret_cast<uint4 *>(smem + SM_SEGINFO); // x: end of the last match before, y: byte offset, z: payload, w: size sum
+        uint8_t *const segcnt = smem + SM_SEGCNT;                            // matches per segment (<= SEG)
+        uint8_t *const segph = segcnt + 512;                                 // phantom sequences among the parked ones
+        uint16_t *const myslots = slots + tid * SLOTS;
         const bool has_seg = (uint32_t)tid < nseg && entry[tid] != 0xFF;
-        uint32_t cnt = 0, seg_last_end = 0, first_p = 0, first_ml = 0;
-        uint32_t rest_pay = 0, rest_sizes = 0, rest_ph = 0;
+        uint32_t cnt = 0, seg_last_end = 0, ov_p = 0, ov_pe = 0;
         if (has_seg) {
             uint32_t p = s0 + entry[tid], pe = 0;
             while (p < s1) {
                 const uint32_t st = step[p];
                 if (st) {
-                    if (cnt < (uint32_t)SLOTS) myslots[cnt] = (uint16_t)p; // becomes the match distance below
-                    if (cnt == 0) {
-                        first_p = p;
-                        first_ml = st;
-                    } else {
-                        const SeqSize z = seq_size(p - pe, st);
-                        rest_pay += z.payload;
-                        rest_sizes += z.byte_size;
-                        rest_ph += (z.payload != z.byte_size) ? 1u : 0u;
+                    if (cnt < (uint32_t)SLOTS) {
+                        myslots[cnt] = (uint16_t)p;
+                    } else if (cnt == (uint32_t)SLOTS) {
+                        ov_p = p;
+                        ov_pe = pe;
                     }
                     pe = p + st;
                     ++cnt;
@@ -970,22 +977,7 @@ __global__ void __launch_bounds__(THREADS, 1) lz4_encode_kernel(Params P)
             }
             seg_last_end = pe;
         }
-        // match distances of the parked matches, for the emit pass: gathered from the records six at a time (the walk above
-        // would otherwise wait for one L2 round trip per match)
-        {
-            const uint32_t m = min(cnt, (uint32_t)SLOTS);
-#pragma unroll 1
-            for (uint32_t i = 0; i < m; i += 6) {
-                uint32_t q[6], r[6];
-#pragma unroll
-                for (int j = 0; j < 6; ++j) q[j] = i + j < m ? (uint32_t)myslots[i + j] : 0u;
-#pragma unroll
-                for (int j = 0; j < 6; ++j) r[j] = i + j < m ? R[q[j]] : 0u;
-#pragma unroll
-                for (int j = 0; j < 6; ++j)
-                    if (i + j < m) myslots[i + j] = (uint16_t)(q[j] - (r[j] & 0xFFFF));
-            }
-        }
+        if (tid < 512) segcnt[tid] = (uint8_t)cnt;
         LJB_PHASE(10); // (probe) E1 walk
         // scan 1: end of the last match before this segment (exclusive max; ends grow along the chain)
         uint32_t prev_end_in;
@@ -1003,20 +995,78 @@ __global__ void __launch_bounds__(THREADS, 1) lz4_encode_kernel(Params P)
             uint32_t wmax = 0;
             for (int k = 0; k < warp; ++k) wmax = max(wmax, M.scan_tmp[k]);
             prev_end_in = max(wmax, ex);
+            if (tid < 512) seginfo[tid].x = prev_end_in;
         }
         uint32_t last_end = 0; // end of the last match of the block
         for (int k = 0; k < NWARPS; ++k) last_end = max(last_end, M.scan_tmp[k]);
+        __syncthreads();
+        // the sequence parked in slot i of a segment: its match, and the end of the match before it
+        auto parked = [&](const uint16_t *sl, uint32_t i, uint32_t seg_prev_end, uint32_t &p, uint32_t &ml, uint32_t &pe) {
+            p = sl[i];
+            ml = step[p];
+            if (i) {
+                const uint32_t pp = sl[i - 1];
+                pe = pp + step[pp];
+            } else {
+                pe = seg_prev_end;
+            }
+        };
+        // S: eight lanes per segment, 128 segments per pass
+        const int gj = tid & 7;
+#pragma unroll 1
+        for (uint32_t seg = (uint32_t)tid >> 3; seg < 512u; seg += THREADS / 8) {
+            const uint32_t c = seg < nseg ? (uint32_t)segcnt[seg] : 0u, m = min(c, (uint32_t)SLOTS);
+            const uint16_t *sl = slots + seg * SLOTS;
+            const uint32_t spe = seginfo[seg].x;
+            uint32_t gp = 0, gs = 0, gph = 0;
+            for (uint32_t i = gj; i < m; i += 8) {
+                uint32_t p, ml, pe;
+                parked(sl, i, spe, p, ml, pe);
+                const SeqSize z = seq_size(p - pe, ml);
+                gp += z.payload;
+                gs += z.byte_size;
+                gph += (z.payload != z.byte_size) ? 1u : 0u;
+            }
+#pragma unroll
+            for (int o = 1; o < 8; o <<= 1) {
+                gp += __shfl_xor_sync(0xffffffffu, gp, o);
+                gs += __shfl_xor_sync(0xffffffffu, gs, o);
+                gph += __shfl_xor_sync(0xffffffffu, gph, o);
+            }
+            if (gj == 0) {
+                seginfo[seg].z = gp;
+                seginfo[seg].w = gs;
+                segph[seg] = (uint8_t)gph;
+            }
+        }
+        __syncthreads();
         // scan 2: bytes, size-field sums, sequence and phantom counts before this segment
         unsigned long long my_prefix; // offset of this segment's first sequence in the encoded block
         unsigned long long pay = 3, sizes = 3;
-        uint32_t nseq = 0, phantom = 0;
+        uint32_t nseq = 0, phantom = 0, par_pay = 0;
         {
-            uint32_t seg_pay = rest_pay, seg_sizes = rest_sizes, seg_ph = rest_ph;
-            if (cnt) {
-                const SeqSize z = seq_size(first_p - prev_end_in, first_ml);
-                seg_pay += z.payload;
-                seg_sizes += z.byte_size;
-                seg_ph += (z.payload != z.byte_size) ? 1u : 0u;
+            uint32_t seg_pay = 0, seg_sizes = 0, seg_ph = 0;
+            if (tid < 512) {
+                seg_pay = seginfo[tid].z;
+                seg_sizes = seginfo[tid].w;
+                seg_ph = segph[tid];
+            }
+            par_pay = seg_pay;
+            if (cnt > (uint32_t)SLOTS) { // what could not be parked: sized here
+                uint32_t p = ov_p, pe = ov_pe;
+                while (p < s1) {
+                    const uint32_t st = step[p];
+                    if (st) {
+                        const SeqSize z = seq_size(p - pe, st);
+                        seg_pay += z.payload;
+                        seg_sizes += z.byte_size;
+                        seg_ph += (z.payload != z.byte_size) ? 1u : 0u;
+                        pe = p + st;
+                        p += st;
+                    } else {
+                        ++p;
+                    }
+                }
             }
             unsigned long long x = (unsigned long long)seg_pay | ((unsigned long long)seg_sizes << 32);
             unsigned long long y = (unsigned long long)cnt | ((unsigned long long)seg_ph << 32);
@@ -1041,6 +1091,7 @@ __global__ void __launch_bounds__(THREADS, 1) lz4_encode_kernel(Params P)
                 ty += M.warp_y[k];
             }
             my_prefix = 3 + ((bx + x - own) & 0xFFFFFFFFull);
+            if (tid < 512) seginfo[tid].y = (uint32_t)my_prefix;
             pay += tx & 0xFFFFFFFFull;
             sizes += tx >> 32;
             nseq = (uint32_t)(ty & 0xFFFFFFFFull);
@@ -1065,66 +1116,102 @@ __global__ void __launch_bounds__(THREADS, 1) lz4_encode_kernel(Params P)
         }
         LJB_PHASE(7); // look-back
         // The block is encoded in shared memory and copied to its staging buffer with 16-byte stores; a block too large for
-        // that (it expanded by more than ~10 %) is encoded straight into the staging buffer through the same generic pointer.
+        // that (it expanded) is encoded straight into the staging buffer through the same generic pointer.
         uint8_t *const stage = stage0 + (size_t)buf * P.stage_stride;
         const bool in_shared = pay <= (unsigned long long)SOUT_CAP;
         uint8_t *const obase = in_shared ? smem + SM_OUT : stage;
+        // one sequence: token, size field, literal-length extension, literals (short runs here, long ones by the caller),
+        // match offset, match-length extension (LZ4.c:365-413).  Returns where the literals go.
+        auto put_sequence = [&](uint8_t *dst, uint32_t lit, uint32_t ml, uint32_t pe, uint32_t dist, const SeqSize &sz, bool copy_all) -> uint32_t {
+            const uint32_t tok_lit = lit >= 15 ? 15u : lit;
+            const uint32_t tok_m = ml >= 19 ? 15u : ((ml - 4) & 0xFF);
+            uint32_t o = 0;
+            dst[o++] = (uint8_t)((tok_lit << 4) | tok_m);
+            dst[o++] = (uint8_t)(sz.byte_size & 0xFF);
+            dst[o++] = (uint8_t)((sz.byte_size >> 8) & 0xFF);
+            if (lit >= 15) {
+                uint32_t rem = (lit - 15) & 0xFF;
+                if (rem == 255) { dst[o++] = 255; rem = 0; }
+                dst[o++] = (uint8_t)rem;
+            }
+            const uint32_t lit_dst_off = o;
+            if (lit <= 16 || copy_all)
+                for (uint32_t k = 0; k < lit; ++k) dst[o + k] = data[pe + k];
+            o += lit;
+            dst[o++] = (uint8_t)(dist & 0xFF);
+            dst[o++] = (uint8_t)(dist >> 8);
+            if (ml >= 19) dst[o++] = (uint8_t)(ml - 19);
+            return lit_dst_off;
+        };
+        __syncthreads(); // byte offsets of the segments are in place
         {
-            // every lane serialises the sequences of its own segment; the warp stays converged so that long literal runs can
-            // be copied by all its lanes
-            uint32_t p = has_seg ? s0 + entry[tid] : 0u, pe = prev_end_in, idx = 0;
-            unsigned long long off = my_prefix;
-            bool done = !has_seg;
-            for (;;) {
-                uint32_t st = 0;
-                if (!done) {
-                    while (p < s1 && (st = step[p]) == 0) ++p; // literal steps
-                    if (p >= s1) done = true;
+            // E2: eight lanes per segment, four segments per warp and pass; the records of all rounds are fetched first
+            constexpr int ROUNDS = (SLOTS + 7) / 8;
+#pragma unroll 1
+            for (uint32_t seg = (uint32_t)tid >> 3; seg < 512u; seg += THREADS / 8) {
+                const uint32_t c = seg < nseg ? (uint32_t)segcnt[seg] : 0u, m = min(c, (uint32_t)SLOTS);
+                const uint32_t mmax = __reduce_max_sync(0xffffffffu, m);
+                if (mmax == 0) continue;
+                const uint16_t *sl = slots + seg * SLOTS;
+                const uint4 info = seginfo[seg];
+                uint32_t rr[ROUNDS];
+#pragma unroll
+                for (int k = 0; k < ROUNDS; ++k) {
+                    const uint32_t i = (uint32_t)(8 * k + gj);
+                    rr[k] = i < m ? R[sl[i]] : 0u;
                 }
-                const bool found = !done;
-                if (!__any_sync(0xffffffffu, found)) break;
-                uint32_t lit = 0, lit_dst_off = 0;
-                uint8_t *dst = obase + off;
-                if (found) {
-                    const uint32_t ml = st;
-                    lit = p - pe;
-                    const SeqSize sz = seq_size(lit, ml);
-                    const uint32_t dist = idx < (uint32_t)SLOTS ? (uint32_t)myslots[idx] : ((p - (R[p] & 0xFFFF)) & 0xFFFFu);
-                    const uint32_t tok_lit = lit >= 15 ? 15u : lit;
-                    const uint32_t tok_m = ml >= 19 ? 15u : ((ml - 4) & 0xFF);
-                    uint32_t o = 0;
-                    dst[o++] = (uint8_t)((tok_lit << 4) | tok_m);
-                    dst[o++] = (uint8_t)(sz.byte_size & 0xFF);
-                    dst[o++] = (uint8_t)((sz.byte_size >> 8) & 0xFF);
-                    if (lit >= 15) {
-                        uint32_t rem = (lit - 15) & 0xFF;
-                        if (rem == 255) { dst[o++] = 255; rem = 0; }
-                        dst[o++] = (uint8_t)rem;
+                uint32_t running = info.y;
+#pragma unroll
+                for (int k = 0; k < ROUNDS; ++k) {
+                    if ((uint32_t)(8 * k) >= mmax) break; // warp-uniform
+                    const uint32_t i = (uint32_t)(8 * k + gj);
+                    const bool act = i < m;
+                    uint32_t p = 0, ml = 0, pe = 0, lit = 0;
+                    SeqSize sz = {0, 0};
+                    if (act) {
+                        parked(sl, i, info.x, p, ml, pe);
+                        lit = p - pe;
+                        sz = seq_size(lit, ml);
                     }
-                    lit_dst_off = o;
-                    if (lit <= 16)
-                        for (uint32_t k = 0; k < lit; ++k) dst[o + k] = data[pe + k];
-                    o += lit;
-                    dst[o++] = (uint8_t)(dist & 0xFF);
-                    dst[o++] = (uint8_t)(dist >> 8);
-                    if (ml >= 19) dst[o++] = (uint8_t)(ml - 19);
-                    off += sz.payload;
+                    uint32_t inc = sz.payload;
+#pragma unroll
+                    for (int o = 1; o < 8; o <<= 1) {
+                        const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o, 8);
+                        if (gj >= o) inc += v;
+                    }
+                    const uint32_t gtot = __shfl_sync(0xffffffffu, inc, 7, 8);
+                    uint8_t *dst = obase + running + (inc - sz.payload);
+                    uint32_t lit_dst_off = 0;
+                    if (act) lit_dst_off = put_sequence(dst, lit, ml, pe, (p - (rr[k] & 0xFFFFu)) & 0xFFFFu, sz, false);
+                    unsigned lits_long = __ballot_sync(0xffffffffu, act && lit > 16);
+                    while (lits_long) { // long literal runs: the whole warp copies them
+                        const int L = __ffs(lits_long) - 1;
+                        lits_long &= lits_long - 1;
+                        const uint32_t n_l = __shfl_sync(0xffffffffu, lit, L);
+                        const uint32_t s_l = __shfl_sync(0xffffffffu, pe, L);
+                        const unsigned long long d_l =
+                            __shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)(dst + lit_dst_off), L);
+                        uint8_t *dp = reinterpret_cast<uint8_t *>((uintptr_t)d_l);
+                        for (uint32_t q = lane; q < n_l; q += 32) dp[q] = data[s_l + q];
+                    }
+                    running += gtot;
                 }
-                unsigned lits_long = __ballot_sync(0xffffffffu, found && lit > 16);
-                while (lits_long) { // long literal runs: the whole warp copies them
-                    const int L = __ffs(lits_long) - 1;
-                    lits_long &= lits_long - 1;
-                    const uint32_t n_l = __shfl_sync(0xffffffffu, lit, L);
-                    const uint32_t s_l = __shfl_sync(0xffffffffu, pe, L);
-                    const unsigned long long d_l =
-                        __shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)(dst + lit_dst_off), L);
-                    uint8_t *dp = reinterpret_cast<uint8_t *>((uintptr_t)d_l);
-                    for (uint32_t k = lane; k < n_l; k += 32) dp[k] = data[s_l + k];
-                }
-                if (found) {
-                    pe = p + st;
-                    p += st;
-                    ++idx;
+            }
+            if (cnt > (uint32_t)SLOTS) { // what could not be parked: serialised by the segment's own thread
+                uint32_t p = ov_p, pe = ov_pe;
+                unsigned long long off = my_prefix + par_pay;
+                while (p < s1) {
+                    const uint32_t st = step[p];
+                    if (st) {
+                        const uint32_t lit = p - pe;
+                        const SeqSize sz = seq_size(lit, st);
+                        put_sequence(obase + off, lit, st, pe, (p - (R[p] & 0xFFFFu)) & 0xFFFFu, sz, true);
+                        off += sz.payload;
+                        pe = p + st;
+                        p += st;
+                    } else {
+                        ++p;
+                    }
                 }
             }
             LJB_PHASE(11); // (probe) E2 walk

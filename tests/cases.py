@@ -121,6 +121,12 @@ def lz4_cases():
     out.append(("zeros_4096", np.zeros(4096, np.uint8), 4096))
     out.append(("period2_4096", np.tile(np.array([97, 98], np.uint8), 2048), 4096))
     out.append(("period7_6000", np.tile(np.frombuffer(b"abcdefg", dtype=np.uint8), 858)[:6000].copy(), 6000))
+    # back-to-back 4-byte matches: 33 sequences per 132 bytes (more than a parse segment parks for the eight-lane passes)
+    words = rng.integers(128, 256, size=(600, 4), dtype=np.uint8)
+    sec1 = np.concatenate([np.concatenate([w, np.array([j % 128], np.uint8)]) for j, w in enumerate(words)])
+    sec2 = words[rng.integers(0, 600, size=3000)].reshape(-1)
+    dense = np.concatenate([sec1, sec2])
+    out.append(("dense_ml4_15000", dense, dense.size))
     mixed = synth_text(16384, seed=21)
     mixed[3000:9000] = 0
     mixed[11000:13000] = np.tile(np.array([1, 2, 3], np.uint8), 667)[:2000]
