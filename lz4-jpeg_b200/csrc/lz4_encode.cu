@@ -543,21 +543,31 @@ __global__ void __launch_bounds__(THREADS, 1) lz4_encode_kernel(Params P)
                 uint32_t *vlong = firstbits; // the first-occurrence bits are dead once the index is built
                 for (int i = tid; i < MAXB / 32; i += THREADS) vlong[i] = 0;
                 if (tid < 64) reinterpret_cast<uint32_t *>(M.warp_x)[tid] = 0; // per 1024-position row: candidates overflows (B2's schedule)
+                if (tid == 0) M.scan_tmp[1] = 0;                                // B1's ticket counter
                 __syncthreads();
                 {
                     uint32_t d_pos = 0, d_vis = 0, d_eq = 0;
                     const long long tb1 = clock64();
-                    // (the group id of the next entry is fetched while this one is processed)
-                    uint32_t p_n = (uint32_t)tid < nidx ? (uint32_t)S[tid] : 0u;
-                    bool l_n = (uint32_t)tid < nidx && ((longbits[p_n >> 5] >> (p_n & 31)) & 1u);
+                    // Warps take 32 consecutive sorted entries at a time from a ticket counter (group sizes differ widely: a fixed
+                    // assignment left warps waiting 4 % of the kernel at the barrier below); the next ticket, its entries and
+                    // their group ids are fetched while the current entries are processed.
+                    auto grab = [&]() -> uint32_t {
+                        uint32_t t = 0;
+                        if (lane == 0) t = atomicAdd(&M.scan_tmp[1], 1u);
+                        return __shfl_sync(0xffffffffu, t, 0) * 32u + (uint32_t)lane;
+                    };
+                    uint32_t j_n = grab();
+                    uint32_t p_n = j_n < nidx ? (uint32_t)S[j_n] : 0u;
+                    bool l_n = j_n < nidx && ((longbits[p_n >> 5] >> (p_n & 31)) & 1u);
                     uint32_t g_n = l_n ? (uint32_t)gids[p_n] : 0u;
-                    for (uint32_t j = tid; j < nidx; j += THREADS) {
+                    for (;;) {
+                        if (j_n - (uint32_t)lane >= nidx) break; // (warp-uniform)
                         const uint32_t p = p_n, gp = g_n;
                         const bool lp = l_n;
                         {
-                            const uint32_t jn = j + THREADS;
-                            p_n = jn < nidx ? (uint32_t)S[jn] : 0u;
-                            l_n = jn < nidx && ((longbits[p_n >> 5] >> (p_n & 31)) & 1u);
+                            j_n = grab();
+                            p_n = j_n < nidx ? (uint32_t)S[j_n] : 0u;
+                            l_n = j_n < nidx && ((longbits[p_n >> 5] >> (p_n & 31)) & 1u);
                             g_n = l_n ? (uint32_t)gids[p_n] : 0u;
                         }
                         if (!lp) continue; // a first occurrence: candidate only
