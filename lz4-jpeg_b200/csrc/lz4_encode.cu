@@ -42,6 +42,7 @@ constexpr int SEG = 132;             // parse segment: 33 words, so per-thread s
 constexpr int MAXSEG = (MAXB + SEG - 1) / SEG; // 497
 constexpr int SLOTS = 27;            // match positions a segment parks in shared memory for the eight-lane passes (the rest: its own thread)
 constexpr int MAX_MATCH = 1024;      // LZ4.c:20
+constexpr int CH = 12;               // the index keeps the entries of a group ordered by 4096-position chunk (one scatter round each)
 constexpr int B1_BUDGET = 512;       // group entries a position inside a chain looks at before B2 takes over
 
 // ---- shared memory map (bytes) ---------------------------------------------------------------------
@@ -400,7 +401,7 @@ __global__ void __launch_bounds__(THREADS, 1) lz4_encode_kernel(Params P)
                 // ---- group index.  Level 8 of the ladder left, for every flagged position, the FIRST occurrence q of its
                 // 8-gram (R[p] & 0xFFFF) and a bit for every such q: the rank of q among the set bits is an exact, dense id
                 // of the 8-gram ("group").  Counting sort of the flagged positions and the first occurrences by group id:
-                // afterwards S holds every group contiguously (entries of an earlier 1024-position chunk first) and
+                // afterwards S holds every group contiguously (entries of an earlier 4096-position chunk first) and
                 // gdir16[g] = end of group g = start of group g+1.  A position then visits only true occurrences of its
                 // own 8-gram — no hash collisions, no 8-byte compare.  Layout inside the S/dir area: S (2 bytes x entries),
                 // the directory right behind it (2 bytes x groups), the rank table at the end.  Should the directory not
@@ -447,27 +448,37 @@ __global__ void __launch_bounds__(THREADS, 1) lz4_encode_kernel(Params P)
                 for (uint32_t i = tid; i < dwords; i += THREADS) gdirw[i] = 0;
                 __syncthreads();
                 auto rank_of = [&](uint32_t q) -> uint32_t { return (uint32_t)pref[q >> 5] + __popc(firstbits[q >> 5] & ((1u << (q & 31)) - 1u)); };
-                // histogram; the group id of a flagged position is kept in a per-CTA array (it is needed three more times)
+                // histogram; the group id of a flagged position is kept in a per-CTA array (it is needed three more times).
+                // A thread takes four consecutive positions per 4096-position chunk: one word of each bit set, one 16-byte load
+                // of the records (fetched one chunk ahead), one 8-byte store of the ids.
+                {
+                    auto bits4 = [&](const uint32_t *bits, uint32_t q0) -> uint32_t { return q0 < (uint32_t)MAXB ? (bits[q0 >> 5] >> (q0 & 31)) & 0xFu : 0u; };
+                    const uint4 *R4 = reinterpret_cast<const uint4 *>(R);
+                    uint32_t q0n = 4u * (uint32_t)tid;
+                    uint32_t lwn = q0n < npos8 ? bits4(longbits, q0n) : 0u;
+                    uint4 rn = lwn ? R4[q0n >> 2] : make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll 1
-                for (uint32_t base = 0; base < npos8; base += 8 * THREADS) {
-                    uint32_t r[8];
-                    bool lb[8], fb[8];
+                    for (uint32_t base = 0; base < npos8; base += 4 * THREADS) {
+                        const uint32_t q0 = q0n, lw = lwn;
+                        const uint4 r4 = rn;
+                        q0n = base + 4 * THREADS + 4u * (uint32_t)tid;
+                        lwn = q0n < npos8 ? bits4(longbits, q0n) : 0u;
+                        rn = lwn ? R4[q0n >> 2] : make_uint4(0u, 0u, 0u, 0u);
+                        const uint32_t fw = q0 < npos8 ? bits4(firstbits, q0) : 0u;
+                        if ((lw | fw) == 0u) continue;
+                        const uint32_t rr[4] = {r4.x, r4.y, r4.z, r4.w};
+                        uint32_t g[4];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const uint32_t q = base + j * THREADS + tid;
-                        lb[j] = q < npos8 && ((longbits[q >> 5] >> (q & 31)) & 1u);
-                        fb[j] = q < npos8 && ((firstbits[q >> 5] >> (q & 31)) & 1u);
-                        r[j] = lb[j] ? R[q] : 0u;
-                    }
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const uint32_t q = base + j * THREADS + tid;
-                        if (lb[j] || fb[j]) {
-                            const uint32_t g = rank_of(lb[j] ? (r[j] & 0xFFFFu) : q);
-                            if (lb[j]) gids[q] = (uint16_t)g;
-                            const uint32_t bk = g >> shift;
-                            atomicAdd(&gdirw[bk >> 1], (bk & 1) ? 0x10000u : 1u);
+                        for (int j = 0; j < 4; ++j) {
+                            g[j] = 0;
+                            if (((lw | fw) >> j) & 1u) {
+                                g[j] = rank_of(((lw >> j) & 1u) ? (rr[j] & 0xFFFFu) : q0 + j);
+                                const uint32_t bk = g[j] >> shift;
+                                atomicAdd(&gdirw[bk >> 1], (bk & 1) ? 0x10000u : 1u);
+                            }
                         }
+                        // (ids of positions that are not flagged are never read: the four are stored together)
+                        *reinterpret_cast<uint2 *>(gids + q0) = make_uint2(g[0] | (g[1] << 16), g[2] | (g[3] << 16));
                     }
                 }
                 __syncthreads();
@@ -501,39 +512,30 @@ __global__ void __launch_bounds__(THREADS, 1) lz4_encode_kernel(Params P)
                 }
                 __syncthreads();
                 {
-                    // scatter in position-ordered rounds; the group ids of four rounds are fetched four rounds ahead (a round is
-                    // much shorter than the L2 round trip)
-                    uint32_t gn[4];
-                    bool ln[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const uint32_t q = j * THREADS + tid;
-                        ln[j] = q < npos8 && ((longbits[q >> 5] >> (q & 31)) & 1u);
-                        gn[j] = ln[j] ? (uint32_t)gids[q] : 0u;
-                    }
+                    // scatter in position-ordered rounds of 4096 positions (four consecutive ones per thread); the ids of the next
+                    // round are fetched while this one runs
+                    auto bits4 = [&](const uint32_t *bits, uint32_t q0) -> uint32_t { return q0 < (uint32_t)MAXB ? (bits[q0 >> 5] >> (q0 & 31)) & 0xFu : 0u; };
+                    uint32_t q0n = 4u * (uint32_t)tid;
+                    uint32_t lwn = q0n < npos8 ? bits4(longbits, q0n) : 0u;
+                    uint2 gn = lwn ? *reinterpret_cast<const uint2 *>(gids + q0n) : make_uint2(0u, 0u);
 #pragma unroll 1
                     for (uint32_t base = 0; base < npos8; base += 4 * THREADS) {
-                        uint32_t gc[4];
-                        bool lc[4];
+                        const uint32_t q0 = q0n, lw = lwn;
+                        const uint2 g2 = gn;
+                        q0n = base + 4 * THREADS + 4u * (uint32_t)tid;
+                        lwn = q0n < npos8 ? bits4(longbits, q0n) : 0u;
+                        gn = lwn ? *reinterpret_cast<const uint2 *>(gids + q0n) : make_uint2(0u, 0u);
+                        const uint32_t fw = q0 < npos8 ? bits4(firstbits, q0) : 0u;
+                        const uint32_t gg[4] = {g2.x & 0xFFFFu, g2.x >> 16, g2.y & 0xFFFFu, g2.y >> 16};
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            gc[j] = gn[j];
-                            lc[j] = ln[j];
-                            const uint32_t q = base + (4 + j) * THREADS + tid;
-                            ln[j] = q < npos8 && ((longbits[q >> 5] >> (q & 31)) & 1u);
-                            gn[j] = ln[j] ? (uint32_t)gids[q] : 0u;
-                        }
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const uint32_t q = base + j * THREADS + tid;
-                            const bool fbq = q < npos8 && ((firstbits[q >> 5] >> (q & 31)) & 1u);
-                            if (lc[j] || fbq) {
-                                const uint32_t bk = (lc[j] ? gc[j] : rank_of(q)) >> shift;
+                            if (((lw | fw) >> j) & 1u) {
+                                const uint32_t bk = (((lw >> j) & 1u) ? gg[j] : rank_of(q0 + j)) >> shift;
                                 const uint32_t old = atomicAdd(&gdirw[bk >> 1], (bk & 1) ? 0x10000u : 1u);
-                                S[(bk & 1) ? (old >> 16) : (old & 0xFFFF)] = (uint16_t)q;
+                                S[(bk & 1) ? (old >> 16) : (old & 0xFFFF)] = (uint16_t)(q0 + j);
                             }
-                            __syncthreads();
                         }
+                        __syncthreads(); // one round = one 4096-position chunk
                     }
                 }
                 LJB_PHASE(3); // index (8-gram groups)
@@ -579,7 +581,7 @@ __global__ void __launch_bounds__(THREADS, 1) lz4_encode_kernel(Params P)
                         const uint32_t bk = gp >> shift;
                         const uint32_t lo = bk ? gdir16[bk - 1] : 0u, hi = gdir16[bk];
                         const uint32_t cap16 = min(16u, nb - p);
-                        const uint32_t pch = p >> 10;
+                        const uint32_t pch = p >> CH;
                         // a chain = consecutive flagged positions inside one 32-position chunk (B2's unit of sequential work)
                         const bool chain_start = (p & 31u) == 0u || !((longbits[(p - 1) >> 5] >> ((p - 1) & 31)) & 1u);
                         const uint32_t prev_byte = p ? data[p - 1] : 0u;
@@ -591,7 +593,7 @@ __global__ void __launch_bounds__(THREADS, 1) lz4_encode_kernel(Params P)
                         for (; i < hi_w; ++i) {
                             const uint32_t c = c_next;
                             c_next = S[i + 1]; // one entry ahead (S has slack past the last bucket): shortens the dependent chain
-                            const uint32_t cch = c >> 10;
+                            const uint32_t cch = c >> CH;
                             if (cch > pch) break; // only later positions from here on
                             ++d_vis;
                             // Inside a chain only the (few) pairs that start a diagonal count, so nothing ends the walk of a huge
@@ -599,7 +601,7 @@ __global__ void __launch_bounds__(THREADS, 1) lz4_encode_kernel(Params P)
                             // entries the position is handed to B2, whose own walk is pruned by the pairs it carries.
                             // (the budget is the loop bound: hi_w)
                             // later positions cannot win a tie; but B2 needs EVERY 16-byte candidate unless it walks the bucket itself
-                            if ((best >> 16) == cap16 && (cap16 < 16 || n16 > 2) && cch > ((0xFFFFu - (best & 0xFFFFu)) >> 10)) break;
+                            if ((best >> 16) == cap16 && (cap16 < 16 || n16 > 2) && cch > ((0xFFFFu - (best & 0xFFFFu)) >> CH)) break;
                             if (c < p) {
                                 const uint32_t ci = c >> 2, cs = (c & 3) * 8;
                                 // an entry of the same group has the same 8 bytes; shared buckets need the comparison
@@ -834,13 +836,13 @@ __global__ void __launch_bounds__(THREADS, 1) lz4_encode_kernel(Params P)
                             } else {
                                 const uint32_t bk = (uint32_t)gids[p] >> shift;
                                 const uint32_t lo = bk ? gdir16[bk - 1] : 0u, hi = gdir16[bk];
-                                const uint32_t pch = p >> 10;
+                                const uint32_t pch = p >> CH;
                                 for (uint32_t k = lo; k < hi; ++k) {
                                     const uint32_t c = S[k];
-                                    if ((c >> 10) > pch) break; // only later positions from here on
+                                    if ((c >> CH) > pch) break; // only later positions from here on
                                     if (c >= p) continue;
                                     const uint32_t bl = bestkey >> 16, bp = 0xFFFFu - (bestkey & 0xFFFFu);
-                                    if (bl == cap && (c >> 10) > (bp >> 10)) { // later positions cannot win a tie ...
+                                    if (bl == cap && (c >> CH) > (bp >> CH)) { // later positions cannot win a tie ...
                                         ninc = true;                            // ... but may reach the cap as well
                                         break;
                                     }
