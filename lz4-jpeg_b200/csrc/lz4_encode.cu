@@ -43,7 +43,7 @@ constexpr int MAXSEG = (MAXB + SEG - 1) / SEG; // 497
 constexpr int SLOTS = 27;            // match positions a segment parks in shared memory for the eight-lane passes (the rest: its own thread)
 constexpr int MAX_MATCH = 1024;      // LZ4.c:20
 constexpr int CH = 12;               // the index keeps the entries of a group ordered by 4096-position chunk (one scatter round each)
-constexpr int B1_BUDGET = 512;       // group entries a position inside a chain looks at before B2 takes over
+constexpr int B1_BUDGET = 512;       // positions inside a chain leave groups larger than this to B2
 
 // ---- shared memory map (bytes) ---------------------------------------------------------------------
 constexpr int SM_DATA = 0;                         // 65536 + 64 pad
@@ -587,7 +587,7 @@ __global__ void __launch_bounds__(THREADS, 1) lz4_encode_kernel(Params P)
                         const uint32_t prev_byte = p ? data[p - 1] : 0u;
                         uint32_t best = 0, n16 = 0, cand = 0xFFFFFFFFu;
                         const bool budgeted = !chain_start && nb - p > 16 && hi - lo > (uint32_t)B1_BUDGET;
-                        const uint32_t hi_w = budgeted ? lo + (uint32_t)B1_BUDGET : hi;
+                        const uint32_t hi_w = budgeted ? lo : hi; // (a position inside a chain does not look at a huge group at all)
                         uint32_t c_next = lo < hi ? S[lo] : 0u;
                         uint32_t i = lo;
                         for (; i < hi_w; ++i) {
@@ -596,10 +596,11 @@ __global__ void __launch_bounds__(THREADS, 1) lz4_encode_kernel(Params P)
                             const uint32_t cch = c >> CH;
                             if (cch > pch) break; // only later positions from here on
                             ++d_vis;
-                            // Inside a chain only the (few) pairs that start a diagonal count, so nothing ends the walk of a huge
-                            // group early (runs of one byte, short periods: every position is in one group): after B1_BUDGET
-                            // entries the position is handed to B2, whose own walk is pruned by the pairs it carries.
-                            // (the budget is the loop bound: hi_w)
+                            // Inside a chain only the (few) pairs that start a diagonal count, so nothing would end the walk of a huge
+                            // group early (runs of one byte, short periods: every position is in one group): positions inside a
+                            // chain whose group has more than B1_BUDGET entries are handed to B2 at once, whose own walk is pruned
+                            // by the pairs it carries (hi_w == lo).  A third 16-byte candidate means B2 walks the group anyway.
+                            if (n16 > 2 && nb - p > 16) break;
                             // later positions cannot win a tie; but B2 needs EVERY 16-byte candidate unless it walks the bucket itself
                             if ((best >> 16) == cap16 && (cap16 < 16 || n16 > 2) && cch > ((0xFFFFu - (best & 0xFFFFu)) >> CH)) break;
                             if (c < p) {
