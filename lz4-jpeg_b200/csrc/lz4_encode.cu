@@ -295,27 +295,32 @@ __global__ void __launch_bounds__(THREADS, 1) lz4_encode_kernel(Params P)
                 g0 = __funnelshift_r(w0, w1, qs);
                 g1 = __funnelshift_r(w1, w2, qs) & mask1;
             };
-#pragma unroll 1
-            for (int i = 0; i < 64; ++i)
-                if (pos_of(i) < nb) unres |= 1ull << i;
+            // positions tid + 1024 * i below a limit: the low ceil((limit - tid) / 1024) bits
+            auto below = [&](uint32_t limit) -> unsigned long long {
+                if (limit <= (uint32_t)tid) return 0ull;
+                const uint32_t cnt = (limit - (uint32_t)tid + 1023u) >> 10;
+                return cnt >= 64u ? ~0ull : ((1ull << cnt) - 1ull);
+            };
+            unres = below(nb);
+            {
+                // the table is filled once per block: a slot holds (generation << 16) | position with generations counting
+                // DOWN, so an entry of the current round always beats what earlier rounds left behind (no clearing, one
+                // barrier less per round)
+                uint4 *T4 = reinterpret_cast<uint4 *>(T);
+                const uint4 ff = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+                for (int i = tid; i < (1 << TBITS) / 4; i += THREADS) T4[i] = ff;
+            }
+            uint32_t gen = 0xFFFEu;
+            __syncthreads();
 #pragma unroll 1
             for (int k = 8; k >= 4; --k) {
                 const uint32_t npk = nb >= (uint32_t)k ? nb - k + 1 : 0;
                 const uint32_t m1 = k >= 8 ? 0xFFFFFFFFu : (k == 4 ? 0u : ((1u << (8 * (k - 4))) - 1u));
-                unsigned long long ins = 0;
-                for (unsigned long long m = unres; m;) {
-                    const int i = __ffsll((long long)m) - 1;
-                    m &= m - 1;
-                    if (pos_of(i) < npk) ins |= 1ull << i;
-                }
+                unsigned long long ins = unres & below(npk);
                 int round = 0;
                 for (;;) {
-                    {
-                        uint4 *T4 = reinterpret_cast<uint4 *>(T);
-                        const uint4 ff = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
-                        for (int i = tid; i < (1 << TBITS) / 4; i += THREADS) T4[i] = ff;
-                    }
-                    __syncthreads();
+                    const uint32_t tag = gen << 16; // (the barrier that ended the previous round separates its reads from these writes)
+                    --gen;
                     const uint32_t A = 2654435761u + 0x9E3779B1u * (uint32_t)round * 2u;
                     const uint32_t B = 2246822519u + 0x85EBCA77u * (uint32_t)round * 2u;
                     if (P.phase_cycles) { // (one atomic per warp: per-thread atomics here tripled the ladder's time)
@@ -331,7 +336,7 @@ __global__ void __launch_bounds__(THREADS, 1) lz4_encode_kernel(Params P)
                         gram_at(p, m1, P0, P1);
                         uint32_t h = (P0 * A) ^ (P1 * B);
                         h = ((h ^ (h >> 15)) * 2246822519u) >> (32 - TBITS);
-                        atomicMin(&T[h], p);
+                        atomicMin(&T[h], tag | p);
                     }
                     __syncthreads();
                     unsigned long long next = 0;
@@ -343,7 +348,7 @@ __global__ void __launch_bounds__(THREADS, 1) lz4_encode_kernel(Params P)
                         gram_at(p, m1, P0, P1);
                         uint32_t h = (P0 * A) ^ (P1 * B);
                         h = ((h ^ (h >> 15)) * 2246822519u) >> (32 - TBITS);
-                        const uint32_t q = T[h];
+                        const uint32_t q = T[h] & 0xFFFFu;
                         if (q != p) { // q < p: the earliest position that hashes here
                             uint32_t Q0, Q1;
                             gram_at(q, m1, Q0, Q1);
