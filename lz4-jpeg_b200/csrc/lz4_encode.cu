@@ -190,9 +190,16 @@ __global__ void __launch_bounds__(THREADS, 1) lz4_encode_kernel(Params P)
     bool pend = false;
     long long pend_b = 0;
     unsigned long long pend_pay = 0;
-    // moves the pending block from its staging buffer to its place in the stream (all threads)
-    auto flush_pending = [&]() {
-        if (warp == 0) {
+    // moves the pending block from its staging buffer to its place in the stream.  Done by warps fw .. 31: by all of them
+    // (fw = 0) after the last block, by warps 1 .. 31 (a named barrier among them) while thread 0 hops along the parse
+    // chain of the next block — the one stretch of the kernel in which the other 1023 threads would only wait.
+    auto flush_pending = [&](int fw) {
+        const int nthr = THREADS - 32 * fw, t = tid - 32 * fw;
+        auto group_sync = [&]() {
+            if (fw == 0) __syncthreads();
+            else asm volatile("bar.sync 1, %0;" ::"r"(nthr) : "memory");
+        };
+        if (warp == fw) {
             const unsigned long long base = ljb_lookback_resolve(P.status + 1, pend_b, pend_pay, P.lead);
             if (lane == 0) {
                 M.base = base;
@@ -205,21 +212,21 @@ __global__ void __launch_bounds__(THREADS, 1) lz4_encode_kernel(Params P)
                 if (!M.emit_ok) atomicOr((unsigned long long *)&P.result[2], 1ull);
             }
         }
-        __syncthreads();
+        group_sync();
         if (M.emit_ok) {
             const uint8_t *src = stage0 + (size_t)(buf ^ 1) * P.stage_stride;
             const uint32_t *srcw = reinterpret_cast<const uint32_t *>(src);
             uint8_t *dst = P.out + M.base;
             const uint32_t n = (uint32_t)pend_pay;
             const uint32_t head = min((uint32_t)((4 - (reinterpret_cast<uintptr_t>(dst) & 3)) & 3), n);
-            if ((uint32_t)tid < head) dst[tid] = src[tid];
+            if ((uint32_t)t < head) dst[t] = src[t];
             const uint32_t nwords = (n - head) >> 2;
             uint32_t *d4 = reinterpret_cast<uint32_t *>(dst + head);
-            for (uint32_t j = tid; j < nwords; j += THREADS) __stcs(&d4[j], __funnelshift_r(srcw[j], srcw[j + 1], 8 * head)); // streaming store
+            for (uint32_t j = t; j < nwords; j += nthr) __stcs(&d4[j], __funnelshift_r(srcw[j], srcw[j + 1], 8 * head)); // streaming store
             const uint32_t done = head + 4 * nwords;
-            if ((uint32_t)tid < n - done) dst[done + tid] = src[done + tid];
+            if ((uint32_t)t < n - done) dst[done + t] = src[done + t];
         }
-        __syncthreads(); // M.base / M.emit_ok are reused
+        if (fw == 0) __syncthreads(); // M.base / M.emit_ok are reused (after a partial flush: the barrier behind the chain hop)
     };
 
     long long t_prev = clock64();
@@ -237,7 +244,7 @@ __global__ void __launch_bounds__(THREADS, 1) lz4_encode_kernel(Params P)
         __syncthreads();
         const long long b = M.ticket;
         if (b >= (long long)P.nblocks) {
-            if (pend) flush_pending();
+            if (pend) flush_pending(0);
             break;
         }
         const size_t boff = (size_t)b * P.block_len;
@@ -947,14 +954,18 @@ __global__ void __launch_bounds__(THREADS, 1) lz4_encode_kernel(Params P)
         __syncthreads();
         LJB_PHASE(15); // (probe) step extraction + pass A
         // pass C: one thread hops segment to segment and records where the chain enters each one
-        if (tid == 0) {
-            uint32_t pos = 0;
-            while (pos < nb) {
-                const uint32_t x = flag[pos]; // issued first: the only dependent load of the hop
-                const uint32_t s = pos / SEG;
-                entry[s] = (uint8_t)(pos - s * SEG);
-                pos = min((s + 1) * SEG, nb) + x;
+        if (warp == 0) {
+            if (lane == 0) {
+                uint32_t pos = 0;
+                while (pos < nb) {
+                    const uint32_t x = flag[pos]; // issued first: the only dependent load of the hop
+                    const uint32_t s = pos / SEG;
+                    entry[s] = (uint8_t)(pos - s * SEG);
+                    pos = min((s + 1) * SEG, nb) + x;
+                }
             }
+        } else if (pend) {
+            flush_pending(1); // ---------------- P7: place the PREVIOUS block, in the shadow of the hop ----------------
         }
         __syncthreads(); // the exit table is dead from here on: its memory becomes the slots and the output area
         LJB_PHASE(5); // parse: chain resolution
@@ -1270,8 +1281,6 @@ __global__ void __launch_bounds__(THREADS, 1) lz4_encode_kernel(Params P)
         }
         __syncthreads(); // staging writes of this block are complete; region B and data are free
         LJB_PHASE(8); // emit
-        // ---------------- P7: place the PREVIOUS block ----------------
-        if (pend) flush_pending();
         pend = true;
         pend_b = b;
         pend_pay = pay;
