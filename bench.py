@@ -236,6 +236,20 @@ def run_gpu(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # Pin this rank to the CPU cores next to its GPU before any host buffer is allocated and touched: the pinned buffers of
+        # the end-to-end measurement then live on the GPU's own NUMA node (first touch) instead of all on node 0.
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+            words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+            cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+            cpus &= os.sched_getaffinity(0)
+            if cpus:
+                os.sched_setaffinity(0, cpus)
+        except Exception:
+            pass
         dist.init_process_group("nccl", device_id=dev)
     ctx = ljb.Context(local_rank)
     ext_stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
