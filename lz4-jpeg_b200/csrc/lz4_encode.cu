@@ -6,24 +6,23 @@
 // concatenation of write_output() (LZ4.c:427-441).
 //
 // One persistent CTA (1024 threads) per SM pulls blocks from a ticket counter and runs, per block:
-//   P1 stage    : the block is copied once from HBM into shared memory (128-bit coalesced loads)
-//   P2 index    : counting sort of every position by a 13-bit hash of its 4-gram (shared-memory atomics:
-//                 histogram, exclusive scan, scatter in 64 position-ordered rounds)
-//   P3 search   : exact longest-previous-match for EVERY position — equivalent to the reference's
-//                 exhaustive scan because a match of length >= 4 shares its 4-gram with the current
-//                 position; ties resolved to the earliest position (strict '>' in LZ4.c:307), length
-//                 capped at min(1024, block end).  Two phases:
-//                 A  threads walk the index in SORTED order, so the lanes of a warp sit in the same
-//                    bucket: equal trip counts, and the candidate's bytes are one broadcast load.  Only
-//                    the first 8 bytes are compared: matches shorter than 8 are final here.
-//                 B  positions that have an 8-byte match are resolved from a second index keyed by the
-//                    8-gram (tiny buckets), in position order, each thread inheriting the previous
-//                    position's match along its diagonal instead of re-comparing up to 1024 bytes.
-//   P4 parse    : the greedy chain 0 -> p+step[p] is resolved in parallel with per-segment exit tables,
-//                 then sequences are sized with the reference's uint8/uint16 wrap rules
-//   P5 place    : decoupled look-back over the per-block byte counts gives the block's output offset
-//   P6 emit     : sequences are serialised straight to their final position in the output stream
-// HBM traffic per block is therefore N_in + N_out (+ a per-CTA scratch that stays in L2).
+//   stage    : the block is copied once from HBM into shared memory (128-bit coalesced loads)
+//   search   : exact longest-previous-match for EVERY position — equivalent to the reference's exhaustive scan
+//              because a match of length >= 4 shares its 4-gram with the current position; ties resolved to the
+//              earliest position (strict '>' in LZ4.c:307), length capped at min(1024, block end).
+//              ladder  k = 8 .. 4: first occurrence of every k-gram by atomicMin into a hashed table; a position
+//                      with an earlier occurrence of its k-gram and none of its (k+1)-gram is final
+//              index   the positions with an >= 8 byte match and the first occurrences of their 8-grams, counting-
+//                      sorted by an exact group id (rank of the first occurrence)
+//              B1      sorted-order walk of the groups comparing bytes 8 .. 16: matches below 16 are final
+//              B2      position order, each lane inheriting the previous position's match along its diagonal
+//   parse    : the greedy chain 0 -> p + step[p] through per-segment exit tables
+//   size     : match positions parked per segment, sequences sized by eight lanes per segment with the reference's
+//              uint8/uint16 wrap rules, two block scans
+//   publish  : decoupled look-back over the per-block byte counts
+//   emit     : sequences serialised into shared memory, copied to a staging buffer with 16-byte stores
+//   place    : one block later (in the shadow of the next block's chain hop) the block moves to its offset in the stream
+// HBM traffic per block is N_in + N_out (+ per-CTA scratch that stays in L2: match records, group ids, staging).
 #include "common.cuh"
 
 #include <stdio.h>
