@@ -29,6 +29,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <type_traits>
+#include <vector>
 
 namespace lz4k {
 
@@ -1406,12 +1407,42 @@ extern "C" int ljb_lz4_compress(ljb_ctx *ctx, const uint8_t *in, size_t n, size_
     const size_t nblocks = ljb_lz4_block_count(n, block_len);
     LJB_CUDA(cudaSetDevice(ctx->device));
     int rc;
-    // 4 x the base chunk (512 MiB): every chunk is a kernel launch whose last wave leaves SMs idle (~1.5 ms at 64 KiB
-    // blocks), which at ~10 GB/s outweighs the exposed first upload / last download of a larger chunk
-    size_t cblocks = 4 * ljb_pipe_chunk() / block_len; // blocks per chunk
+    // Chunk schedule: 4 x the base chunk (512 MiB) in the middle — every chunk is a kernel launch whose last wave leaves SMs
+    // idle, which at ~15 GB/s outweighs finer overlap — ramping up from 1/8 of that at the start and down to 1/8 at the end,
+    // because the first upload and the last download are the only transfers nothing hides.
+    size_t cblocks = 4 * ljb_pipe_chunk() / block_len; // blocks per full chunk
     if (cblocks == 0) cblocks = 1;
-    const size_t nchunks = (nblocks + cblocks - 1) / cblocks;
-    const size_t cbytes = cblocks * block_len < n ? cblocks * block_len : n;
+    std::vector<size_t> start; // first block of every chunk, plus the end
+    {
+        const size_t ramp[3] = {cblocks / 8, cblocks / 4, cblocks / 2};
+        const size_t ramp_total = ramp[0] + ramp[1] + ramp[2];
+        std::vector<size_t> sizes;
+        if (ramp[0] >= 1 && nblocks >= 2 * ramp_total + cblocks) {
+            for (int i = 0; i < 3; ++i) sizes.push_back(ramp[i]);
+            size_t mid = nblocks - 2 * ramp_total;
+            while (mid) {
+                const size_t t = mid < cblocks ? mid : cblocks;
+                sizes.push_back(t);
+                mid -= t;
+            }
+            for (int i = 2; i >= 0; --i) sizes.push_back(ramp[i]);
+        } else {
+            for (size_t left = nblocks; left;) {
+                const size_t t = left < cblocks ? left : cblocks;
+                sizes.push_back(t);
+                left -= t;
+            }
+        }
+        size_t at = 0;
+        for (size_t t : sizes) {
+            start.push_back(at);
+            at += t;
+        }
+        start.push_back(at);
+    }
+    const size_t nchunks = start.size() - 1;
+    if (cblocks > nblocks) cblocks = nblocks;
+    const size_t cbytes = cblocks * block_len < n ? cblocks * block_len : n; // largest chunk
     // device capacity per chunk: never more than the caller can take, never more than the dialect can produce
     size_t ccap = ljb_lz4_bound(cbytes, block_len);
     if (out_cap < ccap) ccap = out_cap;
@@ -1421,10 +1452,11 @@ extern "C" int ljb_lz4_compress(ljb_ctx *ctx, const uint8_t *in, size_t n, size_
         if ((rc = ljb_ensure(&ctx->d_pout[i], &ctx->pout_bytes[i], ccap + 64)) != 0) return rc;
     }
     if ((rc = ljb_ensure(&ctx->d_small, &ctx->small_bytes, (nblocks + nchunks + 3 * nchunks + 8) * sizeof(uint64_t))) != 0) return rc;
-    uint64_t *d_offs = (uint64_t *)ctx->d_small;          // per chunk: cblocks + 1 entries at k * (cblocks + 1)
+    uint64_t *d_offs = (uint64_t *)ctx->d_small;          // chunk k: its blocks + 1 entries at start[k] + k
     uint64_t *d_res = d_offs + nblocks + nchunks + 4;      // per chunk: 3 entries
     uint64_t *h_res = ctx->h_res;
-    auto chunk_n = [&](size_t k) { return (k + 1 < nchunks) ? cbytes : n - k * cbytes; };
+    auto chunk_off = [&](size_t k) { return start[k] * block_len; };
+    auto chunk_n = [&](size_t k) { return (k + 1 < nchunks ? start[k + 1] * block_len : n) - chunk_off(k); };
     size_t running = 0;
     uint64_t ph_total = 0;
     int status = LJB_OK;
@@ -1442,13 +1474,13 @@ extern "C" int ljb_lz4_compress(ljb_ctx *ctx, const uint8_t *in, size_t n, size_
     PIPE(cudaEventRecord(ctx->ev_h2d[0], ctx->s_in));
     for (size_t k = 0; k < nchunks; ++k) {
         const int b = (int)(k & 1);
-        const size_t kb = (chunk_n(k) + block_len - 1) / block_len;
+        const size_t kb = start[k + 1] - start[k];
         PIPE(cudaStreamWaitEvent(ctx->stream, ctx->ev_h2d[b], 0));
         if (k >= 2) PIPE(cudaStreamWaitEvent(ctx->stream, ctx->ev_d2h[b], 0)); // output buffer b is free again
         size_t cap_k = out_cap - running < ccap ? out_cap - running : ccap;
         // `running` is known here (chunk k-1 has been waited for), so the kernel writes stream-global offsets itself
         rc = lz4_launch(ctx, (const uint8_t *)ctx->d_pin[b], chunk_n(k), block_len, (uint8_t *)ctx->d_pout[b], cap_k,
-                        d_offs + k * (cblocks + 1), d_res + 3 * k, k * cblocks, nblocks, nullptr, nullptr, running);
+                        d_offs + start[k] + k, d_res + 3 * k, start[k], nblocks, nullptr, nullptr, running);
         if (rc != 0) {
             status = rc;
             goto done;
@@ -1457,7 +1489,7 @@ extern "C" int ljb_lz4_compress(ljb_ctx *ctx, const uint8_t *in, size_t n, size_
         PIPE(cudaEventRecord(ctx->ev_kern[b], ctx->stream));
         if (k + 1 < nchunks) { // next chunk's upload overlaps this chunk's kernel; its buffer was read by kernel k-1
             if (k >= 1) PIPE(cudaStreamWaitEvent(ctx->s_in, ctx->ev_kern[b ^ 1], 0));
-            PIPE(cudaMemcpyAsync(ctx->d_pin[b ^ 1], in + (k + 1) * cbytes, chunk_n(k + 1), cudaMemcpyHostToDevice, ctx->s_in));
+            PIPE(cudaMemcpyAsync(ctx->d_pin[b ^ 1], in + chunk_off(k + 1), chunk_n(k + 1), cudaMemcpyHostToDevice, ctx->s_in));
             PIPE(cudaEventRecord(ctx->ev_h2d[b ^ 1], ctx->s_in));
         }
         PIPE(cudaEventSynchronize(ctx->ev_kern[b]));
@@ -1475,7 +1507,7 @@ extern "C" int ljb_lz4_compress(ljb_ctx *ctx, const uint8_t *in, size_t n, size_
         PIPE(cudaStreamWaitEvent(ctx->s_out, ctx->ev_kern[b], 0));
         PIPE(cudaMemcpyAsync(out + running, ctx->d_pout[b], (size_t)len_k, cudaMemcpyDeviceToHost, ctx->s_out));
         if (block_offsets) // consecutive chunks overlap in one entry (end of k == start of k+1): the values agree
-            PIPE(cudaMemcpyAsync(block_offsets + k * cblocks, d_offs + k * (cblocks + 1), (kb + 1) * sizeof(uint64_t),
+            PIPE(cudaMemcpyAsync(block_offsets + start[k], d_offs + start[k] + k, (kb + 1) * sizeof(uint64_t),
                                  cudaMemcpyDeviceToHost, ctx->s_out));
         PIPE(cudaEventRecord(ctx->ev_d2h[b], ctx->s_out));
         running += (size_t)len_k;
