@@ -82,6 +82,8 @@ struct Params {
     int mcux;           // MCUs per row
     int rounds_per_tile;
     uint32_t nmcu, nrounds, ntiles;
+    uint32_t tile_begin, tile_end; // the tiles of this launch (a band of the image whose pixels are on the device)
+    unsigned long long *ticket;    // this launch's ticket counter
     uint8_t *ustream;   // unstuffed entropy-coded bytes
     size_t ucap;
     uint64_t *status;   // [0] ticket, [1 + t] look-back word of tile t (bits)
@@ -431,9 +433,9 @@ __global__ void __launch_bounds__(THREADS, 2) jfif_encode_kernel(const __grid_co
     uint32_t pend_tile = 0, pend_bits = 0; // finished tile waiting in `pend` for its offset
     for (;;) {
         uint32_t tile = 0;
-        if (lane == 0) tile = (uint32_t)atomicAdd((unsigned long long *)&P.status[0], 1ull);
+        if (lane == 0) tile = P.tile_begin + (uint32_t)atomicAdd(P.ticket, 1ull);
         tile = __shfl_sync(0xffffffffu, tile, 0);
-        const bool have = tile < P.ntiles;
+        const bool have = tile < P.tile_end;
         const uint32_t r0 = tile * (uint32_t)R;
         const uint32_t r1 = !have ? r0 : r0 + (uint32_t)R < P.nrounds ? r0 + (uint32_t)R : P.nrounds;
         int carry_y = 0, carry_u = 0, carry_v = 0; // DC of the last Y / Cb / Cr data unit before the current round
@@ -1012,8 +1014,11 @@ extern "C" size_t ljb_jfif_bound(int w, int h)
     return (size_t)jfk::HEADER_BYTES + 2 + jfif_units(w, h, 0) * 216 * 2 + 64;
 }
 
-extern "C" int ljb_jfif_encode_dev(ljb_ctx *ctx, const uint8_t *d_pixels, int w, int h, int comp, size_t stride, int quality,
-                                   int subsample, uint8_t *d_out, size_t out_cap, uint64_t *d_result, int16_t *d_coefs)
+// One image: the encode kernel once per band of pixel rows (band b: rows below band_end[b]; launched after band_ready[b]
+// on the context stream), then the stuffing kernel.  nbands == 1 with band_ready == nullptr is the device-resident call.
+static int jfif_run(ljb_ctx *ctx, const uint8_t *d_pixels, int w, int h, int comp, size_t stride, int quality, int subsample,
+                    uint8_t *d_out, size_t out_cap, uint64_t *d_result, int16_t *d_coefs, int nbands, const int *band_end,
+                    const cudaEvent_t *band_ready)
 {
     using namespace jfk;
     if (!ctx || !d_pixels || !d_out || !d_result || w <= 0 || h <= 0 || comp < 1 || comp > 4 || stride < (size_t)w * (size_t)comp ||
@@ -1050,7 +1055,8 @@ extern "C" int ljb_jfif_encode_dev(ljb_ctx *ctx, const uint8_t *d_pixels, int w,
     const size_t o_st1 = o_total + 8;
     const size_t o_st2 = o_st1 + ((size_t)ntiles + 1) * 8;
     const size_t o_tailw = o_st2 + (nchunks_max + 1) * 8;
-    const size_t o_end = o_tailw + (size_t)ntiles * 4;
+    const size_t o_tick = (o_tailw + (size_t)ntiles * 4 + 7) & ~(size_t)7; // one ticket counter per band
+    const size_t o_end = o_tick + (size_t)nbands * 8;
     // spill area: a tile is at most R rounds of 30 data units of 216 bytes
     const int spill_slots = (R * UNITS_PER_ROUND * 216 * 8) / (CAP_BITS - UNITS_PER_ROUND * 216 * 8 / 15) + 2;
     const size_t o_spill = (o_end + 15) & ~(size_t)15;
@@ -1094,13 +1100,31 @@ extern "C" int ljb_jfif_encode_dev(ljb_ctx *ctx, const uint8_t *d_pixels, int w,
         LJB_CUDA(cudaFuncSetAttribute(jfif_encode_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_BYTES));
         attr_done = true;
     }
-    const size_t want = ((size_t)ntiles + NWARPS - 1) / NWARPS;
     const size_t full = (size_t)ctx->num_sms * 2;
-    const int grid = (int)(want < full ? want : full);
-    LJB_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
-    if (pl.subsample) jfif_encode_kernel<true><<<grid, THREADS, SM_BYTES, ctx->stream>>>(P);
-    else jfif_encode_kernel<false><<<grid, THREADS, SM_BYTES, ctx->stream>>>(P);
-    LJB_CUDA(cudaGetLastError());
+    uint32_t t_begin = 0;
+    for (int b = 0; b < nbands; ++b) {
+        // tiles whose MCUs (and the one before the first: the DC halo) lie in the rows that are on the device by now
+        uint32_t t_end = ntiles;
+        if (b + 1 < nbands) {
+            const uint64_t mcus = (uint64_t)(band_end[b] / msz) * (uint64_t)mcux;
+            const uint64_t tiles = mcus / mpr / (uint64_t)R;
+            t_end = (uint32_t)(tiles < ntiles ? tiles : ntiles);
+        }
+        if (band_ready) LJB_CUDA(cudaStreamWaitEvent(ctx->stream, band_ready[b], 0));
+        if (b == 0) LJB_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+        if (t_end > t_begin) {
+            P.tile_begin = t_begin;
+            P.tile_end = t_end;
+            P.ticket = (unsigned long long *)(sb + o_tick) + b;
+            const size_t want = ((size_t)(t_end - t_begin) + NWARPS - 1) / NWARPS;
+            const int grid = (int)(want < full ? want : full);
+            if (pl.subsample) jfif_encode_kernel<true><<<grid, THREADS, SM_BYTES, ctx->stream>>>(P);
+            else jfif_encode_kernel<false><<<grid, THREADS, SM_BYTES, ctx->stream>>>(P);
+            LJB_CUDA(cudaGetLastError());
+            ctx->launches += 1;
+            t_begin = t_end;
+        }
+    }
     LJB_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
     StuffParams S;
     S.ustream = P.ustream;
@@ -1115,16 +1139,28 @@ extern "C" int ljb_jfif_encode_dev(ljb_ctx *ctx, const uint8_t *d_pixels, int w,
     const int sgrid = (int)(nchunks_max < sfull ? nchunks_max : sfull);
     jfif_stuff_kernel<<<sgrid, STUFF_THREADS, 0, ctx->stream>>>(S);
     LJB_CUDA(cudaGetLastError());
-    ctx->launches += 2;
+    ctx->launches += 1;
     return LJB_OK;
 }
 
-// Host-buffer entry point: upload, encode, download.  (One bit stream per image: no band pipeline as in
-// ljb_jpeg_encode_rgba; the whole image is uploaded before the kernels start.)
+extern "C" int ljb_jfif_encode_dev(ljb_ctx *ctx, const uint8_t *d_pixels, int w, int h, int comp, size_t stride, int quality,
+                                   int subsample, uint8_t *d_out, size_t out_cap, uint64_t *d_result, int16_t *d_coefs)
+{
+    if (!ctx || !d_pixels || !d_out || !d_result || w <= 0 || h <= 0 || comp < 1 || comp > 4 || stride < (size_t)w * (size_t)comp ||
+        subsample < -1 || subsample > 1 || out_cap < (size_t)jfk::HEADER_BYTES + 2)
+        return LJB_E_ARG;
+    return jfif_run(ctx, d_pixels, w, h, comp, stride, quality, subsample, d_out, out_cap, d_result, d_coefs, 1, nullptr, nullptr);
+}
+
+// Host-buffer entry point.  The image is one bit stream, but its tiles only look BACK (bit offsets, the DC of the data unit
+// before the tile): the rows are uploaded in bands on a second stream and the tiles of a band are encoded as soon as the
+// band has arrived, so the encode kernel hides behind the upload; stuffing and the download of the file follow.
 extern "C" int ljb_jfif_encode(ljb_ctx *ctx, const uint8_t *pixels, int w, int h, int comp, size_t stride, int quality, int subsample,
                                uint8_t *out, size_t out_cap, size_t *out_len)
 {
-    if (!ctx || !pixels || !out || !out_len || w <= 0 || h <= 0 || comp < 1 || comp > 4 || stride < (size_t)w * (size_t)comp) return LJB_E_ARG;
+    if (!ctx || !pixels || !out || !out_len || w <= 0 || h <= 0 || comp < 1 || comp > 4 || stride < (size_t)w * (size_t)comp ||
+        subsample < -1 || subsample > 1)
+        return LJB_E_ARG;
     if (out_cap < (size_t)jfk::HEADER_BYTES + 2) return LJB_E_CAPACITY;
     LJB_CUDA(cudaSetDevice(ctx->device));
     int rc;
@@ -1136,14 +1172,48 @@ extern "C" int ljb_jfif_encode(ljb_ctx *ctx, const uint8_t *pixels, int w, int h
     if (dcap > bound) dcap = bound;
     if ((rc = ljb_ensure(&ctx->d_pout[0], &ctx->pout_bytes[0], dcap + 64)) != 0) return rc;
     if ((rc = ljb_ensure(&ctx->d_small, &ctx->small_bytes, 64)) != 0) return rc;
-    LJB_CUDA(cudaMemcpy2DAsync(ctx->d_pin[0], dstride, pixels, stride, rowbytes, (size_t)h, cudaMemcpyHostToDevice, ctx->stream));
-    rc = ljb_jfif_encode_dev(ctx, (const uint8_t *)ctx->d_pin[0], w, h, comp, dstride, quality, subsample, (uint8_t *)ctx->d_pout[0], dcap,
-                             (uint64_t *)ctx->d_small, nullptr);
-    if (rc != 0) return rc;
-    uint64_t res[3];
-    LJB_CUDA(cudaMemcpyAsync(res, ctx->d_small, sizeof res, cudaMemcpyDeviceToHost, ctx->stream));
-    LJB_CUDA(cudaStreamSynchronize(ctx->stream));
-    if (out_len) *out_len = (size_t)res[0];
+    // bands of whole 16-row MCU rows, about one pipeline chunk of pixels each, at most MAXBANDS
+    constexpr int MAXBANDS = 16;
+    int band_end[MAXBANDS];
+    cudaEvent_t ready[MAXBANDS];
+    int nbands = 0;
+    {
+        size_t rows = ljb_pipe_chunk() / (dstride ? dstride : 1);
+        rows = (rows + 15) & ~(size_t)15;
+        if (rows < 16) rows = 16;
+        if (rows * MAXBANDS < (size_t)h) rows = (((size_t)h + MAXBANDS - 1) / MAXBANDS + 15) & ~(size_t)15;
+        for (size_t y = 0; y < (size_t)h; y += rows) band_end[nbands++] = (int)(y + rows < (size_t)h ? y + rows : (size_t)h);
+    }
+    int made = 0;
+    int status = LJB_OK;
+    for (; made < nbands; ++made)
+        if (cudaEventCreateWithFlags(&ready[made], cudaEventDisableTiming) != cudaSuccess) break;
+    if (made < nbands) status = ljb_set_cuda_error(cudaGetLastError(), "cudaEventCreateWithFlags", __LINE__);
+    if (status == LJB_OK) {
+        // the upload stream must not overtake work still reading the buffer from an earlier call on the context stream
+        cudaError_t e = cudaEventRecord(ctx->ev_kern[0], ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->s_in, ctx->ev_kern[0], 0);
+        for (int b = 0, y0 = 0; b < nbands && e == cudaSuccess; y0 = band_end[b], ++b) {
+            e = cudaMemcpy2DAsync((uint8_t *)ctx->d_pin[0] + (size_t)y0 * dstride, dstride, pixels + (size_t)y0 * stride, stride, rowbytes,
+                                  (size_t)(band_end[b] - y0), cudaMemcpyHostToDevice, ctx->s_in);
+            if (e == cudaSuccess) e = cudaEventRecord(ready[b], ctx->s_in);
+        }
+        if (e != cudaSuccess) status = ljb_set_cuda_error(e, "band upload", __LINE__);
+    }
+    if (status == LJB_OK)
+        status = jfif_run(ctx, (const uint8_t *)ctx->d_pin[0], w, h, comp, dstride, quality, subsample, (uint8_t *)ctx->d_pout[0], dcap,
+                          (uint64_t *)ctx->d_small, nullptr, nbands, band_end, ready);
+    uint64_t res[3] = {0, 0, 0};
+    if (status == LJB_OK) {
+        cudaError_t e = cudaMemcpyAsync(res, ctx->d_small, sizeof res, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) status = ljb_set_cuda_error(e, "result download", __LINE__);
+    }
+    cudaStreamSynchronize(ctx->s_in);
+    cudaStreamSynchronize(ctx->stream);
+    for (int i = 0; i < made; ++i) cudaEventDestroy(ready[i]);
+    if (status != LJB_OK) return status;
+    *out_len = (size_t)res[0];
     if (res[2] & 3) return LJB_E_CAPACITY;
     LJB_CUDA(cudaMemcpyAsync(out, ctx->d_pout[0], (size_t)res[0], cudaMemcpyDeviceToHost, ctx->stream));
     LJB_CUDA(cudaStreamSynchronize(ctx->stream));

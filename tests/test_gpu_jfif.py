@@ -103,6 +103,23 @@ def test_spilled_tiles(ljb, ctx, oracle, monkeypatch):
         assert np.array_equal(ljb.jfif.write_jpg(img, q, sub, ctx=ctx), oracle.jfif_encode(img, q, sub)), (q, sub)
 
 
+@pytest.mark.parametrize("chunk", [1, 20000, 300000])
+def test_banded_upload(ljb, ctx, oracle, monkeypatch, chunk):
+    """The host-buffer entry point uploads the rows in bands and encodes the tiles of a band as soon as it has arrived; a
+    small LJB_PIPE_CHUNK_BYTES drives up to sixteen bands (16-row bands, bands that hold no complete tile, ragged last
+    bands) through small images; the file does not change."""
+    monkeypatch.setenv("LJB_PIPE_CHUNK_BYTES", str(chunk))
+    rng = np.random.default_rng(5)
+    for (w, h, comp) in ((640, 480, 4), (333, 257, 3), (1000, 50, 4), (48, 700, 1), (16, 16, 4)):
+        px = rng.integers(0, 256, size=(h, w, comp), dtype=np.uint8)
+        for q, sub in ((75, -1), (75, 0), (92, 1)):
+            got, want = ljb.jfif.write_jpg(px, q, sub, ctx=ctx), oracle.jfif_encode(px, q, sub)
+            assert np.array_equal(got, want), (w, h, comp, q, sub, _first_diff(got, want))
+    crop = cases.og_crop()
+    img = np.tile(crop, (6, 3, 1))
+    assert np.array_equal(ljb.jfif.write_jpg(img, 75, -1, ctx=ctx), oracle.jfif_encode(img, 75, -1))
+
+
 def test_natural_image_tiles(ljb, ctx, oracle):
     """The og.png crop tiled to 2048 x 1500: smooth content, most coefficients zero, long runs, many tiles."""
     crop = cases.og_crop()
