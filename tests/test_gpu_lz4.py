@@ -105,9 +105,15 @@ def test_pathological_blocks_terminate(ljb, ctx, oracle):
     mixed = cases.synth_text(2 * 65536, seed=33)
     mixed[10000:50000] = 0
     mixed[70000:90000] = np.tile(np.array([7, 8, 9], np.uint8), 6667)[:20000]
-    for data in (np.zeros(65536, np.uint8), rng.integers(0, 2, 65536, dtype=np.uint8) + 65,
+    twice = np.tile(rng.integers(0, 256, 32768, dtype=np.uint8), 2)
+    twice[32768 + 20::40] ^= 0xFF  # ... with a changed byte every 40: ~39-byte matches instead of capped ones
+    for data in (np.zeros(65536, np.uint8), rng.integers(0, 2, 65536, dtype=np.uint8) + 65, twice,
                  np.tile(np.array([97, 98], np.uint8), 32768), np.tile(rng.integers(0, 256, 1000, dtype=np.uint8), 66)[:65536].copy(),
-                 np.tile(np.frombuffer(b"abcdefg", dtype=np.uint8), 9363)[:65536].copy(), mixed):
+                 np.tile(np.frombuffer(b"abcdefg", dtype=np.uint8), 9363)[:65536].copy(), mixed,
+                 # half a block of noise, twice: 32 Ki groups of two, the group directory no longer fits behind the sorted
+                 # positions and neighbouring groups share buckets (the search's hashed-bucket mode)
+                 np.tile(rng.integers(0, 256, 32768, dtype=np.uint8), 2),
+                 np.tile(rng.integers(0, 256, 21846, dtype=np.uint8), 3)[:65536].copy()):
         f = ljb.lz4.lz4_encode(data, 65536, ctx=ctx)
         s, offs, ph = oracle.lz4_compress(data, 65536, 1)
         assert np.array_equal(f.stream, s) and f.phantom == ph
