@@ -40,6 +40,7 @@ constexpr int HASH_BITS = 13;
 constexpr int NBUCKET = 1 << HASH_BITS;
 constexpr int SEG = 132;             // parse segment: 33 words, so per-thread segment walks are bank-conflict free
 constexpr int MAXSEG = (MAXB + SEG - 1) / SEG; // 497
+constexpr int SUP = 16;              // segments per super-segment of the two-level chain hop (32 super-segments at most)
 constexpr int SLOTS = 27;            // match positions a segment parks in shared memory for the eight-lane passes (the rest: its own thread)
 constexpr int MAX_MATCH = 1024;      // LZ4.c:20
 constexpr int CH = 12;               // the index keeps the entries of a group ordered by 4096-position chunk (one scatter round each)
@@ -55,6 +56,7 @@ constexpr int SM_DIR = SM_S + 2 * MAXB;            // u32 dirw[4096 + 1]    pack
 constexpr int SM_STEP = SM_B;                      // u8 step[65536 + 64]
 constexpr int SM_ENTRY = SM_STEP + MAXB + 64;      // u8 entry[1024]
 constexpr int SM_FLAG = SM_ENTRY + 1024;           // u8 exit table[65536 + 64]; dead once the chain's segment entries are known, then:
+constexpr int SM_EXIT2 = SM_FLAG + MAXB + 64;       // u8 exit2[32][256] + u16 supentry[32]: behind the exit table, parse only
 constexpr int SM_SEGINFO = SM_FLAG;                // uint4 seginfo[512]            per segment: previous match end, byte offset, payload, size sum
 constexpr int SM_SEGCNT = SM_SEGINFO + 16 * 512;   // u8 segcnt[512], u8 segph[512]
 constexpr int SM_SLOT = SM_SEGCNT + 1024;          // u16 slots[MAXSEG * SLOTS]     positions of the segment's first matches
@@ -66,7 +68,8 @@ constexpr int SM_PREF = SM_LONG - (2 * (MAXB / 32) + 16); // u16 pref[2048]: fir
 constexpr int GIDX_BYTES = SM_PREF - SM_S;             // what S and the group directory share
 constexpr int SM_TOTAL = SM_MISC + 1024;
 constexpr int SOUT_CAP = ((SM_MISC - SM_OUT) & ~15) - 16; // larger blocks are encoded straight into the global staging buffer
-static_assert(SM_FLAG + MAXB + 64 <= SM_MISC, "parse view must fit inside region B");
+static_assert(SM_EXIT2 + 32 * 256 + 64 <= SM_MISC, "parse view must fit inside region B");
+static_assert((MAXSEG + SUP - 1) / SUP <= 32 && SUP * SEG > 255, "one lane per super-segment; a hop cannot skip one");
 static_assert(SOUT_CAP >= 56 * 1024, "the shared staging area should hold a typical encoded block");
 static_assert(SM_SEGINFO % 16 == 0, "seginfo is a uint4 array");
 static_assert(SEG <= 254 && MAXSEG <= 512, "entry offsets are bytes; one segment per thread");
@@ -953,19 +956,49 @@ __global__ void __launch_bounds__(THREADS, 1) lz4_encode_kernel(Params P)
         }
         __syncthreads();
         LJB_PHASE(15); // (probe) step extraction + pass A
-        // pass C: one thread hops segment to segment and records where the chain enters each one
+        // pass B: the same for super-segments of SUP segments: where the chain leaves one, for every offset (< 255) at which it can
+        // enter it.  8160 short independent walks instead of one long dependent one.
+        uint8_t *const exit2 = smem + SM_EXIT2; // [32][256]
+        const uint32_t nsup = (nseg + SUP - 1) / SUP;
+        for (uint32_t task = tid; task < nsup * 256u; task += THREADS) {
+            const uint32_t u = task >> 8, e = task & 255u;
+            const uint32_t end_u = min((u + 1) * (uint32_t)(SUP * SEG), nb);
+            uint32_t pos = u * (uint32_t)(SUP * SEG) + e;
+            while (pos < end_u) {
+                const uint32_t x = flag[pos];
+                const uint32_t sg = pos / SEG;
+                pos = min((sg + 1) * SEG, nb) + x;
+            }
+            exit2[task] = (uint8_t)min(pos - end_u, 255u); // (only read for offsets the chain can really enter at; past the end: unused)
+        }
+        __syncthreads();
+        // pass C: thread 0 hops from super-segment to super-segment, then one lane per super-segment records where the chain
+        // enters each of its segments.  Meanwhile warps 1 .. 31 place the previous block.
         if (warp == 0) {
+            uint16_t *const supentry = reinterpret_cast<uint16_t *>(smem + SM_EXIT2 + 32 * 256); // [32]
+            supentry[lane] = 0xFFFFu; // (a short last super-segment may be jumped over)
+            __syncwarp();
             if (lane == 0) {
                 uint32_t pos = 0;
-                while (pos < nb) {
-                    const uint32_t x = flag[pos]; // issued first: the only dependent load of the hop
-                    const uint32_t s = pos / SEG;
-                    entry[s] = (uint8_t)(pos - s * SEG);
-                    pos = min((s + 1) * SEG, nb) + x;
+                for (uint32_t u = 0; u < nsup && pos < nb; ++u) {
+                    const uint32_t e = pos - u * (uint32_t)(SUP * SEG);
+                    supentry[u] = (uint16_t)e;
+                    pos = min((u + 1) * (uint32_t)(SUP * SEG), nb) + exit2[u * 256u + e];
+                }
+            }
+            __syncwarp();
+            if ((uint32_t)lane < nsup && supentry[lane] != 0xFFFFu) {
+                const uint32_t end_u = min(((uint32_t)lane + 1) * (uint32_t)(SUP * SEG), nb);
+                uint32_t pos = (uint32_t)lane * (uint32_t)(SUP * SEG) + supentry[lane];
+                while (pos < end_u) {
+                    const uint32_t x = flag[pos];
+                    const uint32_t sg = pos / SEG;
+                    entry[sg] = (uint8_t)(pos - sg * SEG);
+                    pos = min((sg + 1) * SEG, nb) + x;
                 }
             }
         } else if (pend) {
-            flush_pending(1); // ---------------- P7: place the PREVIOUS block, in the shadow of the hop ----------------
+            flush_pending(1); // ---------------- P7: place the PREVIOUS block, in the shadow of the hops ----------------
         }
         __syncthreads(); // the exit table is dead from here on: its memory becomes the slots and the output area
         LJB_PHASE(5); // parse: chain resolution
