@@ -453,11 +453,16 @@ __global__ void __launch_bounds__(THREADS, 1) lz4_encode_kernel(Params P)
                     ngroups = tot_f;
                     nidx = tot_f + tot_l;
                 }
-                const uint32_t sbytes = (2 * nidx + 4 + 3) & ~3u; // S, with slack for the one-ahead reads
+                // S holds the flagged positions only; the first occurrence of every group sits in a table of its own (it is a
+                // candidate, never a worker: in S it would idle a third of the lanes of the sorted walk)
+                const uint32_t nS = nidx - ngroups;
+                const uint32_t sbytes = (2 * nS + 4 + 3) & ~3u; // S, with slack for the one-ahead reads
+                const uint32_t fpbytes = (2 * ngroups + 3) & ~3u;
                 uint32_t shift = 0;
-                while (sbytes + 4 * (((ngroups >> shift) + 1) / 2 + 2) > (uint32_t)GIDX_BYTES) ++shift;
+                while (sbytes + fpbytes + 4 * (((ngroups >> shift) + 1) / 2 + 2) > (uint32_t)GIDX_BYTES) ++shift;
                 const bool exact = shift == 0;
-                uint32_t *const gdirw = reinterpret_cast<uint32_t *>(smem + SM_S + sbytes);
+                uint16_t *const firstpos = reinterpret_cast<uint16_t *>(smem + SM_S + sbytes); // [ngroups]
+                uint32_t *const gdirw = reinterpret_cast<uint32_t *>(smem + SM_S + sbytes + fpbytes);
                 const uint16_t *const gdir16 = reinterpret_cast<const uint16_t *>(gdirw);
                 const uint32_t dwords = ((ngroups >> shift) + 1) / 2 + 1;
                 for (uint32_t i = tid; i < dwords; i += THREADS) gdirw[i] = 0;
@@ -486,10 +491,12 @@ __global__ void __launch_bounds__(THREADS, 1) lz4_encode_kernel(Params P)
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             g[j] = 0;
-                            if (((lw | fw) >> j) & 1u) {
-                                g[j] = rank_of(((lw >> j) & 1u) ? (rr[j] & 0xFFFFu) : q0 + j);
+                            if ((lw >> j) & 1u) {
+                                g[j] = rank_of(rr[j] & 0xFFFFu);
                                 const uint32_t bk = g[j] >> shift;
                                 atomicAdd(&gdirw[bk >> 1], (bk & 1) ? 0x10000u : 1u);
+                            } else if ((fw >> j) & 1u) {
+                                firstpos[rank_of(q0 + j)] = (uint16_t)(q0 + j);
                             }
                         }
                         // (ids of positions that are not flagged are never read: the four are stored together)
@@ -540,12 +547,11 @@ __global__ void __launch_bounds__(THREADS, 1) lz4_encode_kernel(Params P)
                         q0n = base + 4 * THREADS + 4u * (uint32_t)tid;
                         lwn = q0n < npos8 ? bits4(longbits, q0n) : 0u;
                         gn = lwn ? *reinterpret_cast<const uint2 *>(gids + q0n) : make_uint2(0u, 0u);
-                        const uint32_t fw = q0 < npos8 ? bits4(firstbits, q0) : 0u;
                         const uint32_t gg[4] = {g2.x & 0xFFFFu, g2.x >> 16, g2.y & 0xFFFFu, g2.y >> 16};
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            if (((lw | fw) >> j) & 1u) {
-                                const uint32_t bk = (((lw >> j) & 1u) ? gg[j] : rank_of(q0 + j)) >> shift;
+                            if ((lw >> j) & 1u) {
+                                const uint32_t bk = gg[j] >> shift;
                                 const uint32_t old = atomicAdd(&gdirw[bk >> 1], (bk & 1) ? 0x10000u : 1u);
                                 S[(bk & 1) ? (old >> 16) : (old & 0xFFFF)] = (uint16_t)(q0 + j);
                             }
@@ -574,20 +580,20 @@ __global__ void __launch_bounds__(THREADS, 1) lz4_encode_kernel(Params P)
                         return __shfl_sync(0xffffffffu, t, 0) * 32u + (uint32_t)lane;
                     };
                     uint32_t j_n = grab();
-                    uint32_t p_n = j_n < nidx ? (uint32_t)S[j_n] : 0u;
-                    bool l_n = j_n < nidx && ((longbits[p_n >> 5] >> (p_n & 31)) & 1u);
+                    uint32_t p_n = j_n < nS ? (uint32_t)S[j_n] : 0u;
+                    bool l_n = j_n < nS;
                     uint32_t g_n = l_n ? (uint32_t)gids[p_n] : 0u;
                     for (;;) {
-                        if (j_n - (uint32_t)lane >= nidx) break; // (warp-uniform)
+                        if (j_n - (uint32_t)lane >= nS) break; // (warp-uniform)
                         const uint32_t p = p_n, gp = g_n;
                         const bool lp = l_n;
                         {
                             j_n = grab();
-                            p_n = j_n < nidx ? (uint32_t)S[j_n] : 0u;
-                            l_n = j_n < nidx && ((longbits[p_n >> 5] >> (p_n & 31)) & 1u);
+                            p_n = j_n < nS ? (uint32_t)S[j_n] : 0u;
+                            l_n = j_n < nS;
                             g_n = l_n ? (uint32_t)gids[p_n] : 0u;
                         }
-                        if (!lp) continue; // a first occurrence: candidate only
+                        if (!lp) continue; // beyond the last entry
                         ++d_pos;
                         const uint32_t pi = p >> 2, ps = (p & 3) * 8;
                         const uint32_t w0 = dataw[pi], w1 = dataw[pi + 1], w2 = dataw[pi + 2], w3 = dataw[pi + 3], w4 = dataw[pi + 4];
@@ -602,12 +608,12 @@ __global__ void __launch_bounds__(THREADS, 1) lz4_encode_kernel(Params P)
                         const uint32_t prev_byte = p ? data[p - 1] : 0u;
                         uint32_t best = 0, n16 = 0, cand = 0xFFFFFFFFu;
                         const bool budgeted = !chain_start && nb - p > 16 && hi - lo > (uint32_t)B1_BUDGET;
-                        const uint32_t hi_w = budgeted ? lo : hi; // (a position inside a chain does not look at a huge group at all)
-                        uint32_t c_next = lo < hi ? S[lo] : 0u;
-                        uint32_t i = lo;
-                        for (; i < hi_w; ++i) {
+                        // candidates: the first occurrence of the group, then its flagged members in chunk order
+                        const uint32_t nvis = budgeted ? 0u : hi - lo + 1u; // (a position inside a chain does not look at a huge group at all)
+                        uint32_t c_next = firstpos[gp];
+                        for (uint32_t i = 0; i < nvis; ++i) {
                             const uint32_t c = c_next;
-                            c_next = S[i + 1]; // one entry ahead (S has slack past the last bucket): shortens the dependent chain
+                            c_next = S[lo + i]; // one entry ahead (S has slack past the last bucket): shortens the dependent chain
                             const uint32_t cch = c >> CH;
                             if (cch > pch) break; // only later positions from here on
                             ++d_vis;
@@ -639,7 +645,7 @@ __global__ void __launch_bounds__(THREADS, 1) lz4_encode_kernel(Params P)
                                 }
                             }
                         }
-                        const bool forced = budgeted && i == hi_w; // the walk ran into its budget
+                        const bool forced = budgeted;
                         const uint32_t bl = best >> 16, bp = 0xFFFFu - (best & 0xFFFFu);
                         if ((bl == 16 && nb - p > 16) || forced) { // may be longer: B2 decides
                             atomicOr(&vlong[p >> 5], 1u << (p & 31));
@@ -853,8 +859,9 @@ __global__ void __launch_bounds__(THREADS, 1) lz4_encode_kernel(Params P)
                                 const uint32_t bk = (uint32_t)gids[p] >> shift;
                                 const uint32_t lo = bk ? gdir16[bk - 1] : 0u, hi = gdir16[bk];
                                 const uint32_t pch = p >> CH;
-                                for (uint32_t k = lo; k < hi; ++k) {
-                                    const uint32_t c = S[k];
+                                const uint32_t fq = firstpos[gids[p]];
+                                for (uint32_t k = lo; k <= hi; ++k) { // the first occurrence of the group, then its flagged members
+                                    const uint32_t c = k == lo ? fq : (uint32_t)S[k - 1];
                                     if ((c >> CH) > pch) break; // only later positions from here on
                                     if (c >= p) continue;
                                     const uint32_t bl = bestkey >> 16, bp = 0xFFFFu - (bestkey & 0xFFFFu);
