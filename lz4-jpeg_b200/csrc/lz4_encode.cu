@@ -43,6 +43,7 @@ constexpr int MAXSEG = (MAXB + SEG - 1) / SEG; // 497
 constexpr int SUP = 16;              // segments per super-segment of the two-level chain hop (32 super-segments at most)
 constexpr int SLOTS = 27;            // match positions a segment parks in shared memory for the eight-lane passes (the rest: its own thread)
 constexpr int MAX_MATCH = 1024;      // LZ4.c:20
+constexpr int CHUNK = 16;            // positions a lane of B2 works through in sequence (a chain of carried pairs never crosses a chunk)
 constexpr int CH = 12;               // the index keeps the entries of a group ordered by 4096-position chunk (one scatter round each)
 constexpr int B1_BUDGET = 512;       // positions inside a chain leave groups larger than this to B2
 
@@ -565,7 +566,6 @@ __global__ void __launch_bounds__(THREADS, 1) lz4_encode_kernel(Params P)
                 // shorter than 16 bytes is final here; the others ("very long") go to B2.
                 uint32_t *vlong = firstbits; // the first-occurrence bits are dead once the index is built
                 for (int i = tid; i < MAXB / 32; i += THREADS) vlong[i] = 0;
-                if (tid < 64) reinterpret_cast<uint32_t *>(M.warp_x)[tid] = 0; // per 1024-position row: candidates overflows (B2's schedule)
                 if (tid == 0) M.scan_tmp[1] = 0;                                // B1's ticket counter
                 __syncthreads();
                 {
@@ -604,7 +604,7 @@ __global__ void __launch_bounds__(THREADS, 1) lz4_encode_kernel(Params P)
                         const uint32_t cap16 = min(16u, nb - p);
                         const uint32_t pch = p >> CH;
                         // a chain = consecutive flagged positions inside one 32-position chunk (B2's unit of sequential work)
-                        const bool chain_start = (p & 31u) == 0u || !((longbits[(p - 1) >> 5] >> ((p - 1) & 31)) & 1u);
+                        const bool chain_start = (p & (uint32_t)(CHUNK - 1)) == 0u || !((longbits[(p - 1) >> 5] >> ((p - 1) & 31)) & 1u);
                         const uint32_t prev_byte = p ? data[p - 1] : 0u;
                         uint32_t best = 0, n16 = 0, cand = 0xFFFFFFFFu;
                         const bool budgeted = !chain_start && nb - p > 16 && hi - lo > (uint32_t)B1_BUDGET;
@@ -651,7 +651,6 @@ __global__ void __launch_bounds__(THREADS, 1) lz4_encode_kernel(Params P)
                             atomicOr(&vlong[p >> 5], 1u << (p & 31));
                             if (n16 > 2 || forced) { // overflow: B2 walks the group itself
                                 cand = (cand & 0xFFFFu) | 0xFFFE0000u;
-                                atomicAdd(&reinterpret_cast<uint32_t *>(M.warp_x)[p >> 10], 1u);
                             }
                             R[p] = cand; // provisional: the two candidates, in place of (length, position)
                         } else {
@@ -683,24 +682,29 @@ __global__ void __launch_bounds__(THREADS, 1) lz4_encode_kernel(Params P)
                 // walk stopped early, the next position walks its bucket again).
                 constexpr int KEEP = 4;
                 constexpr uint32_t SHORT = 32; // a lane compares this much on its own; longer runs are compared by the whole warp
-                const uint32_t nrows = (nb + 1023) >> 10;
-                // rows are handed out heaviest first (longest-processing-time rule): with two rows per warp on average, the
-                // last rows to finish decide how long the other warps wait at the barrier
+                // a row = 32 chunks of CHUNK positions, one per lane
+                constexpr int NROWS = MAXB / (32 * CHUNK);
+                const uint32_t nrows = (nb + 32 * CHUNK - 1) / (32 * CHUNK);
+                // rows are handed out heaviest first (longest-processing-time rule): the slowest row decides how long the
+                // other warps wait at the barrier
                 {
-                    const uint32_t *rheavy = reinterpret_cast<const uint32_t *>(M.warp_x); // positions per row that will walk their group
-                    uint16_t *rcost = reinterpret_cast<uint16_t *>(M.warp_y);       // 64 costs
-                    uint8_t *rorder = reinterpret_cast<uint8_t *>(M.warp_y) + 128;  // 64 row numbers
-                    for (int r = warp; r < 64; r += NWARPS) {
-                        const uint32_t c = __popc(longbits[r * 32 + lane]) + 3u * __popc(vlong[r * 32 + lane]);
-                        const uint32_t t = __reduce_add_sync(0xffffffffu, c) + 24u * rheavy[r];
+                    uint16_t *rcost = reinterpret_cast<uint16_t *>(M.warp_x); // NROWS costs
+                    uint8_t *rorder = reinterpret_cast<uint8_t *>(M.warp_y);  // NROWS row numbers
+                    static_assert(NROWS * 2 <= (int)sizeof(M.warp_x) && NROWS <= 255 && NROWS <= (int)sizeof(M.warp_y), "row schedule");
+                    for (int r = warp; r < NROWS; r += NWARPS) {
+                        const uint32_t chn = (uint32_t)r * 32u + (uint32_t)lane; // chunk
+                        const uint32_t w = chn * CHUNK >> 5, sh = (chn * CHUNK) & 31u;
+                        const uint32_t cm = CHUNK == 32 ? 0xFFFFFFFFu : ((1u << CHUNK) - 1u);
+                        const uint32_t c = __popc((longbits[w] >> sh) & cm) + 3u * __popc((vlong[w] >> sh) & cm);
+                        const uint32_t t = __reduce_add_sync(0xffffffffu, c);
                         if (lane == 0) rcost[r] = (uint16_t)min(t, 65535u);
                     }
                     if (tid == 0) M.scan_tmp[0] = 0;
                     __syncthreads();
-                    if (tid < 64) {
+                    if (tid < NROWS) {
                         const uint32_t mine = rcost[tid];
                         uint32_t rank = 0;
-                        for (int r = 0; r < 64; ++r) {
+                        for (int r = 0; r < NROWS; ++r) {
                             const uint32_t o = rcost[r];
                             rank += (o > mine || (o == mine && r < tid)) ? 1u : 0u;
                         }
@@ -712,16 +716,18 @@ __global__ void __launch_bounds__(THREADS, 1) lz4_encode_kernel(Params P)
                     uint32_t row = 0;
                     if (lane == 0) {
                         row = atomicAdd(&M.scan_tmp[0], 1u);
-                        row = row < 64u ? (uint32_t)(reinterpret_cast<const uint8_t *>(M.warp_y) + 128)[row] : 64u;
+                        row = row < (uint32_t)NROWS ? (uint32_t) reinterpret_cast<const uint8_t *>(M.warp_y)[row] : (uint32_t)NROWS;
                     }
                     row = __shfl_sync(0xffffffffu, row, 0);
                     if (row >= nrows) { // (rows beyond the block sort last: nothing is left)
-                        if (row >= 64u) break;
+                        if (row >= (uint32_t)NROWS) break;
                         continue;
                     }
-                    const uint32_t ch = row * 32 + lane;
-                    const uint32_t bits = (ch * 32 < nb) ? longbits[ch] : 0u; // positions of this lane's chunk with an >= 8 byte match
-                    const uint32_t vbits = (ch * 32 < nb) ? vlong[ch] : 0u;   // ... whose record holds 16-byte candidates
+                    const uint32_t ch = row * 32 + lane; // chunk: positions ch * CHUNK ...
+                    const uint32_t cw = ch * CHUNK >> 5, csh = (ch * CHUNK) & 31u;
+                    const uint32_t cmask = CHUNK == 32 ? 0xFFFFFFFFu : ((1u << CHUNK) - 1u);
+                    const uint32_t bits = (ch * CHUNK < nb) ? (longbits[cw] >> csh) & cmask : 0u; // positions of this lane's chunk with an >= 8 byte match
+                    const uint32_t vbits = (ch * CHUNK < nb) ? (vlong[cw] >> csh) & cmask : 0u;   // ... whose record holds 16-byte candidates
                     uint32_t pc[KEEP], pl[KEEP]; // pairs carried from the previous position: candidate position, length | capped << 16
                     uint32_t pn = 0;
                     bool pinc = false;           // the carried set may be incomplete: walk the bucket
@@ -734,7 +740,7 @@ __global__ void __launch_bounds__(THREADS, 1) lz4_encode_kernel(Params P)
                     auto fetch = [&](uint32_t m) -> uint32_t {
                         if (!m) return 0u;
                         const int i = __ffs(m) - 1;
-                        return ((bits >> i) & 1u) ? R[ch * 32 + i] : 0u;
+                        return ((bits >> i) & 1u) ? R[ch * CHUNK + i] : 0u;
                     };
                     uint32_t sl_a, sl_b, sl_c;
                     {
@@ -754,7 +760,7 @@ __global__ void __launch_bounds__(THREADS, 1) lz4_encode_kernel(Params P)
                             sl_c = fetch(m2 & (m2 - 1));
                         }
                         const bool active = (bits >> i) & 1u;
-                        const uint32_t p = ch * 32 + i;
+                        const uint32_t p = ch * CHUNK + i;
                         const bool chained = active && i > 0 && ((bits >> (i - 1)) & 1u);
                         if (!chained) {
                             pn = 0;
