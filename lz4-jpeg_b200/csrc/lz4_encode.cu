@@ -682,84 +682,60 @@ __global__ void __launch_bounds__(THREADS, 1) lz4_encode_kernel(Params P)
                 // walk stopped early, the next position walks its bucket again).
                 constexpr int KEEP = 4;
                 constexpr uint32_t SHORT = 32; // a lane compares this much on its own; longer runs are compared by the whole warp
-                // a row = 32 chunks of CHUNK positions, one per lane
-                constexpr int NROWS = MAXB / (32 * CHUNK);
-                const uint32_t nrows = (nb + 32 * CHUNK - 1) / (32 * CHUNK);
-                // rows are handed out heaviest first (longest-processing-time rule): the slowest row decides how long the
-                // other warps wait at the barrier
+                // Every lane works through chunks of CHUNK positions, one flagged position per step, carrying the pairs of the
+                // previous position along; a lane that has finished its chunk takes the next one from a queue (the chunks in
+                // block order), so all lanes of a warp have a position to work on at every step.
+                if (tid == 0) M.scan_tmp[0] = 0;
+                __syncthreads();
                 {
-                    uint16_t *rcost = reinterpret_cast<uint16_t *>(M.warp_x); // NROWS costs
-                    uint8_t *rorder = reinterpret_cast<uint8_t *>(M.warp_y);  // NROWS row numbers
-                    static_assert(NROWS * 2 <= (int)sizeof(M.warp_x) && NROWS <= 255 && NROWS <= (int)sizeof(M.warp_y), "row schedule");
-                    for (int r = warp; r < NROWS; r += NWARPS) {
-                        const uint32_t chn = (uint32_t)r * 32u + (uint32_t)lane; // chunk
-                        const uint32_t w = chn * CHUNK >> 5, sh = (chn * CHUNK) & 31u;
-                        const uint32_t cm = CHUNK == 32 ? 0xFFFFFFFFu : ((1u << CHUNK) - 1u);
-                        const uint32_t c = __popc((longbits[w] >> sh) & cm) + 3u * __popc((vlong[w] >> sh) & cm);
-                        const uint32_t t = __reduce_add_sync(0xffffffffu, c);
-                        if (lane == 0) rcost[r] = (uint16_t)min(t, 65535u);
-                    }
-                    if (tid == 0) M.scan_tmp[0] = 0;
-                    __syncthreads();
-                    if (tid < NROWS) {
-                        const uint32_t mine = rcost[tid];
-                        uint32_t rank = 0;
-                        for (int r = 0; r < NROWS; ++r) {
-                            const uint32_t o = rcost[r];
-                            rank += (o > mine || (o == mine && r < tid)) ? 1u : 0u;
-                        }
-                        rorder[rank] = (uint8_t)tid;
-                    }
-                    __syncthreads();
-                }
-                for (;;) {
-                    uint32_t row = 0;
-                    if (lane == 0) {
-                        row = atomicAdd(&M.scan_tmp[0], 1u);
-                        row = row < (uint32_t)NROWS ? (uint32_t) reinterpret_cast<const uint8_t *>(M.warp_y)[row] : (uint32_t)NROWS;
-                    }
-                    row = __shfl_sync(0xffffffffu, row, 0);
-                    if (row >= nrows) { // (rows beyond the block sort last: nothing is left)
-                        if (row >= (uint32_t)NROWS) break;
-                        continue;
-                    }
-                    const uint32_t ch = row * 32 + lane; // chunk: positions ch * CHUNK ...
-                    const uint32_t cw = ch * CHUNK >> 5, csh = (ch * CHUNK) & 31u;
+                    const uint32_t nq = (nb + CHUNK - 1) / CHUNK;
                     const uint32_t cmask = CHUNK == 32 ? 0xFFFFFFFFu : ((1u << CHUNK) - 1u);
-                    const uint32_t bits = (ch * CHUNK < nb) ? (longbits[cw] >> csh) & cmask : 0u; // positions of this lane's chunk with an >= 8 byte match
-                    const uint32_t vbits = (ch * CHUNK < nb) ? (vlong[cw] >> csh) & cmask : 0u;   // ... whose record holds 16-byte candidates
+                    uint32_t ch = 0, bits = 0, vbits = 0, rem = 0; // this lane's chunk, its flagged positions, the ones still to do
                     uint32_t pc[KEEP], pl[KEEP]; // pairs carried from the previous position: candidate position, length | capped << 16
                     uint32_t pn = 0;
                     bool pinc = false;           // the carried set may be incomplete: walk the bucket
                     uint32_t dbg_pos = 0, dbg_inh = 0, dbg_walk = 0;
                     const long long trow0 = clock64();
-                    // all lanes step through the 32 positions of their chunks together (warp-uniform control flow),
-                    // so that long compares can be done by the whole warp
-                    uint32_t steps = __reduce_or_sync(0xffffffffu, bits);
-                    // the records of the next three steps are in flight (L2 round trips) while this step is processed
-                    auto fetch = [&](uint32_t m) -> uint32_t {
-                        if (!m) return 0u;
-                        const int i = __ffs(m) - 1;
-                        return ((bits >> i) & 1u) ? R[ch * CHUNK + i] : 0u;
-                    };
-                    uint32_t sl_a, sl_b, sl_c;
-                    {
-                        const uint32_t m2 = steps & (steps - 1), m3 = m2 & (m2 - 1);
-                        sl_a = fetch(steps);
-                        sl_b = fetch(m2);
-                        sl_c = fetch(m3);
-                    }
-                    while (steps) {
-                        const int i = __ffs(steps) - 1;
-                        steps &= steps - 1;
+                    // the records of the next three positions of the lane are in flight (L2 round trips) while one is processed
+                    auto fetch = [&](uint32_t m) -> uint32_t { return m ? R[ch * CHUNK + (__ffs(m) - 1)] : 0u; };
+                    uint32_t sl_a = 0, sl_b = 0, sl_c = 0;
+                    bool drained = false; // (warp-uniform) the queue is empty
+                    for (;;) {
+                        while (!drained) {
+                            const unsigned need = __ballot_sync(0xffffffffu, rem == 0);
+                            if (!need) break;
+                            uint32_t base = 0;
+                            if (lane == 0) base = atomicAdd(&M.scan_tmp[0], (uint32_t)__popc(need));
+                            base = __shfl_sync(0xffffffffu, base, 0);
+                            const uint32_t idx = base + (uint32_t)__popc(need & ((1u << lane) - 1u));
+                            if (rem == 0 && idx < nq) {
+                                ch = idx;
+                                const uint32_t cw = ch * CHUNK >> 5, csh = (ch * CHUNK) & 31u;
+                                bits = (longbits[cw] >> csh) & cmask;
+                                vbits = (vlong[cw] >> csh) & cmask;
+                                rem = bits;
+                                if (rem) {
+                                    pn = 0;
+                                    pinc = false;
+                                    const uint32_t m2 = rem & (rem - 1);
+                                    sl_a = fetch(rem);
+                                    sl_b = fetch(m2);
+                                    sl_c = fetch(m2 & (m2 - 1));
+                                }
+                            }
+                            drained = base + (uint32_t)__popc(need) >= nq;
+                        }
+                        if (!__any_sync(0xffffffffu, rem != 0)) break; // (then the queue is empty as well)
+                        const bool active = rem != 0;
+                        const int i = active ? __ffs(rem) - 1 : 0;
+                        rem &= rem - 1; // (0 stays 0)
                         const uint32_t sl = sl_a;
                         sl_a = sl_b;
                         sl_b = sl_c;
                         {
-                            const uint32_t m2 = steps & (steps - 1);
+                            const uint32_t m2 = rem & (rem - 1);
                             sl_c = fetch(m2 & (m2 - 1));
                         }
-                        const bool active = (bits >> i) & 1u;
                         const uint32_t p = ch * CHUNK + i;
                         const bool chained = active && i > 0 && ((bits >> (i - 1)) & 1u);
                         if (!chained) {
