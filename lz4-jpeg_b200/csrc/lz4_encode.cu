@@ -709,7 +709,7 @@ __global__ void __launch_bounds__(THREADS, 1) lz4_encode_kernel(Params P)
                             base = __shfl_sync(0xffffffffu, base, 0);
                             const uint32_t idx = base + (uint32_t)__popc(need & ((1u << lane) - 1u));
                             if (rem == 0 && idx < nq) {
-                                ch = idx;
+                                ch = nq - 1u - idx; // (from the end of the block: the chunks whose matches run into the block end are the slow ones)
                                 const uint32_t cw = ch * CHUNK >> 5, csh = (ch * CHUNK) & 31u;
                                 bits = (longbits[cw] >> csh) & cmask;
                                 vbits = (vlong[cw] >> csh) & cmask;
