@@ -621,9 +621,9 @@ __global__ void __launch_bounds__(THREADS, 1) lz4_encode_kernel(Params P)
                             // group early (runs of one byte, short periods: every position is in one group): positions inside a
                             // chain whose group has more than B1_BUDGET entries are handed to B2 at once, whose own walk is pruned
                             // by the pairs it carries (hi_w == lo).  A third 16-byte candidate means B2 walks the group anyway.
-                            if (n16 > 2 && nb - p > 16) break;
-                            // later positions cannot win a tie; but B2 needs EVERY 16-byte candidate unless it walks the bucket itself
-                            if ((best >> 16) == cap16 && (cap16 < 16 || n16 > 2) && cch > ((0xFFFFu - (best & 0xFFFFu)) >> CH)) break;
+                            // (that exit sits where the candidates are counted.)  Close to the block end, where a match cannot exceed
+                            // 16 bytes, later positions cannot win a tie once the best pair reaches the end
+                            if (nb - p <= 16 && (best >> 16) == cap16 && cch > ((0xFFFFu - (best & 0xFFFFu)) >> CH)) break;
                             if (c < p) {
                                 const uint32_t ci = c >> 2, cs = (c & 3) * 8;
                                 // an entry of the same group has the same 8 bytes; shared buckets need the comparison
@@ -641,6 +641,7 @@ __global__ void __launch_bounds__(THREADS, 1) lz4_encode_kernel(Params P)
                                         if (n16 == 0) cand = (cand & 0xFFFF0000u) | c;
                                         if (n16 == 1) cand = (cand & 0xFFFFu) | (c << 16);
                                         ++n16;
+                                        if (n16 > 2 && nb - p > 16) break; // B2 walks the group anyway
                                     }
                                 }
                             }
