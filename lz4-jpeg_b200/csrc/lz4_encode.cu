@@ -848,8 +848,9 @@ __global__ void __launch_bounds__(THREADS, 1) lz4_encode_kernel(Params P)
                                     if ((c >> CH) > pch) break; // only later positions from here on
                                     if (c >= p) continue;
                                     const uint32_t bl = bestkey >> 16, bp = 0xFFFFu - (bestkey & 0xFFFFu);
-                                    if (bl == cap && (c >> CH) > (bp >> CH)) { // later positions cannot win a tie ...
-                                        ninc = true;                            // ... but may reach the cap as well
+                                    // later positions cannot win a tie (and nothing in the group lies before its first occurrence) ...
+                                    if (bl == cap && ((c >> CH) > (bp >> CH) || bp == fq)) {
+                                        ninc = true; // ... but may reach the cap as well
                                         break;
                                     }
                                     // a candidate matters only if it beats the best length, or ties it from an earlier position
