@@ -38,9 +38,9 @@ BLOCK_LEN = 65536
 LZ4_BYTES = int(os.environ.get("LJB_BENCH_LZ4_BYTES", 4 * GIB))
 JPEG_DIM = int(os.environ.get("LJB_BENCH_JPEG_DIM", 16384))
 # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the ncu pass over this same command committed as
-# profiles/r1/launches_r1k_bench_steps2_warmup1.csv (LZ4, JFIF) and profiles/r1/jpeg_r1k_summary.txt (JPEG, ncu --set full of the kernel
+# profiles/r1/launches_r1l_bench_steps2_warmup1.csv (LZ4, JFIF) and profiles/r1/jpeg_r1k_summary.txt (JPEG, ncu --set full of the kernel
 # alone: its per-warp staging records are partly written back); bytes at the default workload sizes, None for other sizes.
-NCU_TRAFFIC = {"lz4": 4.95e9 + 6.75e9 if LZ4_BYTES == 4 * GIB else None, "jpeg": 1.087e9 + 0.465e9 if JPEG_DIM == 16384 else None,
+NCU_TRAFFIC = {"lz4": 4.94e9 + 6.79e9 if LZ4_BYTES == 4 * GIB else None, "jpeg": 1.087e9 + 0.465e9 if JPEG_DIM == 16384 else None,
                "jfif444": 1.0746e9 + 0.3176e9 if JPEG_DIM == 16384 else None, "jfif420": 1.0740e9 + 0.1446e9 if JPEG_DIM == 16384 else None}
 JFIF_QUALITY = 75
 
