@@ -6,6 +6,7 @@ include/lz4jpeg_b200.h; all compute happens in lz4-jpeg_b200/csrc/*.cu.  There i
 """
 from . import _native  # noqa: F401
 from ._native import Context, LjbError, default_context  # noqa: F401
+from ._native import OK as LJB_OK, E_ARG as LJB_E_ARG, E_CUDA as LJB_E_CUDA, E_CAPACITY as LJB_E_CAPACITY, E_FORMAT as LJB_E_FORMAT, E_UNSUPPORTED as LJB_E_UNSUPPORTED  # noqa: F401,E501
 from . import lz4  # noqa: F401
 from . import jpeg  # noqa: F401
 from . import jfif  # noqa: F401

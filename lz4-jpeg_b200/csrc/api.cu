@@ -82,31 +82,53 @@ extern "C" int ljb_ctx_create(int device, ljb_ctx **out)
                  prop.major, prop.minor);
         return LJB_E_CUDA;
     }
-    ljb_ctx *c = new ljb_ctx();
-    memset(c, 0, sizeof *c);
+    ljb_ctx *c = new ljb_ctx(); // value-initialised: every member starts at zero / null
     c->device = device;
     c->num_sms = prop.multiProcessorCount;
-    LJB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    // a failure below releases whatever has been created so far (ljb_ctx_destroy tolerates null members)
+#define CTX_TRY(x)                                                    \
+    do {                                                              \
+        cudaError_t e__ = (x);                                        \
+        if (e__ != cudaSuccess) {                                     \
+            const int rc__ = ljb_set_cuda_error(e__, #x, __LINE__);   \
+            ljb_ctx_destroy(c);                                       \
+            return rc__;                                              \
+        }                                                             \
+    } while (0)
+    CTX_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     if (!getenv("LJB_NO_L2_PERSIST") && prop.persistingL2CacheMaxSize > 0 && prop.accessPolicyMaxWindowSize > 0) {
+        // Device-wide setting (other users of the device in this process see it too): the previous limit is kept and put
+        // back by ljb_ctx_destroy.  LJB_NO_L2_PERSIST=1 leaves the device untouched.
         size_t want = (size_t)64 << 20; // room for the 38 MB of LZ4 match records of 148 CTAs
         if (want > (size_t)prop.persistingL2CacheMaxSize) want = (size_t)prop.persistingL2CacheMaxSize;
-        if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) {
+        size_t prev = 0;
+        if (cudaDeviceGetLimit(&prev, cudaLimitPersistingL2CacheSize) != cudaSuccess) {
+            cudaGetLastError();
+            prev = 0;
+        }
+        if (prev >= want) {
+            c->l2_persist_bytes = prev;
+            c->l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
+        } else if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) {
             c->l2_persist_bytes = want;
             c->l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
+            c->l2_persist_prev = prev;
+            c->l2_persist_set = 1;
         } else {
             cudaGetLastError();
         }
     }
-    LJB_CUDA(cudaEventCreate(&c->ev0));
-    LJB_CUDA(cudaEventCreate(&c->ev1));
-    LJB_CUDA(cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
-    LJB_CUDA(cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
+    CTX_TRY(cudaEventCreate(&c->ev0));
+    CTX_TRY(cudaEventCreate(&c->ev1));
+    CTX_TRY(cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
+    CTX_TRY(cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
     for (int i = 0; i < 2; ++i) {
-        LJB_CUDA(cudaEventCreateWithFlags(&c->ev_h2d[i], cudaEventDisableTiming));
-        LJB_CUDA(cudaEventCreateWithFlags(&c->ev_kern[i], cudaEventDisableTiming));
-        LJB_CUDA(cudaEventCreateWithFlags(&c->ev_d2h[i], cudaEventDisableTiming));
+        CTX_TRY(cudaEventCreateWithFlags(&c->ev_h2d[i], cudaEventDisableTiming));
+        CTX_TRY(cudaEventCreateWithFlags(&c->ev_kern[i], cudaEventDisableTiming));
+        CTX_TRY(cudaEventCreateWithFlags(&c->ev_d2h[i], cudaEventDisableTiming));
     }
-    LJB_CUDA(cudaEventCreateWithFlags(&c->ev_res, cudaEventDisableTiming));
+    CTX_TRY(cudaEventCreateWithFlags(&c->ev_res, cudaEventDisableTiming));
+#undef CTX_TRY
     *out = c;
     return LJB_OK;
 }
@@ -115,26 +137,28 @@ extern "C" void ljb_ctx_destroy(ljb_ctx *c)
 {
     if (!c) return;
     cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->stream);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->s_in) cudaStreamSynchronize(c->s_in);
+    if (c->s_out) cudaStreamSynchronize(c->s_out);
     cudaFree(c->d_scratch);
     cudaFree(c->d_status);
     cudaFree(c->d_small);
-    cudaStreamSynchronize(c->s_in);
-    cudaStreamSynchronize(c->s_out);
     for (int i = 0; i < 2; ++i) {
         cudaFree(c->d_pin[i]);
         cudaFree(c->d_pout[i]);
-        cudaEventDestroy(c->ev_h2d[i]);
-        cudaEventDestroy(c->ev_kern[i]);
-        cudaEventDestroy(c->ev_d2h[i]);
+        if (c->ev_h2d[i]) cudaEventDestroy(c->ev_h2d[i]);
+        if (c->ev_kern[i]) cudaEventDestroy(c->ev_kern[i]);
+        if (c->ev_d2h[i]) cudaEventDestroy(c->ev_d2h[i]);
     }
-    cudaEventDestroy(c->ev_res);
-    cudaFreeHost(c->h_res);
-    cudaStreamDestroy(c->s_in);
-    cudaStreamDestroy(c->s_out);
-    cudaEventDestroy(c->ev0);
-    cudaEventDestroy(c->ev1);
-    cudaStreamDestroy(c->stream);
+    if (c->ev_res) cudaEventDestroy(c->ev_res);
+    if (c->h_res) cudaFreeHost(c->h_res);
+    if (c->s_in) cudaStreamDestroy(c->s_in);
+    if (c->s_out) cudaStreamDestroy(c->s_out);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    if (c->l2_persist_set) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, c->l2_persist_prev);
+    cudaGetLastError();
     delete c;
 }
 
@@ -145,6 +169,7 @@ extern "C" float ljb_ctx_last_kernel_ms(const ljb_ctx *cc)
 {
     ljb_ctx *c = const_cast<ljb_ctx *>(cc);
     if (!c) return -1.f;
+    if (c->kernel_ms_summed) return c->last_kernel_ms; // a host-buffer call: the sum over its chunks' kernels
     float ms = -1.f;
     if (cudaEventSynchronize(c->ev1) != cudaSuccess) return -1.f;
     if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) != cudaSuccess) return -1.f;

@@ -17,6 +17,10 @@ struct ljb_ctx {
     cudaEvent_t ev0, ev1;
     uint64_t launches;
     float last_kernel_ms;
+    int kernel_ms_summed;    // last_kernel_ms holds the sum over the chunks of a host-buffer call (not re-read from ev0/ev1)
+    uint32_t attr_mask;      // kernels whose dynamic shared-memory limit has been raised on THIS device (per context, not per process)
+    size_t l2_persist_prev;  // the device's persisting-L2 limit before this context raised it (restored on destroy)
+    int l2_persist_set;
     size_t l2_persist_bytes; // L2 set aside for persisting accesses (0 = unsupported / disabled by LJB_NO_L2_PERSIST)
     size_t l2_window_max;    // largest access-policy window the device accepts
     // persistent scratch (grown on demand, never shrunk)
@@ -41,6 +45,9 @@ struct ljb_ctx {
 // (128 MiB; LJB_PIPE_CHUNK_BYTES overrides it so that tests can drive many chunks through small inputs.)
 size_t ljb_pipe_chunk(void);
 int ljb_pipe_init(ljb_ctx *ctx, size_t nchunks);
+
+// bits of ljb_ctx::attr_mask
+enum { LJB_ATTR_LZ4 = 1, LJB_ATTR_JPEG = 2, LJB_ATTR_JFIF = 4, LJB_ATTR_LZ4_LAZY = 8, LJB_ATTR_LZ4_DEC = 16, LJB_ATTR_JPEG_DEC = 32, LJB_ATTR_LZ4_SMALL = 64 };
 
 int ljb_set_cuda_error(cudaError_t e, const char *what, int line);
 int ljb_ensure(void **p, size_t *have, size_t want);

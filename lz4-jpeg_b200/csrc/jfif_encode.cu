@@ -1094,12 +1094,12 @@ static int jfif_run(ljb_ctx *ctx, const uint8_t *d_pixels, int w, int h, int com
     P.tables = (const uint32_t *)(sb + o_tab);
     memcpy(P.mult, pl.mult, sizeof P.mult);
 
-    static bool attr_done = false;
-    if (!attr_done) {
+    if (!(ctx->attr_mask & LJB_ATTR_JFIF)) { // per device (context), not per process
         LJB_CUDA(cudaFuncSetAttribute(jfif_encode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_BYTES));
         LJB_CUDA(cudaFuncSetAttribute(jfif_encode_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_BYTES));
-        attr_done = true;
+        ctx->attr_mask |= LJB_ATTR_JFIF;
     }
+    ctx->kernel_ms_summed = 0;
     const size_t full = (size_t)ctx->num_sms * 2;
     uint32_t t_begin = 0;
     for (int b = 0; b < nbands; ++b) {

@@ -915,11 +915,11 @@ static int jpeg_launch(ljb_ctx *ctx, const uint8_t *d_rgba, int w, int h, size_t
     P.ntiles = (uint32_t)ntiles;
     P.offs_bias = offs_bias;
     P.force_slow = getenv("LJB_JPEG_FORCE_SLOW") ? 1 : 0; // test hook
-    static bool attr_done = false;
-    if (!attr_done) {
+    if (!(ctx->attr_mask & LJB_ATTR_JPEG)) { // per device (context), not per process
         LJB_CUDA(cudaFuncSetAttribute(jpeg_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
-        attr_done = true;
+        ctx->attr_mask |= LJB_ATTR_JPEG;
     }
+    ctx->kernel_ms_summed = 0;
     LJB_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
     jpeg_encode_kernel<<<grid, THREADS, SM_TOTAL, ctx->stream>>>(P);
     LJB_CUDA(cudaGetLastError());

@@ -18,6 +18,7 @@ constexpr int WARPS_PER_CTA = 8;
 struct Params {
     const uint8_t *comp;
     const uint64_t *offs; // nblocks + 1
+    size_t comp_len;
     uint32_t nblocks;
     uint32_t block_len;
     uint8_t *out;
@@ -33,6 +34,13 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) lz4_decode_kernel(Params P
     if (b >= P.nblocks) return;
     const uint8_t *c = P.comp;
     size_t s = (size_t)P.offs[b], e = (size_t)P.offs[b + 1];
+    if (s > e || e > P.comp_len) { // a table that is not monotonic or points past the stream: nothing is read through it
+        if (lane == 0) {
+            P.block_out_len[b] = 0;
+            atomicOr((unsigned long long *)&P.result[2], 2ull);
+        }
+        return;
+    }
     const size_t out0 = (size_t)b * P.block_len;
     const size_t out_lim = min(P.out_cap, out0 + (size_t)P.block_len);
     uint8_t *out = P.out;
@@ -47,13 +55,14 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) lz4_decode_kernel(Params P
         size_t q = s + 3;
         size_t lit = token >> 4;
         const uint32_t mtok = token & 15;
-        if (s + size16 + 65536 <= e) size16 += 65536; // u16 wrap of the size field (>= 65531 literals)
         if (lit == 15) {
             if (q >= e) { err = 2; break; }
             const uint32_t e1 = c[q];
             const uint32_t next = e1 == 255 ? 2 : 1;
             const size_t fixed = 5 + next + (mtok == 15 ? 1 : 0);
-            if (size16 < fixed + 15) { err = 2; break; }
+            // u16 wrap of the size field (>= 65531 literals): an unwrapped field of a sequence with >= 15 literals is at least
+            // fixed + 15, a wrapped one (true size <= 65536 + 8) has low 16 bits <= 8 — the two cases exclude each other
+            if (size16 < fixed + 15) size16 += 65536;
             lit = size16 - fixed;
             if (((lit - 15) & 0xFF) != (next == 2 ? 255u : e1)) { err = 2; break; }
             q += next;
@@ -84,6 +93,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) lz4_decode_kernel(Params P
         }
         s = q;
     }
+    if (!err && b + 1 < P.nblocks && o - out0 != P.block_len) err = 2; // only the last block may be short: no holes in the output
     if (lane == 0) {
         P.block_out_len[b] = (uint32_t)(o - out0);
         if (err) atomicOr((unsigned long long *)&P.result[2], (unsigned long long)err);
@@ -115,6 +125,7 @@ extern "C" int ljb_lz4_decompress(ljb_ctx *ctx, const uint8_t *comp, size_t comp
     Params P;
     P.comp = (const uint8_t *)ctx->d_pin[0];
     P.offs = d_offs;
+    P.comp_len = comp_len;
     P.nblocks = (uint32_t)nblocks;
     P.block_len = (uint32_t)block_len;
     P.out = (uint8_t *)ctx->d_pout[0];

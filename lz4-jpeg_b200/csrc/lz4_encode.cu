@@ -1366,10 +1366,9 @@ static int lz4_launch(ljb_ctx *ctx, const uint8_t *d_in, size_t n, size_t block_
     if (getenv("LJB_LZ4_PHASES")) { // profiling aid: per-phase cycle counters behind the status words
         P.phase_cycles = (unsigned long long *)ctx->d_status + (nblocks + 2);
     }
-    static bool attr_done = false;
-    if (!attr_done) {
+    if (!(ctx->attr_mask & LJB_ATTR_LZ4)) { // per device (context), not per process
         LJB_CUDA(cudaFuncSetAttribute(lz4_encode_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
-        attr_done = true;
+        ctx->attr_mask |= LJB_ATTR_LZ4;
     }
     // The per-CTA match records (256 KiB each, rewritten for every block) are the only data the kernel re-reads: pin
     // them in L2 for the duration of the launch so that the input / output streams cannot push them out to HBM.
@@ -1383,6 +1382,7 @@ static int lz4_launch(ljb_ctx *ctx, const uint8_t *d_in, size_t n, size_t block_
         win.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
         LJB_CUDA(cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &win));
     }
+    ctx->kernel_ms_summed = 0;
     LJB_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
     lz4_encode_kernel<8><<<grid, THREADS, SM_TOTAL, ctx->stream>>>(P);
     LJB_CUDA(cudaGetLastError());
@@ -1543,6 +1543,7 @@ done:
     cudaStreamSynchronize(ctx->stream);
     cudaStreamSynchronize(ctx->s_out);
     ctx->last_kernel_ms = kernel_ms;
+    ctx->kernel_ms_summed = 1;
     if (out_len) *out_len = running;
     if (phantom) *phantom = ph_total;
     return status;

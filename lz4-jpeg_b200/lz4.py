@@ -71,8 +71,8 @@ def lz4_encode(data, block_len: int = DEFAULT_BLOCK_LENGTH, ctx: N.Context | Non
     ph = C.c_uint64(0)
     rc = N.lib().ljb_lz4_compress(ctx.handle, a.ctypes.data, a.size, block_len, out.ctypes.data, cap, offs.ctypes.data,
                                   C.byref(out_len), C.byref(ph))
-    if rc == N.E_CAPACITY and out_cap is None:
-        return lz4_encode(a, block_len, ctx, out_cap=int(out_len.value) + 64)
+    if rc == N.E_CAPACITY and out_cap is None:  # (on LJB_E_CAPACITY out_len is only a lower bound when the input went up in chunks)
+        return lz4_encode(a, block_len, ctx, out_cap=bound(a.size, block_len))
     N.check(rc, "ljb_lz4_compress")
     return LZ4Frame(out[: out_len.value].copy(), offs, block_len, int(a.size), int(ph.value))
 
@@ -95,16 +95,22 @@ def find_longest_match(block, ctx: N.Context | None = None):
     return ln, ds
 
 
-def LZ4_decode(frame: LZ4Frame, ctx: N.Context | None = None) -> np.ndarray:
-    """Decode a frame produced by lz4_encode (compute of LZ4_decode, LZ4.c:1038-1121)."""
+def lz4_decompress_raw(stream, block_offsets, block_length: int, out_cap: int, ctx: N.Context | None = None) -> np.ndarray:
+    """ljb_lz4_decompress on a stream and an offset table given separately (what a caller holding compressed.bin and its
+    table passes); raises LjbError(LJB_E_FORMAT) on a malformed stream or table."""
     ctx = ctx or N.default_context()
-    out = np.empty(max(frame.input_size, 1), dtype=np.uint8)
+    out = np.empty(max(int(out_cap), 1), dtype=np.uint8)
     out_len = C.c_size_t(0)
-    offs = np.ascontiguousarray(frame.block_offsets, dtype=np.uint64)
-    s = np.ascontiguousarray(frame.stream)
-    N.check(N.lib().ljb_lz4_decompress(ctx.handle, s.ctypes.data, s.size, offs.ctypes.data, offs.size - 1, frame.block_length,
+    offs = np.ascontiguousarray(block_offsets, dtype=np.uint64)
+    s = _u8(stream)
+    N.check(N.lib().ljb_lz4_decompress(ctx.handle, s.ctypes.data, s.size, offs.ctypes.data, offs.size - 1, block_length,
                                        out.ctypes.data, out.size, C.byref(out_len)), "ljb_lz4_decompress")
     return out[: out_len.value]
+
+
+def LZ4_decode(frame: LZ4Frame, ctx: N.Context | None = None) -> np.ndarray:
+    """Decode a frame produced by lz4_encode (compute of LZ4_decode, LZ4.c:1038-1121)."""
+    return lz4_decompress_raw(frame.stream, frame.block_offsets, frame.block_length, frame.input_size, ctx)
 
 
 parallel_LZ4_decode = LZ4_decode  # Algorithms/parallel/LZ4/LZ4.c:1105

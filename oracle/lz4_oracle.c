@@ -296,10 +296,10 @@ int oracle_lz4_decompress(const uint8_t *comp, size_t clen, const uint64_t *bloc
                           size_t block_len, uint8_t *out, size_t out_cap, size_t *out_len)
 {
     size_t o = 0;
-    (void)clen;
     for (size_t b = 0; b < nblocks; ++b) {
         size_t s = (size_t)block_offsets[b], e = (size_t)block_offsets[b + 1];
         size_t blk_out0 = o;
+        if (s > e || e > clen) return -2; /* offsets must be monotonic and inside the stream */
         if (e < s + 3) return -1;
         s += 3;
         while (s < e) {
@@ -309,9 +309,6 @@ int oracle_lz4_decompress(const uint8_t *comp, size_t clen, const uint64_t *bloc
             size_t q = s + 3;
             size_t lit = token >> 4;
             unsigned mtok = token & 15;
-            /* the size field is the low 16 bits of byte_size (S-LZ4:369); a sequence of >= 65531
-             * literals wraps it.  A block never holds two such sequences, so the extent decides. */
-            if (s + size16 + 65536 <= e) size16 += 65536;
             if (lit == 15) {
                 /* one ext byte, or (255,0); true literal count is recovered from the size field */
                 unsigned next = 1;
@@ -319,7 +316,10 @@ int oracle_lz4_decompress(const uint8_t *comp, size_t clen, const uint64_t *bloc
                 if (comp[q] == 255) next = 2;
                 /* size = lit + 5 + next (+1 if a match-ext byte follows the offset) */
                 size_t fixed = 5 + next + (mtok == 15 ? 1 : 0);
-                if (size16 < fixed + 15) return -2;
+                /* the size field is the low 16 bits of byte_size (S-LZ4:369); a sequence of >= 65531
+                 * literals wraps it.  Unwrapped, a sequence with >= 15 literals has size >= fixed + 15;
+                 * wrapped (true size <= 65536 + 8) the low 16 bits are <= 8: the cases exclude each other. */
+                if (size16 < fixed + 15) size16 += 65536;
                 lit = size16 - fixed;
                 if (((lit - 15) & 0xFF) != (next == 2 ? 255u : comp[q])) return -2;
                 q += next;
@@ -346,6 +346,7 @@ int oracle_lz4_decompress(const uint8_t *comp, size_t clen, const uint64_t *bloc
             s = q;
         }
         if (o - blk_out0 > block_len) return -2;
+        if (b + 1 < nblocks && o - blk_out0 != block_len) return -2; /* only the last block may be short */
     }
     if (out_len) *out_len = o;
     return 0;

@@ -131,6 +131,13 @@ def lz4_cases():
     mixed[3000:9000] = 0
     mixed[11000:13000] = np.tile(np.array([1, 2, 3], np.uint8), 667)[:2000]
     out.append(("text_with_runs_16384", mixed, 16384))
+    # low-alphabet random text at 64 KiB: blocks that EXPAND (many 4-byte matches, 5 bytes of sequence overhead each), so an
+    # ordinary short sequence sits 64 KiB or more before the block's end — what a size-field wrap heuristic keyed on the
+    # block extent mistook for a wrapped field.  Own generator: the cases above keep their bytes.
+    rng2 = np.random.default_rng(4242)
+    out.append(("hex_65536", np.frombuffer(b"0123456789abcdef", dtype=np.uint8)[rng2.integers(0, 16, size=65536)].copy(), 65536))
+    out.append(("base32_2x65536", np.frombuffer(b"ABCDEFGHIJKLMNOPQRSTUVWXYZ234567", dtype=np.uint8)[rng2.integers(0, 32, size=2 * 65536)].copy(), 65536))
+    out.append(("two_symbol_65536", (rng2.integers(0, 2, size=65536) + 65).astype(np.uint8), 65536))
     return out
 
 

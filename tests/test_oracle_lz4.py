@@ -11,7 +11,8 @@ import cases
 GOLDEN = cases.GOLDEN
 VEC = json.load(open(os.path.join(GOLDEN, "lz4_ref_vectors.json")))
 ALL = {name: (data, bl) for name, data, bl in cases.lz4_cases()}
-SLOW_EXHAUSTIVE = {"metamorphosis_64k", "synth_64k_x3", "random_65536", "random_65535", "random_65536_plus"}
+SLOW_EXHAUSTIVE = {"metamorphosis_64k", "synth_64k_x3", "random_65536", "random_65535", "random_65536_plus", "hex_65536",
+                   "base32_2x65536", "two_symbol_65536"}
 
 
 def _sha(a):
@@ -110,9 +111,38 @@ def test_zero_sequence_block(oracle):
 
 def test_roundtrip_format_decoder(oracle):
     for name in ("golden_input", "extract_30000", "periodic_text", "repeats_ge1024_b4096", "metamorphosis_64k",
-                 "lit_271", "lit_526", "random_65535", "long_runs_b3000", "same_byte_2500", "tiny_1", "tiny_9"):
+                 "lit_271", "lit_526", "random_65535", "long_runs_b3000", "same_byte_2500", "tiny_1", "tiny_9", "hex_65536",
+                 "base32_2x65536", "two_symbol_65536"):
         data, bl = ALL[name]
         s, offs, ph = oracle.lz4_compress(data, bl, 1)
         rc, out = oracle.lz4_decompress(s, offs, bl, data.size)
         if ph == 0:
             assert rc == 0 and np.array_equal(out, data), name
+
+
+def test_expanding_blocks_roundtrip(oracle):
+    """Blocks that expand past 64 KiB (random hex / base32 text): every short sequence then lies 64 KiB or more before the
+    block's end, and the size field of a sequence wraps only when it really holds >= 65531 literals."""
+    for name in ("hex_65536", "base32_2x65536"):
+        data, bl = ALL[name]
+        s, offs, ph = oracle.lz4_compress(data, bl, 1)
+        assert ph == 0 and int(offs[1]) - int(offs[0]) >= 65536
+        rc, out = oracle.lz4_decompress(s, offs, bl, data.size)
+        assert rc == 0 and np.array_equal(out, data), name
+
+
+def test_decoder_rejects_bad_tables(oracle):
+    """A short intermediate block or a non-monotonic offset table is a format error, not a hole in the output."""
+    data, bl = ALL["synth_64k_x3"]
+    s, offs, _ = oracle.lz4_compress(data, bl, 1)
+    bad = offs.copy()
+    bad[1], bad[2] = offs[2], offs[1]
+    rc, _ = oracle.lz4_decompress(s, bad, bl, data.size)
+    assert rc != 0
+    s2, offs2, _ = oracle.lz4_compress(data[: 2 * bl - 100], bl, 1)  # last block short: fine as the last block ...
+    rc, out = oracle.lz4_decompress(s2, offs2, bl, 2 * bl)
+    assert rc == 0 and out.size == 2 * bl - 100
+    s3 = np.concatenate([s2, s[int(offs[2]):]])                      # ... but not with another block behind it
+    offs3 = np.concatenate([offs2, [offs2[-1] + (offs[3] - offs[2])]]).astype(np.uint64)
+    rc, _ = oracle.lz4_decompress(s3, offs3, bl, 3 * bl)
+    assert rc != 0
