@@ -1,6 +1,12 @@
 // lz4-jpeg_b200/csrc/common.cuh — shared device helpers and the context object (sm_100a only).
 #pragma once
+#ifdef LJB_EMU_BUILD
+// tests/emu: the kernel sources compiled for the host under a lock-step emulator of the CUDA builtins (test infrastructure;
+// the host-side half of every file is left out of that build)
+#include "cuda_emu.h"
+#else
 #include <cuda_runtime.h>
+#endif
 #include <stdint.h>
 #include <stddef.h>
 
@@ -10,6 +16,7 @@
 #define LJB_HOST_ONLY 1
 #endif
 
+#ifndef LJB_EMU_BUILD
 struct ljb_ctx {
     int device;
     int num_sms;
@@ -57,6 +64,7 @@ int ljb_ensure(void **p, size_t *have, size_t want);
         cudaError_t e__ = (x);                                             \
         if (e__ != cudaSuccess) return ljb_set_cuda_error(e__, #x, __LINE__); \
     } while (0)
+#endif // !LJB_EMU_BUILD
 
 // ---- decoupled look-back (single-pass chained scan of per-block byte counts) -------------------------
 // status word: bits 63..62 = state (0 invalid, 1 aggregate published, 2 inclusive prefix published),
@@ -65,7 +73,11 @@ int ljb_ensure(void **p, size_t *have, size_t want);
 #define LJB_ST_INC (2ull << 62)
 #define LJB_ST_MASK (3ull << 62)
 
-#ifdef __CUDACC__
+#if defined(__CUDACC__) || defined(LJB_EMU_BUILD)
+#ifdef LJB_EMU_BUILD
+static inline uint64_t ljb_ld_volatile(const uint64_t *p) { return *(const volatile uint64_t *)p; }
+static inline void ljb_st_volatile(uint64_t *p, uint64_t v) { *(volatile uint64_t *)p = v; }
+#else
 __device__ __forceinline__ uint64_t ljb_ld_volatile(const uint64_t *p)
 {
     uint64_t v;
@@ -76,6 +88,7 @@ __device__ __forceinline__ void ljb_st_volatile(uint64_t *p, uint64_t v)
 {
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+#endif
 
 // Called by one full warp.  Publishes `mine` for unit `idx` and returns the exclusive prefix
 // (`lead` + sum of all earlier units).  Units must have been claimed in increasing order by CTAs that

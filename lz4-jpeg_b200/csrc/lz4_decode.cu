@@ -102,6 +102,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) lz4_decode_kernel(Params P
 
 } // namespace lz4d
 
+#ifndef LJB_EMU_BUILD
 extern "C" int ljb_lz4_decompress(ljb_ctx *ctx, const uint8_t *comp, size_t comp_len, const uint64_t *block_offsets,
                                   size_t nblocks, size_t block_len, uint8_t *out, size_t out_cap, size_t *out_len)
 {
@@ -152,3 +153,4 @@ extern "C" int ljb_lz4_decompress(ljb_ctx *ctx, const uint8_t *comp, size_t comp
     LJB_CUDA(cudaStreamSynchronize(ctx->stream));
     return LJB_OK;
 }
+#endif // !LJB_EMU_BUILD

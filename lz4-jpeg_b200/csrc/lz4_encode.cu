@@ -169,7 +169,9 @@ __device__ __forceinline__ SeqSize seq_size(uint32_t lit, uint32_t ml)
     return s;
 }
 
-template <int TEAM>
+#include "lz4_lazy.cuh"
+
+template <int MODE> // 0: every position is searched (ladder / group index / B1 / B2); 1: only the positions the greedy parse visits (lz4_lazy.cuh)
 __global__ void __launch_bounds__(THREADS, 1) lz4_encode_kernel(Params P)
 {
     extern __shared__ __align__(16) uint8_t smem[];
@@ -201,7 +203,11 @@ __global__ void __launch_bounds__(THREADS, 1) lz4_encode_kernel(Params P)
         const int nthr = THREADS - 32 * fw, t = tid - 32 * fw;
         auto group_sync = [&]() {
             if (fw == 0) __syncthreads();
+#ifdef LJB_EMU_BUILD
+            else emu_named_barrier((unsigned)nthr);
+#else
             else asm volatile("bar.sync 1, %0;" ::"r"(nthr) : "memory");
+#endif
         };
         if (warp == fw) {
             const unsigned long long base = ljb_lookback_resolve(P.status + 1, pend_b, pend_pay, P.lead);
@@ -272,7 +278,13 @@ __global__ void __launch_bounds__(THREADS, 1) lz4_encode_kernel(Params P)
         LJB_PHASE(0); // stage
 
         const uint32_t npos = nb >= 4 ? nb - 3 : 0; // positions that still have a 4-gram inside the block
+        const uint32_t nseg = (nb + SEG - 1) / SEG;
+        const uint32_t s0 = (uint32_t)tid * SEG, s1 = min(s0 + SEG, nb); // this thread's segment (tid < nseg)
 
+        if constexpr (MODE == 1) {
+            // ---------------- search + parse, only along the greedy chain (lz4_lazy.cuh) ----------------
+            lazy_search(smem, nb, R, P, M, [&](int idx) { LJB_PHASE(idx); }, [&]() { if (pend) flush_pending(0); });
+        } else {
         // ---------------- P2/P3 ----------------
         uint32_t *longbits = reinterpret_cast<uint32_t *>(smem + SM_LONG);
         uint32_t *firstbits = reinterpret_cast<uint32_t *>(smem + SM_FIRST);
@@ -935,8 +947,6 @@ __global__ void __launch_bounds__(THREADS, 1) lz4_encode_kernel(Params P)
         }
         for (int i = tid; i < 1024; i += THREADS) entry[i] = 0xFF;
         __syncthreads();
-        const uint32_t nseg = (nb + SEG - 1) / SEG;
-        const uint32_t s0 = (uint32_t)tid * SEG, s1 = min(s0 + SEG, nb); // this thread's segment (tid < nseg)
         // pass A: x1[p] = (first chain position >= segment end) - segment end, for every p (walk descending)
         if ((uint32_t)tid < nseg) {
             for (uint32_t p = s1; p-- > s0;) {
@@ -993,6 +1003,7 @@ __global__ void __launch_bounds__(THREADS, 1) lz4_encode_kernel(Params P)
         }
         __syncthreads(); // the exit table is dead from here on: its memory becomes the slots and the output area
         LJB_PHASE(5); // parse: chain resolution
+        } // MODE == 0
 
         // ---------------- sizing and emission ----------------
         // A sequence = the literals since the previous match + one match (LZ4.c:516-583).
@@ -1315,6 +1326,7 @@ __global__ void __launch_bounds__(THREADS, 1) lz4_encode_kernel(Params P)
 
 } // namespace lz4k
 
+#ifndef LJB_EMU_BUILD
 // ---- host side ---------------------------------------------------------------------------------------
 extern "C" size_t ljb_lz4_block_count(size_t n, size_t block_len) { return block_len ? (n + block_len - 1) / block_len : 0; }
 
@@ -1366,8 +1378,12 @@ static int lz4_launch(ljb_ctx *ctx, const uint8_t *d_in, size_t n, size_t block_
     if (getenv("LJB_LZ4_PHASES")) { // profiling aid: per-phase cycle counters behind the status words
         P.phase_cycles = (unsigned long long *)ctx->d_status + (nblocks + 2);
     }
+    // the full search (every position) serves ljb_lz4_block_matches and LJB_LZ4_SEARCH=full; the product path searches along the chain
+    const char *mode_env = getenv("LJB_LZ4_SEARCH");
+    const bool lazy = !d_dump_len && !(mode_env && strcmp(mode_env, "full") == 0);
     if (!(ctx->attr_mask & LJB_ATTR_LZ4)) { // per device (context), not per process
-        LJB_CUDA(cudaFuncSetAttribute(lz4_encode_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
+        LJB_CUDA(cudaFuncSetAttribute(lz4_encode_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
+        LJB_CUDA(cudaFuncSetAttribute(lz4_encode_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
         ctx->attr_mask |= LJB_ATTR_LZ4;
     }
     // The per-CTA match records (256 KiB each, rewritten for every block) are the only data the kernel re-reads: pin
@@ -1384,7 +1400,8 @@ static int lz4_launch(ljb_ctx *ctx, const uint8_t *d_in, size_t n, size_t block_
     }
     ctx->kernel_ms_summed = 0;
     LJB_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
-    lz4_encode_kernel<8><<<grid, THREADS, SM_TOTAL, ctx->stream>>>(P);
+    if (lazy) lz4_encode_kernel<1><<<grid, THREADS, SM_TOTAL, ctx->stream>>>(P);
+    else lz4_encode_kernel<0><<<grid, THREADS, SM_TOTAL, ctx->stream>>>(P);
     LJB_CUDA(cudaGetLastError());
     LJB_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
     ctx->launches += 1;
@@ -1402,6 +1419,11 @@ static int lz4_launch(ljb_ctx *ctx, const uint8_t *d_in, size_t n, size_t block_
         fprintf(stderr, "[ljb lz4 phases] cycles per block:");
         for (int i = 0; i < 9; ++i) fprintf(stderr, " %s=%.0f(%.0f%%)", names[i], (double)ph[i] / (double)nblocks, 100.0 * (double)ph[i] / (double)tot);
         fprintf(stderr, " total=%.0f\n", (double)tot / (double)nblocks);
+        if (lazy) {
+            fprintf(stderr, "[ljb lz4 lazy] names: phaseB1 = walk rounds >= 1, ladderA = first walks, index8 = 4-gram index, phaseB = steps + entries | per block: searches=%.0f candidates=%.0f warp-steps=%.0f long compares=%.0f positions in capped runs=%.0f\n",
+                    (double)ph[16] / nblocks, (double)ph[17] / nblocks, (double)ph[18] / nblocks, (double)ph[12] / nblocks, (double)ph[13] / nblocks);
+            return LJB_OK;
+        }
         fprintf(stderr, "[ljb lz4 probes] per block: T1+passA=%.0f E1=%.0f E2=%.0f\n", (double)ph[15] / nblocks, (double)ph[10] / nblocks, (double)ph[11] / nblocks);
         fprintf(stderr, "[ljb lz4 phaseB1] per block: indexed=%.0f positions=%.0f visited=%.0f equal8=%.0f warp-cycles=%.0f | ladder: inserts=%.0f rounds=%.1f\n",
                 (double)ph[20] / nblocks, (double)ph[16] / nblocks, (double)ph[17] / nblocks, (double)ph[18] / nblocks, (double)ph[19] / nblocks,
@@ -1571,3 +1593,4 @@ extern "C" int ljb_lz4_block_matches(ljb_ctx *ctx, const uint8_t *in, size_t n, 
     LJB_CUDA(cudaStreamSynchronize(ctx->stream));
     return LJB_OK;
 }
+#endif // !LJB_EMU_BUILD

@@ -1,0 +1,458 @@
+// lz4-jpeg_b200/csrc/lz4_lazy.cuh — search + parse of one LZ4 block along the greedy chain only (included by lz4_encode.cu,
+// inside namespace lz4k, after the shared-memory layout).
+//
+// block_encode() (Algorithms/sequential/LZ4/LZ4.c:516-583) asks find_longest_match() (LZ4.c:290-323) only at the positions
+// its greedy parse visits: p -> p + (uint8_t)len for a match, p -> p + 1 otherwise.  On the benchmark text that is 11 k of
+// the 65 k positions of a block once the runs of capped matches are skipped (below), and the candidates of those positions
+// — the earlier positions with the same 4-gram — number 0.2 M per block, against 2.1 M for all positions.  The chain is
+// sequential, so it is cut into walker segments of WG bytes that are parsed speculatively and stitched together:
+//
+//   index    counting sort of all positions by a hash of their 4-gram (8192 buckets, entries of a bucket ordered by
+//            4096-position chunk): S[] holds every bucket contiguously, dir16[h] its end
+//   round 0  walker s (one lane each) parses from the start of segment s to its end: at an unknown position it searches
+//            (exactly: every earlier member of the bucket is compared, longest wins, earliest among the longest — the
+//            strict '>' of LZ4.c:307), records (length, position) in R[p], sets known[p] and steps on
+//   round r  walker s restarts from where the walk of segment s-1 left that segment, if that differs from where it started
+//            before; it stops at the first known position (chains that meet stay together: the rest of the segment, and
+//            its exit, are those of the walk that got there first).  Rounds repeat until no entry changes: then
+//            entry(s) = exit(s-1) for all s, entry(0) = 0, which is the reference's chain.
+//   Measured on the benchmark text: round 0 does 97 % of the searches, chains meet after a few steps, 2-3 rounds.
+//
+// A search is done by the warp for its 32 lanes together: teams of eight lanes take one lane's candidate list each, so the
+// lanes of a warp stay busy whatever the sizes of the 32 lists are (p50 = 3, p99 = 311 candidates on text).
+//
+// Capped matches.  A match of MAX_MATCH = 1024 bytes is a literal step ((uint8_t)1024 == 0, LZ4.c:317) whose distance is
+// never used, and if (c, p) match 1024 + j bytes then (c + j', p + j') match >= 1024 for j' <= j: those positions are
+// literal steps too, whatever their earliest best candidate is.  The walker marks them known without searching (the
+// benchmark text, 30 000-byte passages of a 118 KB corpus, has 10 k .. 30 k such positions per block).
+#pragma once
+
+constexpr int WG = 66;                              // bytes per walker segment: two per emission segment
+constexpr int NWALK_MAX = (MAXB + WG - 1) / WG;     // 993
+constexpr int LCH = 12;                             // the index keeps a bucket ordered by 4096-position chunk
+constexpr int BIGLIST = 32;                          // candidate lists this long are taken by the whole warp, shorter ones by a team of eight lanes
+constexpr uint32_t VLONG = 32;                      // a lane compares this much on its own; longer runs are compared by the whole warp
+static_assert(2 * WG == SEG, "an emission segment is two walker segments");
+static_assert(NWALK_MAX <= THREADS, "one lane per walker");
+// walker state in the area the full search uses for its first-occurrence bits
+constexpr int SM_XIN = SM_FIRST;                    // u16 xin[1024]   where the latest walk of the segment started (relative to the segment start)
+constexpr int SM_XOUT = SM_FIRST + 2048;            // u16 xout[1024]  where it left the segment (relative to the segment start)
+constexpr int SM_XCAN = SM_FIRST + 4096;            // u16 xcan[1024]  exit of the segment's first walk
+constexpr int SM_SPLIT = SM_FIRST + 6144;           // u8 split[1024]  a later walk left the segment without meeting an earlier one
+static_assert(SM_SPLIT + 1024 <= SM_MISC, "walker state must fit its area");
+
+template <class Phase, class Flush>
+__device__ __forceinline__ void lazy_search(uint8_t *smem, const uint32_t nb, uint32_t *R, const Params &P, Misc &M, Phase &&phase,
+                                            Flush &&flush_prev)
+{
+    constexpr unsigned FULL = 0xffffffffu;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const uint8_t *data = smem + SM_DATA;
+    const uint32_t *dataw = reinterpret_cast<const uint32_t *>(data);
+    uint16_t *S = reinterpret_cast<uint16_t *>(smem + SM_S);
+    uint32_t *dirw = reinterpret_cast<uint32_t *>(smem + SM_DIR);
+    const uint16_t *dir16 = reinterpret_cast<const uint16_t *>(dirw);
+    uint32_t *known = reinterpret_cast<uint32_t *>(smem + SM_LONG);
+    uint16_t *xin = reinterpret_cast<uint16_t *>(smem + SM_XIN);
+    uint16_t *xout = reinterpret_cast<uint16_t *>(smem + SM_XOUT);
+    uint16_t *xcan = reinterpret_cast<uint16_t *>(smem + SM_XCAN);
+    uint8_t *split = smem + SM_SPLIT;
+    uint8_t *step = smem + SM_STEP;
+    uint8_t *entry = smem + SM_ENTRY;
+    const uint32_t npos = nb >= 4 ? nb - 3 : 0; // positions that still have a 4-gram inside the block
+
+    // ---------------- index: counting sort of the positions by 4-gram hash ----------------
+    for (int i = tid; i < NBUCKET / 2 + 4; i += THREADS) dirw[i] = 0;
+    for (int i = tid; i < MAXB / 32; i += THREADS) known[i] = 0;
+    split[tid] = 0;
+    __syncthreads();
+    // a thread takes four consecutive positions per 4096-position chunk (two words of the block give their four 4-grams)
+    for (uint32_t base = 0; base < npos; base += 4 * THREADS) {
+        const uint32_t q0 = base + 4u * (uint32_t)tid;
+        if (q0 < npos) {
+            const uint32_t w0 = dataw[q0 >> 2], w1 = dataw[(q0 >> 2) + 1];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (q0 + j < npos) {
+                    const uint32_t h = hash4(__funnelshift_r(w0, w1, 8 * j));
+                    atomicAdd(&dirw[h >> 1], (h & 1) ? 0x10000u : 1u);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    {
+        // exclusive scan of the 8192 u16 counts (two per word); every thread owns four consecutive words
+        constexpr uint32_t cw = (NBUCKET / 2) / THREADS;
+        static_assert(cw * THREADS == NBUCKET / 2, "directory words divide evenly among the threads");
+        const uint32_t w0 = (uint32_t)tid * cw;
+        uint32_t wv[cw], sum = 0;
+#pragma unroll
+        for (uint32_t k = 0; k < cw; ++k) {
+            wv[k] = dirw[w0 + k];
+            sum += (wv[k] & 0xFFFF) + (wv[k] >> 16);
+        }
+        uint32_t inc = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t v = __shfl_up_sync(FULL, inc, o);
+            if (lane >= o) inc += v;
+        }
+        if (lane == 31) M.scan_tmp[tid >> 5] = inc;
+        __syncthreads();
+        uint32_t run = inc - sum;
+        for (int k = 0; k < (tid >> 5); ++k) run += M.scan_tmp[k];
+#pragma unroll
+        for (uint32_t k = 0; k < cw; ++k) {
+            const uint32_t lo = run;
+            run += wv[k] & 0xFFFF;
+            const uint32_t hi = run;
+            run += wv[k] >> 16;
+            dirw[w0 + k] = (lo & 0xFFFF) | (hi << 16);
+        }
+    }
+    __syncthreads();
+    // scatter in position-ordered rounds of 4096 positions: afterwards dir16[h] is the END of bucket h
+    for (uint32_t base = 0; base < npos; base += 4 * THREADS) {
+        const uint32_t q0 = base + 4u * (uint32_t)tid;
+        if (q0 < npos) {
+            const uint32_t w0 = dataw[q0 >> 2], w1 = dataw[(q0 >> 2) + 1];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (q0 + j < npos) {
+                    const uint32_t h = hash4(__funnelshift_r(w0, w1, 8 * j));
+                    const uint32_t old = atomicAdd(&dirw[h >> 1], (h & 1) ? 0x10000u : 1u);
+                    S[(h & 1) ? (old >> 16) : (old & 0xFFFF)] = (uint16_t)(q0 + j);
+                }
+            }
+        }
+        __syncthreads();
+    }
+    phase(3); // index
+
+    // ---------------- walk rounds ----------------
+    const uint32_t nwalk = (nb + WG - 1) / WG;
+    const uint32_t s = (uint32_t)tid;
+    const bool has = s < nwalk;
+    const uint32_t seg0 = s * WG, segend = min(seg0 + (uint32_t)WG, nb);
+    uint32_t d_search = 0, d_cand = 0, d_steps = 0, d_vl = 0, d_run = 0, d_iter = 0;
+    for (uint32_t round = 0;; ++round) {
+        bool run = false;
+        uint32_t p = 0;
+        if (has) {
+            if (round == 0) {
+                run = true;
+                p = seg0;
+            } else if (s > 0) {
+                const uint32_t e = (uint32_t)xout[s - 1] + (s - 1) * WG; // where the chain leaves the segment before this one
+                if (e != (uint32_t)xin[s] + seg0) {
+                    run = true;
+                    p = e;
+                }
+            }
+        }
+        if (!__syncthreads_or(run)) break; // (also separates the reads above from this round's writes)
+        const uint32_t start = p;
+        uint32_t ex = p;                   // a chain that jumps over the segment leaves it where it enters it
+        bool act = run && p < segend;
+        bool met = false;                  // stopped at a known position
+        const bool walked = act;
+        while (__any_sync(FULL, act)) {
+            ++d_steps;
+            bool need = false;
+            if (act) {
+                if ((known[p >> 5] >> (p & 31)) & 1u) {
+                    if (!split[s]) { // every known position of the segment leads to the exit of its first walk
+                        ex = (uint32_t)xcan[s] + seg0;
+                        act = false;
+                        met = true;
+                    } else { // two chains cross this segment side by side: follow the recorded steps
+                        const uint32_t len = __ldcg(&R[p]) >> 16, st = len & 0xFFu;
+                        p += (len >= 4 && st) ? st : 1u;
+                        met = true;
+                        if (p >= segend) {
+                            ex = p;
+                            act = false;
+                        }
+                    }
+                } else {
+                    need = true;
+                }
+            }
+            // ---- the candidates of this lane's position: the members of its bucket in earlier chunks and in its own
+            uint32_t g0 = 0, g1 = 0, lo = 0, n = 0;
+            if (need && p < npos) {
+                g0 = load32u(dataw, p);
+                g1 = load32u(dataw, p + 4);
+                const uint32_t h = hash4(g0);
+                lo = h ? dir16[h - 1] : 0u;
+                const uint32_t pch = p >> LCH;
+                uint32_t a = lo, b = dir16[h];
+                while (a < b) { // first entry of a later chunk
+                    const uint32_t m = (a + b) >> 1;
+                    if ((uint32_t)(S[m] >> LCH) <= pch) a = m + 1;
+                    else b = m;
+                }
+                n = a - lo;
+            }
+            if (need) {
+                ++d_search;
+                d_cand += n;
+            }
+            // ---- evaluation.  key = (length << 16) | (0xFFFF - position): the maximum is the longest match, the earliest among
+            // equals.  Lists of BIGLIST candidates or more are taken by the whole warp, one list at a time; the others by teams
+            // of eight lanes, four lists at a time (measured on the benchmark text: 9.9 k warp iterations per block this
+            // way, 19.5 k with teams only, 13 k if every list had the warp to itself).
+            // One candidate: its first 8 bytes against the position's, then up to VLONG bytes by the lane itself.
+            auto eval = [&](uint32_t c, uint32_t op, uint32_t og0, uint32_t og1, uint32_t ocap, uint32_t tb, bool &vl) -> uint32_t {
+                // a pair that already reaches the cap is only beaten by an earlier position
+                if (c >= op || ((tb >> 16) == ocap && c > 0xFFFFu - (tb & 0xFFFFu))) return 0u;
+                const uint32_t ci = c >> 2, cs = (c & 3) * 8;
+                const uint32_t a0 = dataw[ci], a1 = dataw[ci + 1], a2 = dataw[ci + 2];
+                if (__funnelshift_r(a0, a1, cs) != og0) return 0u; // (a bucket holds several 4-grams)
+                const uint32_t x1 = __funnelshift_r(a1, a2, cs) ^ og1;
+                uint32_t l;
+                if (x1) {
+                    l = 4u + ((uint32_t)(__ffs(x1) - 1) >> 3);
+                } else {
+                    l = 8;
+                    const uint32_t lim = min(ocap, VLONG);
+                    while (l < lim) {
+                        const uint32_t x = load32u(dataw, c + l) ^ load32u(dataw, op + l);
+                        if (x) {
+                            l += (uint32_t)(__ffs(x) - 1) >> 3;
+                            break;
+                        }
+                        l += 4;
+                    }
+                    if (l >= VLONG && ocap > VLONG) { // still matching after VLONG bytes: the warp goes on
+                        vl = true;
+                        return 0u;
+                    }
+                }
+                return (min(l, ocap) << 16) | (0xFFFFu - c);
+            };
+            // The pair (bc, bp) of lane sv matches VLONG bytes: the warp compares on, 256 bytes per step, unless the pair cannot
+            // beat btb (it must exceed the best length, or tie it from an earlier position).  Warp-uniform.
+            auto long_compare = [&](uint32_t bc, uint32_t bp, uint32_t bcap, uint32_t btb) -> uint32_t {
+                const uint32_t bl = btb >> 16, bpos = 0xFFFFu - (btb & 0xFFFFu);
+                const uint32_t needl = btb == 0u ? 0u : (bc < bpos ? bl : bl + 1u);
+                if (needl > bcap || (needl > VLONG && data[bc + needl - 1] != data[bp + needl - 1])) return 0u;
+                ++d_vl;
+                uint32_t res = bcap;
+                for (uint32_t base = VLONG; base < bcap; base += 256) {
+                    const uint32_t off = base + 8u * (uint32_t)lane;
+                    uint32_t x0 = 0, x1 = 0;
+                    if (off < bcap) {
+                        const uint32_t ci = (bc + off) >> 2, cs = ((bc + off) & 3) * 8;
+                        const uint32_t pi = (bp + off) >> 2, ps = ((bp + off) & 3) * 8;
+                        const uint32_t a0 = dataw[ci], a1 = dataw[ci + 1], a2 = dataw[ci + 2];
+                        const uint32_t e0 = dataw[pi], e1 = dataw[pi + 1], e2 = dataw[pi + 2];
+                        x0 = __funnelshift_r(a0, a1, cs) ^ __funnelshift_r(e0, e1, ps);
+                        x1 = __funnelshift_r(a1, a2, cs) ^ __funnelshift_r(e1, e2, ps);
+                    }
+                    const unsigned mm = __ballot_sync(FULL, (x0 | x1) != 0u);
+                    if (mm) {
+                        const int f = __ffs(mm) - 1;
+                        const uint32_t mine = off + (x0 ? ((uint32_t)(__ffs(x0) - 1) >> 3) : 4u + ((uint32_t)(__ffs(x1) - 1) >> 3));
+                        res = min(__shfl_sync(FULL, mine, f), bcap);
+                        break;
+                    }
+                }
+                return (res << 16) | (0xFFFFu - bc);
+            };
+            uint32_t best = 0;
+            // (i) long lists
+            unsigned big = __ballot_sync(FULL, need && n >= (uint32_t)BIGLIST);
+            while (big) {
+                const int src = __ffs(big) - 1;
+                big &= big - 1;
+                const uint32_t op = __shfl_sync(FULL, p, src), og0 = __shfl_sync(FULL, g0, src), og1 = __shfl_sync(FULL, g1, src);
+                const uint32_t olo = __shfl_sync(FULL, lo, src), on = __shfl_sync(FULL, n, src);
+                const uint32_t ocap = min((uint32_t)MAX_MATCH, nb - op);
+                uint32_t lb = 0, tb = 0; // this lane's best; what the whole warp knows (pairs at the cap, long compares)
+                for (uint32_t it = 0; it < on; it += 32) {
+                    ++d_iter;
+                    const uint32_t i = it + (uint32_t)lane;
+                    uint32_t key = 0, c = 0;
+                    bool vl = false;
+                    if (i < on) {
+                        c = S[olo + i];
+                        key = eval(c, op, og0, og1, ocap, tb, vl);
+                    }
+                    lb = max(lb, key);
+                    if (__any_sync(FULL, vl || (key >> 16) == ocap)) { // rare on text: a pair at the cap, or one for the warp
+                        unsigned pendv = __ballot_sync(FULL, vl);
+                        while (pendv) {
+                            const int sv = __ffs(pendv) - 1;
+                            pendv &= pendv - 1;
+                            tb = max(tb, long_compare(__shfl_sync(FULL, c, sv), op, ocap, tb));
+                        }
+                        tb = max(tb, __reduce_max_sync(FULL, key));
+                    }
+                    // once the cap is reached only earlier positions matter: the entries of later chunks cannot win
+                    if ((tb >> 16) == ocap && it + 32 < on && (uint32_t)(S[olo + it + 32] >> LCH) > ((0xFFFFu - (tb & 0xFFFFu)) >> LCH)) break;
+                }
+                tb = max(tb, __reduce_max_sync(FULL, lb));
+                if (lane == src) best = tb;
+            }
+            // (ii) short lists
+            unsigned rem = __ballot_sync(FULL, need && n > 0 && n < (uint32_t)BIGLIST);
+            while (rem) {
+                const int b0 = __ffs(rem) - 1;
+                rem &= rem - 1;
+                const int b1 = __ffs(rem) - 1;
+                rem &= rem - 1;
+                const int b2 = __ffs(rem) - 1;
+                rem &= rem - 1;
+                const int b3 = __ffs(rem) - 1;
+                rem &= rem - 1;
+                const int team = lane >> 3, tl = lane & 7;
+                const int src = team == 0 ? b0 : (team == 1 ? b1 : (team == 2 ? b2 : b3));
+                const int srcl = src < 0 ? 0 : src;
+                const uint32_t op = __shfl_sync(FULL, p, srcl), og0 = __shfl_sync(FULL, g0, srcl), og1 = __shfl_sync(FULL, g1, srcl);
+                const uint32_t olo = __shfl_sync(FULL, lo, srcl);
+                uint32_t on = __shfl_sync(FULL, n, srcl);
+                if (src < 0) on = 0;
+                const uint32_t ocap = min((uint32_t)MAX_MATCH, nb - op);
+                uint32_t lb = 0, tb = 0; // this lane's best; what the whole team knows (the same in its eight lanes)
+                for (uint32_t it = 0; __any_sync(FULL, it < on); it += 8) {
+                    ++d_iter;
+                    const uint32_t i = it + (uint32_t)tl;
+                    uint32_t key = 0, c = 0;
+                    bool vl = false;
+                    if (i < on) {
+                        c = S[olo + i];
+                        key = eval(c, op, og0, og1, ocap, tb, vl);
+                    }
+                    lb = max(lb, key);
+                    if (__any_sync(FULL, vl || (key >> 16) == ocap)) {
+                        unsigned pendv = __ballot_sync(FULL, vl);
+                        while (pendv) {
+                            const int sv = __ffs(pendv) - 1;
+                            pendv &= pendv - 1;
+                            const uint32_t rkey = long_compare(__shfl_sync(FULL, c, sv), __shfl_sync(FULL, op, sv), __shfl_sync(FULL, ocap, sv),
+                                                               __shfl_sync(FULL, tb, sv));
+                            if ((lane >> 3) == (sv >> 3)) tb = max(tb, rkey); // known to the whole team at once
+                        }
+                        key = max(key, __shfl_xor_sync(FULL, key, 4));
+                        key = max(key, __shfl_xor_sync(FULL, key, 2));
+                        key = max(key, __shfl_xor_sync(FULL, key, 1));
+                        tb = max(tb, key);
+                        if (it + 8 < on && (tb >> 16) == ocap && (uint32_t)(S[olo + it + 8] >> LCH) > ((0xFFFFu - (tb & 0xFFFFu)) >> LCH)) on = 0;
+                    }
+                }
+                lb = max(lb, __shfl_xor_sync(FULL, lb, 4));
+                lb = max(lb, __shfl_xor_sync(FULL, lb, 2));
+                lb = max(lb, __shfl_xor_sync(FULL, lb, 1));
+                tb = max(tb, lb);
+                const uint32_t v0 = __shfl_sync(FULL, tb, 0), v1 = __shfl_sync(FULL, tb, 8), v2 = __shfl_sync(FULL, tb, 16), v3 = __shfl_sync(FULL, tb, 24);
+                if (lane == b0) best = v0;
+                if (lane == b1) best = v1;
+                if (lane == b2) best = v2;
+                if (lane == b3) best = v3;
+            }
+            // ---- record
+            if (need) {
+                R[p] = best ? (((best >> 16) << 16) | (0xFFFFu - (best & 0xFFFFu))) : 0u;
+                atomicOr(&known[p >> 5], 1u << (p & 31));
+            }
+            // ---- capped matches: the following positions of the segment that inherit a 1024-byte match are literal steps
+            uint32_t skip = 0;
+            unsigned runs = __ballot_sync(FULL, need && (best >> 16) == (uint32_t)MAX_MATCH);
+            while (runs) {
+                const int sr = __ffs(runs) - 1;
+                runs &= runs - 1;
+                const uint32_t rp = __shfl_sync(FULL, p, sr), rc = 0xFFFFu - (__shfl_sync(FULL, best, sr) & 0xFFFFu);
+                const uint32_t rend = __shfl_sync(FULL, segend, sr);
+                // position rp + j has a 1024-byte match at rc + j if the pair (rc, rp) goes on for j more bytes and rp + j + 1024 <= nb
+                const uint32_t lim = min(rend - 1u - rp, nb - (uint32_t)MAX_MATCH - rp);
+                uint32_t k = lim;
+                for (uint32_t j0 = 0; j0 < lim; j0 += 32) {
+                    const uint32_t j = j0 + (uint32_t)lane + 1u;
+                    const bool mis = j <= lim && data[rc + (uint32_t)MAX_MATCH - 1u + j] != data[rp + (uint32_t)MAX_MATCH - 1u + j];
+                    const unsigned mm = __ballot_sync(FULL, mis);
+                    if (mm) {
+                        k = j0 + (uint32_t)(__ffs(mm) - 1);
+                        break;
+                    }
+                }
+                for (uint32_t j = (uint32_t)lane + 1u; j <= k; j += 32) {
+                    R[rp + j] = ((uint32_t)MAX_MATCH << 16) | ((rc + j) & 0xFFFFu);
+                    atomicOr(&known[(rp + j) >> 5], 1u << ((rp + j) & 31));
+                }
+                if (lane == sr) skip = k;
+                d_run += lane == sr ? k : 0u;
+            }
+            // ---- step on
+            if (need) {
+                const uint32_t len = best >> 16, st = len & 0xFFu; // (uint8_t) cast of LZ4.c:317; 0 = literal step
+                p += ((len >= 4 && st) ? st : 1u) + skip;
+                if (p >= segend) {
+                    ex = p;
+                    act = false;
+                }
+            }
+        }
+        if (run) { // (own lane's slots; the predecessor's exit was read before this round's barrier)
+            xin[s] = (uint16_t)(start - seg0);
+            xout[s] = (uint16_t)(ex - seg0);
+            if (round == 0) xcan[s] = (uint16_t)(ex - seg0);
+            else if (walked && !met && ex != (uint32_t)xcan[s] + seg0) split[s] = 1;
+        }
+        __syncthreads(); // the exits of this round are what the next round starts from
+        if (round == 0) phase(2); // first walks
+    }
+    phase(1); // later rounds
+    flush_prev(); // the previous block moves to its place in the stream (its predecessors have long published their sizes)
+
+    // ---------------- what the emission passes read: step[] along the chain, entry[] per emission segment ----------------
+    // (S is dead; step[] and entry[] take its place)
+    {
+        uint4 *z = reinterpret_cast<uint4 *>(step);
+        for (int i = tid; i < (MAXB + 64) / 16; i += THREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);
+        const uint32_t nseg = (nb + SEG - 1) / SEG;
+        uint32_t e8 = 0xFFu;
+        if ((uint32_t)tid < nseg) {
+            const uint32_t e = (uint32_t)xin[2 * tid] + 2u * (uint32_t)tid * WG; // first chain position at or behind the segment's start
+            if (e < min(((uint32_t)tid + 1u) * SEG, nb)) e8 = e - (uint32_t)tid * SEG;
+        }
+        entry[tid] = (uint8_t)e8;
+    }
+    __syncthreads();
+    {
+        // every known position: its step.  A thread takes 64 consecutive positions (two words of the bit set), eight records in flight
+        unsigned long long m = (unsigned long long)known[2 * tid] | ((unsigned long long)known[2 * tid + 1] << 32);
+        const uint32_t pbase = 64u * (uint32_t)tid;
+        while (m) {
+            uint32_t pp[8], rr[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                pp[j] = 0xFFFFFFFFu;
+                if (m) {
+                    pp[j] = pbase + (uint32_t)(__ffsll((long long)m) - 1);
+                    m &= m - 1;
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) rr[j] = pp[j] != 0xFFFFFFFFu ? __ldcg(&R[pp[j]]) : 0u;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (pp[j] != 0xFFFFFFFFu) step[pp[j]] = (uint8_t)(rr[j] >> 16);
+        }
+    }
+    if (P.phase_cycles) {
+        const unsigned t_s = __reduce_add_sync(FULL, d_search), t_c = __reduce_add_sync(FULL, d_cand);
+        const unsigned t_r = __reduce_add_sync(FULL, d_run);
+        if (lane == 0) {
+            atomicAdd(&P.phase_cycles[16], (unsigned long long)t_s);
+            atomicAdd(&P.phase_cycles[17], (unsigned long long)t_c);
+            atomicAdd(&P.phase_cycles[18], (unsigned long long)d_steps);
+            atomicAdd(&P.phase_cycles[12], (unsigned long long)d_vl);
+            atomicAdd(&P.phase_cycles[9], (unsigned long long)d_iter);
+            atomicAdd(&P.phase_cycles[13], (unsigned long long)t_r);
+        }
+    }
+    __syncthreads();
+    phase(4); // steps and entries
+}

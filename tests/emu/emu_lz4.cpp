@@ -1,0 +1,75 @@
+// tests/emu/emu_lz4.cpp — TEST INFRASTRUCTURE: the LZ4 encoder kernel (lz4-jpeg_b200/csrc/lz4_encode.cu, both search modes)
+// compiled for the host under the lock-step emulator and driven with host buffers.  Used by tests/test_emu_lz4.py to check
+// the kernel's logic against the oracle without a GPU.  Not a product path.
+#define LJB_EMU_BUILD 1
+#include "../../lz4-jpeg_b200/csrc/lz4_encode.cu"
+#include "../../lz4-jpeg_b200/csrc/lz4_decode.cu"
+
+namespace lz4k {
+alignas(16) uint8_t smem[SM_TOTAL + 256]; // the kernel's `extern __shared__` array; 256 canary bytes behind it
+}
+
+extern "C" int emu_lz4_compress(const uint8_t *in, size_t n, size_t block_len, uint8_t *out, size_t out_cap, uint64_t *block_offsets,
+                                uint64_t *result, int mode, uint16_t *dump_len, uint16_t *dump_dist, unsigned long long *phase24)
+{
+    using namespace lz4k;
+    if (!in || !out || n == 0 || block_len == 0 || block_len > (size_t)MAXB) return -1;
+    const size_t nblocks = (n + block_len - 1) / block_len;
+    std::vector<uint8_t> din(n + 64, 0);
+    memcpy(din.data(), in, n);
+    const size_t stage_stride = (1 + 3 + 6 * block_len + 64 + 16 + 255) & ~(size_t)255;
+    std::vector<uint64_t> status(nblocks + 2 + 24, 0);
+    std::vector<uint32_t> scratch(MAXB, 0xDEADBEEFu); // (stale records of "the previous block" must never be read)
+    std::vector<uint16_t> gids(MAXB, 0xBEEF);
+    std::vector<uint8_t> staging(2 * stage_stride + 64, 0xEE);
+    Params P;
+    memset(&P, 0, sizeof P);
+    P.in = din.data();
+    P.n = n;
+    P.block_len = (uint32_t)block_len;
+    P.nblocks = (uint32_t)nblocks;
+    P.out = out;
+    P.out_cap = out_cap;
+    P.block_offsets = block_offsets;
+    P.result = result;
+    P.status = status.data();
+    P.scratch = scratch.data();
+    P.gids = gids.data();
+    P.staging = staging.data();
+    P.stage_stride = stage_stride;
+    P.offs_bias = 0;
+    P.lead = 1;
+    P.frame_byte = (uint32_t)(nblocks & 0xFF);
+    P.dump_len = dump_len;
+    P.dump_dist = dump_dist;
+    P.phase_cycles = phase24; // optional: 24 counters (the kernel's LJB_LZ4_PHASES probes; 'cycles' are emulator ticks)
+    if (phase24) memset(phase24, 0, 24 * sizeof *phase24);
+    result[0] = result[1] = result[2] = 0;
+    memset(smem, 0xA5, sizeof smem);
+    if (mode == 1) emu::launch(1, THREADS, [&]() { lz4_encode_kernel<1>(P); });
+    else emu::launch(1, THREADS, [&]() { lz4_encode_kernel<0>(P); });
+    for (int i = 0; i < 256; ++i)
+        if (smem[SM_TOTAL + i] != 0xA5) return -7; // a write past the kernel's shared-memory extent
+    return 0;
+}
+
+extern "C" int emu_lz4_decompress(const uint8_t *comp, size_t comp_len, const uint64_t *block_offsets, size_t nblocks, size_t block_len,
+                                  uint8_t *out, size_t out_cap, uint32_t *block_out_len, uint64_t *result)
+{
+    using namespace lz4d;
+    Params P;
+    memset(&P, 0, sizeof P);
+    P.comp = comp;
+    P.offs = block_offsets;
+    P.comp_len = comp_len;
+    P.nblocks = (uint32_t)nblocks;
+    P.block_len = (uint32_t)block_len;
+    P.out = out;
+    P.out_cap = out_cap;
+    P.block_out_len = block_out_len;
+    P.result = result;
+    result[0] = result[1] = result[2] = 0;
+    const unsigned grid = (unsigned)((nblocks + WARPS_PER_CTA - 1) / WARPS_PER_CTA);
+    emu::launch(grid, WARPS_PER_CTA * 32, [&]() { lz4_decode_kernel(P); });
+    return 0;
+}
