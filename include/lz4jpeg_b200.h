@@ -27,7 +27,8 @@ extern "C" {
 #define LJB_OK 0
 #define LJB_E_ARG (-1)         /* invalid argument (NULL, zero size, block_len > 65536, odd image width ...) */
 #define LJB_E_CUDA (-2)        /* CUDA runtime error or no device; ljb_last_cuda_error() has the text */
-#define LJB_E_CAPACITY (-3)    /* output buffer too small; *out_len holds the required size where known */
+#define LJB_E_CAPACITY (-3)    /* output buffer too small; *out_len holds a lower bound of the required size (the bytes produced up to
+                                  and including the chunk that did not fit); ljb_*_bound() is always enough */
 #define LJB_E_FORMAT (-4)      /* decoder: stream is inconsistent / ambiguous (SURVEY.md A.3-b phantom sequences) */
 #define LJB_E_UNSUPPORTED (-5) /* input outside the reference's defined behaviour (e.g. code longer than 31 bits) */
 
@@ -45,7 +46,8 @@ const char *ljb_strerror(int code);
 const char *ljb_last_cuda_error(void);
 /* Number of kernels this library has launched on ctx since creation (bench.py's gpu_launches). */
 uint64_t ljb_ctx_launch_count(const ljb_ctx *ctx);
-/* Duration in ms of the most recent ljb_*_dev call's dominant kernel (CUDA events on the ctx stream). */
+/* Duration in ms of the most recent ljb_*_dev call's dominant kernel (CUDA events on the ctx stream); after a host-buffer
+ * call (which launches one kernel per chunk): the sum over its chunks. */
 float ljb_ctx_last_kernel_ms(const ljb_ctx *ctx);
 
 /* ------------------------------------------------------------------------------------------------
@@ -92,6 +94,14 @@ int ljb_lz4_block_matches(ljb_ctx *ctx, const uint8_t *in, size_t n, uint16_t *l
  * parallel_LZ4_decode, Algorithms/parallel/LZ4/LZ4.c:1105).  Needs the out-of-band block_offsets. */
 int ljb_lz4_decompress(ljb_ctx *ctx, const uint8_t *comp, size_t comp_len, const uint64_t *block_offsets,
                        size_t nblocks, size_t block_len, uint8_t *out, size_t out_cap, size_t *out_len);
+
+/* The same on device-resident buffers, asynchronous on the context stream.
+ *   d_block_out_len  nblocks device uint32: decoded length of every block (scratch the caller provides)
+ *   d_result         3 device uint64: [0] decoded bytes, [2] error flags (bit0 = out_cap exceeded,
+ *                    bit1 = malformed stream or offset table; a short block that is not the last one is malformed) */
+int ljb_lz4_decompress_dev(ljb_ctx *ctx, const uint8_t *d_comp, size_t comp_len, const uint64_t *d_block_offsets,
+                           size_t nblocks, size_t block_len, uint8_t *d_out, size_t out_cap, uint32_t *d_block_out_len,
+                           uint64_t *d_result);
 
 /* ------------------------------------------------------------------------------------------------
  * JPEG-like encoder

@@ -36,6 +36,8 @@ SIGNATURES = {
     "ljb_lz4_block_matches": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
     "ljb_lz4_decompress": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p,
                                      C.c_size_t, _szp]),
+    "ljb_lz4_decompress_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t,
+                                         C.c_void_p, C.c_void_p]),
     "ljb_jpeg_group_count": (C.c_size_t, [C.c_int, C.c_int]),
     "ljb_jpeg_bound": (C.c_size_t, [C.c_size_t]),
     "ljb_jpeg_encode_rgba": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_size_t, C.c_size_t, C.c_void_p,

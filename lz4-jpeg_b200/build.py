@@ -26,8 +26,8 @@ def _stale() -> bool:
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = sources() + [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "jpeg_colour.cuh"), os.path.join(CSRC, "jpeg_tables.inc"), os.path.join(os.path.dirname(HERE), "include", "lz4jpeg_b200.h"),
-                        os.path.abspath(__file__)]
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(os.path.dirname(HERE), "include", "lz4jpeg_b200.h"),
+                                                                os.path.abspath(__file__)]
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 

@@ -96,6 +96,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) lz4_decode_kernel(Params P
     if (!err && b + 1 < P.nblocks && o - out0 != P.block_len) err = 2; // only the last block may be short: no holes in the output
     if (lane == 0) {
         P.block_out_len[b] = (uint32_t)(o - out0);
+        if (b + 1 == P.nblocks) P.result[0] = (uint64_t)(o); // decoded bytes (every earlier block is block_len long, checked above)
         if (err) atomicOr((unsigned long long *)&P.result[2], (unsigned long long)err);
     }
 }
@@ -103,10 +104,41 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) lz4_decode_kernel(Params P
 } // namespace lz4d
 
 #ifndef LJB_EMU_BUILD
+// Device-resident form: compressed stream, offset table and output stay in HBM; asynchronous on the context's stream.
+// d_result[3] (u64): [0] decoded bytes, [2] error flags (bit 0 capacity, bit 1 format).  d_block_out_len: nblocks u32.
+extern "C" int ljb_lz4_decompress_dev(ljb_ctx *ctx, const uint8_t *d_comp, size_t comp_len, const uint64_t *d_block_offsets,
+                                      size_t nblocks, size_t block_len, uint8_t *d_out, size_t out_cap, uint32_t *d_block_out_len,
+                                      uint64_t *d_result)
+{
+    using namespace lz4d;
+    if (!ctx || !d_comp || !d_block_offsets || !d_out || !d_block_out_len || !d_result || nblocks == 0 || nblocks > 0x7fffffffull ||
+        block_len == 0 || block_len > 65536)
+        return LJB_E_ARG;
+    LJB_CUDA(cudaSetDevice(ctx->device));
+    LJB_CUDA(cudaMemsetAsync(d_result, 0, 3 * sizeof(uint64_t), ctx->stream));
+    Params P;
+    P.comp = d_comp;
+    P.offs = d_block_offsets;
+    P.comp_len = comp_len;
+    P.nblocks = (uint32_t)nblocks;
+    P.block_len = (uint32_t)block_len;
+    P.out = d_out;
+    P.out_cap = out_cap;
+    P.block_out_len = d_block_out_len;
+    P.result = d_result;
+    const unsigned grid = (unsigned)((nblocks + WARPS_PER_CTA - 1) / WARPS_PER_CTA);
+    ctx->kernel_ms_summed = 0;
+    LJB_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+    lz4_decode_kernel<<<grid, WARPS_PER_CTA * 32, 0, ctx->stream>>>(P);
+    LJB_CUDA(cudaGetLastError());
+    LJB_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+    ctx->launches += 1;
+    return LJB_OK;
+}
+
 extern "C" int ljb_lz4_decompress(ljb_ctx *ctx, const uint8_t *comp, size_t comp_len, const uint64_t *block_offsets,
                                   size_t nblocks, size_t block_len, uint8_t *out, size_t out_cap, size_t *out_len)
 {
-    using namespace lz4d;
     if (!ctx || !comp || !block_offsets || !out || nblocks == 0 || block_len == 0 || block_len > 65536) return LJB_E_ARG;
     if (block_offsets[nblocks] > comp_len) return LJB_E_ARG;
     LJB_CUDA(cudaSetDevice(ctx->device));
@@ -122,23 +154,9 @@ extern "C" int ljb_lz4_decompress(ljb_ctx *ctx, const uint8_t *comp, size_t comp
     uint32_t *d_len = (uint32_t *)(d_res + 3);
     LJB_CUDA(cudaMemcpyAsync(ctx->d_pin[0], comp, comp_len, cudaMemcpyHostToDevice, ctx->stream));
     LJB_CUDA(cudaMemcpyAsync(d_offs, block_offsets, (nblocks + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
-    LJB_CUDA(cudaMemsetAsync(d_res, 0, 3 * sizeof(uint64_t), ctx->stream));
-    Params P;
-    P.comp = (const uint8_t *)ctx->d_pin[0];
-    P.offs = d_offs;
-    P.comp_len = comp_len;
-    P.nblocks = (uint32_t)nblocks;
-    P.block_len = (uint32_t)block_len;
-    P.out = (uint8_t *)ctx->d_pout[0];
-    P.out_cap = dcap;
-    P.block_out_len = d_len;
-    P.result = d_res;
-    const unsigned grid = (unsigned)((nblocks + WARPS_PER_CTA - 1) / WARPS_PER_CTA);
-    LJB_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
-    lz4_decode_kernel<<<grid, WARPS_PER_CTA * 32, 0, ctx->stream>>>(P);
-    LJB_CUDA(cudaGetLastError());
-    LJB_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
-    ctx->launches += 1;
+    if ((rc = ljb_lz4_decompress_dev(ctx, (const uint8_t *)ctx->d_pin[0], comp_len, d_offs, nblocks, block_len, (uint8_t *)ctx->d_pout[0],
+                                     dcap, d_len, d_res)) != 0)
+        return rc;
     uint64_t res[3];
     uint32_t last_len = 0;
     LJB_CUDA(cudaMemcpyAsync(res, d_res, sizeof res, cudaMemcpyDeviceToHost, ctx->stream));

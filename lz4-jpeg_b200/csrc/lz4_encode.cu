@@ -105,6 +105,7 @@ struct Params {
     uint32_t frame_byte;
     uint16_t *dump_len;      // optional single-block stage dump
     uint16_t *dump_dist;
+    uint32_t tune;           // experiment switches (LJB_LZ4_TUNE), 0 in production
     unsigned long long *phase_cycles; // optional: per-phase SM cycles summed over CTAs (profiling aid)
 };
 
@@ -1374,6 +1375,7 @@ static int lz4_launch(ljb_ctx *ctx, const uint8_t *d_in, size_t n, size_t block_
     P.frame_byte = (uint32_t)(frame_blocks & 0xFF);
     P.dump_len = d_dump_len;
     P.dump_dist = d_dump_dist;
+    P.tune = getenv("LJB_LZ4_TUNE") ? (uint32_t)atoi(getenv("LJB_LZ4_TUNE")) : 0u;
     P.phase_cycles = nullptr;
     if (getenv("LJB_LZ4_PHASES")) { // profiling aid: per-phase cycle counters behind the status words
         P.phase_cycles = (unsigned long long *)ctx->d_status + (nblocks + 2);

@@ -30,6 +30,7 @@
 constexpr int WG = 66;                              // bytes per walker segment: two per emission segment
 constexpr int NWALK_MAX = (MAXB + WG - 1) / WG;     // 993
 constexpr int LCH = 12;                             // the index keeps a bucket ordered by 4096-position chunk
+constexpr int TINYLIST = 8;                          // candidate lists up to this length are walked by the lane that owns them
 constexpr int BIGLIST = 32;                          // candidate lists this long are taken by the whole warp, shorter ones by a team of eight lanes
 constexpr uint32_t VLONG = 32;                      // a lane compares this much on its own; longer runs are compared by the whole warp
 static_assert(2 * WG == SEG, "an emission segment is two walker segments");
@@ -55,8 +56,7 @@ __device__ __forceinline__ void lazy_search(uint8_t *smem, const uint32_t nb, ui
     uint32_t *known = reinterpret_cast<uint32_t *>(smem + SM_LONG);
     uint16_t *xin = reinterpret_cast<uint16_t *>(smem + SM_XIN);
     uint16_t *xout = reinterpret_cast<uint16_t *>(smem + SM_XOUT);
-    uint16_t *xcan = reinterpret_cast<uint16_t *>(smem + SM_XCAN);
-    uint8_t *split = smem + SM_SPLIT;
+    uint8_t *const stepg = reinterpret_cast<uint8_t *>(P.gids + (size_t)blockIdx.x * MAXB); // per CTA: the step of every visited position
     uint8_t *step = smem + SM_STEP;
     uint8_t *entry = smem + SM_ENTRY;
     const uint32_t npos = nb >= 4 ? nb - 3 : 0; // positions that still have a 4-gram inside the block
@@ -64,7 +64,6 @@ __device__ __forceinline__ void lazy_search(uint8_t *smem, const uint32_t nb, ui
     // ---------------- index: counting sort of the positions by 4-gram hash ----------------
     for (int i = tid; i < NBUCKET / 2 + 4; i += THREADS) dirw[i] = 0;
     for (int i = tid; i < MAXB / 32; i += THREADS) known[i] = 0;
-    split[tid] = 0;
     __syncthreads();
     // a thread takes four consecutive positions per 4096-position chunk (two words of the block give their four 4-grams)
     for (uint32_t base = 0; base < npos; base += 4 * THREADS) {
@@ -131,11 +130,76 @@ __device__ __forceinline__ void lazy_search(uint8_t *smem, const uint32_t nb, ui
     phase(3); // index
 
     // ---------------- walk rounds ----------------
+    // Consecutive segments go to different warps (lane l of warp w parses segment 32 l + w): the expensive stretches of a block
+    // (fresh text) and the cheap ones (capped runs) are then spread over all warps — with contiguous segments per warp the round
+    // waited for its slowest warp for a quarter of the kernel.
     const uint32_t nwalk = (nb + WG - 1) / WG;
-    const uint32_t s = (uint32_t)tid;
+    const uint32_t s = (P.tune & 1u) ? (uint32_t)tid : (uint32_t)lane * 32u + (uint32_t)(tid >> 5); // (tune bit 0: contiguous segments per warp, for measurements)
     const bool has = s < nwalk;
     const uint32_t seg0 = s * WG, segend = min(seg0 + (uint32_t)WG, nb);
-    uint32_t d_search = 0, d_cand = 0, d_steps = 0, d_vl = 0, d_run = 0, d_iter = 0;
+    uint32_t my_in = 0, my_can = 0; // (own lane only) where the latest walk of the segment started; exit of its first walk
+    bool my_split = false;          // a later walk left the segment without meeting an earlier one
+    uint32_t d_search = 0, d_cand = 0, d_steps = 0, d_vl = 0, d_run = 0;
+    // One candidate: its first 8 bytes against the position's, then up to VLONG bytes by the lane itself.
+    // key = (length << 16) | (0xFFFF - position): the maximum is the longest match, the earliest among equals.
+    auto eval = [&](uint32_t c, uint32_t op, uint32_t og0, uint32_t og1, uint32_t ocap, uint32_t tb, bool &vl) -> uint32_t {
+        if (c >= op) return 0u;
+        const uint32_t ci = c >> 2, cs = (c & 3) * 8;
+        const uint32_t a0 = dataw[ci], a1 = dataw[ci + 1], a2 = dataw[ci + 2];
+        if (__funnelshift_r(a0, a1, cs) != og0) return 0u; // (a bucket holds several 4-grams)
+        const uint32_t x1 = __funnelshift_r(a1, a2, cs) ^ og1;
+        uint32_t l;
+        if (x1) {
+            l = 4u + ((uint32_t)(__ffs(x1) - 1) >> 3);
+        } else {
+            // a pair that already reaches the cap is only beaten by an earlier position
+            if ((tb >> 16) == ocap && c > 0xFFFFu - (tb & 0xFFFFu)) return 0u;
+            l = 8;
+            const uint32_t lim = min(ocap, VLONG);
+            while (l < lim) {
+                const uint32_t x = load32u(dataw, c + l) ^ load32u(dataw, op + l);
+                if (x) {
+                    l += (uint32_t)(__ffs(x) - 1) >> 3;
+                    break;
+                }
+                l += 4;
+            }
+            if (l >= VLONG && ocap > VLONG) { // still matching after VLONG bytes: the warp goes on
+                vl = true;
+                return 0u;
+            }
+        }
+        return (min(l, ocap) << 16) | (0xFFFFu - c);
+    };
+    // The pair (bc, bp) matches VLONG bytes: the warp compares on, 256 bytes per step, unless the pair cannot beat btb (it must
+    // exceed the best length, or tie it from an earlier position).  Warp-uniform.
+    auto long_compare = [&](uint32_t bc, uint32_t bp, uint32_t bcap, uint32_t btb) -> uint32_t {
+        const uint32_t bl = btb >> 16, bpos = 0xFFFFu - (btb & 0xFFFFu);
+        const uint32_t needl = btb == 0u ? 0u : (bc < bpos ? bl : bl + 1u);
+        if (needl > bcap || (needl > VLONG && data[bc + needl - 1] != data[bp + needl - 1])) return 0u;
+        ++d_vl;
+        uint32_t res = bcap;
+        for (uint32_t base = VLONG; base < bcap; base += 256) {
+            const uint32_t off = base + 8u * (uint32_t)lane;
+            uint32_t x0 = 0, x1 = 0;
+            if (off < bcap) {
+                const uint32_t ci = (bc + off) >> 2, cs = ((bc + off) & 3) * 8;
+                const uint32_t pi = (bp + off) >> 2, ps = ((bp + off) & 3) * 8;
+                const uint32_t a0 = dataw[ci], a1 = dataw[ci + 1], a2 = dataw[ci + 2];
+                const uint32_t e0 = dataw[pi], e1 = dataw[pi + 1], e2 = dataw[pi + 2];
+                x0 = __funnelshift_r(a0, a1, cs) ^ __funnelshift_r(e0, e1, ps);
+                x1 = __funnelshift_r(a1, a2, cs) ^ __funnelshift_r(e1, e2, ps);
+            }
+            const unsigned mm = __ballot_sync(FULL, (x0 | x1) != 0u);
+            if (mm) {
+                const int f = __ffs(mm) - 1;
+                const uint32_t mine = off + (x0 ? ((uint32_t)(__ffs(x0) - 1) >> 3) : 4u + ((uint32_t)(__ffs(x1) - 1) >> 3));
+                res = min(__shfl_sync(FULL, mine, f), bcap);
+                break;
+            }
+        }
+        return (res << 16) | (0xFFFFu - bc);
+    };
     for (uint32_t round = 0;; ++round) {
         bool run = false;
         uint32_t p = 0;
@@ -145,14 +209,14 @@ __device__ __forceinline__ void lazy_search(uint8_t *smem, const uint32_t nb, ui
                 p = seg0;
             } else if (s > 0) {
                 const uint32_t e = (uint32_t)xout[s - 1] + (s - 1) * WG; // where the chain leaves the segment before this one
-                if (e != (uint32_t)xin[s] + seg0) {
+                if (e != my_in) {
                     run = true;
                     p = e;
                 }
             }
         }
         if (!__syncthreads_or(run)) break; // (also separates the reads above from this round's writes)
-        const uint32_t start = p;
+        if (run) my_in = p;
         uint32_t ex = p;                   // a chain that jumps over the segment leaves it where it enters it
         bool act = run && p < segend;
         bool met = false;                  // stopped at a known position
@@ -162,14 +226,13 @@ __device__ __forceinline__ void lazy_search(uint8_t *smem, const uint32_t nb, ui
             bool need = false;
             if (act) {
                 if ((known[p >> 5] >> (p & 31)) & 1u) {
-                    if (!split[s]) { // every known position of the segment leads to the exit of its first walk
-                        ex = (uint32_t)xcan[s] + seg0;
+                    met = true;
+                    if (!my_split) { // every known position of the segment leads to the exit of its first walk
+                        ex = my_can;
                         act = false;
-                        met = true;
                     } else { // two chains cross this segment side by side: follow the recorded steps
-                        const uint32_t len = __ldcg(&R[p]) >> 16, st = len & 0xFFu;
-                        p += (len >= 4 && st) ? st : 1u;
-                        met = true;
+                        const uint32_t st = __ldcg(&stepg[p]);
+                        p += st ? st : 1u;
                         if (p >= segend) {
                             ex = p;
                             act = false;
@@ -181,88 +244,57 @@ __device__ __forceinline__ void lazy_search(uint8_t *smem, const uint32_t nb, ui
             }
             // ---- the candidates of this lane's position: the members of its bucket in earlier chunks and in its own
             uint32_t g0 = 0, g1 = 0, lo = 0, n = 0;
+            const uint32_t cap = min((uint32_t)MAX_MATCH, nb - p);
             if (need && p < npos) {
                 g0 = load32u(dataw, p);
                 g1 = load32u(dataw, p + 4);
                 const uint32_t h = hash4(g0);
                 lo = h ? dir16[h - 1] : 0u;
-                const uint32_t pch = p >> LCH;
-                uint32_t a = lo, b = dir16[h];
-                while (a < b) { // first entry of a later chunk
-                    const uint32_t m = (a + b) >> 1;
-                    if ((uint32_t)(S[m] >> LCH) <= pch) a = m + 1;
-                    else b = m;
+                const uint32_t hi = dir16[h];
+                if (hi - lo <= (uint32_t)TINYLIST) {
+                    n = hi - lo; // (later positions are turned away one by one)
+                } else {
+                    const uint32_t pch = p >> LCH;
+                    uint32_t a = lo, b = hi;
+                    while (a < b) { // first entry of a later chunk
+                        const uint32_t m = (a + b) >> 1;
+                        if ((uint32_t)(S[m] >> LCH) <= pch) a = m + 1;
+                        else b = m;
+                    }
+                    n = a - lo;
                 }
-                n = a - lo;
             }
             if (need) {
                 ++d_search;
                 d_cand += n;
             }
-            // ---- evaluation.  key = (length << 16) | (0xFFFF - position): the maximum is the longest match, the earliest among
-            // equals.  Lists of BIGLIST candidates or more are taken by the whole warp, one list at a time; the others by teams
-            // of eight lanes, four lists at a time (measured on the benchmark text: 9.9 k warp iterations per block this
-            // way, 19.5 k with teams only, 13 k if every list had the warp to itself).
-            // One candidate: its first 8 bytes against the position's, then up to VLONG bytes by the lane itself.
-            auto eval = [&](uint32_t c, uint32_t op, uint32_t og0, uint32_t og1, uint32_t ocap, uint32_t tb, bool &vl) -> uint32_t {
-                // a pair that already reaches the cap is only beaten by an earlier position
-                if (c >= op || ((tb >> 16) == ocap && c > 0xFFFFu - (tb & 0xFFFFu))) return 0u;
-                const uint32_t ci = c >> 2, cs = (c & 3) * 8;
-                const uint32_t a0 = dataw[ci], a1 = dataw[ci + 1], a2 = dataw[ci + 2];
-                if (__funnelshift_r(a0, a1, cs) != og0) return 0u; // (a bucket holds several 4-grams)
-                const uint32_t x1 = __funnelshift_r(a1, a2, cs) ^ og1;
-                uint32_t l;
-                if (x1) {
-                    l = 4u + ((uint32_t)(__ffs(x1) - 1) >> 3);
-                } else {
-                    l = 8;
-                    const uint32_t lim = min(ocap, VLONG);
-                    while (l < lim) {
-                        const uint32_t x = load32u(dataw, c + l) ^ load32u(dataw, op + l);
-                        if (x) {
-                            l += (uint32_t)(__ffs(x) - 1) >> 3;
-                            break;
-                        }
-                        l += 4;
-                    }
-                    if (l >= VLONG && ocap > VLONG) { // still matching after VLONG bytes: the warp goes on
-                        vl = true;
-                        return 0u;
-                    }
-                }
-                return (min(l, ocap) << 16) | (0xFFFFu - c);
-            };
-            // The pair (bc, bp) of lane sv matches VLONG bytes: the warp compares on, 256 bytes per step, unless the pair cannot
-            // beat btb (it must exceed the best length, or tie it from an earlier position).  Warp-uniform.
-            auto long_compare = [&](uint32_t bc, uint32_t bp, uint32_t bcap, uint32_t btb) -> uint32_t {
-                const uint32_t bl = btb >> 16, bpos = 0xFFFFu - (btb & 0xFFFFu);
-                const uint32_t needl = btb == 0u ? 0u : (bc < bpos ? bl : bl + 1u);
-                if (needl > bcap || (needl > VLONG && data[bc + needl - 1] != data[bp + needl - 1])) return 0u;
-                ++d_vl;
-                uint32_t res = bcap;
-                for (uint32_t base = VLONG; base < bcap; base += 256) {
-                    const uint32_t off = base + 8u * (uint32_t)lane;
-                    uint32_t x0 = 0, x1 = 0;
-                    if (off < bcap) {
-                        const uint32_t ci = (bc + off) >> 2, cs = ((bc + off) & 3) * 8;
-                        const uint32_t pi = (bp + off) >> 2, ps = ((bp + off) & 3) * 8;
-                        const uint32_t a0 = dataw[ci], a1 = dataw[ci + 1], a2 = dataw[ci + 2];
-                        const uint32_t e0 = dataw[pi], e1 = dataw[pi + 1], e2 = dataw[pi + 2];
-                        x0 = __funnelshift_r(a0, a1, cs) ^ __funnelshift_r(e0, e1, ps);
-                        x1 = __funnelshift_r(a1, a2, cs) ^ __funnelshift_r(e1, e2, ps);
-                    }
-                    const unsigned mm = __ballot_sync(FULL, (x0 | x1) != 0u);
-                    if (mm) {
-                        const int f = __ffs(mm) - 1;
-                        const uint32_t mine = off + (x0 ? ((uint32_t)(__ffs(x0) - 1) >> 3) : 4u + ((uint32_t)(__ffs(x1) - 1) >> 3));
-                        res = min(__shfl_sync(FULL, mine, f), bcap);
-                        break;
-                    }
-                }
-                return (res << 16) | (0xFFFFu - bc);
-            };
+            // ---- evaluation, three ways by the length of the list (p50 = 3, p90 = 52, p99 = 311 candidates on the benchmark
+            // text): up to TINYLIST every lane walks its own list; up to BIGLIST teams of eight lanes take a list each, four at a
+            // time; longer ones are taken by the whole warp, one at a time.
             uint32_t best = 0;
-            // (i) long lists
+            // (i) short lists: every lane its own
+            {
+                const bool mine = need && n > 0 && n <= (uint32_t)TINYLIST;
+                const uint32_t nmax = __reduce_max_sync(FULL, mine ? n : 0u);
+                for (uint32_t it = 0; it < nmax; ++it) {
+                    uint32_t key = 0, c = 0;
+                    bool vl = false;
+                    if (mine && it < n) {
+                        c = S[lo + it];
+                        key = eval(c, p, g0, g1, cap, best, vl);
+                    }
+                    best = max(best, key);
+                    unsigned pendv = __ballot_sync(FULL, vl);
+                    while (pendv) {
+                        const int sv = __ffs(pendv) - 1;
+                        pendv &= pendv - 1;
+                        const uint32_t rkey = long_compare(__shfl_sync(FULL, c, sv), __shfl_sync(FULL, p, sv), __shfl_sync(FULL, cap, sv),
+                                                           __shfl_sync(FULL, best, sv));
+                        if (lane == sv) best = max(best, rkey);
+                    }
+                }
+            }
+            // (ii) long lists: the whole warp
             unsigned big = __ballot_sync(FULL, need && n >= (uint32_t)BIGLIST);
             while (big) {
                 const int src = __ffs(big) - 1;
@@ -272,7 +304,6 @@ __device__ __forceinline__ void lazy_search(uint8_t *smem, const uint32_t nb, ui
                 const uint32_t ocap = min((uint32_t)MAX_MATCH, nb - op);
                 uint32_t lb = 0, tb = 0; // this lane's best; what the whole warp knows (pairs at the cap, long compares)
                 for (uint32_t it = 0; it < on; it += 32) {
-                    ++d_iter;
                     const uint32_t i = it + (uint32_t)lane;
                     uint32_t key = 0, c = 0;
                     bool vl = false;
@@ -296,8 +327,8 @@ __device__ __forceinline__ void lazy_search(uint8_t *smem, const uint32_t nb, ui
                 tb = max(tb, __reduce_max_sync(FULL, lb));
                 if (lane == src) best = tb;
             }
-            // (ii) short lists
-            unsigned rem = __ballot_sync(FULL, need && n > 0 && n < (uint32_t)BIGLIST);
+            // (iii) the lists in between: teams
+            unsigned rem = __ballot_sync(FULL, need && n > (uint32_t)TINYLIST && n < (uint32_t)BIGLIST);
             while (rem) {
                 const int b0 = __ffs(rem) - 1;
                 rem &= rem - 1;
@@ -316,8 +347,8 @@ __device__ __forceinline__ void lazy_search(uint8_t *smem, const uint32_t nb, ui
                 if (src < 0) on = 0;
                 const uint32_t ocap = min((uint32_t)MAX_MATCH, nb - op);
                 uint32_t lb = 0, tb = 0; // this lane's best; what the whole team knows (the same in its eight lanes)
-                for (uint32_t it = 0; __any_sync(FULL, it < on); it += 8) {
-                    ++d_iter;
+                uint32_t nit = __reduce_max_sync(FULL, on);
+                for (uint32_t it = 0; it < nit; it += 8) {
                     const uint32_t i = it + (uint32_t)tl;
                     uint32_t key = 0, c = 0;
                     bool vl = false;
@@ -339,7 +370,12 @@ __device__ __forceinline__ void lazy_search(uint8_t *smem, const uint32_t nb, ui
                         key = max(key, __shfl_xor_sync(FULL, key, 2));
                         key = max(key, __shfl_xor_sync(FULL, key, 1));
                         tb = max(tb, key);
-                        if (it + 8 < on && (tb >> 16) == ocap && (uint32_t)(S[olo + it + 8] >> LCH) > ((0xFFFFu - (tb & 0xFFFFu)) >> LCH)) on = 0;
+                        if (it + 8 < on && (tb >> 16) == ocap && (uint32_t)(S[olo + it + 8] >> LCH) > ((0xFFFFu - (tb & 0xFFFFu)) >> LCH)) {
+                            on = 0;
+                            nit = __reduce_max_sync(FULL, on); // (the branch is warp-uniform)
+                        } else {
+                            nit = __reduce_max_sync(FULL, on);
+                        }
                     }
                 }
                 lb = max(lb, __shfl_xor_sync(FULL, lb, 4));
@@ -352,14 +388,16 @@ __device__ __forceinline__ void lazy_search(uint8_t *smem, const uint32_t nb, ui
                 if (lane == b2) best = v2;
                 if (lane == b3) best = v3;
             }
-            // ---- record
+            // ---- record: the step (the reference's uint8_t cast of the length, LZ4.c:317; 0 = literal step) and, for a match, where
+            const uint32_t blen = best >> 16, bstep = blen & 0xFFu;
             if (need) {
-                R[p] = best ? (((best >> 16) << 16) | (0xFFFFu - (best & 0xFFFFu))) : 0u;
+                stepg[p] = (uint8_t)bstep;
+                if (bstep) R[p] = (blen << 16) | (0xFFFFu - (best & 0xFFFFu));
                 atomicOr(&known[p >> 5], 1u << (p & 31));
             }
             // ---- capped matches: the following positions of the segment that inherit a 1024-byte match are literal steps
             uint32_t skip = 0;
-            unsigned runs = __ballot_sync(FULL, need && (best >> 16) == (uint32_t)MAX_MATCH);
+            unsigned runs = __ballot_sync(FULL, need && blen == (uint32_t)MAX_MATCH);
             while (runs) {
                 const int sr = __ffs(runs) - 1;
                 runs &= runs - 1;
@@ -378,7 +416,7 @@ __device__ __forceinline__ void lazy_search(uint8_t *smem, const uint32_t nb, ui
                     }
                 }
                 for (uint32_t j = (uint32_t)lane + 1u; j <= k; j += 32) {
-                    R[rp + j] = ((uint32_t)MAX_MATCH << 16) | ((rc + j) & 0xFFFFu);
+                    stepg[rp + j] = 0;
                     atomicOr(&known[(rp + j) >> 5], 1u << ((rp + j) & 31));
                 }
                 if (lane == sr) skip = k;
@@ -386,31 +424,33 @@ __device__ __forceinline__ void lazy_search(uint8_t *smem, const uint32_t nb, ui
             }
             // ---- step on
             if (need) {
-                const uint32_t len = best >> 16, st = len & 0xFFu; // (uint8_t) cast of LZ4.c:317; 0 = literal step
-                p += ((len >= 4 && st) ? st : 1u) + skip;
+                p += (bstep ? bstep : 1u) + skip;
                 if (p >= segend) {
                     ex = p;
                     act = false;
                 }
             }
         }
-        if (run) { // (own lane's slots; the predecessor's exit was read before this round's barrier)
-            xin[s] = (uint16_t)(start - seg0);
+        if (run) { // (the predecessor's exit was read before this round's barrier)
             xout[s] = (uint16_t)(ex - seg0);
-            if (round == 0) xcan[s] = (uint16_t)(ex - seg0);
-            else if (walked && !met && ex != (uint32_t)xcan[s] + seg0) split[s] = 1;
+            if (round == 0) my_can = ex;
+            else if (walked && !met && ex != my_can) my_split = true;
         }
         __syncthreads(); // the exits of this round are what the next round starts from
         if (round == 0) phase(2); // first walks
     }
     phase(1); // later rounds
+    if (has) xin[s] = (uint16_t)(my_in - seg0);
+    __syncthreads(); // the entries are read by other threads below
     flush_prev(); // the previous block moves to its place in the stream (its predecessors have long published their sizes)
 
     // ---------------- what the emission passes read: step[] along the chain, entry[] per emission segment ----------------
-    // (S is dead; step[] and entry[] take its place)
+    // (S is dead: step[] and entry[] take its place.  step[] is copied whole from the per-CTA array the walkers wrote; what it
+    // holds at positions no walker visited is left over from earlier blocks and never read: the emission passes only follow the chain.)
     {
+        const uint4 *g4 = reinterpret_cast<const uint4 *>(stepg);
         uint4 *z = reinterpret_cast<uint4 *>(step);
-        for (int i = tid; i < (MAXB + 64) / 16; i += THREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);
+        for (uint32_t i = (uint32_t)tid; i < (nb + 15u) / 16u; i += THREADS) z[i] = __ldcg(&g4[i]);
         const uint32_t nseg = (nb + SEG - 1) / SEG;
         uint32_t e8 = 0xFFu;
         if ((uint32_t)tid < nseg) {
@@ -418,28 +458,6 @@ __device__ __forceinline__ void lazy_search(uint8_t *smem, const uint32_t nb, ui
             if (e < min(((uint32_t)tid + 1u) * SEG, nb)) e8 = e - (uint32_t)tid * SEG;
         }
         entry[tid] = (uint8_t)e8;
-    }
-    __syncthreads();
-    {
-        // every known position: its step.  A thread takes 64 consecutive positions (two words of the bit set), eight records in flight
-        unsigned long long m = (unsigned long long)known[2 * tid] | ((unsigned long long)known[2 * tid + 1] << 32);
-        const uint32_t pbase = 64u * (uint32_t)tid;
-        while (m) {
-            uint32_t pp[8], rr[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                pp[j] = 0xFFFFFFFFu;
-                if (m) {
-                    pp[j] = pbase + (uint32_t)(__ffsll((long long)m) - 1);
-                    m &= m - 1;
-                }
-            }
-#pragma unroll
-            for (int j = 0; j < 8; ++j) rr[j] = pp[j] != 0xFFFFFFFFu ? __ldcg(&R[pp[j]]) : 0u;
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-                if (pp[j] != 0xFFFFFFFFu) step[pp[j]] = (uint8_t)(rr[j] >> 16);
-        }
     }
     if (P.phase_cycles) {
         const unsigned t_s = __reduce_add_sync(FULL, d_search), t_c = __reduce_add_sync(FULL, d_cand);
@@ -449,7 +467,6 @@ __device__ __forceinline__ void lazy_search(uint8_t *smem, const uint32_t nb, ui
             atomicAdd(&P.phase_cycles[17], (unsigned long long)t_c);
             atomicAdd(&P.phase_cycles[18], (unsigned long long)d_steps);
             atomicAdd(&P.phase_cycles[12], (unsigned long long)d_vl);
-            atomicAdd(&P.phase_cycles[9], (unsigned long long)d_iter);
             atomicAdd(&P.phase_cycles[13], (unsigned long long)t_r);
         }
     }

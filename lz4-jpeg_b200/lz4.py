@@ -128,3 +128,11 @@ def compress_device(d_in, block_len: int, d_out, d_block_offsets, d_result, ctx:
                                       d_block_offsets.data_ptr(), d_result.data_ptr(), first_block,
                                       nblocks if frame_blocks is None else frame_blocks)
     N.check(rc, "ljb_lz4_compress_dev")
+
+
+def decompress_device(d_comp, comp_len: int, d_block_offsets, nblocks: int, block_len: int, d_out, d_block_out_len, d_result,
+                      ctx: N.Context) -> None:
+    """Asynchronous on ctx.stream: decode a device-resident stream (ljb_lz4_decompress_dev)."""
+    rc = N.lib().ljb_lz4_decompress_dev(ctx.handle, d_comp.data_ptr(), comp_len, d_block_offsets.data_ptr(), nblocks, block_len,
+                                        d_out.data_ptr(), d_out.numel(), d_block_out_len.data_ptr(), d_result.data_ptr())
+    N.check(rc, "ljb_lz4_decompress_dev")
