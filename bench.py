@@ -18,6 +18,10 @@ Inputs are far larger than the 126 MB L2, so no explicit L2 flush is needed betw
 
 ``--impl reference`` times the reference's own CPU code (oracle/_ref, compiled from /root/reference; falls
 back to this repo's C port of it) on all host threads over a bounded sample of the same workload.
+
+Every object of the GPU line also carries ``parity_sample``: after the timed region, randomly chosen units of the
+benchmark's own output (64 LZ4 blocks, 4096 JPEG groups; for JFIF a 64-row band re-encoded alone) are compared with the
+CPU oracle — the one use of oracle/ in the GPU arm besides ``cpu_baseline``, and never inside a timed region.
 """
 from __future__ import annotations
 
@@ -126,6 +130,54 @@ def _cpu_lz4(sample_blocks: int, threads: int):
     return data.size / sec / 1e9, kind, sec
 
 
+def _cpu_lz4_detail(threads: int):
+    """The three CPU figures BASELINE.json's north_star asks for: the sequential build on one core, the sequential per-block
+    function on all threads (the `value` the reference arm reports), and the parallel build's thread body with its global
+    locks (Algorithms/parallel/LZ4/LZ4.c:518-628) on all threads.  Bounded samples of the benchmark text."""
+    import numpy as np
+
+    from oracle.pyoracle import Oracle, Ref
+
+    out = {}
+    if not Ref.available("lz4"):
+        return out
+    orc = Oracle()
+    corpus = np.fromfile(os.path.join(ROOT, "tests", "golden", "Metamorphosis.txt"), dtype=np.uint8)
+    d1 = orc.synth_text(corpus, 42, 30000, 2 * BLOCK_LEN)
+    sec, _ = Ref("lz4").lz4_time_blocks(d1, BLOCK_LEN, 1)
+    out["sequential_1core"] = {"value": d1.size / sec / 1e9, "unit": "GB/s", "cores": 1, "kind": "reference",
+                               "sample": f"2 blocks of 64 KiB of the same text, block_encode (Algorithms/sequential/LZ4/LZ4.c:506) on 1 thread, {sec:.1f} s"}
+    if Ref.available("lz4_par"):
+        sb = max(threads, 16)
+        dp = orc.synth_text(corpus, 42, 30000, sb * BLOCK_LEN)
+        sec, _ = Ref("lz4_par").lz4par_time_blocks(dp, BLOCK_LEN, threads)
+        out["parallel_build"] = {"value": dp.size / sec / 1e9, "unit": "GB/s", "cores": threads, "kind": "reference",
+                                 "sample": f"{sb} blocks of 64 KiB of the same text, parallel_block_encode with its global add_seq lock "
+                                           f"(Algorithms/parallel/LZ4/LZ4.c:518-628, windows.h shim over pthreads) from a pool of {threads} "
+                                           f"threads instead of one thread per block, {sec:.1f} s"}
+    return out
+
+
+def _cpu_jpeg_detail(threads: int):
+    from oracle.pyoracle import Oracle, Ref
+
+    out = {}
+    if not Ref.available("jpeg"):
+        return out
+    orc = Oracle()
+    img1 = orc.synth_image(42, 2048, 1024)
+    sec, _ = Ref("jpeg").jpeg_time_groups(img1, 1)
+    out["sequential_1core"] = {"value": 2048 * 1024 / sec / 1e6, "unit": "MPix/s", "cores": 1, "kind": "reference",
+                               "sample": f"2048x1024 seed-42 noise image, the sequential build's per-group encode stages on 1 thread, {sec:.1f} s"}
+    if Ref.available("jpeg_par"):
+        imgp = orc.synth_image(42, 4096, 2048)
+        sec = Ref("jpeg_par").jpegpar_time_groups(imgp, threads)
+        out["parallel_build"] = {"value": 4096 * 2048 / sec / 1e6, "unit": "MPix/s", "cores": threads, "kind": "reference",
+                                 "sample": f"4096x2048 seed-42 noise image, process() (Algorithms/parallel/JPEG/JPEG.c:1103: forward AND inverse chain, "
+                                           f"results discarded as in the reference) from a pool of {threads} threads instead of one thread per group, {sec:.1f} s"}
+    return out
+
+
 def _cpu_jpeg(w: int, h: int, threads: int):
     import numpy as np
 
@@ -192,6 +244,7 @@ def run_reference(args):
     jvalue = sum(jp) / len(jp)
     f4value, f2value = sum(jf4) / len(jf4), sum(jf2) / len(jf2)
     sample = f"{sample_blocks} blocks of 64 KiB of the seed-42 random_extract text, block_encode on {threads} threads"
+    lz_detail, jp_detail = _cpu_lz4_detail(threads), _cpu_jpeg_detail(threads)  # once, outside the step loop
     line = {
         "impl": "reference", "metric": "LZ4 compress GB/s (headline) & JPEG encode MPix/s (jpeg)", "value": value, "unit": "GB/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -199,11 +252,11 @@ def run_reference(args):
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": {"workload": "LZ4 block compression of 4 GiB random_extract-style text, 64 KiB blocks (BASELINE configs[2])",
                    "block_len": BLOCK_LEN, "sampled": sample},
-        "cpu_baseline": {"value": value, "unit": "GB/s", "cores": threads, "kind": kind, "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "GB/s", "cores": threads, "kind": kind, "sample": sample, **lz_detail},
         "e2e": {"value": value, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "jpeg": {"metric": "JPEG encode MPix/s", "value": jvalue, "unit": "MPix/s",
                  "cpu_baseline": {"value": jvalue, "unit": "MPix/s", "cores": threads, "kind": kindj,
-                                  "sample": f"{jw}x{jh} seed-42 noise image, per-group encode stages on {threads} threads"},
+                                  "sample": f"{jw}x{jh} seed-42 noise image, per-group encode stages on {threads} threads", **jp_detail},
                  "e2e": {"value": jvalue, "unit": "MPix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}},
         "jfif": {"metric": "baseline JPEG (JFIF) encode MPix/s, quality 75, 4:4:4", "value": f4value, "unit": "MPix/s",
                  "cpu_baseline": {"value": f4value, "unit": "MPix/s", "cores": threads, "kind": kindf,
@@ -341,8 +394,8 @@ def run_gpu(args):
     lz_err = int(d_res[2].item())
     if lz_err:
         raise SystemExit(f"LZ4 kernel reported error flags {lz_err}")
-    e2e_ms, e2e_wall, _ = timed(lz4_step_e2e, max(1, min(args.steps, 3)), 1, use_events=False)
-    e2e_steps = max(1, min(args.steps, 3))
+    e2e_steps, e2e_warm = args.steps, max(1, args.warmup)  # the end-to-end path is timed over the same K steps (W >= 1 warm-up)
+    e2e_ms, e2e_wall, _ = timed(lz4_step_e2e, e2e_steps, e2e_warm, use_events=False)
     lz_e2e_ms = max_over_ranks(e2e_wall * 1e3 / e2e_steps)
     # the host-buffer call encodes a whole frame (leading frame byte); the device call on rank > 0 encodes a shard without it
     assert int(out_len.value) == lz_out_bytes + (1 if first_block else 0), "host-buffer path and device path disagree on the stream length"
@@ -351,6 +404,92 @@ def run_gpu(args):
     lz_value = total_in / (lz_ms / args.steps * 1e-3) / 1e9
     lz_e2e_value = total_in / (lz_e2e_ms * 1e-3) / 1e9
     lz_achieved = (n + lz_out_bytes) / (lz_kernel_ms * 1e-3) / 1e9
+
+    # ---- what the host link can do at most: the same bytes, plain pinned copies both ways at once, all ranks together
+    def host_ceiling(h_src, d_dst, d_src, h_dst, nbytes_out):
+        s_up, s_dn = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+        best = None
+        for _ in range(3):
+            barrier()
+            t0 = time.perf_counter()
+            with torch.cuda.stream(s_up):
+                d_dst.copy_(h_src, non_blocking=True)
+            with torch.cuda.stream(s_dn):
+                h_dst[:nbytes_out].copy_(d_src[:nbytes_out], non_blocking=True)
+            s_up.synchronize()
+            s_dn.synchronize()
+            dt = max_over_ranks(time.perf_counter() - t0)
+            best = dt if best is None else min(best, dt)
+        return best
+
+    lz_ceiling_s = host_ceiling(h_in, d_in, d_out, h_out, lz_out_bytes)
+    lz_ceiling = total_in / lz_ceiling_s / 1e9
+
+    # ---- parity sample: 64 random blocks of the benchmark's own output against the CPU oracle (outside every timed region)
+    def lz4_parity_sample(k=64):
+        from oracle.pyoracle import Oracle
+
+        orc = Oracle()
+        ljb.lz4.compress_device(d_in, BLOCK_LEN, d_out, d_offs, d_res, ctx, first_block=first_block, frame_blocks=frame_blocks)
+        torch.cuda.synchronize()
+        offs = d_offs.cpu().numpy().astype(np.int64)
+        rng = np.random.default_rng(1234 + rank)
+        bad = 0
+        picks = sorted(int(x) for x in rng.choice(nblocks, size=min(k, nblocks), replace=False))
+        hin = h_in.numpy()
+        for bidx in picks:
+            blk = hin[bidx * BLOCK_LEN: min(n, (bidx + 1) * BLOCK_LEN)]
+            ref_stream, _, _ = orc.lz4_compress(blk, BLOCK_LEN, 1)  # frame byte + the block
+            got = d_out[int(offs[bidx]):int(offs[bidx + 1])].cpu().numpy()
+            if not np.array_equal(got, ref_stream[1:]):
+                bad += 1
+        return {"checked": len(picks), "mismatch": int(sum_over_ranks(float(bad))), "unit": "64 KiB blocks of the timed output vs oracle/lz4_oracle.c"}
+
+    lz_parity = lz4_parity_sample() if not args.no_parity_sample else None
+
+    # ---- decoder: the stream just produced, device-resident, and through the host-buffer call
+    d_dec = torch.empty(n, dtype=torch.uint8, device=dev)
+    d_blen = torch.empty(nblocks, dtype=torch.int32, device=dev)
+    d_dres = torch.zeros(3, dtype=torch.int64, device=dev)
+
+    def lz4_decode_step():
+        ljb.lz4.decompress_device(d_out, lz_out_bytes, d_offs, nblocks, BLOCK_LEN, d_dec, d_blen, d_dres, ctx)
+
+    dec_ms, _, dec_launches = timed(lz4_decode_step, args.steps, args.warmup)
+    dec_kernel_ms = ctx.last_kernel_ms()
+    torch.cuda.synchronize()
+    ok_blocks = int(((d_dec.view(nblocks, BLOCK_LEN) == d_in.view(nblocks, BLOCK_LEN)).all(dim=1)).sum().item()) if n % BLOCK_LEN == 0 else None
+    phantom = int(d_res[1].item())
+    dec_value = total_in / (dec_ms / args.steps * 1e-3) / 1e9
+    decode_obj = {"metric": "LZ4 decompress GB/s (of decoded bytes)", "value": dec_value, "unit": "GB/s", "ms_per_step": dec_ms / args.steps,
+                  "config": {"workload": "decode of the stream the compress step produced (device-resident, ljb_lz4_decompress_dev)",
+                             "undecodable_sequences_in_stream": phantom,
+                             "note": "a 257..259-byte match is a sequence the reference's format cannot represent (SURVEY.md A.3-b): the block that "
+                                     "holds one is reported as a format error by any decoder; every other block must round-trip"},
+                  "roundtrip": {"blocks": nblocks, "blocks_equal_to_input": ok_blocks, "blocks_with_undecodable_sequence_at_most": phantom},
+                  "roofline": {"bound": "hbm", "achieved": (n + lz_out_bytes) / (dec_kernel_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                               "frac": (n + lz_out_bytes) / (dec_kernel_ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                               "kernel": "lz4d::lz4_decode_kernel", "kernel_ms": dec_kernel_ms, "algorithmic_bytes": n + lz_out_bytes}}
+    if ok_blocks is not None and ok_blocks + phantom < nblocks:
+        raise SystemExit(f"LZ4 round trip: only {ok_blocks} of {nblocks} blocks decode to their input ({phantom} undecodable sequences)")
+    del d_dec, d_blen
+
+    # ---- strong scaling (BASELINE configs[2]: 4 GiB in total across 1/2/4/8 GPUs): this rank's 1/N of one 4 GiB stream
+    strong = {}
+    if world > 1:
+        sb = nblocks // world
+        d_in_s = d_in[: sb * BLOCK_LEN]
+
+        def lz4_step_strong():
+            ljb.lz4.compress_device(d_in_s, BLOCK_LEN, d_out, d_offs, d_res, ctx, first_block=rank * sb, frame_blocks=world * sb)
+            with torch.cuda.stream(ext_stream):
+                ljb.sharding.gather_totals_device(d_res[0:1])
+
+        s_ms, _, _ = timed(lz4_step_strong, args.steps, args.warmup)
+        strong["lz4"] = {"value": sb * BLOCK_LEN * world / (s_ms / args.steps * 1e-3) / 1e9, "unit": "GB/s", "ms_per_step": s_ms / args.steps,
+                         "config": f"{sb * BLOCK_LEN * world / GIB:g} GiB in total, {sb} blocks per GPU"}
+    else:
+        strong["lz4"] = {"value": lz_value, "unit": "GB/s", "ms_per_step": lz_ms / args.steps, "config": f"{n / GIB:g} GiB in total on 1 GPU"}
     del h_out, d_out, d_in, h_in
     torch.cuda.empty_cache()
 
@@ -393,12 +532,50 @@ def run_gpu(args):
     jp_out_bytes = int(dj_res[0].item())
     if int(dj_res[2].item()):
         raise SystemExit(f"JPEG kernel reported error flags {int(dj_res[2].item())}")
-    _, je2e_wall, _ = timed(jpeg_step_e2e, e2e_steps, 1, use_events=False)
+    _, je2e_wall, _ = timed(jpeg_step_e2e, e2e_steps, e2e_warm, use_events=False)
     jp_e2e_ms = max_over_ranks(je2e_wall * 1e3 / e2e_steps)
     total_px = sum_over_ranks(float(W) * H)
     jp_value = total_px / (jp_ms / args.steps * 1e-3) / 1e6
     jp_e2e_value = total_px / (jp_e2e_ms * 1e-3) / 1e6
     jp_achieved = (4.0 * W * H + jp_out_bytes) / (jp_kernel_ms * 1e-3) / 1e9
+    jp_ceiling_s = host_ceiling(hj_in, dj_in, dj_out, hj_out, jp_out_bytes)
+    jp_ceiling = total_px / jp_ceiling_s / 1e6
+
+    def jpeg_parity_sample(runs=16, run_len=256):
+        """runs x run_len consecutive groups of the timed output (records, bit lengths) against the CPU oracle."""
+        from oracle.pyoracle import Oracle
+
+        orc = Oracle()
+        ljb.jpeg.encode_device(dj_in, W, H, dj_out, dj_offs, dj_bits, dj_res, ctx)
+        torch.cuda.synchronize()
+        offs = dj_offs.cpu().numpy().astype(np.int64)
+        bits = dj_bits.cpu().numpy().astype(np.uint16).reshape(-1, 3)
+        rng = np.random.default_rng(4321 + rank)
+        img = hj_in.numpy()
+        bad = checked = 0
+        for g0 in sorted(int(x) for x in rng.integers(0, ng - run_len, size=runs)):
+            ref = orc.jpeg_encode(img, g0, g0 + run_len, want_coefs=False)
+            got = dj_out[int(offs[g0]):int(offs[g0 + run_len])].cpu().numpy()
+            same = np.array_equal(got, ref["stream"]) and np.array_equal(offs[g0:g0 + run_len + 1] - offs[g0], ref["offsets"].astype(np.int64)) \
+                and np.array_equal(bits[g0:g0 + run_len], np.asarray(ref["bits"]).reshape(-1, 3).astype(np.uint16))
+            checked += run_len
+            bad += 0 if same else run_len
+        return {"checked": checked, "mismatch": int(sum_over_ranks(float(bad))), "unit": "8x8 groups of the timed output vs oracle/jpeg_oracle.c"}
+
+    jp_parity = jpeg_parity_sample() if not args.no_parity_sample else None
+    if world > 1:  # strong scaling (BASELINE configs[3]): ONE image, this rank's 1/N of its group rows
+        gs = ng // world
+
+        def jpeg_step_strong():
+            ljb.jpeg.encode_device(dj_in, W, H, dj_out, dj_offs, dj_bits, dj_res, ctx, first_group=rank * gs, ngroups=gs)
+            with torch.cuda.stream(ext_stream):
+                ljb.sharding.gather_totals_device(dj_res[0:1])
+
+        s_ms, _, _ = timed(jpeg_step_strong, args.steps, args.warmup)
+        strong["jpeg"] = {"value": float(W) * H / (s_ms / args.steps * 1e-3) / 1e6, "unit": "MPix/s", "ms_per_step": s_ms / args.steps,
+                          "config": f"one {W}x{H} image in total, {gs} groups per GPU"}
+    else:
+        strong["jpeg"] = {"value": jp_value, "unit": "MPix/s", "ms_per_step": jp_ms / args.steps, "config": f"one {W}x{H} image on 1 GPU"}
 
     # ------------------------------- JFIF (true baseline JPEG) ------------------------------------------
     del hj_out, dj_out, dj_offs, dj_bits
@@ -433,13 +610,30 @@ def run_gpu(args):
         f_out_bytes = int(df_res[0].item())
         if int(df_res[2].item()):
             raise SystemExit(f"JFIF kernels reported error flags {int(df_res[2].item())}")
-        _, fe2e_wall, _ = timed(jfif_step_e2e, e2e_steps, 1, use_events=False)
+        _, fe2e_wall, _ = timed(jfif_step_e2e, e2e_steps, e2e_warm, use_events=False)
         f_e2e_ms = max_over_ranks(fe2e_wall * 1e3 / e2e_steps)
         assert int(fout_len.value) == f_out_bytes, "host-buffer path and device path disagree on the file length"
         jfif[name] = {"value": total_px / (f_ms / args.steps * 1e-3) / 1e6, "ms_per_step": f_ms / args.steps, "kernel_ms": f_kernel_ms,
                       "out_bytes": f_out_bytes, "e2e_value": total_px / (f_e2e_ms * 1e-3) / 1e6, "e2e_ms": f_e2e_ms,
                       "achieved": (4.0 * W * H + f_out_bytes) / (f_kernel_ms * 1e-3) / 1e9, "launches": f_launches}
 
+    def jfif_parity_sample(sub, rows=64):
+        """A band of the benchmark image encoded alone by the GPU path, byte for byte against the CPU oracle's file (the
+        benchmark file itself is one bit stream whose every unit depends on all units before it)."""
+        from oracle.pyoracle import Oracle
+
+        orc = Oracle()
+        r0 = int(np.random.default_rng(99 + rank).integers(0, H - rows))
+        band = np.ascontiguousarray(hj_in.numpy()[r0:r0 + rows])
+        got = ljb.jfif.write_jpg(band, JFIF_QUALITY, sub, ctx=ctx)
+        ref = orc.jfif_encode(band, JFIF_QUALITY, sub)
+        ref = ref[0] if isinstance(ref, tuple) else ref
+        return {"checked": 1, "mismatch": int(sum_over_ranks(0.0 if np.array_equal(got, ref) else 1.0)),
+                "unit": f"{rows}-row band ({W}x{rows}) of the benchmark image, whole .jpg file vs oracle/jfif_oracle.c"}
+
+    if not args.no_parity_sample:
+        jfif["444"]["parity"] = jfif_parity_sample(0)
+        jfif["420"]["parity"] = jfif_parity_sample(-1)
     clocks = sampler.stop()
 
     # ------------------------------- CPU baseline (rank 0, N = 1 only) ----------------------------------
@@ -450,9 +644,11 @@ def run_gpu(args):
         v, kind, sec = _cpu_lz4(sb, threads)
         cpu_lz = {"value": v, "unit": "GB/s", "cores": threads, "kind": kind,
                   "sample": f"{sb} blocks of 64 KiB of the same seed-42 text, reference block_encode on {threads} threads, {sec:.1f} s"}
+        cpu_lz.update(_cpu_lz4_detail(threads))  # + the sequential build on 1 core, + the parallel build's thread body
         vj, kindj, secj = _cpu_jpeg(4096, 2048, threads)
         cpu_jp = {"value": vj, "unit": "MPix/s", "cores": threads, "kind": kindj,
                   "sample": f"4096x2048 seed-42 noise image, reference per-group encode stages on {threads} threads, {secj:.1f} s"}
+        cpu_jp.update(_cpu_jpeg_detail(threads))
         cpu_jf = {}
         for name, sub in (("444", 0), ("420", -1)):
             vf, kindf, secf = _cpu_jfif(4096, 4096, threads, sub)
@@ -473,8 +669,13 @@ def run_gpu(args):
                          "kernel_ms": lz_kernel_ms, "algorithmic_bytes": n + lz_out_bytes},
             "e2e": {"value": lz_e2e_value, "unit": "GB/s", "h2d_bytes_per_step": n,
                     "d2h_bytes_per_step": lz_out_bytes + 8 * (nblocks + 1) + 24, "ms_per_step": lz_e2e_ms,
-                    "api": "ljb_lz4_compress (host buffers, pinned)"},
-            "gpu_launches": lz_launches + jp_launches + sum(v["launches"] for v in jfif.values()),
+                    "api": "ljb_lz4_compress (host buffers, pinned)", "steps": e2e_steps, "warmup": e2e_warm,
+                    "host_ceiling_gbs": lz_ceiling,
+                    "host_ceiling": "the same bytes as plain pinned cudaMemcpyAsync H2D + D2H at once, all ranks together, best of 3"},
+            "parity_sample": lz_parity,
+            "lz4_decode": decode_obj,
+            "strong_scaling": strong,
+            "gpu_launches": lz_launches + jp_launches + dec_launches + sum(v["launches"] for v in jfif.values()),
             "clocks": clocks,
             "jpeg": {
                 "metric": "JPEG encode MPix/s", "value": jp_value, "unit": "MPix/s", "ms_per_step": jp_ms / args.steps,
@@ -485,7 +686,9 @@ def run_gpu(args):
                              "kernel_ms": jp_kernel_ms, "algorithmic_bytes": 4 * W * H + jp_out_bytes},
                 "e2e": {"value": jp_e2e_value, "unit": "MPix/s", "h2d_bytes_per_step": 4 * W * H,
                         "d2h_bytes_per_step": jp_out_bytes + 8 * (ng + 1) + 24, "ms_per_step": jp_e2e_ms,
-                        "api": "ljb_jpeg_encode_rgba (host buffers, pinned)"},
+                        "api": "ljb_jpeg_encode_rgba (host buffers, pinned)", "steps": e2e_steps, "warmup": e2e_warm,
+                        "host_ceiling_mpix": jp_ceiling},
+                "parity_sample": jp_parity,
             },
         }
         def jfif_obj(name, label):
@@ -500,7 +703,8 @@ def run_gpu(args):
                                  "kernel_ms": v["kernel_ms"], "algorithmic_bytes": 4 * W * H + v["out_bytes"]},
                     "e2e": {"value": v["e2e_value"], "unit": "MPix/s", "h2d_bytes_per_step": 4 * W * H,
                             "d2h_bytes_per_step": v["out_bytes"] + 24, "ms_per_step": v["e2e_ms"],
-                            "api": "ljb_jfif_encode (host buffers, pinned)"}}
+                            "api": "ljb_jfif_encode (host buffers, pinned)", "steps": e2e_steps, "warmup": e2e_warm},
+                    "parity_sample": v.get("parity")}
 
         line["jfif"] = jfif_obj("444", "4:4:4 (BASELINE.json's wording)")
         line["jfif"]["stb_rule_420"] = jfif_obj("420", "4:2:0 (what stbi_write_jpg itself does at quality <= 90)")
@@ -524,6 +728,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity-sample", action="store_true", help="skip the post-run oracle check of sampled output units")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -84,6 +84,8 @@ def build_reference(force: bool = False) -> dict[str, str]:
         "lz4_verbatim": os.path.join(REF_OUT, "libref_lz4_verbatim.so"),
         "jpeg": os.path.join(REF_OUT, "libref_jpeg.so"),
         "jfif": os.path.join(REF_OUT, "libref_jfif.so"),
+        "lz4_par": os.path.join(REF_OUT, "libref_lz4_par.so"),    # the parallel builds (windows.h shim), CPU baselines only
+        "jpeg_par": os.path.join(REF_OUT, "libref_jpeg_par.so"),
     }
     lz4_src = os.path.join(REF, "Algorithms/sequential/LZ4/LZ4.c")
     jpg_dir = os.path.join(REF, "Algorithms/sequential/JPEG")
@@ -123,7 +125,42 @@ def build_reference(force: bool = False) -> dict[str, str]:
             _run(["gcc", *CFLAGS, f'-DREF_STBW="{patched}"', "-o", names["jfif"], glue_jfif, "-lm", "-lpthread"])
         finally:
             shutil.rmtree(tmp, ignore_errors=True)
+    # ---- the parallel builds (Algorithms/parallel/*), against oracle/shim/windows.h: bench.py's "parallel build" CPU baselines
+    plz4_src = os.path.join(REF, "Algorithms/parallel/LZ4/LZ4.c")
+    glue_plz4 = os.path.join(HERE, "ref_glue_lz4_par.c")
+    shim_w = os.path.join(shim, "windows.h")
+    if os.path.exists(plz4_src) and (force or not _newer(names["lz4_par"], [glue_plz4, plz4_src, shim_w, me])):
+        tmp = tempfile.mkdtemp(prefix="ljb_ref_")
+        try:
+            patched = os.path.join(tmp, "LZ4_par_bounded.c")
+            with open(plz4_src, "r", encoding="latin-1") as f:
+                text = f.read()
+            with open(patched, "w", encoding="latin-1") as f:
+                f.write(_patch_bounded_parallel(text))
+            _run(["gcc", *CFLAGS, "-Wl,-Bsymbolic", f"-I{shim}", f'-DREF_SRC="{patched}"', "-o", names["lz4_par"], glue_plz4, "-lpthread"])
+        finally:
+            shutil.rmtree(tmp, ignore_errors=True)
+    pjpg_dir = os.path.join(REF, "Algorithms/parallel/JPEG")
+    pjpg_src = os.path.join(pjpg_dir, "JPEG.c")
+    glue_pjpg = os.path.join(HERE, "ref_glue_jpeg_par.c")
+    if os.path.exists(pjpg_src) and (force or not _newer(names["jpeg_par"], [glue_pjpg, pjpg_src, shim_w, me])):
+        _run(["gcc", *CFLAGS, "-Wl,-Bsymbolic", f"-I{shim}", f"-I{pjpg_dir}", f'-DREF_SRC="{pjpg_src}"', "-o", names["jpeg_par"], glue_pjpg,
+              "-lm", "-lpthread"])
     return {k: v for k, v in names.items() if os.path.exists(v)}
+
+
+def _patch_bounded_parallel(src_text: str) -> str:
+    """The same three edits as _patch_bounded, on the parallel source's spelling of the anchors."""
+    a1 = "uint8_t find_longest_match(uint8_t* input, size_t current_index, uint16_t* match_distance) {"
+    a2 = "while (current_match_length < MAX_MATCH_LENGTH &&"
+    a3 = "    size_t block_length = args->block_length;\n    LZ4Block* block = args->block;"
+    for a in (a1, a2, a3):
+        if src_text.count(a) != 1:
+            raise RuntimeError(f"reference parallel LZ4.c changed: anchor not unique: {a!r}")
+    src_text = src_text.replace(a1, "static __thread size_t g_block_length;\n" + a1)
+    src_text = src_text.replace(a2, a2 + " current_index + current_match_length < g_block_length &&")
+    src_text = src_text.replace(a3, a3 + "\n    g_block_length = block_length;")
+    return src_text
 
 
 def build_all(force: bool = False) -> dict[str, str]:

@@ -263,7 +263,7 @@ class Ref(_LZ4Mixin):
         d = os.path.join(HERE, "_ref")
         return {k: os.path.join(d, f) for k, f in
                 (("lz4", "libref_lz4.so"), ("lz4_verbatim", "libref_lz4_verbatim.so"), ("jpeg", "libref_jpeg.so"),
-                 ("jfif", "libref_jfif.so"))}
+                 ("jfif", "libref_jfif.so"), ("lz4_par", "libref_lz4_par.so"), ("jpeg_par", "libref_jpeg_par.so"))}
 
     @staticmethod
     def available(which: str = "lz4") -> bool:
@@ -272,7 +272,11 @@ class Ref(_LZ4Mixin):
     def __init__(self, which: str = "lz4"):
         self.which = which
         self.lib = C.CDLL(Ref.paths()[which])
-        if which.startswith("lz4"):
+        if which == "lz4_par":    # the reference's parallel build (CPU baseline only)
+            self.lib.ref_lz4par_time_blocks.restype = C.c_int
+        elif which == "jpeg_par":
+            self.lib.ref_jpegpar_time_groups.restype = C.c_int
+        elif which.startswith("lz4"):
             self.lib.ref_lz4_compress.restype = C.c_int
             self.lib.ref_lz4_time_blocks.restype = C.c_int
         elif which == "jfif":
@@ -291,6 +295,24 @@ class Ref(_LZ4Mixin):
         nb = C.c_uint64(0)
         self.lib.ref_lz4_time_blocks(_p(a), C.c_size_t(a.size), C.c_size_t(block_len), C.c_int(nthreads), C.byref(sec), C.byref(nb))
         return sec.value, int(nb.value)
+
+    def lz4par_time_blocks(self, data, block_len: int, nthreads: int):
+        """parallel_block_encode (with its global locks) over a pool of `nthreads` workers; (seconds, sum of block byte sizes)."""
+        a = _as_u8(data)
+        sec = C.c_double(0)
+        nb = C.c_uint64(0)
+        rc = self.lib.ref_lz4par_time_blocks(_p(a), C.c_size_t(a.size), C.c_size_t(block_len), C.c_int(nthreads), C.byref(sec), C.byref(nb))
+        if rc != 0:
+            raise RuntimeError(f"ref_lz4par_time_blocks rc={rc}")
+        return sec.value, int(nb.value)
+
+    def jpegpar_time_groups(self, rgba, nthreads: int):
+        """process() (forward + inverse chain, results discarded as in the reference) over a pool of `nthreads` workers."""
+        a = _check_rgba(rgba)
+        h, w, _ = a.shape
+        sec = C.c_double(0)
+        self.lib.ref_jpegpar_time_groups(_p(a), C.c_int(w), C.c_int(h), C.c_size_t(4 * w), C.c_int(nthreads), C.byref(sec))
+        return sec.value
 
     def jfif_encode(self, px: np.ndarray, quality: int, force_subsample: int = -1) -> np.ndarray:
         """stbi_write_jpg_to_func of the reference's vendored stb_image_write.h on tightly packed pixels."""
