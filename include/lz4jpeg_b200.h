@@ -139,11 +139,30 @@ int ljb_jpeg_encode_rgba_dev(ljb_ctx *ctx, const uint8_t *d_rgba, int w, int h, 
                              size_t ngroups, uint8_t *d_out, size_t out_cap, uint64_t *d_group_offsets,
                              uint16_t *d_group_bits, int16_t *d_coefs, uint64_t *d_result);
 
+/* The entropy half of the inverse chain: decode_huffman (JPEG.c:1009-1033) -> inverse_RLE (JPEG.c:811-842) ->
+ * reverse_zigzag_pattern (JPEG.c:729-764).  The reference decodes while the Huffman tree is still in memory and never
+ * serialises it; here the tree of every (group, channel) is serialised at LJB_JPEG_TREE_BYTES per group:
+ *     luma at +0, Cr at +512, Cb at +768, each:  u8 k | i16 value[k] (leaves, first-appearance order, node ids 0..k-1)
+ *                                                | { u8 left, u8 right }[k-1] (internal nodes k..2k-2 in creation order; root last)
+ *   ljb_jpeg_trees           quantised coefficients (as ljb_jpeg_encode_rgba returns them) -> trees, by the reference's
+ *                            calculate_frequency / build_heap / build_huffman_tree (JPEG.c:864-961)
+ *   ljb_jpeg_entropy_decode  packed stream + group_offsets (relative to `stream`) + group_bits + trees -> coefficients;
+ *                            LJB_E_FORMAT if an offset, a tree or a bit string is malformed
+ * The _dev forms work on device-resident buffers, asynchronously on the context stream; d_result[2] bit1 = malformed;
+ * offs_base is subtracted from every offset (the offsets of a shard are stream-global). */
+#define LJB_JPEG_TREE_BYTES 1024
+int ljb_jpeg_trees(ljb_ctx *ctx, const int16_t *coefs, size_t ngroups, uint8_t *trees);
+int ljb_jpeg_trees_dev(ljb_ctx *ctx, const int16_t *d_coefs, size_t ngroups, uint8_t *d_trees);
+int ljb_jpeg_entropy_decode(ljb_ctx *ctx, const uint8_t *stream, size_t stream_len, const uint64_t *group_offsets,
+                            const uint16_t *group_bits, const uint8_t *trees, size_t ngroups, int16_t *coefs);
+int ljb_jpeg_entropy_decode_dev(ljb_ctx *ctx, const uint8_t *d_stream, size_t stream_len, const uint64_t *d_group_offsets,
+                                const uint16_t *d_group_bits, const uint8_t *d_trees, size_t ngroups, uint64_t offs_base,
+                                int16_t *d_coefs, uint64_t *d_result);
+
 /* Decode half of the reference's main() (JPEG.c:1408-1428): Inverse_quantize (JPEG.c:631) ->
  * inverse_discrete_cosine_transform (JPEG.c:399) -> assemble_image (JPEG.c:552, YCbCr -> RGB), bit-exact.
  *   coefs       128 int16 per group for all ljb_jpeg_group_count(w, h) groups, as ljb_jpeg_encode_rgba returns
- *               them (the reference's Huffman / RLE / zig-zag stages are a loss-free in-memory round trip,
- *               JPEG.c:1253-1403, and its code tables are never serialised: a bit stream alone is not decodable)
+ *               them or as ljb_jpeg_entropy_decode recovers them from the bit stream
  *   orig_rgba   the original image, or NULL.  When w or h is not a multiple of 8 the reference leaves the last
  *               tiled groups unprocessed (JPEG.c:1131) and its reconstructed.png shows their
  *               colour-converted original samples; NULL is an error (LJB_E_ARG) for such sizes.

@@ -14,7 +14,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "liblz4jpeg_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-CU_SOURCES = ["api.cu", "lz4_encode.cu", "lz4_decode.cu", "jpeg_encode.cu", "jpeg_decode.cu", "jfif_encode.cu"]
+CU_SOURCES = ["api.cu", "lz4_encode.cu", "lz4_decode.cu", "jpeg_encode.cu", "jpeg_decode.cu", "jpeg_entropy.cu", "jfif_encode.cu"]
 C_SOURCES = ["synth.c"]
 
 

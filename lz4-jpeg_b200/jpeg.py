@@ -7,6 +7,10 @@ reference stages fused in one kernel                                 here
   zigzag_pattern / RLE                                JPEG.c:693 / :767
   encode_huffman / generate_encoded_sequence          JPEG.c:1035 / :993    process(rgba) -> EncodedImage
 (`process` is the reference's fused per-block function, Algorithms/parallel/JPEG/JPEG.c:1103.)
+inverse chain, entropy half (JPEG.c:1253-1403)
+  decode_huffman / inverse_RLE / reverse_zigzag_pattern   JPEG.c:1009 / :811 / :729
+                                                                            huffman_trees(coefs) -> trees
+                                                                            decode_huffman(enc, trees) -> coefs
 decode half (JPEG.c:1408-1428)
   Inverse_quantize / inverse_discrete_cosine_transform / assemble_image   JPEG.c:631 / :399 / :552
                                                                             assemble_image(coefs, w, h) -> RGBA
@@ -102,4 +106,32 @@ def assemble_image(coefs, w: int, h: int, original=None, ctx: N.Context | None =
     rc = N.lib().ljb_jpeg_decode_coefs(ctx.handle, c.ctypes.data, w, h, o.ctypes.data if o is not None else None, 4 * w,
                                        out.ctypes.data, 4 * w)
     N.check(rc, "ljb_jpeg_decode_coefs")
+    return out
+
+
+TREE_BYTES = 1024  # LJB_JPEG_TREE_BYTES
+
+
+def huffman_trees(coefs, ctx: N.Context | None = None) -> np.ndarray:
+    """The Huffman tree of every (group, channel) — what calculate_frequency / build_heap / build_huffman_tree build
+    (JPEG.c:864-961) and the reference keeps in memory for its decoder — serialised at TREE_BYTES per group."""
+    c = np.ascontiguousarray(coefs, dtype=np.int16).reshape(-1, 128)
+    ctx = ctx or N.default_context()
+    trees = np.zeros((c.shape[0], TREE_BYTES), dtype=np.uint8)
+    N.check(N.lib().ljb_jpeg_trees(ctx.handle, c.ctypes.data, c.shape[0], trees.ctypes.data), "ljb_jpeg_trees")
+    return trees
+
+
+def decode_huffman(enc: EncodedImage, trees, ctx: N.Context | None = None) -> np.ndarray:
+    """decode_huffman -> inverse_RLE -> reverse_zigzag_pattern (JPEG.c:1009, :811, :729) of every group's bit strings:
+    returns the quantised coefficients int16[ngroups, 128] recovered from the packed stream alone (+ trees)."""
+    ctx = ctx or N.default_context()
+    ng = enc.group_offsets.size - 1
+    s = np.ascontiguousarray(enc.stream, dtype=np.uint8)
+    offs = np.ascontiguousarray(enc.group_offsets, dtype=np.uint64)
+    bits = np.ascontiguousarray(enc.group_bits, dtype=np.uint16)
+    t = np.ascontiguousarray(trees, dtype=np.uint8)
+    out = np.zeros((ng, 128), dtype=np.int16)
+    N.check(N.lib().ljb_jpeg_entropy_decode(ctx.handle, s.ctypes.data, s.size, offs.ctypes.data, bits.ctypes.data, t.ctypes.data, ng,
+                                            out.ctypes.data), "ljb_jpeg_entropy_decode")
     return out

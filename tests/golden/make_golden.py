@@ -57,6 +57,30 @@ def lz4_vectors_add_missing() -> None:
         json.dump(vec, f, indent=1, sort_keys=True)
 
 
+def og_full() -> None:
+    """BASELINE.json configs[1] on the image the reference really ships (input.jpg does not exist): the whole
+    Assets/Images/og.png (1200 x 630 RGBA; 630 is not a multiple of 8) through the REFERENCE build.  The image is copied as a
+    fixture; of the results only hashes and sizes are committed."""
+    shutil.copy(f"{REF}/Assets/Images/og.png", f"{HERE}/og.png")
+    rgba = np.asarray(Image.open(f"{HERE}/og.png").convert("RGBA"))
+    rj = Ref("jpeg")
+    r = rj.jpeg_encode(rgba)
+    h, w, _ = rgba.shape
+    rec = rj.jpeg_decode(r["coefs"], w, h, rgba)
+    sha = lambda a: hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+    out = {"width": w, "height": h, "groups": int(r["coefs"].shape[0]), "stream_bytes": int(r["stream"].size),
+           "coefs_sha256": sha(r["coefs"]), "stream_sha256": sha(r["stream"]), "bits_sha256": sha(r["bits"]),
+           "offsets_sha256": sha(r["offsets"]), "reconstructed_sha256": sha(rec), "max_code_len": int(r["max_code_len"])}
+    rf = Ref("jfif")
+    for name, sub in (("444", 0), ("420", -1)):
+        f = rf.jfif_encode(rgba, 75, sub)
+        out[f"jfif_q75_{name}_bytes"] = int(f.size)
+        out[f"jfif_q75_{name}_sha256"] = sha(f)
+    with open(f"{HERE}/og_full_ref.json", "w") as fo:
+        json.dump(out, fo, indent=1, sort_keys=True)
+    print(out)
+
+
 def main() -> None:
     shutil.copy(f"{REF}/Output-Input/input/input.txt", f"{HERE}/lz4_input.txt")
     shutil.copy(f"{REF}/Output-Input/out/compressed.bin", f"{HERE}/lz4_compressed.bin")
@@ -103,5 +127,7 @@ def main() -> None:
 if __name__ == "__main__":
     if "--lz4-add" in sys.argv:
         lz4_vectors_add_missing()
+    elif "--og-full" in sys.argv:
+        og_full()
     else:
         main()
