@@ -47,6 +47,8 @@ JPEG_DIM = int(os.environ.get("LJB_BENCH_JPEG_DIM", 16384))
 NCU_TRAFFIC = {"lz4": 4.94e9 + 6.79e9 if LZ4_BYTES == 4 * GIB else None, "jpeg": 1.087e9 + 0.465e9 if JPEG_DIM == 16384 else None,
                "jfif444": 1.0746e9 + 0.3176e9 if JPEG_DIM == 16384 else None, "jfif420": 1.0740e9 + 0.1446e9 if JPEG_DIM == 16384 else None}
 JFIF_QUALITY = 75
+# frames of 1920x1080 per GPU in the batch object (BASELINE configs[4]: 8192 frames across 8 GPUs); 0 skips it
+BATCH_IMAGES = int(os.environ.get("LJB_BENCH_BATCH_IMAGES", 1024))
 
 
 def measured_peak_gbs():
@@ -634,6 +636,115 @@ def run_gpu(args):
     if not args.no_parity_sample:
         jfif["444"]["parity"] = jfif_parity_sample(0)
         jfif["420"]["parity"] = jfif_parity_sample(-1)
+    # ------------------------------- batch (BASELINE configs[4]) -----------------------------------------
+    # 8192 frames of 1920x1080 across 8 GPUs = 1024 per GPU: batch JPEG encode -> LZ4 compress of the concatenated bit streams ->
+    # LZ4 decompress (the round trip), all device-resident in `value`; `e2e` through the three host-buffer calls.
+    batch_obj = None
+    if BATCH_IMAGES > 0:
+        del df_out, hf_out
+        torch.cuda.empty_cache()
+        bw_, bh_ = 1920, 1080
+        nimg = BATCH_IMAGES
+        G = ljb.jpeg.group_count(bw_, bh_)
+        distinct = min(32, nimg)
+        hb = torch.empty((nimg, bh_, bw_, 4), dtype=torch.uint8, pin_memory=True)
+        hbn = hb.numpy()
+        for i in range(distinct):
+            ljb.synth.random_image(bw_, bh_, seed=42 + 1000 * rank + i, out=hbn[i])
+        for i in range(distinct, nimg):
+            hbn[i] = hbn[i % distinct]
+        db = hb.to(dev)
+        bcap = nimg * G * 64 + 4096
+        dbo = torch.empty(bcap, dtype=torch.uint8, device=dev)
+        dboffs = torch.empty(nimg * G + 1, dtype=torch.int64, device=dev)
+        dbres = torch.zeros(3, dtype=torch.int64, device=dev)
+        ljb.jpeg.encode_batch_device(db, bw_, bh_, nimg, dbo, dboffs, None, dbres, ctx)
+        torch.cuda.synchronize()
+        if int(dbres[2].item()):
+            raise SystemExit(f"batch JPEG kernel reported error flags {int(dbres[2].item())}")
+        jlen = int(dbres[0].item())
+        lnb = (jlen + BLOCK_LEN - 1) // BLOCK_LEN
+        dlz = torch.empty(jlen + jlen // 8 + 16 * lnb + 4096, dtype=torch.uint8, device=dev)
+        dlzo = torch.empty(lnb + 1, dtype=torch.int64, device=dev)
+        dlzr = torch.zeros(3, dtype=torch.int64, device=dev)
+        ljb.lz4.compress_device(dbo[:jlen], BLOCK_LEN, dlz, dlzo, dlzr, ctx)
+        torch.cuda.synchronize()
+        lzlen, lzph = int(dlzr[0].item()), int(dlzr[1].item())
+        dback = torch.empty(lnb * BLOCK_LEN, dtype=torch.uint8, device=dev)
+        dblen = torch.empty(lnb, dtype=torch.int32, device=dev)
+        ddres = torch.zeros(3, dtype=torch.int64, device=dev)
+
+        def batch_step_device():
+            ljb.jpeg.encode_batch_device(db, bw_, bh_, nimg, dbo, dboffs, None, dbres, ctx)
+            ljb.lz4.compress_device(dbo[:jlen], BLOCK_LEN, dlz, dlzo, dlzr, ctx)
+            ljb.lz4.decompress_device(dlz, lzlen, dlzo, lnb, BLOCK_LEN, dback, dblen, ddres, ctx)
+
+        b_ms, _, b_launches = timed(batch_step_device, args.steps, args.warmup)
+        torch.cuda.synchronize()
+        rt_ok = bool(torch.equal(dback[:jlen], dbo[:jlen])) and int(ddres[2].item()) == 0 and int(dbres[0].item()) == jlen
+        if not rt_ok or lzph:
+            raise SystemExit(f"batch: LZ4 round trip of the JPEG bit streams failed (flags {int(ddres[2].item())}, phantom {lzph})")
+        # per-kernel times (events of the library's own stream around each launch)
+        ljb.jpeg.encode_batch_device(db, bw_, bh_, nimg, dbo, dboffs, None, dbres, ctx)
+        bj_ms = ctx.last_kernel_ms()
+        ljb.lz4.compress_device(dbo[:jlen], BLOCK_LEN, dlz, dlzo, dlzr, ctx)
+        bl_ms = ctx.last_kernel_ms()
+        ljb.lz4.decompress_device(dlz, lzlen, dlzo, lnb, BLOCK_LEN, dback, dblen, ddres, ctx)
+        bd_ms = ctx.last_kernel_ms()
+        # parity sample: 600 groups of two random frames of the batch output against the oracle
+        b_par = None
+        if not args.no_parity_sample:
+            from oracle.pyoracle import Oracle
+
+            orc = Oracle()
+            offs_h = dboffs.cpu().numpy().astype(np.int64)
+            bad = 0
+            for im in (int(x) for x in np.random.default_rng(5 + rank).integers(0, nimg, size=2)):
+                ref = orc.jpeg_encode(hbn[im], 12000, 12600, want_coefs=False)
+                got = dbo[int(offs_h[im * G + 12000]):int(offs_h[im * G + 12600])].cpu().numpy()
+                bad += 0 if np.array_equal(got, ref["stream"]) else 600
+            b_par = {"checked": 1200, "mismatch": int(sum_over_ranks(float(bad))), "unit": "8x8 groups of two frames of the batch output vs oracle/jpeg_oracle.c"}
+        del dback, dlz, dbo, dboffs
+        torch.cuda.empty_cache()
+        # end to end: the three host-buffer calls a user of the public API makes
+        hjo = torch.empty(bcap, dtype=torch.uint8, pin_memory=True)
+        hlz = torch.empty(jlen + jlen // 8 + 16 * lnb + 4096, dtype=torch.uint8, pin_memory=True)
+        hlo = torch.empty(lnb + 1, dtype=torch.int64, pin_memory=True)
+        hbk = torch.empty(lnb * BLOCK_LEN, dtype=torch.uint8, pin_memory=True)
+        o1, o2, o3 = C.c_size_t(0), C.c_size_t(0), C.c_size_t(0)
+
+        def batch_step_e2e():
+            N.check(lib.ljb_jpeg_encode_batch(ctx.handle, hb.data_ptr(), bw_, bh_, 4 * bw_, 4 * bw_ * bh_, nimg, hjo.data_ptr(), bcap, None, None,
+                                              C.byref(o1)), "ljb_jpeg_encode_batch")
+            N.check(lib.ljb_lz4_compress(ctx.handle, hjo.data_ptr(), o1.value, BLOCK_LEN, hlz.data_ptr(), hlz.numel(), hlo.data_ptr(),
+                                         C.byref(o2), None), "ljb_lz4_compress")
+            N.check(lib.ljb_lz4_decompress(ctx.handle, hlz.data_ptr(), o2.value, hlo.data_ptr(), lnb, BLOCK_LEN, hbk.data_ptr(), hbk.numel(),
+                                           C.byref(o3)), "ljb_lz4_decompress")
+
+        _, be_wall, _ = timed(batch_step_e2e, e2e_steps, e2e_warm, use_events=False)
+        be_ms = max_over_ranks(be_wall * 1e3 / e2e_steps)
+        assert o1.value == jlen and o3.value == jlen and bool(torch.equal(hbk[:jlen], hjo[:jlen])), "batch e2e round trip"
+        total_img = sum_over_ranks(float(nimg))
+        batch_obj = {
+            "metric": "batched 1080p JPEG encode + LZ4 round trip of the bit streams, frames/s", "value": total_img / (b_ms / args.steps * 1e-3),
+            "unit": "frames/s", "mpix_per_s": total_img * bw_ * bh_ / (b_ms / args.steps * 1e-3) / 1e6, "ms_per_step": b_ms / args.steps,
+            "config": {"workload": f"{nimg} frames of {bw_}x{bh_} random_image-style RGBA per GPU (BASELINE configs[4]: 8192 frames across 8 GPUs = 1024 "
+                                   f"per GPU; {distinct} distinct frames, seed 42 + 1000 rank + index, repeated): ljb_jpeg_encode_batch_dev -> "
+                                   f"ljb_lz4_compress_dev (64 KiB blocks over the concatenated bit streams) -> ljb_lz4_decompress_dev",
+                       "frames_per_gpu": nimg, "jpeg_stream_bytes": jlen, "lz4_stream_bytes": lzlen, "launches_per_step": 3},
+            "round_trip": {"lz4_decompress(lz4_compress(jpeg_streams)) == jpeg_streams": rt_ok},
+            "kernels_ms": {"jpgk::jpeg_encode_kernel": bj_ms, "lz4k::lz4_encode_kernel": bl_ms, "lz4d::lz4_decode_kernel": bd_ms},
+            "roofline": {"bound": "hbm", "achieved": (4.0 * bw_ * bh_ * nimg + jlen) / (bj_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": (4.0 * bw_ * bh_ * nimg + jlen) / (bj_ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                         "kernel": "jpgk::jpeg_encode_kernel (the batch's dominant launch by bytes)", "kernel_ms": bj_ms,
+                         "algorithmic_bytes": 4 * bw_ * bh_ * nimg + jlen},
+            "e2e": {"value": total_img / (be_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": 4 * bw_ * bh_ * nimg + jlen + lzlen + 8 * (lnb + 1),
+                    "d2h_bytes_per_step": jlen + lzlen + 8 * (lnb + 1) + jlen, "ms_per_step": be_ms,
+                    "api": "ljb_jpeg_encode_batch + ljb_lz4_compress + ljb_lz4_decompress (host buffers, pinned)", "steps": e2e_steps, "warmup": e2e_warm},
+            "parity_sample": b_par, "launches": b_launches}
+        del hb, db, hjo, hlz, hbk
+        torch.cuda.empty_cache()
+
     clocks = sampler.stop()
 
     # ------------------------------- CPU baseline (rank 0, N = 1 only) ----------------------------------
@@ -649,6 +760,20 @@ def run_gpu(args):
         cpu_jp = {"value": vj, "unit": "MPix/s", "cores": threads, "kind": kindj,
                   "sample": f"4096x2048 seed-42 noise image, reference per-group encode stages on {threads} threads, {secj:.1f} s"}
         cpu_jp.update(_cpu_jpeg_detail(threads))
+        cpu_batch = None
+        if batch_obj:
+            from oracle.pyoracle import Ref
+
+            if Ref.available("lz4"):
+                noise = np.random.default_rng(42).integers(0, 256, size=max(threads, 16) * BLOCK_LEN, dtype=np.uint8)
+                secn, _ = Ref("lz4").lz4_time_blocks(noise, BLOCK_LEN, threads)
+                lz_rate = noise.size / secn  # bytes/s on near-uniform bytes (what a Huffman bit stream looks like to LZ4)
+                frame_px = 1920 * 1080
+                per_frame = frame_px / (vj * 1e6) + (batch_obj["config"]["jpeg_stream_bytes"] / batch_obj["config"]["frames_per_gpu"]) / lz_rate
+                cpu_batch = {"value": 1.0 / per_frame, "unit": "frames/s", "cores": threads, "kind": "reference",
+                             "sample": f"per frame: the reference's per-group JPEG stages at the {vj:.1f} MPix/s measured above + its block_encode on the "
+                                       f"frame's bit-stream bytes at the rate measured on {max(threads, 16)} blocks of 64 KiB of uniform random bytes "
+                                       f"({lz_rate / 1e6:.3f} MB/s, {secn:.1f} s), {threads} threads; decoding not counted"}
         cpu_jf = {}
         for name, sub in (("444", 0), ("420", -1)):
             vf, kindf, secf = _cpu_jfif(4096, 4096, threads, sub)
@@ -675,7 +800,8 @@ def run_gpu(args):
             "parity_sample": lz_parity,
             "lz4_decode": decode_obj,
             "strong_scaling": strong,
-            "gpu_launches": lz_launches + jp_launches + dec_launches + sum(v["launches"] for v in jfif.values()),
+            "batch": batch_obj,
+            "gpu_launches": lz_launches + jp_launches + dec_launches + sum(v["launches"] for v in jfif.values()) + (batch_obj["launches"] if batch_obj else 0),
             "clocks": clocks,
             "jpeg": {
                 "metric": "JPEG encode MPix/s", "value": jp_value, "unit": "MPix/s", "ms_per_step": jp_ms / args.steps,
@@ -713,6 +839,8 @@ def run_gpu(args):
             line["jpeg"]["cpu_baseline"] = cpu_jp
             line["jfif"]["cpu_baseline"] = cpu_jf["444"]
             line["jfif"]["stb_rule_420"]["cpu_baseline"] = cpu_jf["420"]
+            if batch_obj and cpu_batch:
+                line["batch"]["cpu_baseline"] = cpu_batch
         print(json.dumps(line))
     ctx.close()
     if world > 1:

@@ -373,3 +373,55 @@ void LZ4_decode(char *input_bin_file, char *log)
 }
 
 void parallel_LZ4_decode(char *input_bin_file, char *log) { LZ4_decode(input_bin_file, log); }
+
+/* ---- JPEG: process(), Algorithms/parallel/JPEG/JPEG.c:1103-1252 ------------------------------------ */
+static const double kLumTable[64] = {8,  6,  6,  8,  10, 14, 18, 22, 6,  6,  7,  9,  12, 20, 22, 20, 6,  7,  8,  10, 14, 22,
+                                     25, 22, 8,  9,  10, 14, 18, 28, 27, 22, 10, 12, 14, 18, 22, 35, 33, 26, 14, 18, 22, 22,
+                                     27, 33, 36, 30, 18, 22, 26, 28, 33, 40, 40, 34, 22, 26, 28, 30, 36, 34, 35, 33}; /* JPEG.c:12-20 */
+static const double kChrTable[32] = {17, 18, 24, 47, 18, 21, 26, 66, 24, 26, 56, 99, 47, 66, 99, 99,
+                                     66, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99}; /* JPEG.c:22-27 */
+
+int ljb_process_groups(PixelGroup *groups, size_t n)
+{
+    if (!groups || n == 0) return LJB_E_ARG;
+    uint8_t *samples = malloc(n * 128);
+    int16_t *coefs = malloc(n * 128 * sizeof(int16_t));
+    if (!samples || !coefs) {
+        perror("malloc");
+        exit(EXIT_FAILURE);
+    }
+    for (size_t i = 0; i < n; i++) {
+        memcpy(samples + i * 128, groups[i].lum_values, 64);
+        memcpy(samples + i * 128 + 64, groups[i].b_values, 32);
+        memcpy(samples + i * 128 + 96, groups[i].r_values, 32);
+    }
+    int rc = ljb_jpeg_process_groups(ctx(), samples, n, coefs);
+    if (rc != LJB_OK) die(rc, "ljb_jpeg_process_groups");
+    for (size_t i = 0; i < n; i++) {
+        PixelGroup *g = &groups[i];
+        memcpy(g->lum_values, samples + i * 128, 64);
+        memcpy(g->b_values, samples + i * 128 + 64, 32);
+        memcpy(g->r_values, samples + i * 128 + 96, 32);
+        /* the reference leaves the DEQUANTISED coefficients in the arrays discrete_cosine_transform malloc'd (JPEG.c:453, Inverse_quantize
+         * P-JPG:1243-1245); the RLE arrays are never read after process() and are left untouched */
+        g->lum_coefficients = malloc(sizeof(double) * 64);
+        g->r_coefficients = malloc(sizeof(double) * 32);
+        g->b_coefficients = malloc(sizeof(double) * 32);
+        const int16_t *c = coefs + i * 128;
+        for (int k = 0; k < 64; k++) g->lum_coefficients[k] = (double)c[k] * kLumTable[k];
+        for (int k = 0; k < 32; k++) {
+            g->r_coefficients[k] = (double)c[64 + k] * kChrTable[k];
+            g->b_coefficients[k] = (double)c[96 + k] * kChrTable[k];
+        }
+    }
+    free(samples);
+    free(coefs);
+    return 0;
+}
+
+void *process(void *lpParam)
+{
+    parallel_args *args = (parallel_args *)lpParam;
+    ljb_process_groups(&args->block, 1);
+    return NULL;
+}

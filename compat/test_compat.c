@@ -6,6 +6,9 @@
  *   test_compat match   <input> <block_len>             find_longest_match() at every position of the first block against the
  *                                                        exhaustive scan of LZ4.c:290-323 (bounded at the block end); prints mismatches
  *   test_compat files                                    lz4_encode() + LZ4_decode() on the reference's fixed relative paths
+ *   test_compat process <samples.bin> <out.bin>          process() (Algorithms/parallel/JPEG/JPEG.c:1103) on every 128-byte group of the
+ *                                                        file (lum 64 | b 32 | r 32); writes per group the 128 reconstructed samples and
+ *                                                        the 128 dequantised coefficients (doubles: lum 64 | r 32 | b 32)
  */
 #include <stdio.h>
 #include <stdlib.h>
@@ -37,6 +40,32 @@ int main(int argc, char **argv)
         if (c) fclose(c);
         lz4_encode();
         LZ4_decode("../Output-Input/out/compressed.bin", "../Output-Input/log/encoding_log.txt");
+        return 0;
+    }
+    if (argc >= 4 && strcmp(argv[1], "process") == 0) {
+        size_t n = 0;
+        uint8_t *smp = read_all(argv[2], &n);
+        FILE *out = fopen(argv[3], "wb");
+        if (!out) return 2;
+        for (size_t g = 0; g < n / 128; ++g) {
+            parallel_args *args = malloc(sizeof(parallel_args)); /* as the reference's main() prepares them, P-JPG:1299-1300 */
+            memset(args, 0, sizeof *args);
+            memcpy(args->block.lum_values, smp + g * 128, 64);
+            memcpy(args->block.b_values, smp + g * 128 + 64, 32);
+            memcpy(args->block.r_values, smp + g * 128 + 96, 32);
+            process(args);
+            fwrite(args->block.lum_values, 1, 64, out);
+            fwrite(args->block.b_values, 1, 32, out);
+            fwrite(args->block.r_values, 1, 32, out);
+            fwrite(args->block.lum_coefficients, sizeof(double), 64, out);
+            fwrite(args->block.r_coefficients, sizeof(double), 32, out);
+            fwrite(args->block.b_coefficients, sizeof(double), 32, out);
+            free(args->block.lum_coefficients);
+            free(args->block.r_coefficients);
+            free(args->block.b_coefficients);
+            free(args);
+        }
+        fclose(out);
         return 0;
     }
     if (argc < 4) return 2;

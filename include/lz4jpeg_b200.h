@@ -3,7 +3,7 @@
  *
  * Drop-in boundary for the two per-block hot paths of CyrilMorel42/LZ4-JPEG.  The reference has no
  * library boundary of its own: each codec is one C file with a main(), and the timing harnesses
- * (Experiment/*_experiment.c) popen() an executable.  The functions below are the buffer-level
+ * (Experiment/LZ4_*_experiment.c, JPEG_*_experiment.c) popen() an executable.  The functions below are the buffer-level
  * operations those programs are made of; each cites the reference interface it replaces.  Host code
  * stays plain C: include this header, link liblz4jpeg_b200.so (INTEGRATION.md shows the exact edits).
  *
@@ -138,6 +138,28 @@ int ljb_jpeg_encode_rgba(ljb_ctx *ctx, const uint8_t *rgba, int w, int h, size_t
 int ljb_jpeg_encode_rgba_dev(ljb_ctx *ctx, const uint8_t *d_rgba, int w, int h, size_t stride, size_t first_group,
                              size_t ngroups, uint8_t *d_out, size_t out_cap, uint64_t *d_group_offsets,
                              uint16_t *d_group_bits, int16_t *d_coefs, uint64_t *d_result);
+
+/* Batch of nimages equal-sized images (BASELINE.json configs[4]: 8192 x 1920x1080): ONE launch, one ticket counter, one
+ * look-back for the whole batch — the per-image loop of the reference's harness (Experiment/JPEG_sequential_experiment.c:57-144)
+ * costs a launch, a memset and a synchronisation per image, which dominates a 50 us frame.
+ *   image i lies at rgba + i * image_stride and holds groups [i*G, (i+1)*G), G = ljb_jpeg_group_count(w, h);
+ *   group_offsets has nimages*G + 1 entries, group_bits 3 per group; image i's stream is
+ *   out[group_offsets[i*G], group_offsets[(i+1)*G]) — byte for byte what ljb_jpeg_encode_rgba gives for that image alone. */
+int ljb_jpeg_encode_batch(ljb_ctx *ctx, const uint8_t *rgba, int w, int h, size_t stride, size_t image_stride, size_t nimages,
+                          uint8_t *out, size_t out_cap, uint64_t *group_offsets, uint16_t *group_bits, size_t *out_len);
+int ljb_jpeg_encode_batch_dev(ljb_ctx *ctx, const uint8_t *d_rgba, int w, int h, size_t stride, size_t image_stride, size_t nimages,
+                              uint8_t *d_out, size_t out_cap, uint64_t *d_group_offsets, uint16_t *d_group_bits, int16_t *d_coefs,
+                              uint64_t *d_result);
+
+/* process() of the reference's parallel build (Algorithms/parallel/JPEG/JPEG.c:1103-1252) on groups given by their samples
+ * (PixelGroup, JPEG.c:42-46: lum_values[64], b_values[32], r_values[32] = 128 bytes per group):
+ *   ljb_jpeg_encode_groups_dev   the forward chain from the DCT on (device buffers; outputs as ljb_jpeg_encode_rgba_dev)
+ *   ljb_jpeg_decode_groups_dev   Inverse_quantize + inverse DCT of given coefficients -> samples in the same 128-byte layout
+ *   ljb_jpeg_process_groups      both, host buffers: samples in -> reconstructed samples out, plus the quantised coefficients */
+int ljb_jpeg_encode_groups_dev(ljb_ctx *ctx, const uint8_t *d_samples, size_t ngroups, uint8_t *d_out, size_t out_cap,
+                               uint64_t *d_group_offsets, uint16_t *d_group_bits, int16_t *d_coefs, uint64_t *d_result);
+int ljb_jpeg_decode_groups_dev(ljb_ctx *ctx, const int16_t *d_coefs, size_t ngroups, uint8_t *d_samples, uint64_t *d_result);
+int ljb_jpeg_process_groups(ljb_ctx *ctx, uint8_t *samples, size_t ngroups, int16_t *coefs);
 
 /* The entropy half of the inverse chain: decode_huffman (JPEG.c:1009-1033) -> inverse_RLE (JPEG.c:811-842) ->
  * reverse_zigzag_pattern (JPEG.c:729-764).  The reference decodes while the Huffman tree is still in memory and never

@@ -35,8 +35,10 @@ struct Params {
     size_t tiled;         // ceil(w/8) * ceil(h/8)
     const uint8_t *orig;  // original RGBA (only read for groups >= total); may be null
     size_t orig_stride;
-    uint8_t *out;
+    uint8_t *out;         // RGBA image, or null when only the samples are wanted
     size_t out_stride;
+    uint8_t *samples;     // optional: the reconstructed samples of every group in PixelGroup order (JPEG.c:44-46):
+                          // lum_values[64], b_values[32], r_values[32] — what process() leaves in its argument (P-JPG:1247-1251)
     uint64_t *result;     // [2] error flags: bit0 = unprocessed groups exist but no original was given
 };
 
@@ -134,6 +136,17 @@ __global__ void __launch_bounds__(THREADS) jpeg_decode_kernel(Params P)
             }
         }
     }
+    if (P.samples) {
+        uint8_t *sp = P.samples + g * 128;
+#pragma unroll
+        for (int lc = 0; lc < 8; ++lc) sp[x * 8 + lc] = (uint8_t)Y[lc];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            sp[64 + x * 4 + c] = (uint8_t)Cb[c];
+            sp[96 + x * 4 + c] = (uint8_t)Cr[c];
+        }
+    }
+    if (!P.out) return;
     // assemble_image, JPEG.c:552-619
 #pragma unroll
     for (int lc = 0; lc < 8; ++lc) {
@@ -172,6 +185,7 @@ extern "C" int ljb_jpeg_decode_coefs_dev(ljb_ctx *ctx, const int16_t *d_coefs, i
     P.orig_stride = orig_stride;
     P.out = d_out_rgba;
     P.out_stride = out_stride;
+    P.samples = nullptr;
     P.result = d_result;
     LJB_CUDA(cudaMemsetAsync(d_result, 0, 3 * sizeof(uint64_t), ctx->stream));
     const unsigned grid = (unsigned)((P.tiled + GROUPS - 1) / GROUPS);
@@ -208,5 +222,68 @@ extern "C" int ljb_jpeg_decode_coefs(ljb_ctx *ctx, const int16_t *coefs, int w, 
     LJB_CUDA(cudaMemcpy2DAsync(out_rgba, out_stride, ctx->d_pout[0], dstride, dstride, (size_t)h, cudaMemcpyDeviceToHost, ctx->stream));
     LJB_CUDA(cudaStreamSynchronize(ctx->stream));
     if (res[2] & 1) return LJB_E_ARG; // unprocessed groups exist (w or h not a multiple of 8) and no original image was given
+    return LJB_OK;
+}
+
+// The inverse chain of process() (Algorithms/parallel/JPEG/JPEG.c:1242-1251) for groups given by their quantised coefficients:
+// Inverse_quantize -> inverse_discrete_cosine_transform of the three channels, samples in PixelGroup order (128 bytes per group).
+extern "C" int ljb_jpeg_decode_groups_dev(ljb_ctx *ctx, const int16_t *d_coefs, size_t ngroups, uint8_t *d_samples, uint64_t *d_result)
+{
+    using namespace jpgd;
+    if (!ctx || !d_coefs || !d_samples || !d_result || ngroups == 0 || ngroups > 0x0FFFFFFFull) return LJB_E_ARG;
+    LJB_CUDA(cudaSetDevice(ctx->device));
+    Params P;
+    P.coefs = d_coefs;
+    P.w = 8; // a column of groups
+    P.h = (int)(8 * ngroups);
+    P.total = ngroups;
+    P.tiled = ngroups;
+    P.orig = nullptr;
+    P.orig_stride = 0;
+    P.out = nullptr;
+    P.out_stride = 0;
+    P.samples = d_samples;
+    P.result = d_result;
+    LJB_CUDA(cudaMemsetAsync(d_result, 0, 3 * sizeof(uint64_t), ctx->stream));
+    const unsigned grid = (unsigned)((ngroups + GROUPS - 1) / GROUPS);
+    ctx->kernel_ms_summed = 0;
+    LJB_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+    jpeg_decode_kernel<<<grid, THREADS, 0, ctx->stream>>>(P);
+    LJB_CUDA(cudaGetLastError());
+    LJB_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+    ctx->launches += 1;
+    return LJB_OK;
+}
+
+// process() for n groups at once, host buffers: forward chain (DCT, Quantize, zig-zag, RLE, Huffman: the packed strings are
+// produced and dropped, as the reference's are), then the inverse chain.  samples: in = the groups' lum/b/r values, out = what
+// the reference leaves in them; coefs: out, the quantised coefficients (128 int16 per group).
+extern "C" int ljb_jpeg_process_groups(ljb_ctx *ctx, uint8_t *samples, size_t ngroups, int16_t *coefs)
+{
+    if (!ctx || !samples || !coefs || ngroups == 0 || ngroups > 0x0FFFFFFFull) return LJB_E_ARG;
+    LJB_CUDA(cudaSetDevice(ctx->device));
+    int rc;
+    const size_t cap = ljb_jpeg_bound(ngroups);
+    const size_t o_offs = (cap + 255) & ~(size_t)255;
+    const size_t o_bits = o_offs + (((ngroups + 1) * 8 + 255) & ~(size_t)255);
+    const size_t o_coef = o_bits + ((ngroups * 6 + 255) & ~(size_t)255);
+    const size_t o_res = o_coef + ngroups * 256;
+    if ((rc = ljb_ensure(&ctx->d_pin[0], &ctx->pin_bytes[0], ngroups * 128 + 64)) != 0) return rc;
+    if ((rc = ljb_ensure(&ctx->d_pout[0], &ctx->pout_bytes[0], o_res + 64)) != 0) return rc;
+    uint8_t *d_s = (uint8_t *)ctx->d_pin[0], *d = (uint8_t *)ctx->d_pout[0];
+    uint64_t *d_res = (uint64_t *)(d + o_res);
+    LJB_CUDA(cudaMemcpyAsync(d_s, samples, ngroups * 128, cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = ljb_jpeg_encode_groups_dev(ctx, d_s, ngroups, d, cap, (uint64_t *)(d + o_offs), (uint16_t *)(d + o_bits), (int16_t *)(d + o_coef),
+                                         d_res)) != 0)
+        return rc;
+    uint64_t res[3];
+    LJB_CUDA(cudaMemcpyAsync(res, d_res, sizeof res, cudaMemcpyDeviceToHost, ctx->stream));
+    LJB_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (res[2] & 2) return LJB_E_UNSUPPORTED;
+    if (res[2] & 1) return LJB_E_CAPACITY;
+    if ((rc = ljb_jpeg_decode_groups_dev(ctx, (const int16_t *)(d + o_coef), ngroups, d_s, d_res)) != 0) return rc;
+    LJB_CUDA(cudaMemcpyAsync(coefs, d + o_coef, ngroups * 256, cudaMemcpyDeviceToHost, ctx->stream));
+    LJB_CUDA(cudaMemcpyAsync(samples, d_s, ngroups * 128, cudaMemcpyDeviceToHost, ctx->stream));
+    LJB_CUDA(cudaStreamSynchronize(ctx->stream));
     return LJB_OK;
 }

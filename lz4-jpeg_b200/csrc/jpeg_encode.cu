@@ -33,6 +33,8 @@
 // a code longer than 26 bits) are redone by a general per-thread routine on local-memory arrays.
 #include "common.cuh"
 
+#include <vector>
+
 #include <stdlib.h>
 
 namespace jpgk {
@@ -76,6 +78,10 @@ struct Params {
     uint32_t ntiles;
     uint64_t offs_bias;      // added to every group_offsets entry (base of this shard in a larger stream)
     int force_slow;          // test hook: route every channel through the general routine
+    uint32_t img_groups;     // batch: groups per image (0 = one image); group g belongs to image g / img_groups
+    size_t img_stride;       // batch: bytes between consecutive images
+    const uint8_t *planar;   // or: the samples of every group as the reference's PixelGroup holds them (JPEG.c:42-46):
+                             // lum_values[64], b_values[32], r_values[32] = 128 bytes per group; rgba is then unused
 };
 
 // JPEG.c:12-27 as doubles (the chroma table is consumed as 8 rows x 4 columns)
@@ -325,12 +331,15 @@ struct BitWriter {
 // ---- general routine (local-memory arrays): any values, any number of symbols -------------------------------
 // Recomputes the channel from the pixels.  Follows JPEG.c:864-1007 literally (linear-search symbol table).
 __device__ __noinline__ int slow_channel(const uint8_t *rgba, int w, int h, size_t stride, size_t g, int ch, int16_t *co,
-                                         BitWriter *bwp, int max_bits, int *bad)
+                                         BitWriter *bwp, int max_bits, int *bad, const uint8_t *planar_group)
 {
     const int W = ch == 0 ? 8 : 4, N = 8 * W;
     uint8_t smp[64];
     int16_t z[64];
-    {
+    if (planar_group) {
+        const uint8_t *src = planar_group + (ch == 0 ? 0 : (ch == 1 ? 96 : 64)); // lum | b | r (JPEG.c:44-46); channel 1 is Cr
+        for (int i = 0; i < N; ++i) smp[i] = src[i];
+    } else {
         const size_t bpr = ((size_t)w + 7) / 8;
         const size_t brow = g / bpr, bcol = g % bpr;
         for (int lr = 0; lr < 8; ++lr)
@@ -669,7 +678,7 @@ __global__ void __launch_bounds__(THREADS, 1) jpeg_encode_kernel(Params P)
     // their DCT (fp64 pipe), Huffman (integer / shared memory) and copy-out (L2 latency) phases overlap
     uint32_t *stage2 = P.scratch + ((size_t)blockIdx.x * NWARPS + warp) * (2 * REC_WORDS * 32) + lane; // two staging buffers
     const size_t bpr = ((size_t)P.w + 7) / 8;
-    const bool aligned = ((reinterpret_cast<uintptr_t>(P.rgba) | P.stride) & 15) == 0;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(P.rgba) | P.stride | P.img_stride) & 15) == 0;
     // the tile computed in the previous iteration: its records wait in the other staging buffer until its offset
     // is fetched, one tile later, when its predecessors have (almost always) published theirs
     bool pend = false;
@@ -688,13 +697,29 @@ __global__ void __launch_bounds__(THREADS, 1) jpeg_encode_kernel(Params P)
         unsigned int rec_bytes = 0;
         int bl = 0, br = 0, bb = 0;
         if (active) {
-            const size_t g = P.first_group + gl;
+            size_t g = P.first_group + gl;
+            const uint8_t *img = P.rgba;
+            if (P.img_groups) { // batch: image g / img_groups, group g % img_groups of it
+                const uint32_t im = (uint32_t)g / P.img_groups;
+                g -= (size_t)im * P.img_groups;
+                img += (size_t)im * P.img_stride;
+            }
+            const uint8_t *const pgroup = P.planar ? P.planar + (P.first_group + gl) * 128 : nullptr;
             const size_t brow = g / bpr, bcol = g % bpr;
             const size_t col0 = bcol * 8;
             // ---- colour conversion + 4:2:2 point subsampling + tiling -> samples u8[64 | 32 | 32]
             const bool full = brow * 8 + 8 <= (size_t)P.h && col0 + 8 <= (size_t)P.w;
-            if (full && aligned) {
-                const uint8_t *rp = P.rgba + brow * 8 * P.stride + col0 * 4;
+            if (pgroup) { // the samples are given (PixelGroup order lum | b | r): no colour conversion, no tiling
+                const uint32_t *src = reinterpret_cast<const uint32_t *>(pgroup);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) ws_w(wl, W_SMP + i) = src[i];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    ws_w(wl, W_SMP + 16 + i) = src[24 + i]; // r_values
+                    ws_w(wl, W_SMP + 24 + i) = src[16 + i]; // b_values
+                }
+            } else if (full && aligned) {
+                const uint8_t *rp = img + brow * 8 * P.stride + col0 * 4;
                 uint4 na = __ldcs(reinterpret_cast<const uint4 *>(rp)), nb = __ldcs(reinterpret_cast<const uint4 *>(rp) + 1); // streamed once
 #pragma unroll 1
                 for (int lr = 0; lr < 8; ++lr) {
@@ -730,7 +755,7 @@ __global__ void __launch_bounds__(THREADS, 1) jpeg_encode_kernel(Params P)
 #pragma unroll 1
                     for (int lc = 0; lc < 8; ++lc) {
                         if (row < (size_t)P.h && col0 + lc < (size_t)P.w) {
-                            const uint8_t *q = P.rgba + row * P.stride + (col0 + lc) * 4;
+                            const uint8_t *q = img + row * P.stride + (col0 + lc) * 4;
                             const int r = q[0], gg = q[1], bq = q[2];
                             const uint32_t y = (uint32_t)luma_of(r, gg, bq);
                             if (lc < 4) y0 |= y << (8 * lc);
@@ -777,7 +802,7 @@ __global__ void __launch_bounds__(THREADS, 1) jpeg_encode_kernel(Params P)
                 if (!((widemask >> ch) & 1u)) bits = entropy_fast(wl, (uint32_t)ch + 1u, cz, ch == 0 ? 0 : 2 + 2 * ch, ch == 0 ? 4 : 2, bw);
                 if (bits < 0) {
                     BitWriter tmp = bw;
-                    bits = slow_channel(P.rgba, P.w, P.h, P.stride, g, ch, nullptr, &tmp, max_bits, &bad);
+                    bits = slow_channel(img, P.w, P.h, P.stride, g, ch, nullptr, &tmp, max_bits, &bad, pgroup);
                     bw = tmp;
                 } else if (bits > max_bits) {
                     bad = 1; // char encoded_sequence[1024] / [512] (JPEG.c:1248, :1286)
@@ -878,15 +903,27 @@ extern "C" size_t ljb_jpeg_group_count(int w, int h)
 
 extern "C" size_t ljb_jpeg_bound(size_t ngroups) { return ngroups * (size_t)jpgk::REC_BYTES + 64; }
 
+struct BatchMode {
+    size_t nimages = 0, img_stride = 0; // nimages > 0: groups [0, nimages * group_count(w, h)) of a batch of equal-sized images
+    const uint8_t *planar = nullptr;    // samples given per group (128 bytes each): w, h, stride and d_rgba are not used
+};
 static int jpeg_launch(ljb_ctx *ctx, const uint8_t *d_rgba, int w, int h, size_t stride, size_t first_group, size_t ngroups,
                        uint8_t *d_out, size_t out_cap, uint64_t *d_group_offsets, uint16_t *d_group_bits, int16_t *d_coefs,
-                       uint64_t *d_result, uint64_t offs_bias)
+                       uint64_t *d_result, uint64_t offs_bias, const BatchMode &bm = BatchMode())
 {
     using namespace jpgk;
-    if (!ctx || !d_rgba || !d_out || !d_group_offsets || !d_result || w <= 0 || h <= 0 || (w & 1) || stride < (size_t)w * 4)
+    if (!ctx || !d_out || !d_group_offsets || !d_result) return LJB_E_ARG;
+    if (bm.planar) { // samples given: the "image" is a column of groups
+        w = 8;
+        h = 8;
+        stride = 32;
+    } else if (!d_rgba || w <= 0 || h <= 0 || (w & 1) || stride < (size_t)w * 4) {
         return LJB_E_ARG; // odd widths make the reference read past its subsampled rows (JPEG.c:543 with :314)
-    const size_t total = ljb_jpeg_group_count(w, h);
-    if (ngroups == 0 || first_group + ngroups > total) return LJB_E_ARG;
+    }
+    const size_t per_image = ljb_jpeg_group_count(w, h);
+    const size_t total = bm.planar ? ngroups : (bm.nimages ? bm.nimages * per_image : per_image);
+    if (ngroups == 0 || first_group + ngroups > total || total > 0xFFFFFFFFull) return LJB_E_ARG;
+    if (bm.nimages && bm.img_stride < stride * (size_t)h) return LJB_E_ARG;
     LJB_CUDA(cudaSetDevice(ctx->device));
     const size_t ntiles = (ngroups + 31) / 32;
     if (ntiles > 0x7fffffffull) return LJB_E_ARG;
@@ -915,6 +952,9 @@ static int jpeg_launch(ljb_ctx *ctx, const uint8_t *d_rgba, int w, int h, size_t
     P.ntiles = (uint32_t)ntiles;
     P.offs_bias = offs_bias;
     P.force_slow = getenv("LJB_JPEG_FORCE_SLOW") ? 1 : 0; // test hook
+    P.img_groups = bm.nimages ? (uint32_t)per_image : 0u;
+    P.img_stride = bm.nimages ? bm.img_stride : 0;
+    P.planar = bm.planar;
     if (!(ctx->attr_mask & LJB_ATTR_JPEG)) { // per device (context), not per process
         LJB_CUDA(cudaFuncSetAttribute(jpeg_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
         ctx->attr_mask |= LJB_ATTR_JPEG;
@@ -934,6 +974,31 @@ extern "C" int ljb_jpeg_encode_rgba_dev(ljb_ctx *ctx, const uint8_t *d_rgba, int
 {
     return jpeg_launch(ctx, d_rgba, w, h, stride, first_group, ngroups, d_out, out_cap, d_group_offsets, d_group_bits, d_coefs,
                        d_result, 0);
+}
+
+// Batch of equal-sized images in ONE launch (one ticket counter, one look-back): image i holds groups
+// [i * G, (i + 1) * G) of the numbering, G = ljb_jpeg_group_count(w, h); its stream is out[group_offsets[i*G], group_offsets[(i+1)*G]).
+extern "C" int ljb_jpeg_encode_batch_dev(ljb_ctx *ctx, const uint8_t *d_rgba, int w, int h, size_t stride, size_t image_stride, size_t nimages,
+                                         uint8_t *d_out, size_t out_cap, uint64_t *d_group_offsets, uint16_t *d_group_bits, int16_t *d_coefs,
+                                         uint64_t *d_result)
+{
+    if (nimages == 0) return LJB_E_ARG;
+    BatchMode bm;
+    bm.nimages = nimages;
+    bm.img_stride = image_stride;
+    return jpeg_launch(ctx, d_rgba, w, h, stride, 0, nimages * ljb_jpeg_group_count(w, h), d_out, out_cap, d_group_offsets, d_group_bits,
+                       d_coefs, d_result, 0, bm);
+}
+
+// Groups given by their samples, as the reference's process() receives them (PixelGroup, JPEG.c:42-46: lum_values[64],
+// b_values[32], r_values[32] = 128 bytes per group): everything from the DCT on.
+extern "C" int ljb_jpeg_encode_groups_dev(ljb_ctx *ctx, const uint8_t *d_samples, size_t ngroups, uint8_t *d_out, size_t out_cap,
+                                          uint64_t *d_group_offsets, uint16_t *d_group_bits, int16_t *d_coefs, uint64_t *d_result)
+{
+    if (!d_samples || (reinterpret_cast<uintptr_t>(d_samples) & 3)) return LJB_E_ARG;
+    BatchMode bm;
+    bm.planar = d_samples;
+    return jpeg_launch(ctx, nullptr, 8, 8, 32, 0, ngroups, d_out, out_cap, d_group_offsets, d_group_bits, d_coefs, d_result, 0, bm);
 }
 
 // Host-buffer entry point: bands of whole group rows go through a three-stream pipeline (upload of band k+1 and
@@ -1052,4 +1117,34 @@ done:
     if (out_len) *out_len = running;
     if (status == LJB_OK && unsupported) return LJB_E_UNSUPPORTED;
     return status;
+}
+
+// Host-buffer batch: equal-sized images stored one after the other.  Images whose sides are multiples of 8 and that lie back to
+// back are, group for group, one tall image (8 | h: no group straddles two images; ceil(w*h/64) == tiles): they go through the
+// pipelined single-image path in one call.  Anything else is encoded image by image and the offsets are rebased.
+extern "C" int ljb_jpeg_encode_batch(ljb_ctx *ctx, const uint8_t *rgba, int w, int h, size_t stride, size_t image_stride, size_t nimages,
+                                     uint8_t *out, size_t out_cap, uint64_t *group_offsets, uint16_t *group_bits, size_t *out_len)
+{
+    if (!ctx || !rgba || !out || w <= 0 || h <= 0 || (w & 1) || nimages == 0 || stride < (size_t)w * 4 || image_stride < stride * (size_t)h)
+        return LJB_E_ARG;
+    const size_t G = ljb_jpeg_group_count(w, h);
+    if ((w % 8) == 0 && (h % 8) == 0 && image_stride == stride * (size_t)h && (size_t)h * nimages <= 0x7FFFFFFFull)
+        return ljb_jpeg_encode_rgba(ctx, rgba, w, (int)((size_t)h * nimages), stride, 0, G * nimages, out, out_cap, group_offsets, group_bits,
+                                    nullptr, out_len);
+    size_t running = 0;
+    std::vector<uint64_t> offs(G + 1);
+    for (size_t i = 0; i < nimages; ++i) {
+        size_t len = 0;
+        const int rc = ljb_jpeg_encode_rgba(ctx, rgba + i * image_stride, w, h, stride, 0, G, out + running, out_cap - running,
+                                            group_offsets ? offs.data() : nullptr, group_bits ? group_bits + 3 * i * G : nullptr, nullptr, &len);
+        if (rc != LJB_OK) {
+            if (out_len) *out_len = running + len;
+            return rc;
+        }
+        if (group_offsets)
+            for (size_t k = 0; k <= G; ++k) group_offsets[i * G + k] = offs[k] + running;
+        running += len;
+    }
+    if (out_len) *out_len = running;
+    return LJB_OK;
 }

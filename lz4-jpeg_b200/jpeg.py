@@ -135,3 +135,40 @@ def decode_huffman(enc: EncodedImage, trees, ctx: N.Context | None = None) -> np
     N.check(N.lib().ljb_jpeg_entropy_decode(ctx.handle, s.ctypes.data, s.size, offs.ctypes.data, bits.ctypes.data, t.ctypes.data, ng,
                                             out.ctypes.data), "ljb_jpeg_entropy_decode")
     return out
+
+
+def process_batch(images, ctx: N.Context | None = None) -> EncodedImage:
+    """N equal-sized images (N x H x W x 4 uint8) in one call (ljb_jpeg_encode_batch): image i holds groups [i*G, (i+1)*G)."""
+    a = np.ascontiguousarray(images, dtype=np.uint8)
+    if a.ndim != 4 or a.shape[3] != 4:
+        raise ValueError("expect an N x H x W x 4 uint8 array")
+    n, h, w, _ = a.shape
+    ctx = ctx or N.default_context()
+    G = group_count(w, h)
+    cap = int(N.lib().ljb_jpeg_bound(n * G))
+    out = np.empty(cap, dtype=np.uint8)
+    offs = np.zeros(n * G + 1, dtype=np.uint64)
+    bits = np.zeros((n * G, 3), dtype=np.uint16)
+    out_len = C.c_size_t(0)
+    rc = N.lib().ljb_jpeg_encode_batch(ctx.handle, a.ctypes.data, w, h, 4 * w, 4 * w * h, n, out.ctypes.data, cap, offs.ctypes.data,
+                                       bits.ctypes.data, C.byref(out_len))
+    N.check(rc, "ljb_jpeg_encode_batch")
+    return EncodedImage(out[: out_len.value].copy(), offs, bits, None, w, h, 0)
+
+
+def encode_batch_device(d_rgba, w: int, h: int, nimages: int, d_out, d_group_offsets, d_group_bits, d_result, ctx: N.Context) -> None:
+    """Asynchronous on ctx.stream: nimages back-to-back images in one launch (ljb_jpeg_encode_batch_dev)."""
+    rc = N.lib().ljb_jpeg_encode_batch_dev(ctx.handle, d_rgba.data_ptr(), w, h, 4 * w, 4 * w * h, nimages, d_out.data_ptr(), d_out.numel(),
+                                           d_group_offsets.data_ptr(), d_group_bits.data_ptr() if d_group_bits is not None else None, None,
+                                           d_result.data_ptr())
+    N.check(rc, "ljb_jpeg_encode_batch_dev")
+
+
+def process_groups(samples, ctx: N.Context | None = None):
+    """The reference's process() (Algorithms/parallel/JPEG/JPEG.c:1103) on groups given by their samples (uint8[n,128]: lum 64 | b 32
+    | r 32): returns (reconstructed samples uint8[n,128], quantised coefficients int16[n,128])."""
+    s = np.ascontiguousarray(samples, dtype=np.uint8).reshape(-1, 128).copy()
+    ctx = ctx or N.default_context()
+    coefs = np.zeros((s.shape[0], 128), dtype=np.int16)
+    N.check(N.lib().ljb_jpeg_process_groups(ctx.handle, s.ctypes.data, s.shape[0], coefs.ctypes.data), "ljb_jpeg_process_groups")
+    return s, coefs

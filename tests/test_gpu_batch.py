@@ -30,3 +30,73 @@ def test_batched_1080p_encode_and_lz4_round_trip(oracle):
             assert np.array_equal(back, enc.stream)
     finally:
         ctx.close()
+
+
+def test_batch_entry_point_equals_per_image_calls():
+    """ljb_jpeg_encode_batch: N images in one call; image i's records are byte for byte what a call for that image alone gives.
+    1920x1080 (sides multiples of 8: one launch over the whole batch) and 30x20 (not: tail groups differ per image)."""
+    import lz4jpeg_b200 as ljb
+
+    ctx = ljb.Context(0)
+    try:
+        for (w, h, n) in ((1920, 1080, 4), (30, 20, 5), (64, 48, 7)):
+            imgs = np.stack([ljb.synth.random_image(w, h, seed=42 + i) for i in range(n)])
+            enc = ljb.jpeg.process_batch(imgs, ctx=ctx)
+            G = ljb.jpeg.group_count(w, h)
+            assert enc.group_offsets.size == n * G + 1
+            for i in range(n):
+                one = ljb.jpeg.process(imgs[i], want_coefs=False, ctx=ctx)
+                o0, o1 = int(enc.group_offsets[i * G]), int(enc.group_offsets[(i + 1) * G])
+                assert np.array_equal(enc.stream[o0:o1], one.stream), (w, h, i)
+                assert np.array_equal(enc.group_bits[i * G:(i + 1) * G], one.group_bits)
+                assert np.array_equal(enc.group_offsets[i * G:(i + 1) * G + 1] - np.uint64(o0), one.group_offsets)
+    finally:
+        ctx.close()
+
+
+def test_batch_device_pipeline_jpeg_then_lz4_round_trip():
+    """configs[4] on one GPU, device-resident end to end: batch JPEG encode -> LZ4 compress of the concatenated bit streams ->
+    LZ4 decompress == the bit streams.  Also a batch whose image sides are not multiples of 8 through the one-launch device path."""
+    import torch
+
+    import lz4jpeg_b200 as ljb
+
+    ctx = ljb.Context(0)
+    try:
+        for (w, h, n) in ((1920, 1080, 6), (30, 20, 9)):
+            imgs = np.stack([ljb.synth.random_image(w, h, seed=142 + i) for i in range(n)])
+            G = ljb.jpeg.group_count(w, h)
+            d_in = torch.from_numpy(imgs).cuda()
+            cap = n * G * 96 + 4096
+            d_out = torch.empty(cap, dtype=torch.uint8, device="cuda")
+            d_offs = torch.empty(n * G + 1, dtype=torch.int64, device="cuda")
+            d_bits = torch.empty(n * G * 3, dtype=torch.int16, device="cuda")
+            d_res = torch.zeros(3, dtype=torch.int64, device="cuda")
+            ljb.jpeg.encode_batch_device(d_in, w, h, n, d_out, d_offs, d_bits, d_res, ctx)
+            torch.cuda.synchronize()
+            assert int(d_res[2].item()) == 0
+            jlen = int(d_res[0].item())
+            offs = d_offs.cpu().numpy().astype(np.int64)
+            stream = d_out[:jlen].cpu().numpy()
+            for i in range(n):
+                one = ljb.jpeg.process(imgs[i], want_coefs=False, ctx=ctx)
+                assert np.array_equal(stream[offs[i * G]:offs[(i + 1) * G]], one.stream), (w, h, i)
+            if jlen < 65536:
+                continue
+            # LZ4 of the concatenated bit streams, 64 KiB blocks, all on the device
+            nb = (jlen + 65535) // 65536
+            d_lz = torch.empty(jlen + jlen // 4 + 16 * nb + 4096, dtype=torch.uint8, device="cuda")
+            d_boffs = torch.empty(nb + 1, dtype=torch.int64, device="cuda")
+            d_lres = torch.zeros(3, dtype=torch.int64, device="cuda")
+            ljb.lz4.compress_device(d_out[:jlen], 65536, d_lz, d_boffs, d_lres, ctx)
+            torch.cuda.synchronize()
+            assert int(d_lres[2].item()) == 0 and int(d_lres[1].item()) == 0
+            d_back = torch.empty(nb * 65536, dtype=torch.uint8, device="cuda")
+            d_blen = torch.empty(nb, dtype=torch.int32, device="cuda")
+            d_dres = torch.zeros(3, dtype=torch.int64, device="cuda")
+            ljb.lz4.decompress_device(d_lz, int(d_lres[0].item()), d_boffs, nb, 65536, d_back, d_blen, d_dres, ctx)
+            torch.cuda.synchronize()
+            assert int(d_dres[2].item()) == 0 and int(d_dres[0].item()) == jlen
+            assert torch.equal(d_back[:jlen], d_out[:jlen])
+    finally:
+        ctx.close()
