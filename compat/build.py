@@ -44,6 +44,27 @@ def build_test(force: bool = False) -> str:
     return exe
 
 
+def build_comm_test(force: bool = False) -> str:
+    """compat/test_comm: a C host on N GPUs (include/ljb_comm.h, lz4-jpeg_b200/libljb_comm.so)."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("ljb_build", os.path.join(LIBDIR, "build.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    comm = mod.build_comm(force)
+    exe = os.path.join(HERE, "test_comm")
+    src = os.path.join(HERE, "test_comm.c")
+    if force or not os.path.exists(exe) or os.path.getmtime(src) > os.path.getmtime(exe) or os.path.getmtime(comm) > os.path.getmtime(exe):
+        cmd = ["gcc", "-O2", "-Wall", "-I" + os.path.join(ROOT, "include"), "-o", exe, src, "-L" + LIBDIR, "-lljb_comm", "-llz4jpeg_b200",
+               "-Wl,-rpath,$ORIGIN/../lz4-jpeg_b200"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            sys.stderr.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
+            raise RuntimeError("comm test build failed")
+    return exe
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv))
     print(build_test(force="--force" in sys.argv))
+    print(build_comm_test(force="--force" in sys.argv))

@@ -58,5 +58,26 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+COMM_LIB = os.path.join(HERE, "libljb_comm.so")
+
+
+def build_comm(force: bool = False) -> str:
+    """lz4-jpeg_b200/libljb_comm.so: the multi-GPU entry points for a C host (include/ljb_comm.h).  The only object that links
+    NCCL (system libnccl, /usr/include/nccl.h); it sits next to liblz4jpeg_b200.so and resolves the single-GPU entry points there."""
+    build(force)
+    src = os.path.join(CSRC, "comm.cu")
+    deps = [src, os.path.join(CSRC, "common.cuh"), os.path.join(os.path.dirname(HERE), "include", "ljb_comm.h"), LIB, os.path.abspath(__file__)]
+    if not force and os.path.exists(COMM_LIB) and all(os.path.getmtime(d) <= os.path.getmtime(COMM_LIB) for d in deps):
+        return COMM_LIB
+    cmd = [NVCC, *ARCH, "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-shared", "-o", COMM_LIB, src, "-L" + HERE, "-llz4jpeg_b200",
+           "-lnccl", "-lcudart", "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
+        raise RuntimeError("comm build failed")
+    return COMM_LIB
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose=True))
+    print(build_comm(force="--force" in sys.argv))

@@ -101,3 +101,21 @@ def test_process_entry_point(exe, oracle, tmp_path):
         blk = np.stack([lum + tr(1.402 * cr), lum - tr(0.344136 * cb) - tr(0.714136 * cr), lum + tr(1.772 * cb)], axis=-1)
         got[br * 8:br * 8 + 8, bc * 8:bc * 8 + 8] = np.clip(blk, 0, 255)
     assert np.array_equal(got.astype(np.uint8), want[:, :, :3])
+
+
+@pytest.mark.parametrize("ngpus", [1, 2])
+def test_c_host_on_n_gpus(tmp_path, ngpus):
+    """include/ljb_comm.h from a C program: one process, N GPUs, one NCCL all-gather of shard totals; the stream and the offset
+    tables equal the single-GPU ones (compat/test_comm.c compares them itself)."""
+    import torch
+
+    import build as compat_build
+
+    if torch.cuda.device_count() < ngpus:
+        pytest.skip(f"needs {ngpus} GPUs")
+    exe = compat_build.build_comm_test()
+    inp = tmp_path / "in.txt"
+    cases.synth_text(23 * 65536 + 999, seed=5).tofile(inp)
+    r = subprocess.run([exe, str(ngpus), str(inp), "65536", "640", "328"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.count("identical to 1 GPU") == 2, r.stdout
