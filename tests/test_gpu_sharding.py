@@ -110,8 +110,14 @@ def test_offsets_beyond_4_gib(oracle):
     try:
         n, bl = 4 << 30, 65536
         nb = n // bl
-        g = torch.Generator(device="cuda").manual_seed(7)
-        d_in = torch.randint(0, 256, (n,), dtype=torch.uint8, device="cuda", generator=g)
+        d_in = torch.empty(n, dtype=torch.uint8, device="cuda")
+        step = 128 << 20
+        for lo in range(0, n, step):  # bytes of a 64-bit mixing function of the position: incompressible, nothing repeats
+            i = torch.arange(lo, lo + step, dtype=torch.int64, device="cuda")
+            z = (i ^ (i >> 30)) * -4658895280553007687
+            z = (z ^ (z >> 27)) * -7723592293110705685
+            d_in[lo:lo + step] = ((z ^ (z >> 31)) & 0xFF).to(torch.uint8)
+            del i, z
         d_out = torch.empty(n + 32 * nb + 4096, dtype=torch.uint8, device="cuda")
         d_offs = torch.empty(nb + 1, dtype=torch.int64, device="cuda")
         d_res = torch.zeros(3, dtype=torch.int64, device="cuda")
