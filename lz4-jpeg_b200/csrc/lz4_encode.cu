@@ -171,6 +171,7 @@ __device__ __forceinline__ SeqSize seq_size(uint32_t lit, uint32_t ml)
 }
 
 #include "lz4_lazy.cuh"
+#include "lz4_small.cuh"
 
 template <int MODE> // 0: every position is searched (ladder / group index / B1 / B2); 1: only the positions the greedy parse visits (lz4_lazy.cuh)
 __global__ void __launch_bounds__(THREADS, 1) lz4_encode_kernel(Params P)
@@ -1347,6 +1348,46 @@ static int lz4_launch(ljb_ctx *ctx, const uint8_t *d_in, size_t n, size_t block_
     const size_t nblocks = ljb_lz4_block_count(n, block_len);
     if (nblocks > 0x7fffffffull) return LJB_E_ARG;
     LJB_CUDA(cudaSetDevice(ctx->device));
+    if (!d_dump_len && block_len <= (size_t)SMALL_MAXB && !getenv("LJB_LZ4_NO_SMALL")) { // small blocks: one warp per block (lz4_small.cuh)
+        const SmallGeom g = small_geometry((uint32_t)block_len);
+        const size_t want = (nblocks + g.warps - 1) / g.warps;
+        const int sgrid = (int)(want < (size_t)ctx->num_sms ? want : (size_t)ctx->num_sms);
+        const size_t stride = (ljb_lz4_bound(block_len, block_len) + 63) & ~(size_t)63;
+        int src;
+        if ((src = ljb_ensure(&ctx->d_scratch, &ctx->scratch_bytes, (size_t)sgrid * g.warps * stride)) != 0) return src;
+        if ((src = ljb_ensure(&ctx->d_status, &ctx->status_bytes, (nblocks + 2) * sizeof(uint64_t))) != 0) return src;
+        LJB_CUDA(cudaMemsetAsync(ctx->d_status, 0, (nblocks + 2) * sizeof(uint64_t), ctx->stream));
+        LJB_CUDA(cudaMemsetAsync(d_result, 0, 3 * sizeof(uint64_t), ctx->stream));
+        SmallParams S;
+        S.in = d_in;
+        S.n = n;
+        S.block_len = (uint32_t)block_len;
+        S.nblocks = (uint32_t)nblocks;
+        S.out = d_out;
+        S.out_cap = out_cap;
+        S.block_offsets = d_block_offsets;
+        S.result = d_result;
+        S.status = (uint64_t *)ctx->d_status;
+        S.staging = (uint8_t *)ctx->d_scratch;
+        S.stage_stride = stride;
+        S.offs_bias = offs_bias;
+        S.lead = first_block == 0 ? 1u : 0u;
+        S.frame_byte = (uint32_t)(frame_blocks & 0xFF);
+        S.hbits = g.hbits;
+        S.warp_bytes = g.warp_bytes;
+        S.data_bytes = g.data_bytes;
+        if (!(ctx->attr_mask & LJB_ATTR_LZ4_SMALL)) {
+            LJB_CUDA(cudaFuncSetAttribute(lz4_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            ctx->attr_mask |= LJB_ATTR_LZ4_SMALL;
+        }
+        ctx->kernel_ms_summed = 0;
+        LJB_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+        lz4_small_kernel<<<sgrid, 32 * g.warps, g.smem_bytes, ctx->stream>>>(S);
+        LJB_CUDA(cudaGetLastError());
+        LJB_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+        ctx->launches += 1;
+        return LJB_OK;
+    }
     const int grid = (int)((nblocks < (size_t)ctx->num_sms) ? nblocks : (size_t)ctx->num_sms);
     int rc;
     const size_t rec32_bytes = (size_t)ctx->num_sms * MAXB * sizeof(uint32_t);

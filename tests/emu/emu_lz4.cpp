@@ -6,7 +6,8 @@
 #include "../../lz4-jpeg_b200/csrc/lz4_decode.cu"
 
 namespace lz4k {
-alignas(16) uint8_t smem[SM_TOTAL + 256]; // the kernel's `extern __shared__` array; 256 canary bytes behind it
+constexpr int EMU_SMEM = 227 * 1024;      // what a CTA can have on the B200
+alignas(16) uint8_t smem[EMU_SMEM + 256]; // the kernels' `extern __shared__` array; 256 canary bytes behind it
 }
 
 extern "C" int emu_lz4_compress(const uint8_t *in, size_t n, size_t block_len, uint8_t *out, size_t out_cap, uint64_t *block_offsets,
@@ -46,10 +47,36 @@ extern "C" int emu_lz4_compress(const uint8_t *in, size_t n, size_t block_len, u
     if (phase24) memset(phase24, 0, 24 * sizeof *phase24);
     result[0] = result[1] = result[2] = 0;
     memset(smem, 0xA5, sizeof smem);
-    if (mode == 1) emu::launch(1, THREADS, [&]() { lz4_encode_kernel<1>(P); });
+    if (mode == 2) { // the warp-per-block kernel for small blocks
+        if (block_len > (size_t)SMALL_MAXB) return -1;
+        const SmallGeom g = small_geometry((uint32_t)block_len);
+        const size_t stride = (1 + 3 + 6 * block_len + 64 + 63) & ~(size_t)63;
+        std::vector<uint8_t> sstage((size_t)g.warps * stride + 64, 0xEE);
+        SmallParams S;
+        memset(&S, 0, sizeof S);
+        S.in = din.data();
+        S.n = n;
+        S.block_len = (uint32_t)block_len;
+        S.nblocks = (uint32_t)nblocks;
+        S.out = out;
+        S.out_cap = out_cap;
+        S.block_offsets = block_offsets;
+        S.result = result;
+        S.status = status.data();
+        S.staging = sstage.data();
+        S.stage_stride = stride;
+        S.lead = 1;
+        S.frame_byte = (uint32_t)(nblocks & 0xFF);
+        S.hbits = g.hbits;
+        S.warp_bytes = g.warp_bytes;
+        S.data_bytes = g.data_bytes;
+        if (g.smem_bytes > (uint32_t)EMU_SMEM) return -1;
+        emu::launch(1, 32 * g.warps, [&]() { lz4_small_kernel(S); });
+    } else if (mode == 1) emu::launch(1, THREADS, [&]() { lz4_encode_kernel<1>(P); });
     else emu::launch(1, THREADS, [&]() { lz4_encode_kernel<0>(P); });
-    for (int i = 0; i < 256; ++i)
-        if (smem[SM_TOTAL + i] != 0xA5) return -7; // a write past the kernel's shared-memory extent
+    const int extent = mode == 2 ? (int)small_geometry((uint32_t)block_len).smem_bytes : SM_TOTAL;
+    for (int i = extent; i < EMU_SMEM + 256; ++i)
+        if (smem[i] != 0xA5) return -7; // a write past the kernel's shared-memory extent
     return 0;
 }
 

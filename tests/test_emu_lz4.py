@@ -15,7 +15,7 @@ import cases
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu"))
 ALL = {name: (data, bl) for name, data, bl in cases.lz4_cases()}
-LAZY, FULL = 1, 0
+LAZY, FULL, SMALL = 1, 0, 2
 
 
 @pytest.fixture(scope="module")
@@ -119,3 +119,28 @@ def test_decoder_kernel_roundtrip_and_rejects(emu, oracle):
     s3 = np.concatenate([s2, s[int(offs[2]):]])
     offs3 = np.concatenate([offs2, [offs2[-1] + (offs[3] - offs[2])]]).astype(np.uint64)
     assert _decompress(emu, s3, offs3, bl, 3 * bl)[2] & 2
+
+
+@pytest.mark.parametrize("name", sorted(n for n, (d, bl) in ALL.items() if min(bl, d.size) <= 4096))
+def test_small_block_kernel_equals_oracle(emu, oracle, name):
+    """The warp-per-block kernel (lz4_small.cuh: block lengths up to 4096, the reference's own 300 among them)."""
+    data, bl = ALL[name]
+    bl = min(bl, data.size)
+    s, offs, ph = _compress(emu, data, bl, SMALL)
+    s0, o0, p0 = oracle.lz4_compress(data, bl, 1)
+    assert np.array_equal(s, s0) and np.array_equal(offs, o0) and ph == p0
+
+
+def test_small_block_kernel_many_blocks(emu, oracle):
+    """More blocks than warps (ticket counter, look-back between warps), ragged last block, several block lengths; zeros at 4096
+    (matches capped at 1024: the literal-run skip)."""
+    for bl in (300, 1024, 4096, 5, 33):
+        data = cases.synth_text(70 * bl + 17, seed=3)
+        s, offs, ph = _compress(emu, data, bl, SMALL)
+        s0, o0, p0 = oracle.lz4_compress(data, bl, 1)
+        assert np.array_equal(s, s0) and np.array_equal(offs, o0) and ph == p0, bl
+    z = np.zeros(3 * 4096, np.uint8)
+    for bl in (300, 2500, 4096):
+        s, offs, ph = _compress(emu, z, bl, SMALL)
+        s0, o0, p0 = oracle.lz4_compress(z, bl, 1)
+        assert np.array_equal(s, s0) and np.array_equal(offs, o0) and ph == p0, bl

@@ -97,7 +97,9 @@ def test_two_rank_gpu_shards_concatenate_to_the_single_gpu_stream():
 
 
 def test_offsets_beyond_4_gib(oracle):
-    """4 GiB of incompressible bytes in ONE launch: the stream is longer than 2^32 bytes, block offsets are 64-bit all the way.
+    """4 GiB of random hex digits in ONE launch: such text expands (many 4-byte matches at 5 bytes of sequence overhead each), so the
+    stream is longer than 2^32 bytes and block offsets are 64-bit all the way.  (Uniform random BYTES would not do: a 64 KiB block
+    without a single match wraps the reference's uint16 literal counter and is written as three header bytes)
     Blocks behind the 4 GiB mark are compared with the oracle; the whole table is checked for consistency."""
     import torch
 
@@ -112,13 +114,14 @@ def test_offsets_beyond_4_gib(oracle):
         nb = n // bl
         d_in = torch.empty(n, dtype=torch.uint8, device="cuda")
         step = 128 << 20
-        for lo in range(0, n, step):  # bytes of a 64-bit mixing function of the position: incompressible, nothing repeats
+        lut = torch.tensor(list(b"0123456789abcdef"), dtype=torch.uint8, device="cuda")
+        for lo in range(0, n, step):  # hex digits from a 64-bit mixing function of the position
             i = torch.arange(lo, lo + step, dtype=torch.int64, device="cuda")
             z = (i ^ (i >> 30)) * -4658895280553007687
             z = (z ^ (z >> 27)) * -7723592293110705685
-            d_in[lo:lo + step] = ((z ^ (z >> 31)) & 0xFF).to(torch.uint8)
+            d_in[lo:lo + step] = lut[(z ^ (z >> 31)) & 15]
             del i, z
-        d_out = torch.empty(n + 32 * nb + 4096, dtype=torch.uint8, device="cuda")
+        d_out = torch.empty(n + n // 4 + 32 * nb + 4096, dtype=torch.uint8, device="cuda")
         d_offs = torch.empty(nb + 1, dtype=torch.int64, device="cuda")
         d_res = torch.zeros(3, dtype=torch.int64, device="cuda")
         ljb.lz4.compress_device(d_in, bl, d_out, d_offs, d_res, ctx)
