@@ -124,6 +124,7 @@ def test_offsets_beyond_4_gib(oracle):
         d_out = torch.empty(n + n // 4 + 32 * nb + 4096, dtype=torch.uint8, device="cuda")
         d_offs = torch.empty(nb + 1, dtype=torch.int64, device="cuda")
         d_res = torch.zeros(3, dtype=torch.int64, device="cuda")
+        torch.cuda.synchronize()  # the input was generated on torch's stream; the library works on its own
         ljb.lz4.compress_device(d_in, bl, d_out, d_offs, d_res, ctx)
         torch.cuda.synchronize()
         assert int(d_res[2].item()) == 0
