@@ -80,6 +80,24 @@ static void run_cta(Cta &c)
                     if (c.fibers[t].state != DONE) ++alive;
                     if (c.fibers[t].state == WAIT_WARP) ++waiting;
                 }
+                // release the teams (__syncwarp with a partial mask) whose lanes have all arrived
+                for (unsigned t = l0; t < l1; ++t) {
+                    Fiber &f = c.fibers[t];
+                    if (f.state != WAIT_TEAM) continue;
+                    bool all = true;
+                    for (unsigned u = l0; u < l1; ++u)
+                        if ((f.team_mask >> (u - l0)) & 1u) {
+                            const Fiber &o = c.fibers[u];
+                            if (!(o.state == DONE || (o.state == WAIT_TEAM && o.team_mask == f.team_mask))) all = false;
+                        }
+                    if (all) {
+                        const unsigned m = f.team_mask;
+                        for (unsigned u = l0; u < l1; ++u)
+                            if (((m >> (u - l0)) & 1u) && c.fibers[u].state == WAIT_TEAM) c.fibers[u].state = RUNNABLE;
+                        progress = true;
+                        ran = true;
+                    }
+                }
                 if (waiting && waiting == alive) {
                     for (unsigned t = l0; t < l1; ++t)
                         if (c.fibers[t].state == WAIT_WARP) c.fibers[t].state = RUNNABLE;

@@ -37,7 +37,7 @@ static inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) {
 
 namespace emu {
 
-enum State { RUNNABLE, WAIT_WARP, WAIT_CTA, WAIT_NAMED, DONE };
+enum State { RUNNABLE, WAIT_WARP, WAIT_TEAM, WAIT_CTA, WAIT_NAMED, DONE };
 
 struct Fiber {
     void *sp = nullptr;
@@ -45,6 +45,7 @@ struct Fiber {
     State state = RUNNABLE;
     unsigned tid = 0;
     unsigned par = 0; // parity of this lane's next warp collective
+    unsigned team_mask = 0; // WAIT_TEAM: the lanes of the __syncwarp(mask) this lane waits in
     int cta_pred = 0;
 };
 
@@ -148,7 +149,16 @@ template <class T> static inline T atomicCAS(T *p, T c, T v) { T o = *p; if (o =
 
 // ---- warp collectives (full masks only)
 #define EMU_FULL(mask) assert((mask) == 0xffffffffu)
-static inline void __syncwarp(unsigned mask = 0xffffffffu) { EMU_FULL(mask); emu::exchange(0); }
+// (a partial mask is a rendezvous of a team of lanes that takes its own path through the kernel)
+static inline void __syncwarp(unsigned mask = 0xffffffffu)
+{
+    if (mask == 0xffffffffu) {
+        emu::exchange(0);
+    } else {
+        emu::g->cur->team_mask = mask;
+        emu::block(emu::WAIT_TEAM);
+    }
+}
 static inline unsigned __ballot_sync(unsigned mask, int pred)
 {
     EMU_FULL(mask);

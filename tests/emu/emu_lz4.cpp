@@ -96,7 +96,7 @@ extern "C" int emu_lz4_decompress(const uint8_t *comp, size_t comp_len, const ui
     P.block_out_len = block_out_len;
     P.result = result;
     result[0] = result[1] = result[2] = 0;
-    const unsigned grid = (unsigned)((nblocks + WARPS_PER_CTA - 1) / WARPS_PER_CTA);
+    const unsigned grid = (unsigned)((nblocks + BLOCKS_PER_CTA - 1) / BLOCKS_PER_CTA);
     emu::launch(grid, WARPS_PER_CTA * 32, [&]() { lz4_decode_kernel(P); });
     return 0;
 }
