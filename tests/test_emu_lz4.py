@@ -13,14 +13,17 @@ import pytest
 
 import cases
 
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu"))
 ALL = {name: (data, bl) for name, data, bl in cases.lz4_cases()}
 LAZY, FULL, SMALL = 1, 0, 2
 
 
 @pytest.fixture(scope="module")
 def emu():
-    import build as emu_build  # tests/emu/build.py
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("ljb_emu_build", os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu", "build.py"))
+    emu_build = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(emu_build)
 
     L = C.CDLL(emu_build.build())
     L.emu_lz4_compress.restype = C.c_int

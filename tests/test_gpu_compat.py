@@ -12,15 +12,22 @@ import cases
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, os.path.join(ROOT, "compat"))
+
+
+def _compat_build():
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("ljb_compat_build", os.path.join(ROOT, "compat", "build.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
 ALL = {name: (data, bl) for name, data, bl in cases.lz4_cases()}
 
 
 @pytest.fixture(scope="module")
 def exe():
-    import build as compat_build  # compat/build.py
-
-    return compat_build.build_test()
+    return _compat_build().build_test()
 
 
 @pytest.mark.parametrize("mode", ["blocks", "par"])
@@ -109,11 +116,9 @@ def test_c_host_on_n_gpus(tmp_path, ngpus):
     tables equal the single-GPU ones (compat/test_comm.c compares them itself)."""
     import torch
 
-    import build as compat_build
-
     if torch.cuda.device_count() < ngpus:
         pytest.skip(f"needs {ngpus} GPUs")
-    exe = compat_build.build_comm_test()
+    exe = _compat_build().build_comm_test()
     inp = tmp_path / "in.txt"
     cases.synth_text(23 * 65536 + 999, seed=5).tofile(inp)
     r = subprocess.run([exe, str(ngpus), str(inp), "65536", "640", "328"], capture_output=True, text=True)
