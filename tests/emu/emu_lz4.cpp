@@ -90,6 +90,8 @@ extern "C" int emu_lz4_decompress(const uint8_t *comp, size_t comp_len, const ui
     P.offs = block_offsets;
     P.comp_len = comp_len;
     P.nblocks = (uint32_t)nblocks;
+    P.first_block = 0;
+    P.total_blocks = (uint32_t)nblocks;
     P.block_len = (uint32_t)block_len;
     P.out = out;
     P.out_cap = out_cap;
