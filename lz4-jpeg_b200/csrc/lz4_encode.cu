@@ -97,6 +97,7 @@ struct Params {
     uint64_t *result;        // [0] length, [1] phantom, [2] error flags
     uint64_t *status;        // [0] ticket, [1..] look-back words
     uint32_t *scratch;       // per CTA: MAXB u32 match records
+    uint32_t *idx8;          // per CTA: NBUCKET u32 + MAXB u16: the 8-gram index of low-entropy blocks (lz4_lazy.cuh)
     uint16_t *gids;          // per CTA: MAXB u16 group ids (dense rank of the 8-gram's first occurrence)
     uint8_t *staging;        // per CTA: two buffers of stage_stride bytes holding the encoded block until its offset is known
     size_t stage_stride;
@@ -1391,7 +1392,8 @@ static int lz4_launch(ljb_ctx *ctx, const uint8_t *d_in, size_t n, size_t block_
     const int grid = (int)((nblocks < (size_t)ctx->num_sms) ? nblocks : (size_t)ctx->num_sms);
     int rc;
     const size_t rec32_bytes = (size_t)ctx->num_sms * MAXB * sizeof(uint32_t);
-    const size_t rec_bytes = rec32_bytes + (size_t)ctx->num_sms * MAXB * sizeof(uint16_t); // match records + group ids
+    const size_t idx8_bytes = (size_t)ctx->num_sms * (NBUCKET + MAXB / 2) * sizeof(uint32_t); // 8-gram index of low-entropy blocks
+    const size_t rec_bytes = rec32_bytes + (size_t)ctx->num_sms * MAXB * sizeof(uint16_t) + idx8_bytes; // match records + group ids / steps + 8-gram index
     const size_t stage_stride = (ljb_lz4_bound(block_len, block_len) + 16 + 255) & ~(size_t)255; // one encoded block, worst case
     if ((rc = ljb_ensure(&ctx->d_scratch, &ctx->scratch_bytes, rec_bytes + (size_t)grid * 2 * stage_stride)) != 0) return rc;
     if ((rc = ljb_ensure(&ctx->d_status, &ctx->status_bytes, (nblocks + 2 + 24) * sizeof(uint64_t))) != 0) return rc;
@@ -1409,6 +1411,7 @@ static int lz4_launch(ljb_ctx *ctx, const uint8_t *d_in, size_t n, size_t block_
     P.status = (uint64_t *)ctx->d_status;
     P.scratch = (uint32_t *)ctx->d_scratch;
     P.gids = (uint16_t *)((uint8_t *)ctx->d_scratch + rec32_bytes);
+    P.idx8 = (uint32_t *)((uint8_t *)ctx->d_scratch + rec_bytes - idx8_bytes);
     P.staging = (uint8_t *)ctx->d_scratch + rec_bytes;
     P.stage_stride = stage_stride;
     P.offs_bias = offs_bias;

@@ -32,6 +32,8 @@ constexpr int NWALK_MAX = (MAXB + WG - 1) / WG;     // 993
 constexpr int LCH = 12;                             // the index keeps a bucket ordered by 4096-position chunk
 constexpr int TINYLIST = 8;                          // candidate lists up to this length are walked by the lane that owns them
 constexpr int BIGLIST = 32;                          // candidate lists this long are taken by the whole warp, shorter ones by a team of eight lanes
+constexpr uint32_t HOT_BUILD = 2048;                 // a block in which some bucket holds more entries than this also gets an index by 8-gram (in L2)
+constexpr uint32_t HOT_USE = 512;                    // candidate lists longer than this look at the 8-gram bucket first
 constexpr uint32_t VLONG = 32;                      // a lane compares this much on its own; longer runs are compared by the whole warp
 static_assert(2 * WG == SEG, "an emission segment is two walker segments");
 static_assert(NWALK_MAX <= THREADS, "one lane per walker");
@@ -70,16 +72,20 @@ __device__ __forceinline__ void lazy_search(uint8_t *smem, const uint32_t nb, ui
         const uint32_t q0 = base + 4u * (uint32_t)tid;
         if (q0 < npos) {
             const uint32_t w0 = dataw[q0 >> 2], w1 = dataw[(q0 >> 2) + 1];
+            uint32_t h[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                if (q0 + j < npos) {
-                    const uint32_t h = hash4(__funnelshift_r(w0, w1, 8 * j));
-                    atomicAdd(&dirw[h >> 1], (h & 1) ? 0x10000u : 1u);
-                }
+            for (int j = 0; j < 4; ++j) h[j] = q0 + j < npos ? hash4(__funnelshift_r(w0, w1, 8 * j)) : 0xFFFFFFFFu;
+            if (h[0] == h[1] && h[1] == h[2] && h[2] == h[3]) { // a run of one byte: one add for the four (65 k adds to one counter otherwise)
+                atomicAdd(&dirw[h[0] >> 1], (h[0] & 1) ? 0x40000u : 4u);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (h[j] != 0xFFFFFFFFu) atomicAdd(&dirw[h[j] >> 1], (h[j] & 1) ? 0x10000u : 1u);
             }
         }
     }
     __syncthreads();
+    uint32_t maxc = 0; // the largest bucket among this thread's counters
     {
         // exclusive scan of the 8192 u16 counts (two per word); every thread owns four consecutive words
         constexpr uint32_t cw = (NBUCKET / 2) / THREADS;
@@ -90,6 +96,7 @@ __device__ __forceinline__ void lazy_search(uint8_t *smem, const uint32_t nb, ui
         for (uint32_t k = 0; k < cw; ++k) {
             wv[k] = dirw[w0 + k];
             sum += (wv[k] & 0xFFFF) + (wv[k] >> 16);
+            maxc = max(maxc, max(wv[k] & 0xFFFFu, wv[k] >> 16));
         }
         uint32_t inc = sum;
 #pragma unroll
@@ -116,16 +123,85 @@ __device__ __forceinline__ void lazy_search(uint8_t *smem, const uint32_t nb, ui
         const uint32_t q0 = base + 4u * (uint32_t)tid;
         if (q0 < npos) {
             const uint32_t w0 = dataw[q0 >> 2], w1 = dataw[(q0 >> 2) + 1];
+            uint32_t h[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                if (q0 + j < npos) {
-                    const uint32_t h = hash4(__funnelshift_r(w0, w1, 8 * j));
-                    const uint32_t old = atomicAdd(&dirw[h >> 1], (h & 1) ? 0x10000u : 1u);
-                    S[(h & 1) ? (old >> 16) : (old & 0xFFFF)] = (uint16_t)(q0 + j);
+            for (int j = 0; j < 4; ++j) h[j] = q0 + j < npos ? hash4(__funnelshift_r(w0, w1, 8 * j)) : 0xFFFFFFFFu;
+            if (h[0] == h[1] && h[1] == h[2] && h[2] == h[3]) {
+                const uint32_t old = atomicAdd(&dirw[h[0] >> 1], (h[0] & 1) ? 0x40000u : 4u);
+                const uint32_t at = (h[0] & 1) ? (old >> 16) : (old & 0xFFFF);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) S[at + j] = (uint16_t)(q0 + j);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (h[j] != 0xFFFFFFFFu) {
+                        const uint32_t old = atomicAdd(&dirw[h[j] >> 1], (h[j] & 1) ? 0x10000u : 1u);
+                        S[(h[j] & 1) ? (old >> 16) : (old & 0xFFFF)] = (uint16_t)(q0 + j);
+                    }
                 }
             }
         }
         __syncthreads();
+    }
+    // ---- low-entropy blocks (a 4-gram that occurs thousands of times: two-symbol data, long runs of a short period) also get an
+    // index by 8-GRAM, in L2: a position whose 4-gram list is long looks at its 8-gram bucket first — every candidate that
+    // matches 8 bytes or more is in there, and if there is one the answer is among them (longer beats shorter).  Only when
+    // nothing matches 8 bytes is the long 4-gram list walked.  Two-symbol random data: 128 candidates per search instead of 2000.
+    uint32_t *const dir8 = P.idx8 + (size_t)blockIdx.x * (NBUCKET + MAXB / 2); // u32 dir8[NBUCKET] | u16 S8[MAXB]
+    uint16_t *const S8 = reinterpret_cast<uint16_t *>(dir8 + NBUCKET);
+    // (not when a bucket holds a quarter of the block: runs of one byte or of a period up to four have as few 8-grams as 4-grams)
+    const int hotbits = __syncthreads_or((maxc > HOT_BUILD ? 1 : 0) | (maxc > (uint32_t)MAXB / 4 ? 2 : 0));
+    const bool hot = hotbits == 1;
+    if (hot) {
+        const uint32_t npos8 = nb >= 8 ? nb - 7 : 0;
+        for (int i = tid; i < NBUCKET; i += THREADS) dir8[i] = 0;
+        __syncthreads();
+        for (uint32_t base = 0; base < npos8; base += 4 * THREADS) {
+            const uint32_t q0 = base + 4u * (uint32_t)tid;
+            if (q0 < npos8) {
+                const uint32_t w0 = dataw[q0 >> 2], w1 = dataw[(q0 >> 2) + 1], w2 = dataw[(q0 >> 2) + 2];
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (q0 + j < npos8) atomicAdd(&dir8[hash8(__funnelshift_r(w0, w1, 8 * j), __funnelshift_r(w1, w2, 8 * j))], 1u);
+            }
+        }
+        __syncthreads();
+        {
+            constexpr uint32_t per = NBUCKET / THREADS; // 8 counters per thread
+            uint32_t cnt[per], sum = 0;
+#pragma unroll
+            for (uint32_t k = 0; k < per; ++k) {
+                cnt[k] = __ldcg(&dir8[(uint32_t)tid * per + k]);
+                sum += cnt[k];
+            }
+            uint32_t inc = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t v = __shfl_up_sync(FULL, inc, o);
+                if (lane >= o) inc += v;
+            }
+            if (lane == 31) M.scan_tmp[tid >> 5] = inc;
+            __syncthreads();
+            uint32_t run = inc - sum;
+            for (int k = 0; k < (tid >> 5); ++k) run += M.scan_tmp[k];
+#pragma unroll
+            for (uint32_t k = 0; k < per; ++k) {
+                dir8[(uint32_t)tid * per + k] = run;
+                run += cnt[k];
+            }
+        }
+        __syncthreads();
+        for (uint32_t base = 0; base < npos8; base += 4 * THREADS) {
+            const uint32_t q0 = base + 4u * (uint32_t)tid;
+            if (q0 < npos8) {
+                const uint32_t w0 = dataw[q0 >> 2], w1 = dataw[(q0 >> 2) + 1], w2 = dataw[(q0 >> 2) + 2];
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (q0 + j < npos8)
+                        S8[atomicAdd(&dir8[hash8(__funnelshift_r(w0, w1, 8 * j), __funnelshift_r(w1, w2, 8 * j))], 1u)] = (uint16_t)(q0 + j);
+            }
+        }
+        __syncthreads(); // dir8[h] is now the END of bucket h
     }
     phase(3); // index
 
@@ -303,6 +379,37 @@ __device__ __forceinline__ void lazy_search(uint8_t *smem, const uint32_t nb, ui
                 const uint32_t olo = __shfl_sync(FULL, lo, src), on = __shfl_sync(FULL, n, src);
                 const uint32_t ocap = min((uint32_t)MAX_MATCH, nb - op);
                 uint32_t lb = 0, tb = 0; // this lane's best; what the whole warp knows (pairs at the cap, long compares)
+                if (hot && on > HOT_USE && ocap >= 8u) { // the 8-gram bucket first (entries in no particular order)
+                    const uint32_t h8 = hash8(og0, og1);
+                    const uint32_t lo8 = h8 ? __ldcg(&dir8[h8 - 1]) : 0u, n8 = __ldcg(&dir8[h8]) - lo8;
+                    if (n8 <= HOT_USE) {
+                        uint32_t lb8 = 0, tb8 = 0;
+                        for (uint32_t it = 0; it < n8; it += 32) {
+                            const uint32_t i = it + (uint32_t)lane;
+                            uint32_t key = 0, c = 0;
+                            bool vl = false;
+                            if (i < n8) {
+                                c = __ldcg(&S8[lo8 + i]);
+                                key = eval(c, op, og0, og1, ocap, tb8, vl);
+                            }
+                            lb8 = max(lb8, key);
+                            if (__any_sync(FULL, vl || (key >> 16) == ocap)) {
+                                unsigned pendv = __ballot_sync(FULL, vl);
+                                while (pendv) {
+                                    const int sv = __ffs(pendv) - 1;
+                                    pendv &= pendv - 1;
+                                    tb8 = max(tb8, long_compare(__shfl_sync(FULL, c, sv), op, ocap, tb8));
+                                }
+                                tb8 = max(tb8, __reduce_max_sync(FULL, key));
+                            }
+                        }
+                        tb8 = max(tb8, __reduce_max_sync(FULL, lb8));
+                        if ((tb8 >> 16) >= 8u) { // every pair that matches 8 bytes was in that bucket: this is the answer
+                            if (lane == src) best = tb8;
+                            continue;
+                        }
+                    }
+                }
                 for (uint32_t it = 0; it < on; it += 32) {
                     const uint32_t i = it + (uint32_t)lane;
                     uint32_t key = 0, c = 0;

@@ -36,6 +36,8 @@ extern "C" int emu_lz4_compress(const uint8_t *in, size_t n, size_t block_len, u
     P.status = status.data();
     P.scratch = scratch.data();
     P.gids = gids.data();
+    std::vector<uint32_t> idx8(NBUCKET + MAXB / 2, 0xDEADBEEFu);
+    P.idx8 = idx8.data();
     P.staging = staging.data();
     P.stage_stride = stage_stride;
     P.offs_bias = 0;
