@@ -232,13 +232,25 @@ __device__ __forceinline__ void lazy_search(uint8_t *smem, const uint32_t nb, ui
             if ((tb >> 16) == ocap && c > 0xFFFFu - (tb & 0xFFFFu)) return 0u;
             l = 8;
             const uint32_t lim = min(ocap, VLONG);
+            // 8 bytes per step, the word straddling the step carried over on either side
+            const uint32_t pi = op >> 2, ps = (op & 3) * 8;
+            uint32_t cw = a2, pw = dataw[pi + 2];
             while (l < lim) {
-                const uint32_t x = load32u(dataw, c + l) ^ load32u(dataw, op + l);
+                const uint32_t c1 = dataw[ci + (l >> 2) + 1], c2 = dataw[ci + (l >> 2) + 2];
+                const uint32_t p1 = dataw[pi + (l >> 2) + 1], p2 = dataw[pi + (l >> 2) + 2];
+                uint32_t x = __funnelshift_r(cw, c1, cs) ^ __funnelshift_r(pw, p1, ps);
                 if (x) {
                     l += (uint32_t)(__ffs(x) - 1) >> 3;
                     break;
                 }
-                l += 4;
+                x = __funnelshift_r(c1, c2, cs) ^ __funnelshift_r(p1, p2, ps);
+                if (x) {
+                    l += 4u + ((uint32_t)(__ffs(x) - 1) >> 3);
+                    break;
+                }
+                cw = c2;
+                pw = p2;
+                l += 8;
             }
             if (l >= VLONG && ocap > VLONG) { // still matching after VLONG bytes: the warp goes on
                 vl = true;
@@ -379,6 +391,7 @@ __device__ __forceinline__ void lazy_search(uint8_t *smem, const uint32_t nb, ui
                 const uint32_t olo = __shfl_sync(FULL, lo, src), on = __shfl_sync(FULL, n, src);
                 const uint32_t ocap = min((uint32_t)MAX_MATCH, nb - op);
                 uint32_t lb = 0, tb = 0; // this lane's best; what the whole warp knows (pairs at the cap, long compares)
+                bool capped = false;     // tb has reached the cap
                 if (hot && on > HOT_USE && ocap >= 8u) { // the 8-gram bucket first (entries in no particular order)
                     const uint32_t h8 = hash8(og0, og1);
                     const uint32_t lo8 = h8 ? __ldcg(&dir8[h8 - 1]) : 0u, n8 = __ldcg(&dir8[h8]) - lo8;
@@ -427,9 +440,10 @@ __device__ __forceinline__ void lazy_search(uint8_t *smem, const uint32_t nb, ui
                             tb = max(tb, long_compare(__shfl_sync(FULL, c, sv), op, ocap, tb));
                         }
                         tb = max(tb, __reduce_max_sync(FULL, key));
+                        capped = (tb >> 16) == ocap;
                     }
                     // once the cap is reached only earlier positions matter: the entries of later chunks cannot win
-                    if ((tb >> 16) == ocap && it + 32 < on && (uint32_t)(S[olo + it + 32] >> LCH) > ((0xFFFFu - (tb & 0xFFFFu)) >> LCH)) break;
+                    if (capped && it + 32 < on && (uint32_t)(S[olo + it + 32] >> LCH) > ((0xFFFFu - (tb & 0xFFFFu)) >> LCH)) break;
                 }
                 tb = max(tb, __reduce_max_sync(FULL, lb));
                 if (lane == src) best = tb;
