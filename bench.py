@@ -42,10 +42,11 @@ BLOCK_LEN = 65536
 LZ4_BYTES = int(os.environ.get("LJB_BENCH_LZ4_BYTES", 4 * GIB))
 JPEG_DIM = int(os.environ.get("LJB_BENCH_JPEG_DIM", 16384))
 # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the ncu pass over this same command committed as
-# profiles/r1/launches_r1l_bench_steps2_warmup1.csv (LZ4, JFIF) and profiles/r1/jpeg_r1k_summary.txt (JPEG, ncu --set full of the kernel
-# alone: its per-warp staging records are partly written back); bytes at the default workload sizes, None for other sizes.
-NCU_TRAFFIC = {"lz4": 4.94e9 + 6.79e9 if LZ4_BYTES == 4 * GIB else None, "jpeg": 1.087e9 + 0.465e9 if JPEG_DIM == 16384 else None,
-               "jfif444": 1.0746e9 + 0.3176e9 if JPEG_DIM == 16384 else None, "jfif420": 1.0740e9 + 0.1446e9 if JPEG_DIM == 16384 else None}
+# profiles/r2/launches_r2p_bench_steps2_warmup1.csv (the full-size launches of every kernel); bytes at the default workload sizes,
+# None for other sizes.
+NCU_TRAFFIC = {"lz4": 4.43e9 + 5.56e9 if LZ4_BYTES == 4 * GIB else None, "lz4_decode": 45.6e9 + 4.49e9 if LZ4_BYTES == 4 * GIB else None,
+               "jpeg": 1.088e9 + 0.491e9 if JPEG_DIM == 16384 else None,
+               "jfif444": 1.074e9 + 0.318e9 if JPEG_DIM == 16384 else None, "jfif420": 1.074e9 + 0.144e9 if JPEG_DIM == 16384 else None}
 JFIF_QUALITY = 75
 # frames of 1920x1080 per GPU in the batch object (BASELINE configs[4]: 8192 frames across 8 GPUs); 0 skips it
 BATCH_IMAGES = int(os.environ.get("LJB_BENCH_BATCH_IMAGES", 1024))
@@ -470,7 +471,7 @@ def run_gpu(args):
                                      "holds one is reported as a format error by any decoder; every other block must round-trip"},
                   "roundtrip": {"blocks": nblocks, "blocks_equal_to_input": ok_blocks, "blocks_with_undecodable_sequence_at_most": phantom},
                   "roofline": {"bound": "hbm", "achieved": (n + lz_out_bytes) / (dec_kernel_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                               "frac": (n + lz_out_bytes) / (dec_kernel_ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                               "frac": (n + lz_out_bytes) / (dec_kernel_ms * 1e-3) / 1e9 / peak, "traffic": NCU_TRAFFIC["lz4_decode"], "peak_source": peak_src,
                                "kernel": "lz4d::lz4_decode_kernel", "kernel_ms": dec_kernel_ms, "algorithmic_bytes": n + lz_out_bytes}}
     if ok_blocks is not None and ok_blocks + phantom < nblocks:
         raise SystemExit(f"LZ4 round trip: only {ok_blocks} of {nblocks} blocks decode to their input ({phantom} undecodable sequences)")
