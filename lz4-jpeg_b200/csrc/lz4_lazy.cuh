@@ -216,48 +216,58 @@ __device__ __forceinline__ void lazy_search(uint8_t *smem, const uint32_t nb, ui
     uint32_t my_in = 0, my_can = 0; // (own lane only) where the latest walk of the segment started; exit of its first walk
     bool my_split = false;          // a later walk left the segment without meeting an earlier one
     uint32_t d_search = 0, d_cand = 0, d_steps = 0, d_vl = 0, d_run = 0;
-    // One candidate: its first 8 bytes against the position's, then up to VLONG bytes by the lane itself.
-    // key = (length << 16) | (0xFFFF - position): the maximum is the longest match, the earliest among equals.
-    auto eval = [&](uint32_t c, uint32_t op, uint32_t og0, uint32_t og1, uint32_t ocap, uint32_t tb, bool &vl) -> uint32_t {
-        if (c >= op) return 0u;
+    // One candidate in two parts, so that two candidates of a lane can be in flight together:
+    //   probe   (branch-free) its first 8 bytes against the position's: the pair's key if it matches fewer than 8 bytes, or `lng`
+    //   extend  (only for `lng`) up to VLONG bytes by the lane itself; pairs still matching then are left to the warp (`vl`)
+    // key = (length << 16) | (0xFFFF - position): the maximum is the longest match, the earliest among equals.  A candidate of
+    // 0xFFFF stands for "none" (it is never below the position).
+    auto probe = [&](uint32_t c, uint32_t op, uint32_t og0, uint32_t og1, uint32_t ocap, uint32_t &a2, bool &lng) -> uint32_t {
         const uint32_t ci = c >> 2, cs = (c & 3) * 8;
-        const uint32_t a0 = dataw[ci], a1 = dataw[ci + 1], a2 = dataw[ci + 2];
-        if (__funnelshift_r(a0, a1, cs) != og0) return 0u; // (a bucket holds several 4-grams)
-        const uint32_t x1 = __funnelshift_r(a1, a2, cs) ^ og1;
-        uint32_t l;
-        if (x1) {
-            l = 4u + ((uint32_t)(__ffs(x1) - 1) >> 3);
-        } else {
-            // a pair that already reaches the cap is only beaten by an earlier position
-            if ((tb >> 16) == ocap && c > 0xFFFFu - (tb & 0xFFFFu)) return 0u;
-            l = 8;
-            const uint32_t lim = min(ocap, VLONG);
-            // 8 bytes per step, the word straddling the step carried over on either side
-            const uint32_t pi = op >> 2, ps = (op & 3) * 8;
-            uint32_t cw = a2, pw = dataw[pi + 2];
-            while (l < lim) {
-                const uint32_t c1 = dataw[ci + (l >> 2) + 1], c2 = dataw[ci + (l >> 2) + 2];
-                const uint32_t p1 = dataw[pi + (l >> 2) + 1], p2 = dataw[pi + (l >> 2) + 2];
-                uint32_t x = __funnelshift_r(cw, c1, cs) ^ __funnelshift_r(pw, p1, ps);
-                if (x) {
-                    l += (uint32_t)(__ffs(x) - 1) >> 3;
-                    break;
-                }
-                x = __funnelshift_r(c1, c2, cs) ^ __funnelshift_r(p1, p2, ps);
-                if (x) {
-                    l += 4u + ((uint32_t)(__ffs(x) - 1) >> 3);
-                    break;
-                }
-                cw = c2;
-                pw = p2;
-                l += 8;
+        const uint32_t a0 = dataw[ci], a1 = dataw[ci + 1];
+        a2 = dataw[ci + 2];
+        const uint32_t x0 = __funnelshift_r(a0, a1, cs) ^ og0, x1 = __funnelshift_r(a1, a2, cs) ^ og1;
+        const bool ok = c < op && x0 == 0u; // (a bucket holds several 4-grams)
+        lng = ok && x1 == 0u;
+        const uint32_t l = min(4u + ((uint32_t)(__ffs(x1) - 1) >> 3), ocap);
+        return (ok && x1 != 0u) ? ((l << 16) | (0xFFFFu - c)) : 0u;
+    };
+    auto extend = [&](uint32_t c, uint32_t op, uint32_t ocap, uint32_t a2, uint32_t tb, bool &vl) -> uint32_t {
+        // a pair that already reaches the cap is only beaten by an earlier position
+        if ((tb >> 16) == ocap && c > 0xFFFFu - (tb & 0xFFFFu)) return 0u;
+        uint32_t l = 8;
+        const uint32_t lim = min(ocap, VLONG);
+        // 8 bytes per step, the word straddling the step carried over on either side
+        const uint32_t ci = c >> 2, cs = (c & 3) * 8, pi = op >> 2, ps = (op & 3) * 8;
+        uint32_t cw = a2, pw = dataw[pi + 2];
+        while (l < lim) {
+            const uint32_t c1 = dataw[ci + (l >> 2) + 1], c2 = dataw[ci + (l >> 2) + 2];
+            const uint32_t p1 = dataw[pi + (l >> 2) + 1], p2 = dataw[pi + (l >> 2) + 2];
+            uint32_t x = __funnelshift_r(cw, c1, cs) ^ __funnelshift_r(pw, p1, ps);
+            if (x) {
+                l += (uint32_t)(__ffs(x) - 1) >> 3;
+                break;
             }
-            if (l >= VLONG && ocap > VLONG) { // still matching after VLONG bytes: the warp goes on
-                vl = true;
-                return 0u;
+            x = __funnelshift_r(c1, c2, cs) ^ __funnelshift_r(p1, p2, ps);
+            if (x) {
+                l += 4u + ((uint32_t)(__ffs(x) - 1) >> 3);
+                break;
             }
+            cw = c2;
+            pw = p2;
+            l += 8;
+        }
+        if (l >= VLONG && ocap > VLONG) { // still matching after VLONG bytes: the warp goes on
+            vl = true;
+            return 0u;
         }
         return (min(l, ocap) << 16) | (0xFFFFu - c);
+    };
+    auto eval = [&](uint32_t c, uint32_t op, uint32_t og0, uint32_t og1, uint32_t ocap, uint32_t tb, bool &vl) -> uint32_t {
+        uint32_t a2;
+        bool lng;
+        uint32_t key = probe(c, op, og0, og1, ocap, a2, lng);
+        if (lng) key = extend(c, op, ocap, a2, tb, vl);
+        return key;
     };
     // The pair (bc, bp) matches VLONG bytes: the warp compares on, 256 bytes per step, unless the pair cannot beat btb (it must
     // exceed the best length, or tie it from an earlier position).  Warp-uniform.
@@ -364,21 +374,31 @@ __device__ __forceinline__ void lazy_search(uint8_t *smem, const uint32_t nb, ui
             {
                 const bool mine = need && n > 0 && n <= (uint32_t)TINYLIST;
                 const uint32_t nmax = __reduce_max_sync(FULL, mine ? n : 0u);
-                for (uint32_t it = 0; it < nmax; ++it) {
-                    uint32_t key = 0, c = 0;
-                    bool vl = false;
-                    if (mine && it < n) {
-                        c = S[lo + it];
-                        key = eval(c, p, g0, g1, cap, best, vl);
-                    }
-                    best = max(best, key);
-                    unsigned pendv = __ballot_sync(FULL, vl);
-                    while (pendv) {
-                        const int sv = __ffs(pendv) - 1;
-                        pendv &= pendv - 1;
-                        const uint32_t rkey = long_compare(__shfl_sync(FULL, c, sv), __shfl_sync(FULL, p, sv), __shfl_sync(FULL, cap, sv),
-                                                           __shfl_sync(FULL, best, sv));
-                        if (lane == sv) best = max(best, rkey);
+                for (uint32_t it = 0; it < nmax; it += 2) { // two entries per iteration: their loads are in flight together
+                    const uint32_t c0 = (mine && it < n) ? (uint32_t)S[lo + it] : 0xFFFFu, c1 = (mine && it + 1 < n) ? (uint32_t)S[lo + it + 1] : 0xFFFFu;
+                    uint32_t a20, a21;
+                    bool lng0, lng1, vl0 = false, vl1 = false;
+                    uint32_t key0 = probe(c0, p, g0, g1, cap, a20, lng0), key1 = probe(c1, p, g0, g1, cap, a21, lng1);
+                    if (lng0) key0 = extend(c0, p, cap, a20, best, vl0);
+                    if (lng1) key1 = extend(c1, p, cap, a21, best, vl1);
+                    best = max(best, max(key0, key1));
+                    if (__any_sync(FULL, vl0 || vl1)) {
+                        unsigned pendv = __ballot_sync(FULL, vl0);
+                        while (pendv) {
+                            const int sv = __ffs(pendv) - 1;
+                            pendv &= pendv - 1;
+                            const uint32_t rkey = long_compare(__shfl_sync(FULL, c0, sv), __shfl_sync(FULL, p, sv), __shfl_sync(FULL, cap, sv),
+                                                               __shfl_sync(FULL, best, sv));
+                            if (lane == sv) best = max(best, rkey);
+                        }
+                        pendv = __ballot_sync(FULL, vl1);
+                        while (pendv) {
+                            const int sv = __ffs(pendv) - 1;
+                            pendv &= pendv - 1;
+                            const uint32_t rkey = long_compare(__shfl_sync(FULL, c1, sv), __shfl_sync(FULL, p, sv), __shfl_sync(FULL, cap, sv),
+                                                               __shfl_sync(FULL, best, sv));
+                            if (lane == sv) best = max(best, rkey);
+                        }
                     }
                 }
             }
@@ -423,27 +443,34 @@ __device__ __forceinline__ void lazy_search(uint8_t *smem, const uint32_t nb, ui
                         }
                     }
                 }
-                for (uint32_t it = 0; it < on; it += 32) {
-                    const uint32_t i = it + (uint32_t)lane;
-                    uint32_t key = 0, c = 0;
-                    bool vl = false;
-                    if (i < on) {
-                        c = S[olo + i];
-                        key = eval(c, op, og0, og1, ocap, tb, vl);
-                    }
+                for (uint32_t it = 0; it < on; it += 64) { // two entries per lane: their loads are in flight together
+                    const uint32_t i0 = it + (uint32_t)lane, i1 = i0 + 32u;
+                    const uint32_t c0 = i0 < on ? (uint32_t)S[olo + i0] : 0xFFFFu, c1 = i1 < on ? (uint32_t)S[olo + i1] : 0xFFFFu;
+                    uint32_t a20, a21;
+                    bool lng0, lng1, vl0 = false, vl1 = false;
+                    uint32_t key0 = probe(c0, op, og0, og1, ocap, a20, lng0), key1 = probe(c1, op, og0, og1, ocap, a21, lng1);
+                    if (lng0) key0 = extend(c0, op, ocap, a20, tb, vl0);
+                    if (lng1) key1 = extend(c1, op, ocap, a21, tb, vl1);
+                    const uint32_t key = max(key0, key1);
                     lb = max(lb, key);
-                    if (__any_sync(FULL, vl || (key >> 16) == ocap)) { // rare on text: a pair at the cap, or one for the warp
-                        unsigned pendv = __ballot_sync(FULL, vl);
+                    if (__any_sync(FULL, vl0 || vl1 || (key >> 16) == ocap)) { // rare on text: a pair at the cap, or one for the warp
+                        unsigned pendv = __ballot_sync(FULL, vl0);
                         while (pendv) {
                             const int sv = __ffs(pendv) - 1;
                             pendv &= pendv - 1;
-                            tb = max(tb, long_compare(__shfl_sync(FULL, c, sv), op, ocap, tb));
+                            tb = max(tb, long_compare(__shfl_sync(FULL, c0, sv), op, ocap, tb));
+                        }
+                        pendv = __ballot_sync(FULL, vl1);
+                        while (pendv) {
+                            const int sv = __ffs(pendv) - 1;
+                            pendv &= pendv - 1;
+                            tb = max(tb, long_compare(__shfl_sync(FULL, c1, sv), op, ocap, tb));
                         }
                         tb = max(tb, __reduce_max_sync(FULL, key));
                         capped = (tb >> 16) == ocap;
                     }
                     // once the cap is reached only earlier positions matter: the entries of later chunks cannot win
-                    if (capped && it + 32 < on && (uint32_t)(S[olo + it + 32] >> LCH) > ((0xFFFFu - (tb & 0xFFFFu)) >> LCH)) break;
+                    if (capped && it + 64 < on && (uint32_t)(S[olo + it + 64] >> LCH) > ((0xFFFFu - (tb & 0xFFFFu)) >> LCH)) break;
                 }
                 tb = max(tb, __reduce_max_sync(FULL, lb));
                 if (lane == src) best = tb;
@@ -469,34 +496,34 @@ __device__ __forceinline__ void lazy_search(uint8_t *smem, const uint32_t nb, ui
                 const uint32_t ocap = min((uint32_t)MAX_MATCH, nb - op);
                 uint32_t lb = 0, tb = 0; // this lane's best; what the whole team knows (the same in its eight lanes)
                 uint32_t nit = __reduce_max_sync(FULL, on);
-                for (uint32_t it = 0; it < nit; it += 8) {
-                    const uint32_t i = it + (uint32_t)tl;
-                    uint32_t key = 0, c = 0;
-                    bool vl = false;
-                    if (i < on) {
-                        c = S[olo + i];
-                        key = eval(c, op, og0, og1, ocap, tb, vl);
-                    }
+                for (uint32_t it = 0; it < nit; it += 16) { // two entries per lane
+                    const uint32_t i0 = it + (uint32_t)tl, i1 = i0 + 8u;
+                    const uint32_t c0 = i0 < on ? (uint32_t)S[olo + i0] : 0xFFFFu, c1 = i1 < on ? (uint32_t)S[olo + i1] : 0xFFFFu;
+                    uint32_t a20, a21;
+                    bool lng0, lng1, vl0 = false, vl1 = false;
+                    uint32_t key0 = probe(c0, op, og0, og1, ocap, a20, lng0), key1 = probe(c1, op, og0, og1, ocap, a21, lng1);
+                    if (lng0) key0 = extend(c0, op, ocap, a20, tb, vl0);
+                    if (lng1) key1 = extend(c1, op, ocap, a21, tb, vl1);
+                    uint32_t key = max(key0, key1);
                     lb = max(lb, key);
-                    if (__any_sync(FULL, vl || (key >> 16) == ocap)) {
-                        unsigned pendv = __ballot_sync(FULL, vl);
-                        while (pendv) {
-                            const int sv = __ffs(pendv) - 1;
-                            pendv &= pendv - 1;
-                            const uint32_t rkey = long_compare(__shfl_sync(FULL, c, sv), __shfl_sync(FULL, op, sv), __shfl_sync(FULL, ocap, sv),
-                                                               __shfl_sync(FULL, tb, sv));
-                            if ((lane >> 3) == (sv >> 3)) tb = max(tb, rkey); // known to the whole team at once
+                    if (__any_sync(FULL, vl0 || vl1 || (key >> 16) == ocap)) {
+                        for (int half = 0; half < 2; ++half) {
+                            unsigned pendv = __ballot_sync(FULL, half ? vl1 : vl0);
+                            const uint32_t cc = half ? c1 : c0;
+                            while (pendv) {
+                                const int sv = __ffs(pendv) - 1;
+                                pendv &= pendv - 1;
+                                const uint32_t rkey = long_compare(__shfl_sync(FULL, cc, sv), __shfl_sync(FULL, op, sv), __shfl_sync(FULL, ocap, sv),
+                                                                   __shfl_sync(FULL, tb, sv));
+                                if ((lane >> 3) == (sv >> 3)) tb = max(tb, rkey); // known to the whole team at once
+                            }
                         }
                         key = max(key, __shfl_xor_sync(FULL, key, 4));
                         key = max(key, __shfl_xor_sync(FULL, key, 2));
                         key = max(key, __shfl_xor_sync(FULL, key, 1));
                         tb = max(tb, key);
-                        if (it + 8 < on && (tb >> 16) == ocap && (uint32_t)(S[olo + it + 8] >> LCH) > ((0xFFFFu - (tb & 0xFFFFu)) >> LCH)) {
-                            on = 0;
-                            nit = __reduce_max_sync(FULL, on); // (the branch is warp-uniform)
-                        } else {
-                            nit = __reduce_max_sync(FULL, on);
-                        }
+                        if (it + 16 < on && (tb >> 16) == ocap && (uint32_t)(S[olo + it + 16] >> LCH) > ((0xFFFFu - (tb & 0xFFFFu)) >> LCH)) on = 0;
+                        nit = __reduce_max_sync(FULL, on); // (the branch is warp-uniform)
                     }
                 }
                 lb = max(lb, __shfl_xor_sync(FULL, lb, 4));
