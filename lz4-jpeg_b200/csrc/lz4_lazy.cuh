@@ -30,11 +30,20 @@
 constexpr int WG = 66;                              // bytes per walker segment: two per emission segment
 constexpr int NWALK_MAX = (MAXB + WG - 1) / WG;     // 993
 constexpr int LCH = 12;                             // the index keeps a bucket ordered by 4096-position chunk
-constexpr int TINYLIST = 8;                          // candidate lists up to this length are walked by the lane that owns them
-constexpr int BIGLIST = 32;                          // candidate lists this long are taken by the whole warp, shorter ones by a team of eight lanes
+#ifndef LJB_TINYLIST
+#define LJB_TINYLIST 4
+#endif
+#ifndef LJB_BIGLIST
+#define LJB_BIGLIST 32
+#endif
+#ifndef LJB_VLONG
+#define LJB_VLONG 32
+#endif
+constexpr int TINYLIST = LJB_TINYLIST;                          // candidate lists up to this length are walked by the lane that owns them
+constexpr int BIGLIST = LJB_BIGLIST;                          // candidate lists this long are taken by the whole warp, shorter ones by a team of eight lanes
 constexpr uint32_t HOT_BUILD = 2048;                 // a block in which some bucket holds more entries than this also gets an index by 8-gram (in L2)
 constexpr uint32_t HOT_USE = 512;                    // candidate lists longer than this look at the 8-gram bucket first
-constexpr uint32_t VLONG = 32;                      // a lane compares this much on its own; longer runs are compared by the whole warp
+constexpr uint32_t VLONG = LJB_VLONG;                      // a lane compares this much on its own; longer runs are compared by the whole warp
 static_assert(2 * WG == SEG, "an emission segment is two walker segments");
 static_assert(NWALK_MAX <= THREADS, "one lane per walker");
 // walker state in the area the full search uses for its first-occurrence bits
