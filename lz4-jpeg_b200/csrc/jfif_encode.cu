@@ -160,7 +160,19 @@ __device__ __forceinline__ int quantise(float coef, float mult)
     return __float2int_rz(v < 0.f ? FS(v, 0.5f) : FA(v, 0.5f));
 }
 
-// stb_image_write.h:1541-1543; p = r | g << 8 | b << 16
+// stb_image_write.h:1541-1543; p = r | g << 8 | b << 16.  All three components are ((cr*r + cg*g) + cb*b) + off with one IEEE
+// operation per C operator: a subtraction in the source is the addition of the exactly negated product, "- 128.f" is
+// "+ (-128.f)", and off = -0.0f is the identity for Cb and Cr.  One form for the three, so that lanes working on different
+// components of an MCU do not diverge.
+// byte k of p as a float: 2^23 + byte assembled with one byte permute, minus 2^23 (exact)
+// (measured: the permute form is faster where one lane converts one component — 4:4:4 — and the integer conversion where a lane
+// converts all three — 4:2:0)
+__device__ __forceinline__ float byte_f(uint32_t p, uint32_t sel) { return FS(__uint_as_float(__byte_perm(p, 0x4B000000u, sel)), 8388608.f); }
+__device__ __forceinline__ float to_c(uint32_t p, float cr, float cg, float cb, float off)
+{
+    const float r = byte_f(p, 0x7540u), g = byte_f(p, 0x7541u), b = byte_f(p, 0x7542u);
+    return FA(FA(FA(FM(cr, r), FM(cg, g)), FM(cb, b)), off);
+}
 __device__ __forceinline__ float to_y(uint32_t p)
 {
     const float r = (float)(p & 255u), g = (float)((p >> 8) & 255u), b = (float)((p >> 16) & 255u);
@@ -532,40 +544,39 @@ __global__ void __launch_bounds__(THREADS, 2) jfif_encode_kernel(const __grid_co
                     }
                 }
                 __syncwarp();
+            }
+
+            // ---- the lane's 64 samples to registers ----
+            float s[64];
+            if (SUB) {
+#pragma unroll
+                for (int y = 0; y < 8; ++y) {
+                    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+                    if (valid) {
+                        a = *reinterpret_cast<const float4 *>(my_blk + y * my_rs);
+                        b = *reinterpret_cast<const float4 *>(my_blk + y * my_rs + 4);
+                    }
+                    s[y * 8 + 0] = a.x; s[y * 8 + 1] = a.y; s[y * 8 + 2] = a.z; s[y * 8 + 3] = a.w;
+                    s[y * 8 + 4] = b.x; s[y * 8 + 5] = b.y; s[y * 8 + 6] = b.z; s[y * 8 + 7] = b.w;
+                }
             } else {
+                // 4:4:4: the three lanes of an MCU read the same 64 pixels and keep one component each, straight in registers
                 const uint4 *src = reinterpret_cast<const uint4 *>(blocks + mi * MCU_WORDS);
-#pragma unroll 1
-                for (int y = 0; y < 8; ++y) { // the three lanes of an MCU read the same pixel row, then each writes its own
+                const float cr = d == 0 ? 0.29900f : d == 1 ? -0.16874f : 0.50000f, cg = d == 0 ? 0.58700f : d == 1 ? -0.33126f : -0.41869f;
+                const float cb = d == 0 ? 0.11400f : d == 1 ? 0.50000f : -0.08131f, coff = d == 0 ? -128.f : -0.f;
+#pragma unroll
+                for (int y = 0; y < 8; ++y) {
                     uint4 a0 = make_uint4(0, 0, 0, 0), a1 = a0;
                     if (valid) {
                         a0 = src[2 * y];
                         a1 = src[2 * y + 1];
                     }
-                    __syncwarp();
-                    if (valid) {
-                        const uint32_t t[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-                        float o[8];
-#pragma unroll
-                        for (int x = 0; x < 8; ++x) o[x] = d == 0 ? to_y(t[x]) : d == 1 ? to_u(t[x]) : to_v(t[x]);
-                        float4 *dst = reinterpret_cast<float4 *>(my_blk + y * 8);
-                        dst[0] = make_float4(o[0], o[1], o[2], o[3]);
-                        dst[1] = make_float4(o[4], o[5], o[6], o[7]);
-                    }
+                    s[y * 8 + 0] = to_c(a0.x, cr, cg, cb, coff); s[y * 8 + 1] = to_c(a0.y, cr, cg, cb, coff);
+                    s[y * 8 + 2] = to_c(a0.z, cr, cg, cb, coff); s[y * 8 + 3] = to_c(a0.w, cr, cg, cb, coff);
+                    s[y * 8 + 4] = to_c(a1.x, cr, cg, cb, coff); s[y * 8 + 5] = to_c(a1.y, cr, cg, cb, coff);
+                    s[y * 8 + 6] = to_c(a1.z, cr, cg, cb, coff); s[y * 8 + 7] = to_c(a1.w, cr, cg, cb, coff);
                 }
-                __syncwarp();
-            }
-
-            // ---- the lane's 64 samples to registers ----
-            float s[64];
-#pragma unroll
-            for (int y = 0; y < 8; ++y) {
-                float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
-                if (valid) {
-                    a = *reinterpret_cast<const float4 *>(my_blk + y * my_rs);
-                    b = *reinterpret_cast<const float4 *>(my_blk + y * my_rs + 4);
-                }
-                s[y * 8 + 0] = a.x; s[y * 8 + 1] = a.y; s[y * 8 + 2] = a.z; s[y * 8 + 3] = a.w;
-                s[y * 8 + 4] = b.x; s[y * 8 + 5] = b.y; s[y * 8 + 6] = b.z; s[y * 8 + 7] = b.w;
+                __syncwarp(); // every lane holds its samples: the pixel words may be overwritten with coefficients
             }
 
             if (halo) { // DC only: output 0 of the row passes, then of the column pass over them
