@@ -53,6 +53,18 @@ constexpr int MCU_WORDS_420 = 256 + 128 + 4, MCU_WORDS_444 = 192 + 4;
 constexpr int BLOCK_WORDS = 10 * MCU_WORDS_444;
 static_assert(5 * MCU_WORDS_420 <= BLOCK_WORDS, "4:2:0 blocks fit the 4:4:4 area");
 constexpr int WARP_WORDS = 2 * CAP_WORDS + BLOCK_WORDS;
+// entropy coding: per lane 53 words; a data unit has at most 20 + 63 * 26 = 1658 bits = 52 words
+constexpr int AREA_WORDS = 53, COEF_AT = AREA_WORDS - 32;
+static_assert(32 * AREA_WORDS <= BLOCK_WORDS, "the lanes' entropy areas fit the blocks");
+// word COEF_AT + m (coefficients 2m, 2m+1) is read when the DC and the coefficients up to 2m-1 have been coded: the complete
+// words written by then, at most (20 + 26 (2m - 1)) / 32, must end at or below it
+constexpr bool area_is_safe()
+{
+    for (int m = 1; m < 32; ++m)
+        if ((20 + 26 * (2 * m - 1)) / 32 > COEF_AT + m) return false;
+    return (20 + 26 * 63 + 31) / 32 <= AREA_WORDS;
+}
+static_assert(area_is_safe(), "the bits of a data unit never overwrite a coefficient that is still to be read");
 
 // table block (32-bit words): built on the host, copied to shared memory by every CTA
 constexpr int T_AC_Y = 0;      // 256 x ((code << 8) | len), index run*16 + size
@@ -258,52 +270,6 @@ __device__ __forceinline__ void or_bits(uint32_t *buf, uint32_t off, uint32_t va
 {
     or_left64(buf, off, __funnelshift_lc(0u, val, 32 - len), 0u);
 }
-// two strings of at most 27 bits back to back (either may be empty)
-__device__ __forceinline__ void or_pair(uint32_t *buf, uint32_t off, uint32_t v0, int l0, uint32_t v1, int l1)
-{
-    const uint32_t a0 = __funnelshift_lc(0u, v0, 32 - l0), a1 = __funnelshift_lc(0u, v1, 32 - l1); // left aligned; 0 when empty
-    or_left64(buf, off, a0 | (a1 >> l0), __funnelshift_lc(0u, a1, 32 - l0));
-}
-
-// What one lane contributes to one data unit: the code + extra bits of zig-zag positions 2l and 2l+1 (v, length l; 0 when
-// the coefficient is zero) and how many ZRL codes precede each (k: run / 16).
-struct UnitBits {
-    uint32_t v0, v1;
-    int l0, l1, k0, k1;
-};
-// c0, c1: the lane's two coefficients (position 0 holds the DC difference).  Lane 0's even symbol is the DC category
-// (always coded); lane 31's odd position is 63: a zero there codes EOB.  (stb_image_write.h:1357-1395)
-__device__ __forceinline__ void unit_symbols(int c0, int c1, bool active, const uint32_t *tab_ac, const uint32_t *tab_dc, int lane,
-                                             uint32_t below, UnitBits &u)
-{
-    const uint32_t nz_e = __ballot_sync(0xffffffffu, c0 != 0) | 1u; // position 0 (DC) always bounds a run
-    const uint32_t nz_o = __ballot_sync(0xffffffffu, c1 != 0);
-    // nearest coded position before 2l: even positions are 2*i, odd ones 2*i+1
-    const int prev_e = max(62 - 2 * __clz(nz_e & below), 63 - 2 * __clz(nz_o & below)); // lane 0: -1 (unused)
-    const int run0 = 2 * lane - 1 - prev_e;
-    const int run1 = (c0 != 0 || lane == 0) ? 0 : run0 + 1;
-    const int n0 = bitlen(c0), n1 = bitlen(c1);
-    const bool first = lane == 0;
-    const bool emit0 = active && (first || c0 != 0), emit1 = active && (c1 != 0 || lane == 31);
-    const uint32_t e0 = first ? tab_dc[n0] : tab_ac[(run0 & 15) * 16 + n0];
-    const uint32_t e1 = tab_ac[c1 != 0 ? (run1 & 15) * 16 + n1 : 0]; // index 0 = EOB
-    u.v0 = emit0 ? ((e0 >> 8) << n0) | extra_bits(c0, n0) : 0u;
-    u.l0 = emit0 ? (int)(e0 & 255u) + n0 : 0;
-    u.v1 = emit1 ? ((e1 >> 8) << n1) | extra_bits(c1, n1) : 0u;
-    u.l1 = emit1 ? (int)(e1 & 255u) + n1 : 0;
-    u.k0 = (emit0 && !first) ? run0 >> 4 : 0;
-    u.k1 = (emit1 && c1 != 0) ? run1 >> 4 : 0;
-}
-// slow path of a data unit that holds a run of 16 or more zeros somewhere: [ZRL x k0][symbol 0][ZRL x k1][symbol 1]
-__device__ __forceinline__ void or_pair_zrl(uint32_t *buf, uint32_t off, const UnitBits &u, uint32_t zrl, int zl)
-{
-    for (int i = 0; i < u.k0; ++i, off += zl) or_bits(buf, off, zrl, zl);
-    or_bits(buf, off, u.v0, u.l0);
-    off += (uint32_t)u.l0;
-    for (int i = 0; i < u.k1; ++i, off += zl) or_bits(buf, off, zrl, zl);
-    or_bits(buf, off, u.v1, u.l1);
-}
-
 // the last min(7, nbits) bits of a big-endian bit buffer holding nbits bits
 __device__ __forceinline__ uint32_t last_bits(const uint32_t *buf, uint32_t nbits, int &count)
 {
@@ -433,14 +399,15 @@ __global__ void __launch_bounds__(THREADS, 2) jfif_encode_kernel(const __grid_co
     const bool lane_used = lane < UNITS_PER_ROUND;
     const bool is_luma = SUB ? d < 4 : d == 0;
     const float *mult = reinterpret_cast<const float *>(sm + (is_luma ? S_MULT : S_MULT_C));
-    const uint32_t below = (1u << lane) - 1u;
     const int R = P.rounds_per_tile;
     // this lane's data-unit block and its row stride
     const int my_rs = (SUB && d < 4) ? 16 : 8;
     uint32_t *my_blk = blocks + mi * MCU_WORDS + (SUB ? (d < 4 ? (d >> 1) * 128 + (d & 1) * 8 : 256 + (d - 4) * 64) : d * 64);
-    // entropy phase: offsets of zig-zag positions 2l and 2l+1 inside a block of row stride 8; stride 16 adds 8 per row
-    const int nat0 = cZZ.nat[2 * lane], nat1 = cZZ.nat[2 * lane + 1];
-    const int off0_8 = nat0, off1_8 = nat1, off0_16 = nat0 + (nat0 >> 3) * 8, off1_16 = nat1 + (nat1 >> 3) * 8;
+    // entropy phase: a lane-private area of the blocks (odd stride: no bank conflicts between lanes at the same index): the data
+    // unit's bits grow from word 0 while its 64 coefficients (int16, zig-zag order) are read from words COEF_AT.. — a coefficient
+    // yields at most 26 bits, the DC 20, so the bits never catch up with the coefficients still to be read
+    uint32_t *const area = blocks + lane * AREA_WORDS;
+    const uint32_t *const tab_ac = sm + (is_luma ? T_AC_Y : T_AC_C), *const tab_dc = sm + (is_luma ? T_DC_Y : T_DC_C);
 
     uint32_t pend_tile = 0, pend_bits = 0; // finished tile waiting in `pend` for its offset
     for (;;) {
@@ -618,11 +585,6 @@ __global__ void __launch_bounds__(THREADS, 2) jfif_encode_kernel(const __grid_co
                     for (int kk = 0; kk < 64; ++kk) gdst[kk] = (int16_t)q[kZZ.nat[kk]];
                 }
                 q[0] = dc - pred; // position 0 carries the DC DIFFERENCE: that is what gets coded
-#pragma unroll
-                for (int y = 0; y < 8; ++y) {
-                    *reinterpret_cast<int4 *>(my_blk + y * my_rs) = make_int4(q[y * 8], q[y * 8 + 1], q[y * 8 + 2], q[y * 8 + 3]);
-                    *reinterpret_cast<int4 *>(my_blk + y * my_rs + 4) = make_int4(q[y * 8 + 4], q[y * 8 + 5], q[y * 8 + 6], q[y * 8 + 7]);
-                }
             }
             {
                 const int base = (nmcus - 1) * DPM;
@@ -632,67 +594,93 @@ __global__ void __launch_bounds__(THREADS, 2) jfif_encode_kernel(const __grid_co
             }
             __syncwarp();
 
-            // ---- entropy coding: two data units per iteration, lane l codes zig-zag positions 2l and 2l+1 of each ----
-            {
-                const int nunits = nmcus * DPM;
-                int mA = 0, dA = 0; // MCU and data unit within it of unit j
-#pragma unroll 1
-                for (int j = 0; j < nunits; j += 2) {
-                    const bool haveB = j + 1 < nunits;
-                    int mB = mA, dB = dA + 1;
-                    if (dB == DPM) {
-                        dB = 0;
-                        ++mB;
-                    }
-                    const bool lumaA = SUB ? dA < 4 : dA == 0, lumaB = SUB ? dB < 4 : dB == 0;
-                    const int *blkA = reinterpret_cast<const int *>(blocks) + mA * MCU_WORDS +
-                                      (SUB ? (dA < 4 ? (dA >> 1) * 128 + (dA & 1) * 8 : 256 + (dA - 4) * 64) : dA * 64);
-                    const int *blkB = reinterpret_cast<const int *>(blocks) + mB * MCU_WORDS +
-                                      (SUB ? (dB < 4 ? (dB >> 1) * 128 + (dB & 1) * 8 : 256 + (dB - 4) * 64) : dB * 64);
-                    const bool wideA = SUB && dA < 4, wideB = SUB && dB < 4;
-                    const int a0 = blkA[wideA ? off0_16 : off0_8], a1 = blkA[wideA ? off1_16 : off1_8];
-                    int b0 = 0, b1 = 0;
-                    if (haveB) {
-                        b0 = blkB[wideB ? off0_16 : off0_8];
-                        b1 = blkB[wideB ? off1_16 : off1_8];
-                    }
-                    UnitBits A, B;
-                    unit_symbols(a0, a1, true, sm + (lumaA ? T_AC_Y : T_AC_C), sm + (lumaA ? T_DC_Y : T_DC_C), lane, below, A);
-                    unit_symbols(b0, b1, haveB, sm + (lumaB ? T_AC_Y : T_AC_C), sm + (lumaB ? T_DC_Y : T_DC_C), lane, below, B);
-                    // runs of 16 or more zeros need ZRL codes in front of the symbol (rare on dense data): lengths first
-                    const bool any_zrl = __any_sync(0xffffffffu, A.k0 | A.k1 | B.k0 | B.k1);
-                    uint32_t lenA = (uint32_t)(A.l0 + A.l1), lenB = (uint32_t)(B.l0 + B.l1);
-                    int zlA = 0, zlB = 0;
-                    if (any_zrl) {
-                        zlA = (int)(sm[(lumaA ? T_AC_Y : T_AC_C) + 0xF0] & 255u);
-                        zlB = (int)(sm[(lumaB ? T_AC_Y : T_AC_C) + 0xF0] & 255u);
-                        lenA += (uint32_t)((A.k0 + A.k1) * zlA);
-                        lenB += (uint32_t)((B.k0 + B.k1) * zlB);
-                    }
-                    uint32_t incl = lenA | (lenB << 16); // both prefix sums in one scan (a data unit has < 2^16 bits)
+            // ---- entropy coding: every lane codes its own data unit into its area, then the strings are concatenated ----
+            // (stb_image_write.h:1357-1395: DC category + bits, (run, size) codes + bits, ZRL for runs of 16, EOB)
+            uint32_t nbits = 0;
+            if (valid) {
 #pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) {
-                        const uint32_t tt = __shfl_up_sync(0xffffffffu, incl, o);
-                        if (lane >= o) incl += tt;
+                for (int m2 = 0; m2 < 32; ++m2)
+                    area[COEF_AT + m2] = __byte_perm((uint32_t)q[kZZ.nat[2 * m2]], (uint32_t)q[kZZ.nat[2 * m2 + 1]], 0x5410);
+                uint32_t cur = 0;  // the word being filled, left-aligned
+                int nacc = 0;      // bits in it
+                uint32_t *wp = area;
+                auto put = [&](uint32_t code, int len) { // 1 <= len <= 27, code right-aligned
+                    const uint32_t v = code << (32 - len);
+                    cur |= v >> nacc;
+                    const int tot = nacc + len;
+                    if (tot >= 32) { // (then nacc > 0)
+                        *wp++ = cur;
+                        cur = v << (32 - nacc);
                     }
-                    const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
-                    const uint32_t totA = tot & 0xffffu, totB = tot >> 16;
-                    if (running + totA + totB + 7 > (uint32_t)CAP_BITS) spill_buffer();
-                    const uint32_t offA = running + (incl & 0xffffu) - lenA, offB = running + totA + (incl >> 16) - lenB;
-                    if (!any_zrl) {
-                        or_pair(buf, offA, A.v0, A.l0, A.v1, A.l1);
-                        or_pair(buf, offB, B.v0, B.l0, B.v1, B.l1);
-                    } else {
-                        or_pair_zrl(buf, offA, A, sm[(lumaA ? T_AC_Y : T_AC_C) + 0xF0] >> 8, zlA);
-                        or_pair_zrl(buf, offB, B, sm[(lumaB ? T_AC_Y : T_AC_C) + 0xF0] >> 8, zlB);
+                    nacc = tot & 31;
+                };
+                {
+                    const int n = bitlen(q[0]);
+                    const uint32_t e = tab_dc[n];
+                    put(((e >> 8) << n) | extra_bits(q[0], n), (int)(e & 255u) + n);
+                }
+                const uint32_t zrl = tab_ac[0xF0], eob = tab_ac[0];
+                int run = 0;
+                uint32_t w = area[COEF_AT];
+#pragma unroll 2
+                for (int k = 1; k < 64; ++k) {
+                    if ((k & 1) == 0) w = area[COEF_AT + (k >> 1)];
+                    const int c = (k & 1) ? (int)w >> 16 : (int)(w << 16) >> 16;
+                    if (c == 0) {
+                        ++run;
+                        continue;
                     }
-                    running += totA + totB;
-                    mA = mB;
-                    dA = dB + 1;
-                    if (dA == DPM) {
-                        dA = 0;
-                        ++mA;
+                    while (run >= 16) {
+                        put(zrl >> 8, (int)(zrl & 255u));
+                        run -= 16;
                     }
+                    const int n = bitlen(c);
+                    const uint32_t e = tab_ac[run * 16 + n];
+                    put(((e >> 8) << n) | extra_bits(c, n), (int)(e & 255u) + n);
+                    run = 0;
+                }
+                if (run) put(eob >> 8, (int)(eob & 255u));
+                if (nacc) *wp++ = cur;
+                nbits = (uint32_t)(wp - area) * 32u - (nacc ? 32u - (uint32_t)nacc : 0u);
+            }
+            __syncwarp();
+            {
+                uint32_t incl = nbits;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t tt = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += tt;
+                }
+                // normally the whole round fits the buffer; otherwise as many leading data units as fit, a spill, and on
+                uint32_t done = 0; // bits of the round already copied
+                unsigned todo = __ballot_sync(0xffffffffu, nbits != 0);
+                while (todo) {
+                    const bool fits = nbits != 0 && ((todo >> lane) & 1u) && running + (incl - done) + 7 <= (uint32_t)CAP_BITS;
+                    const unsigned now = __ballot_sync(0xffffffffu, fits);
+                    if (now == 0) { // not even the next data unit: empty the buffer (a data unit always fits an empty one)
+                        spill_buffer();
+                        continue;
+                    }
+                    if (fits) {
+                        const uint32_t D = running + (incl - nbits - done);
+                        const int sh = (int)(D & 31u);
+                        uint32_t *dst = buf + (D >> 5);
+                        const int nsrc = (int)((nbits + 31u) >> 5), nout = (int)(((uint32_t)sh + nbits + 31u) >> 5);
+                        uint32_t prev = 0;
+                        for (int j = 0; j < nout; ++j) {
+                            const uint32_t cw = j < nsrc ? area[j] : 0u;
+                            const uint32_t o = __funnelshift_r(cw, prev, sh); // big-endian bit order
+                            if (j == 0 || j == nout - 1) atomicOr(dst + j, o); // the words shared with the neighbours
+                            else dst[j] = o;
+                            prev = cw;
+                        }
+                    }
+                    const int last = 31 - __clz(now); // `now` is a run of lanes: the sum up to its last one is in
+                    const uint32_t upto = __shfl_sync(0xffffffffu, incl, last);
+                    running += upto - done;
+                    done = upto;
+                    todo &= ~now;
+                    __syncwarp();
                 }
             }
             __syncwarp();
