@@ -139,6 +139,14 @@ int ljb_jpeg_encode_rgba_dev(ljb_ctx *ctx, const uint8_t *d_rgba, int w, int h, 
                              size_t ngroups, uint8_t *d_out, size_t out_cap, uint64_t *d_group_offsets,
                              uint16_t *d_group_bits, int16_t *d_coefs, uint64_t *d_result);
 
+/* The same two calls for pixels of THREE bytes (r g b), the layout stbi_load(path, &w, &h, &n, 3) returns and the one the reference's
+ * Pixel rows (JPEG.c:29-40, three uint8_t) have: stride >= 3 * w.  A quarter less to upload for the same result, byte for byte. */
+int ljb_jpeg_encode_rgb(ljb_ctx *ctx, const uint8_t *rgb, int w, int h, size_t stride, size_t first_group, size_t ngroups, uint8_t *out,
+                        size_t out_cap, uint64_t *group_offsets, uint16_t *group_bits, int16_t *coefs, size_t *out_len);
+int ljb_jpeg_encode_rgb_dev(ljb_ctx *ctx, const uint8_t *d_rgb, int w, int h, size_t stride, size_t first_group, size_t ngroups,
+                            uint8_t *d_out, size_t out_cap, uint64_t *d_group_offsets, uint16_t *d_group_bits, int16_t *d_coefs,
+                            uint64_t *d_result);
+
 /* Batch of nimages equal-sized images (BASELINE.json configs[4]: 8192 x 1920x1080): ONE launch, one ticket counter, one
  * look-back for the whole batch — the per-image loop of the reference's harness (Experiment/JPEG_sequential_experiment.c:57-144)
  * costs a launch, a memset and a synchronisation per image, which dominates a 50 us frame.

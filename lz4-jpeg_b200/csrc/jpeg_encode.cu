@@ -80,6 +80,7 @@ struct Params {
     int force_slow;          // test hook: route every channel through the general routine
     uint32_t img_groups;     // batch: groups per image (0 = one image); group g belongs to image g / img_groups
     size_t img_stride;       // batch: bytes between consecutive images
+    int bpp;                 // bytes per pixel of the image: 4 (r g b a) or 3 (r g b)
     const uint8_t *planar;   // or: the samples of every group as the reference's PixelGroup holds them (JPEG.c:42-46):
                              // lum_values[64], b_values[32], r_values[32] = 128 bytes per group; rgba is then unused
 };
@@ -330,7 +331,7 @@ struct BitWriter {
 
 // ---- general routine (local-memory arrays): any values, any number of symbols -------------------------------
 // Recomputes the channel from the pixels.  Follows JPEG.c:864-1007 literally (linear-search symbol table).
-__device__ __noinline__ int slow_channel(const uint8_t *rgba, int w, int h, size_t stride, size_t g, int ch, int16_t *co,
+__device__ __noinline__ int slow_channel(const uint8_t *rgba, int w, int h, size_t stride, int bpp, size_t g, int ch, int16_t *co,
                                          BitWriter *bwp, int max_bits, int *bad, const uint8_t *planar_group)
 {
     const int W = ch == 0 ? 8 : 4, N = 8 * W;
@@ -349,7 +350,7 @@ __device__ __noinline__ int slow_channel(const uint8_t *rgba, int w, int h, size
                 const size_t gate = bcol * 8 + (ch == 0 ? c : 2 * c);    // ... filed under the even column (JPEG.c:543)
                 int s = 0;
                 if (row < (size_t)h && gate < (size_t)w && col < (size_t)w) {
-                    const uint8_t *q = rgba + row * stride + col * 4;
+                    const uint8_t *q = rgba + row * stride + col * (size_t)bpp;
                     s = ch == 0 ? luma_of(q[0], q[1], q[2]) : (ch == 1 ? cr_of(q[0], q[1], q[2]) : cb_of(q[0], q[1], q[2]));
                 }
                 smp[lr * W + c] = (uint8_t)s;
@@ -667,6 +668,8 @@ __device__ __forceinline__ int entropy_fast(uint32_t *wl, uint32_t epoch, const 
     return bits;
 }
 
+// BPP: bytes per pixel of the image, 4 (r g b a) or 3 (r g b) — a template parameter because the kernel's hot code has to stay small
+template <int BPP>
 __global__ void __launch_bounds__(THREADS, 1) jpeg_encode_kernel(Params P)
 {
     extern __shared__ __align__(16) uint8_t smem[];
@@ -678,7 +681,8 @@ __global__ void __launch_bounds__(THREADS, 1) jpeg_encode_kernel(Params P)
     // their DCT (fp64 pipe), Huffman (integer / shared memory) and copy-out (L2 latency) phases overlap
     uint32_t *stage2 = P.scratch + ((size_t)blockIdx.x * NWARPS + warp) * (2 * REC_WORDS * 32) + lane; // two staging buffers
     const size_t bpr = ((size_t)P.w + 7) / 8;
-    const bool aligned = ((reinterpret_cast<uintptr_t>(P.rgba) | P.stride | P.img_stride) & 15) == 0;
+    constexpr bool rgb = BPP == 3; // three bytes per pixel: a group row is 24 bytes, read as three 8-byte words
+    const bool aligned = ((reinterpret_cast<uintptr_t>(P.rgba) | P.stride | P.img_stride) & (rgb ? 7 : 15)) == 0;
     // the tile computed in the previous iteration: its records wait in the other staging buffer until its offset
     // is fetched, one tile later, when its predecessors have (almost always) published theirs
     bool pend = false;
@@ -719,15 +723,30 @@ __global__ void __launch_bounds__(THREADS, 1) jpeg_encode_kernel(Params P)
                     ws_w(wl, W_SMP + 24 + i) = src[16 + i]; // b_values
                 }
             } else if (full && aligned) {
-                const uint8_t *rp = img + brow * 8 * P.stride + col0 * 4;
-                uint4 na = __ldcs(reinterpret_cast<const uint4 *>(rp)), nb = __ldcs(reinterpret_cast<const uint4 *>(rp) + 1); // streamed once
+                const uint8_t *rp = img + brow * 8 * P.stride + col0 * (size_t)BPP;
+                // one row of the group: 8 x 4 bytes as two 16-byte words, or 8 x 3 bytes as three 8-byte words (streamed once)
+                auto load_row = [&](const uint8_t *p, uint4 &a, uint4 &b) {
+                    if (rgb) {
+                        const uint2 t0 = __ldcs(reinterpret_cast<const uint2 *>(p)), t1 = __ldcs(reinterpret_cast<const uint2 *>(p) + 1);
+                        const uint2 t2 = __ldcs(reinterpret_cast<const uint2 *>(p) + 2);
+                        a = make_uint4(t0.x, t0.y, t1.x, t1.y);
+                        b = make_uint4(t2.x, t2.y, 0u, 0u);
+                    } else {
+                        a = __ldcs(reinterpret_cast<const uint4 *>(p));
+                        b = __ldcs(reinterpret_cast<const uint4 *>(p) + 1);
+                    }
+                };
+                uint4 na, nb;
+                load_row(rp, na, nb);
 #pragma unroll 1
                 for (int lr = 0; lr < 8; ++lr) {
                     uint32_t px[8] = {na.x, na.y, na.z, na.w, nb.x, nb.y, nb.z, nb.w};
-                    if (lr < 7) { // next row's pixels are in flight while this row is converted
-                        na = __ldcs(reinterpret_cast<const uint4 *>(rp + (lr + 1) * P.stride));
-                        nb = __ldcs(reinterpret_cast<const uint4 *>(rp + (lr + 1) * P.stride) + 1);
+                    if (rgb) { // pixel j starts at byte 3 j: r | g << 8 | b << 16 in the low three bytes, like the four-byte form
+                        const uint32_t w6[7] = {na.x, na.y, na.z, na.w, nb.x, nb.y, 0u};
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) px[j] = __funnelshift_r(w6[(3 * j) >> 2], w6[((3 * j) >> 2) + 1], 8 * ((3 * j) & 3));
                     }
+                    if (lr < 7) load_row(rp + (lr + 1) * P.stride, na, nb); // next row's pixels are in flight while this row is converted
                     uint32_t yy[2] = {0, 0}, cr = 0, cb = 0;
 #pragma unroll 1
                     for (int it = 0; it < 4; ++it) { // two pixels per step; the odd one also gives the chroma sample
@@ -755,7 +774,7 @@ __global__ void __launch_bounds__(THREADS, 1) jpeg_encode_kernel(Params P)
 #pragma unroll 1
                     for (int lc = 0; lc < 8; ++lc) {
                         if (row < (size_t)P.h && col0 + lc < (size_t)P.w) {
-                            const uint8_t *q = img + row * P.stride + (col0 + lc) * 4;
+                            const uint8_t *q = img + row * P.stride + (col0 + lc) * (size_t)BPP;
                             const int r = q[0], gg = q[1], bq = q[2];
                             const uint32_t y = (uint32_t)luma_of(r, gg, bq);
                             if (lc < 4) y0 |= y << (8 * lc);
@@ -802,7 +821,7 @@ __global__ void __launch_bounds__(THREADS, 1) jpeg_encode_kernel(Params P)
                 if (!((widemask >> ch) & 1u)) bits = entropy_fast(wl, (uint32_t)ch + 1u, cz, ch == 0 ? 0 : 2 + 2 * ch, ch == 0 ? 4 : 2, bw);
                 if (bits < 0) {
                     BitWriter tmp = bw;
-                    bits = slow_channel(img, P.w, P.h, P.stride, g, ch, nullptr, &tmp, max_bits, &bad, pgroup);
+                    bits = slow_channel(img, P.w, P.h, P.stride, BPP, g, ch, nullptr, &tmp, max_bits, &bad, pgroup);
                     bw = tmp;
                 } else if (bits > max_bits) {
                     bad = 1; // char encoded_sequence[1024] / [512] (JPEG.c:1248, :1286)
@@ -906,6 +925,7 @@ extern "C" size_t ljb_jpeg_bound(size_t ngroups) { return ngroups * (size_t)jpgk
 struct BatchMode {
     size_t nimages = 0, img_stride = 0; // nimages > 0: groups [0, nimages * group_count(w, h)) of a batch of equal-sized images
     const uint8_t *planar = nullptr;    // samples given per group (128 bytes each): w, h, stride and d_rgba are not used
+    int bpp = 4;                        // bytes per pixel: 4 (r g b a) or 3 (r g b)
 };
 static int jpeg_launch(ljb_ctx *ctx, const uint8_t *d_rgba, int w, int h, size_t stride, size_t first_group, size_t ngroups,
                        uint8_t *d_out, size_t out_cap, uint64_t *d_group_offsets, uint16_t *d_group_bits, int16_t *d_coefs,
@@ -917,7 +937,7 @@ static int jpeg_launch(ljb_ctx *ctx, const uint8_t *d_rgba, int w, int h, size_t
         w = 8;
         h = 8;
         stride = 32;
-    } else if (!d_rgba || w <= 0 || h <= 0 || (w & 1) || stride < (size_t)w * 4) {
+    } else if (!d_rgba || w <= 0 || h <= 0 || (w & 1) || (bm.bpp != 3 && bm.bpp != 4) || stride < (size_t)w * (size_t)bm.bpp) {
         return LJB_E_ARG; // odd widths make the reference read past its subsampled rows (JPEG.c:543 with :314)
     }
     const size_t per_image = ljb_jpeg_group_count(w, h);
@@ -955,13 +975,16 @@ static int jpeg_launch(ljb_ctx *ctx, const uint8_t *d_rgba, int w, int h, size_t
     P.img_groups = bm.nimages ? (uint32_t)per_image : 0u;
     P.img_stride = bm.nimages ? bm.img_stride : 0;
     P.planar = bm.planar;
+    P.bpp = bm.bpp;
     if (!(ctx->attr_mask & LJB_ATTR_JPEG)) { // per device (context), not per process
-        LJB_CUDA(cudaFuncSetAttribute(jpeg_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
+        LJB_CUDA(cudaFuncSetAttribute(jpeg_encode_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
+        LJB_CUDA(cudaFuncSetAttribute(jpeg_encode_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
         ctx->attr_mask |= LJB_ATTR_JPEG;
     }
     ctx->kernel_ms_summed = 0;
     LJB_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
-    jpeg_encode_kernel<<<grid, THREADS, SM_TOTAL, ctx->stream>>>(P);
+    if (bm.bpp == 3) jpeg_encode_kernel<3><<<grid, THREADS, SM_TOTAL, ctx->stream>>>(P);
+    else jpeg_encode_kernel<4><<<grid, THREADS, SM_TOTAL, ctx->stream>>>(P);
     LJB_CUDA(cudaGetLastError());
     LJB_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
     ctx->launches += 1;
@@ -974,6 +997,16 @@ extern "C" int ljb_jpeg_encode_rgba_dev(ljb_ctx *ctx, const uint8_t *d_rgba, int
 {
     return jpeg_launch(ctx, d_rgba, w, h, stride, first_group, ngroups, d_out, out_cap, d_group_offsets, d_group_bits, d_coefs,
                        d_result, 0);
+}
+
+// The same with three bytes per pixel (r g b), as stbi_load(..., 3) and the reference's Pixel rows hold them: a quarter less to upload.
+extern "C" int ljb_jpeg_encode_rgb_dev(ljb_ctx *ctx, const uint8_t *d_rgb, int w, int h, size_t stride, size_t first_group, size_t ngroups,
+                                       uint8_t *d_out, size_t out_cap, uint64_t *d_group_offsets, uint16_t *d_group_bits, int16_t *d_coefs,
+                                       uint64_t *d_result)
+{
+    BatchMode bm;
+    bm.bpp = 3;
+    return jpeg_launch(ctx, d_rgb, w, h, stride, first_group, ngroups, d_out, out_cap, d_group_offsets, d_group_bits, d_coefs, d_result, 0, bm);
 }
 
 // Batch of equal-sized images in ONE launch (one ticket counter, one look-back): image i holds groups
@@ -1003,17 +1036,18 @@ extern "C" int ljb_jpeg_encode_groups_dev(ljb_ctx *ctx, const uint8_t *d_samples
 
 // Host-buffer entry point: bands of whole group rows go through a three-stream pipeline (upload of band k+1 and
 // download of band k-1 overlap the kernel of band k), like ljb_lz4_compress.
-extern "C" int ljb_jpeg_encode_rgba(ljb_ctx *ctx, const uint8_t *rgba, int w, int h, size_t stride, size_t first_group,
-                                    size_t ngroups, uint8_t *out, size_t out_cap, uint64_t *group_offsets, uint16_t *group_bits,
-                                    int16_t *coefs, size_t *out_len)
+static int jpeg_encode_host(ljb_ctx *ctx, const uint8_t *rgba, int bpp, int w, int h, size_t stride, size_t first_group, size_t ngroups,
+                            uint8_t *out, size_t out_cap, uint64_t *group_offsets, uint16_t *group_bits, int16_t *coefs, size_t *out_len)
 {
-    if (!ctx || !rgba || !out || w <= 0 || h <= 0 || (w & 1) || stride < (size_t)w * 4) return LJB_E_ARG;
+    if (!ctx || !rgba || !out || w <= 0 || h <= 0 || (w & 1) || stride < (size_t)w * (size_t)bpp) return LJB_E_ARG;
+    BatchMode bm;
+    bm.bpp = bpp;
     const size_t total = ljb_jpeg_group_count(w, h);
     if (ngroups == 0 || first_group + ngroups > total) return LJB_E_ARG;
     LJB_CUDA(cudaSetDevice(ctx->device));
     int rc;
     // device layout of a band: image rows packed at a 16-byte aligned stride
-    const size_t dstride = ((size_t)w * 4 + 15) & ~(size_t)15;
+    const size_t dstride = ((size_t)w * (size_t)bpp + 15) & ~(size_t)15;
     const size_t bpr = ((size_t)w + 7) / 8;
     const size_t r_begin = first_group / bpr, r_end = (first_group + ngroups + bpr - 1) / bpr; // group rows touched
     size_t rows_per_band = ljb_pipe_chunk() / (dstride * 8);
@@ -1048,7 +1082,7 @@ extern "C" int ljb_jpeg_encode_rgba(ljb_ctx *ctx, const uint8_t *rgba, int w, in
         band(k, r0, r1, g0, g1);
         const size_t y0 = r0 * 8, y1 = r1 * 8 < (size_t)h ? r1 * 8 : (size_t)h;
         if (y1 <= y0) return cudaSuccess;
-        return cudaMemcpy2DAsync(ctx->d_pin[b], dstride, rgba + y0 * stride, stride, (size_t)w * 4, y1 - y0, cudaMemcpyHostToDevice,
+        return cudaMemcpy2DAsync(ctx->d_pin[b], dstride, rgba + y0 * stride, stride, (size_t)w * (size_t)bpp, y1 - y0, cudaMemcpyHostToDevice,
                                  ctx->s_in);
     };
     size_t running = 0;
@@ -1077,7 +1111,7 @@ extern "C" int ljb_jpeg_encode_rgba(ljb_ctx *ctx, const uint8_t *rgba, int w, in
         const uint8_t *biased = (const uint8_t *)ctx->d_pin[b] - r0 * 8 * dstride;
         // `running` is known here (band k-1 has been waited for), so the kernel writes stream-global offsets itself
         rc = jpeg_launch(ctx, biased, w, h, dstride, g0, g1 - g0, (uint8_t *)ctx->d_pout[b], cap_k, d_offs + gi + k, d_bits + 3 * gi,
-                         d_coefs ? d_coefs + 128 * gi : nullptr, d_res + 3 * k, running);
+                         d_coefs ? d_coefs + 128 * gi : nullptr, d_res + 3 * k, running, bm);
         if (rc != 0) {
             status = rc;
             goto done;
@@ -1117,6 +1151,17 @@ done:
     if (out_len) *out_len = running;
     if (status == LJB_OK && unsupported) return LJB_E_UNSUPPORTED;
     return status;
+}
+
+extern "C" int ljb_jpeg_encode_rgba(ljb_ctx *ctx, const uint8_t *rgba, int w, int h, size_t stride, size_t first_group, size_t ngroups,
+                                    uint8_t *out, size_t out_cap, uint64_t *group_offsets, uint16_t *group_bits, int16_t *coefs, size_t *out_len)
+{
+    return jpeg_encode_host(ctx, rgba, 4, w, h, stride, first_group, ngroups, out, out_cap, group_offsets, group_bits, coefs, out_len);
+}
+extern "C" int ljb_jpeg_encode_rgb(ljb_ctx *ctx, const uint8_t *rgb, int w, int h, size_t stride, size_t first_group, size_t ngroups,
+                                   uint8_t *out, size_t out_cap, uint64_t *group_offsets, uint16_t *group_bits, int16_t *coefs, size_t *out_len)
+{
+    return jpeg_encode_host(ctx, rgb, 3, w, h, stride, first_group, ngroups, out, out_cap, group_offsets, group_bits, coefs, out_len);
 }
 
 // Host-buffer batch: equal-sized images stored one after the other.  Images whose sides are multiples of 8 and that lie back to

@@ -54,11 +54,11 @@ def group_count(w: int, h: int) -> int:
 
 def process(rgba, first_group: int = 0, ngroups: int | None = None, want_coefs: bool = True,
             ctx: N.Context | None = None) -> EncodedImage:
-    """Encode the 8x8 groups [first_group, first_group+ngroups) of an H x W x 4 uint8 image."""
+    """Encode the 8x8 groups [first_group, first_group+ngroups) of an H x W x 4 (r g b a) or H x W x 3 (r g b) uint8 image."""
     a = np.ascontiguousarray(rgba, dtype=np.uint8)
-    if a.ndim != 3 or a.shape[2] != 4:
-        raise ValueError("expect an H x W x 4 uint8 array (the reference's Pixel, JPEG.c:29-32)")
-    h, w, _ = a.shape
+    if a.ndim != 3 or a.shape[2] not in (3, 4):
+        raise ValueError("expect an H x W x 4 or H x W x 3 uint8 array (the reference's Pixel, JPEG.c:29-32)")
+    h, w, bpp = a.shape
     total = group_count(w, h)
     if ngroups is None:
         ngroups = total - first_group
@@ -69,23 +69,23 @@ def process(rgba, first_group: int = 0, ngroups: int | None = None, want_coefs: 
     bits = np.zeros((ngroups, 3), dtype=np.uint16)
     coefs = np.zeros((ngroups, 128), dtype=np.int16) if want_coefs else None
     out_len = C.c_size_t(0)
-    rc = N.lib().ljb_jpeg_encode_rgba(ctx.handle, a.ctypes.data, w, h, 4 * w, first_group, ngroups, out.ctypes.data, cap,
-                                      offs.ctypes.data, bits.ctypes.data, coefs.ctypes.data if want_coefs else None,
-                                      C.byref(out_len))
-    N.check(rc, "ljb_jpeg_encode_rgba")
+    fn = N.lib().ljb_jpeg_encode_rgba if bpp == 4 else N.lib().ljb_jpeg_encode_rgb
+    rc = fn(ctx.handle, a.ctypes.data, w, h, bpp * w, first_group, ngroups, out.ctypes.data, cap, offs.ctypes.data, bits.ctypes.data,
+            coefs.ctypes.data if want_coefs else None, C.byref(out_len))
+    N.check(rc, "ljb_jpeg_encode_rgba" if bpp == 4 else "ljb_jpeg_encode_rgb")
     return EncodedImage(out[: out_len.value].copy(), offs, bits, coefs, w, h, first_group)
 
 
 def encode_device(d_rgba, w: int, h: int, d_out, d_group_offsets, d_group_bits, d_result, ctx: N.Context,
-                  first_group: int = 0, ngroups: int | None = None, d_coefs=None) -> None:
-    """Asynchronous on ctx.stream; d_* are torch CUDA tensors (pointers only)."""
+                  first_group: int = 0, ngroups: int | None = None, d_coefs=None, bpp: int = 4) -> None:
+    """Asynchronous on ctx.stream; d_* are torch CUDA tensors (pointers only).  bpp: bytes per pixel of d_rgba, 4 or 3."""
     if ngroups is None:
         ngroups = group_count(w, h) - first_group
-    rc = N.lib().ljb_jpeg_encode_rgba_dev(ctx.handle, d_rgba.data_ptr(), w, h, 4 * w, first_group, ngroups, d_out.data_ptr(),
-                                          d_out.numel(), d_group_offsets.data_ptr(),
-                                          d_group_bits.data_ptr() if d_group_bits is not None else None,
-                                          d_coefs.data_ptr() if d_coefs is not None else None, d_result.data_ptr())
-    N.check(rc, "ljb_jpeg_encode_rgba_dev")
+    fn = N.lib().ljb_jpeg_encode_rgba_dev if bpp == 4 else N.lib().ljb_jpeg_encode_rgb_dev
+    rc = fn(ctx.handle, d_rgba.data_ptr(), w, h, bpp * w, first_group, ngroups, d_out.data_ptr(), d_out.numel(), d_group_offsets.data_ptr(),
+            d_group_bits.data_ptr() if d_group_bits is not None else None, d_coefs.data_ptr() if d_coefs is not None else None,
+            d_result.data_ptr())
+    N.check(rc, "ljb_jpeg_encode_rgba_dev" if bpp == 4 else "ljb_jpeg_encode_rgb_dev")
 
 
 def assemble_image(coefs, w: int, h: int, original=None, ctx: N.Context | None = None) -> np.ndarray:

@@ -171,3 +171,47 @@ def test_decode_golden_and_noise(ljb, ctx, oracle):
     assert np.array_equal(rec, oracle.jpeg_decode(enc.coefs, 512, 256))
     with pytest.raises(ljb.LjbError):
         ljb.jpeg.assemble_image(ljb.jpeg.process(ALL["noise_18x13"], ctx=ctx).coefs, 18, 13, ctx=ctx)
+
+
+@pytest.mark.parametrize("name", sorted(ALL))
+def test_three_byte_pixels_match_reference_vectors(ljb, ctx, name):
+    """The same images as r g b (3 bytes per pixel, what stbi_load(..., 3) gives): the reference build's vectors again."""
+    enc = ljb.jpeg.process(np.ascontiguousarray(ALL[name][:, :, :3]), ctx=ctx)
+    assert np.array_equal(enc.coefs, VEC[f"{name}__coefs"])
+    assert np.array_equal(enc.group_bits, VEC[f"{name}__bits"])
+    assert np.array_equal(enc.group_offsets, VEC[f"{name}__offsets"])
+    assert np.array_equal(enc.stream, VEC[f"{name}__stream"])
+
+
+@pytest.mark.parametrize("w,h", [(1024, 512), (72, 52), (136, 40), (8, 8), (2, 2)])
+def test_three_byte_pixels_equal_four_byte_pixels(ljb, ctx, w, h):
+    """Widths whose rows are 8-byte aligned (the vector path) and not (the general path), sub-ranges, the device entry point."""
+    import torch
+
+    img = ljb.synth.random_image(w, h, seed=w + h)
+    rgb = np.ascontiguousarray(img[:, :, :3])
+    a, b = ljb.jpeg.process(img, ctx=ctx), ljb.jpeg.process(rgb, ctx=ctx)
+    assert np.array_equal(a.stream, b.stream) and np.array_equal(a.coefs, b.coefs)
+    assert np.array_equal(a.group_offsets, b.group_offsets) and np.array_equal(a.group_bits, b.group_bits)
+    ng = ljb.jpeg.group_count(w, h)
+    if ng > 8:
+        pa = ljb.jpeg.process(img, first_group=3, ngroups=ng - 5, ctx=ctx)
+        pb = ljb.jpeg.process(rgb, first_group=3, ngroups=ng - 5, ctx=ctx)
+        assert np.array_equal(pa.stream, pb.stream) and np.array_equal(pa.coefs, pb.coefs)
+    d_in = torch.from_numpy(rgb).cuda()
+    d_out = torch.empty(ng * 96 + 4096, dtype=torch.uint8, device="cuda")
+    d_offs = torch.empty(ng + 1, dtype=torch.int64, device="cuda")
+    d_bits = torch.empty(ng * 3, dtype=torch.int16, device="cuda")
+    d_res = torch.zeros(3, dtype=torch.int64, device="cuda")
+    torch.cuda.synchronize()
+    ljb.jpeg.encode_device(d_in, w, h, d_out, d_offs, d_bits, d_res, ctx, bpp=3)
+    torch.cuda.synchronize()
+    n = int(d_res[0].item())
+    assert n == a.stream.size and np.array_equal(d_out[:n].cpu().numpy(), a.stream)
+
+
+def test_three_byte_pixels_general_routine(ljb, ctx, monkeypatch):
+    monkeypatch.setenv("LJB_JPEG_FORCE_SLOW", "1")
+    img = ljb.synth.random_image(72, 52, seed=9)
+    a, b = ljb.jpeg.process(img, ctx=ctx), ljb.jpeg.process(np.ascontiguousarray(img[:, :, :3]), ctx=ctx)
+    assert np.array_equal(a.stream, b.stream) and np.array_equal(a.coefs, b.coefs)
