@@ -160,11 +160,6 @@ __device__ __forceinline__ void aan8(float &v0, float &v1, float &v2, float &v3,
     v1 = FA(p, z4);
     v7 = FS(p, z4);
 }
-// output 0 of the same graph
-__device__ __forceinline__ float aan8_dc(float v0, float v1, float v2, float v3, float v4, float v5, float v6, float v7)
-{
-    return FA(FA(FA(v0, v7), FA(v3, v4)), FA(FA(v1, v6), FA(v2, v5)));
-}
 // (int)(v < 0 ? v - 0.5f : v + 0.5f)  (stb_image_write.h:1353)
 __device__ __forceinline__ int quantise(float coef, float mult)
 {
@@ -444,13 +439,68 @@ __global__ void __launch_bounds__(THREADS, 2) jfif_encode_kernel(const __grid_co
             __syncwarp();
         };
 
-        const long long first = r0 == 0 ? 0 : (long long)r0 - 1;
-        for (long long rr = first; rr < (long long)r1; ++rr) {
-            // rr == r0 - 1 is the halo pass: only the MCU just before the tile, DC values only
-            const bool halo = rr < (long long)r0;
-            const uint32_t m0 = halo ? r0 * MPR - 1 : (uint32_t)rr * MPR;
+        // ---- the halo: the DC values of the last Y, Cb and Cr data units before the tile (they predict the tile's first ones),
+        // recomputed from the pixels of MCU r0 * MPR - 1.  A DC is output 0 of the row passes, then of the column pass over them:
+        // ((v0 + v7) + (v3 + v4)) + ((v1 + v6) + (v2 + v5)) over the rows, the same over the eight row sums.  Lane 4 r + j holds
+        // columns j and 7 - j of row r; the three levels of each tree are shuffles (IEEE addition commutes, so both partners get
+        // the same sum).  The conversions are the ones of the main path, operation for operation.
+        if (have && r0 > 0) {
+            const uint32_t mh = r0 * MPR - 1;
+            const int hx = (int)(mh % (uint32_t)P.mcux) * (SUB ? 16 : 8), hy = (int)(mh / (uint32_t)P.mcux) * (SUB ? 16 : 8);
+            const int og = P.comp > 2 ? 1 : 0, ob = P.comp > 2 ? 2 : 0;
+            auto pixel = [&](int x, int y) -> uint32_t { // coordinates beyond the image repeat the last column / row (stb :1533-1540)
+                const int xx = x < P.w ? x : P.w - 1, yy = y < P.h ? y : P.h - 1;
+                const uint8_t *q = P.px + (size_t)yy * P.stride + (size_t)xx * (size_t)P.comp;
+                return (uint32_t)q[0] | ((uint32_t)q[og] << 8) | ((uint32_t)q[ob] << 16);
+            };
+            auto tree = [&](float a, float b) -> float {
+                float t = FA(a, b);
+                t = FA(t, __shfl_xor_sync(0xffffffffu, t, 3));
+                t = FA(t, __shfl_xor_sync(0xffffffffu, t, 1));
+                t = FA(t, __shfl_xor_sync(0xffffffffu, t, 28));
+                t = FA(t, __shfl_xor_sync(0xffffffffu, t, 12));
+                return FA(t, __shfl_xor_sync(0xffffffffu, t, 4));
+            };
+            const int hr = lane >> 2, hj = lane & 3;
+            const float *mult_y = reinterpret_cast<const float *>(sm + S_MULT), *mult_c = reinterpret_cast<const float *>(sm + S_MULT_C);
+            float ya, yb, ua, ub, va, vb;
+            if (SUB) { // the last Y unit is the bottom-right one; a chroma sample is the mean of 2 x 2 pixels (stb :1557-1558)
+                const uint32_t pa = pixel(hx + 8 + hj, hy + 8 + hr), pb = pixel(hx + 8 + 7 - hj, hy + 8 + hr);
+                ya = to_c(pa, 0.29900f, 0.58700f, 0.11400f, -128.f);
+                yb = to_c(pb, 0.29900f, 0.58700f, 0.11400f, -128.f);
+                float uu[2], vv[2];
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    const int cx = k ? 7 - hj : hj;
+                    const uint32_t tl = pixel(hx + 2 * cx, hy + 2 * hr), tr = pixel(hx + 2 * cx + 1, hy + 2 * hr);
+                    const uint32_t bl = pixel(hx + 2 * cx, hy + 2 * hr + 1), br = pixel(hx + 2 * cx + 1, hy + 2 * hr + 1);
+                    uu[k] = FM(FA(FA(FA(to_c(tl, -0.16874f, -0.33126f, 0.50000f, -0.f), to_c(tr, -0.16874f, -0.33126f, 0.50000f, -0.f)),
+                                     to_c(bl, -0.16874f, -0.33126f, 0.50000f, -0.f)), to_c(br, -0.16874f, -0.33126f, 0.50000f, -0.f)), 0.25f);
+                    vv[k] = FM(FA(FA(FA(to_c(tl, 0.50000f, -0.41869f, -0.08131f, -0.f), to_c(tr, 0.50000f, -0.41869f, -0.08131f, -0.f)),
+                                     to_c(bl, 0.50000f, -0.41869f, -0.08131f, -0.f)), to_c(br, 0.50000f, -0.41869f, -0.08131f, -0.f)), 0.25f);
+                }
+                ua = uu[0];
+                ub = uu[1];
+                va = vv[0];
+                vb = vv[1];
+            } else {
+                const uint32_t pa = pixel(hx + hj, hy + hr), pb = pixel(hx + 7 - hj, hy + hr);
+                ya = to_c(pa, 0.29900f, 0.58700f, 0.11400f, -128.f);
+                yb = to_c(pb, 0.29900f, 0.58700f, 0.11400f, -128.f);
+                ua = to_c(pa, -0.16874f, -0.33126f, 0.50000f, -0.f);
+                ub = to_c(pb, -0.16874f, -0.33126f, 0.50000f, -0.f);
+                va = to_c(pa, 0.50000f, -0.41869f, -0.08131f, -0.f);
+                vb = to_c(pb, 0.50000f, -0.41869f, -0.08131f, -0.f);
+            }
+            carry_y = quantise(tree(ya, yb), mult_y[0]);
+            carry_u = quantise(tree(ua, ub), mult_c[0]);
+            carry_v = quantise(tree(va, vb), mult_c[0]);
+        }
+#pragma unroll 1
+        for (long long rr = (long long)r0; rr < (long long)r1; ++rr) {
+            const uint32_t m0 = (uint32_t)rr * MPR;
             const uint32_t left = P.nmcu - m0;
-            const int nmcus = halo ? 1 : (left < (uint32_t)MPR ? (int)left : MPR);
+            const int nmcus = left < (uint32_t)MPR ? (int)left : MPR;
             const bool valid = lane_used && mi < nmcus;
             const uint32_t m = m0 + (uint32_t)mi;
             {
@@ -544,19 +594,6 @@ __global__ void __launch_bounds__(THREADS, 2) jfif_encode_kernel(const __grid_co
                     s[y * 8 + 6] = to_c(a1.z, cr, cg, cb, coff); s[y * 8 + 7] = to_c(a1.w, cr, cg, cb, coff);
                 }
                 __syncwarp(); // every lane holds its samples: the pixel words may be overwritten with coefficients
-            }
-
-            if (halo) { // DC only: output 0 of the row passes, then of the column pass over them
-                float rs[8];
-#pragma unroll
-                for (int y = 0; y < 8; ++y)
-                    rs[y] = aan8_dc(s[y * 8], s[y * 8 + 1], s[y * 8 + 2], s[y * 8 + 3], s[y * 8 + 4], s[y * 8 + 5], s[y * 8 + 6], s[y * 8 + 7]);
-                const int dc = quantise(aan8_dc(rs[0], rs[1], rs[2], rs[3], rs[4], rs[5], rs[6], rs[7]), mult[0]);
-                carry_y = __shfl_sync(0xffffffffu, dc, SUB ? 3 : 0);
-                carry_u = __shfl_sync(0xffffffffu, dc, SUB ? 4 : 1);
-                carry_v = __shfl_sync(0xffffffffu, dc, SUB ? 5 : 2);
-                __syncwarp();
-                continue;
             }
 
             // ---- DCT, quantisation, DC difference; 64 int32 back into the block ----
