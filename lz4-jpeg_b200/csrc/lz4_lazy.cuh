@@ -33,12 +33,20 @@ constexpr int LCH = 12;                             // the index keeps a bucket 
 #ifndef LJB_TINYLIST
 #define LJB_TINYLIST 4
 #endif
+#ifndef LJB_TINYMAX
+#define LJB_TINYMAX 8
+#endif
+#ifndef LJB_TINYCROWD
+#define LJB_TINYCROWD 4
+#endif
 #ifndef LJB_BIGLIST
 #define LJB_BIGLIST 32
 #endif
 #ifndef LJB_VLONG
 #define LJB_VLONG 32
 #endif
+constexpr int TINYMAX = LJB_TINYMAX;                          // ... up to this length when TINYCROWD or more lanes of the warp have such a list (high-entropy data: every lane has one)
+constexpr int TINYCROWD = LJB_TINYCROWD;
 constexpr int TINYLIST = LJB_TINYLIST;                          // candidate lists up to this length are walked by the lane that owns them
 constexpr int BIGLIST = LJB_BIGLIST;                          // candidate lists this long are taken by the whole warp, shorter ones by a team of eight lanes
 constexpr uint32_t HOT_BUILD = 2048;                 // a block in which some bucket holds more entries than this also gets an index by 8-gram (in L2)
@@ -358,7 +366,7 @@ __device__ __forceinline__ void lazy_search(uint8_t *smem, const uint32_t nb, ui
                 const uint32_t h = hash4(g0);
                 lo = h ? dir16[h - 1] : 0u;
                 const uint32_t hi = dir16[h];
-                if (hi - lo <= (uint32_t)TINYLIST) {
+                if (hi - lo <= (uint32_t)TINYMAX) {
                     n = hi - lo; // (later positions are turned away one by one)
                 } else {
                     const uint32_t pch = p >> LCH;
@@ -380,8 +388,12 @@ __device__ __forceinline__ void lazy_search(uint8_t *smem, const uint32_t nb, ui
             // time; longer ones are taken by the whole warp, one at a time.
             uint32_t best = 0;
             // (i) short lists: every lane its own
+            bool taken = false; // this lane's list was dealt with in (i)
             {
-                const bool mine = need && n > 0 && n <= (uint32_t)TINYLIST;
+                // teams finish a list of 5 .. 8 in one pass, four lists at a time; when many lanes hold one, every lane walking its own is faster
+                const uint32_t tiny = __popc(__ballot_sync(FULL, need && n > (uint32_t)TINYLIST && n <= (uint32_t)TINYMAX)) >= TINYCROWD ? (uint32_t)TINYMAX : (uint32_t)TINYLIST;
+                const bool mine = need && n > 0 && n <= tiny;
+                taken = mine;
                 const uint32_t nmax = __reduce_max_sync(FULL, mine ? n : 0u);
                 for (uint32_t it = 0; it < nmax; it += 2) { // two entries per iteration: their loads are in flight together
                     const uint32_t c0 = (mine && it < n) ? (uint32_t)S[lo + it] : 0xFFFFu, c1 = (mine && it + 1 < n) ? (uint32_t)S[lo + it + 1] : 0xFFFFu;
@@ -485,7 +497,7 @@ __device__ __forceinline__ void lazy_search(uint8_t *smem, const uint32_t nb, ui
                 if (lane == src) best = tb;
             }
             // (iii) the lists in between: teams
-            unsigned rem = __ballot_sync(FULL, need && n > (uint32_t)TINYLIST && n < (uint32_t)BIGLIST);
+            unsigned rem = __ballot_sync(FULL, need && !taken && n > 0u && n < (uint32_t)BIGLIST);
             while (rem) {
                 const int b0 = __ffs(rem) - 1;
                 rem &= rem - 1;
