@@ -51,6 +51,10 @@ constexpr int TINYLIST = LJB_TINYLIST;                          // candidate lis
 constexpr int BIGLIST = LJB_BIGLIST;                          // candidate lists this long are taken by the whole warp, shorter ones by a team of eight lanes
 constexpr uint32_t HOT_BUILD = 2048;                 // a block in which some bucket holds more entries than this also gets an index by 8-gram (in L2)
 constexpr uint32_t HOT_USE = 512;                    // candidate lists longer than this look at the 8-gram bucket first
+#ifndef LJB_MINFRONT
+#define LJB_MINFRONT 1024
+#endif
+constexpr int MINFRONT = LJB_MINFRONT;                         // buckets with more entries than this keep their earliest position in front
 constexpr uint32_t VLONG = LJB_VLONG;                      // a lane compares this much on its own; longer runs are compared by the whole warp
 static_assert(2 * WG == SEG, "an emission segment is two walker segments");
 static_assert(NWALK_MAX <= THREADS, "one lane per walker");
@@ -159,6 +163,37 @@ __device__ __forceinline__ void lazy_search(uint8_t *smem, const uint32_t nb, ui
             }
         }
         __syncthreads();
+    }
+    // ---- big buckets: the EARLIEST position goes to the front (the entries of a chunk are in no particular order).  A search whose
+    // best pair reaches the cap at that position is over: no other member of the bucket lies before it.  Blocks of one byte, or
+    // of a short period, have one or two buckets of tens of thousands of entries and every search ends at their first entry.
+    {
+        constexpr uint32_t per_warp = NBUCKET / (THREADS / 32);
+        for (uint32_t b0 = (uint32_t)(tid >> 5) * per_warp; b0 < (uint32_t)(tid >> 5) * per_warp + per_warp; b0 += 32) {
+            const uint32_t h = b0 + (uint32_t)lane;
+            const uint32_t lo = h ? dir16[h - 1] : 0u, hi = dir16[h];
+            unsigned bigm = __ballot_sync(FULL, hi - lo > (uint32_t)MINFRONT);
+            while (bigm) {
+                const int src = __ffs(bigm) - 1;
+                bigm &= bigm - 1;
+                const uint32_t blo = __shfl_sync(FULL, lo, src), bhi = __shfl_sync(FULL, hi, src);
+                const uint32_t ch0 = (uint32_t)S[blo] >> LCH;
+                uint32_t mn = 0xFFFFFFFFu; // (position << 16) | index in the bucket
+                for (uint32_t base = 0;; base += 32) {
+                    const uint32_t i = base + (uint32_t)lane;
+                    uint32_t v = 0;
+                    const bool in = blo + i < bhi && ((v = S[blo + i]) >> LCH) == ch0; // the earliest position is in the bucket's first chunk
+                    if (in) mn = min(mn, (v << 16) | i);
+                    if (!__all_sync(FULL, in)) break;
+                }
+                mn = __reduce_min_sync(FULL, mn);
+                if (lane == 0 && (mn & 0xFFFFu) != 0u) {
+                    const uint16_t first = S[blo];
+                    S[blo] = (uint16_t)(mn >> 16);
+                    S[blo + (mn & 0xFFFFu)] = first;
+                }
+            }
+        }
     }
     // ---- low-entropy blocks (a 4-gram that occurs thousands of times: two-symbol data, long runs of a short period) also get an
     // index by 8-GRAM, in L2: a position whose 4-gram list is long looks at its 8-gram bucket first — every candidate that
@@ -433,6 +468,8 @@ __device__ __forceinline__ void lazy_search(uint8_t *smem, const uint32_t nb, ui
                 const uint32_t ocap = min((uint32_t)MAX_MATCH, nb - op);
                 uint32_t lb = 0, tb = 0; // this lane's best; what the whole warp knows (pairs at the cap, long compares)
                 bool capped = false;     // tb has reached the cap
+                // the bucket's earliest position as the low half of a key (only buckets of more than MINFRONT entries keep it in front)
+                const uint32_t ofront = on > (uint32_t)MINFRONT ? 0xFFFFu - (uint32_t)S[olo] : 0xFFFFFFFFu;
                 if (hot && on > HOT_USE && ocap >= 8u) { // the 8-gram bucket first (entries in no particular order)
                     const uint32_t h8 = hash8(og0, og1);
                     const uint32_t lo8 = h8 ? __ldcg(&dir8[h8 - 1]) : 0u, n8 = __ldcg(&dir8[h8]) - lo8;
@@ -476,13 +513,13 @@ __device__ __forceinline__ void lazy_search(uint8_t *smem, const uint32_t nb, ui
                     lb = max(lb, key);
                     if (__any_sync(FULL, vl0 || vl1 || (key >> 16) == ocap)) { // rare on text: a pair at the cap, or one for the warp
                         unsigned pendv = __ballot_sync(FULL, vl0);
-                        while (pendv) {
+                        while (pendv && tb != ((ocap << 16) | ofront)) { // (the cap at the earliest position of all: nothing beats it)
                             const int sv = __ffs(pendv) - 1;
                             pendv &= pendv - 1;
                             tb = max(tb, long_compare(__shfl_sync(FULL, c0, sv), op, ocap, tb));
                         }
                         pendv = __ballot_sync(FULL, vl1);
-                        while (pendv) {
+                        while (pendv && tb != ((ocap << 16) | ofront)) {
                             const int sv = __ffs(pendv) - 1;
                             pendv &= pendv - 1;
                             tb = max(tb, long_compare(__shfl_sync(FULL, c1, sv), op, ocap, tb));
@@ -491,7 +528,7 @@ __device__ __forceinline__ void lazy_search(uint8_t *smem, const uint32_t nb, ui
                         capped = (tb >> 16) == ocap;
                     }
                     // once the cap is reached only earlier positions matter: the entries of later chunks cannot win
-                    if (capped && it + 64 < on && (uint32_t)(S[olo + it + 64] >> LCH) > ((0xFFFFu - (tb & 0xFFFFu)) >> LCH)) break;
+                    if (capped && it + 64 < on && ((tb & 0xFFFFu) == ofront || (uint32_t)(S[olo + it + 64] >> LCH) > ((0xFFFFu - (tb & 0xFFFFu)) >> LCH))) break;
                 }
                 tb = max(tb, __reduce_max_sync(FULL, lb));
                 if (lane == src) best = tb;
