@@ -401,7 +401,10 @@ __device__ __forceinline__ void lazy_search(uint8_t *smem, const uint32_t nb, ui
                 const uint32_t h = hash4(g0);
                 lo = h ? dir16[h - 1] : 0u;
                 const uint32_t hi = dir16[h];
-                if (hi - lo <= (uint32_t)TINYMAX) {
+#ifndef LJB_SHORTCUT
+#define LJB_SHORTCUT TINYLIST
+#endif
+                if (hi - lo <= (uint32_t)(LJB_SHORTCUT)) {
                     n = hi - lo; // (later positions are turned away one by one)
                 } else {
                     const uint32_t pch = p >> LCH;
