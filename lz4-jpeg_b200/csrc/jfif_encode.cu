@@ -784,6 +784,14 @@ struct StuffParams {
     uint8_t *out;
     size_t out_cap;
     uint64_t *result;
+    // One launch per band of the host-buffer entry point, so that the finished part of the file can go down while later bands
+    // still come up: a launch stuffs the complete 4 KiB chunks below the bytes the tiles [0, upto_tile) have produced and
+    // were not yet below those of [0, prev_tile); the last launch (final) takes what is left, EOI and the length.
+    const uint64_t *tile_status; // the encode kernel's look-back words: inclusive bit count of the tiles placed so far
+    uint32_t prev_tile, upto_tile;
+    int final;
+    unsigned long long *ticket; // this launch's chunk counter
+    uint64_t *band_len;         // out: [0] file bytes complete after this launch (header included); [-1] the launch before (if prev_tile)
     Header hdr;
 };
 
@@ -796,20 +804,29 @@ __global__ void __launch_bounds__(STUFF_THREADS) jfif_stuff_kernel(const __grid_
     __shared__ uint32_t s_chunk;
     uint8_t *stage8 = reinterpret_cast<uint8_t *>(stage);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint64_t nbytes = *P.total_bits >> 3; // whole bytes only: a trailing partial byte is dropped (stb :1586)
-    const uint64_t nchunks = (nbytes + STUFF_CHUNK - 1) / STUFF_CHUNK;
+    // whole bytes only: a trailing partial byte is dropped (stb :1586); before the last launch, the bytes of the tiles placed so far
+    const uint64_t nbytes = P.final ? *P.total_bits >> 3 : (P.tile_status[P.upto_tile] & ~LJB_ST_MASK) >> 3;
+    const uint64_t before_bytes = P.prev_tile ? (P.tile_status[P.prev_tile] & ~LJB_ST_MASK) >> 3 : 0;
+    const uint64_t chunk_begin = before_bytes / STUFF_CHUNK; // the earlier launches did the complete chunks below their bytes
+    const uint64_t nchunks = P.final ? (nbytes + STUFF_CHUNK - 1) / STUFF_CHUNK : nbytes / STUFF_CHUNK;
+    const uint64_t chunk_end = P.final ? (nchunks ? nchunks : 1) : nchunks; // an empty stream still runs chunk 0 (header + EOI)
     if (nbytes > P.ucap) { // the encode kernel ran out of scratch (= the caller's buffer is too small): report a lower bound
         if (blockIdx.x == 0 && tid == 0) {
-            P.result[0] = HEADER_BYTES + nbytes + 2;
+            if (P.final) P.result[0] = HEADER_BYTES + nbytes + 2;
             atomicOr((unsigned long long *)&P.result[2], 1ull);
+            P.band_len[0] = P.prev_tile ? P.band_len[-1] : 0;
         }
         return;
     }
+    if (chunk_end <= chunk_begin) { // nothing new is complete
+        if (blockIdx.x == 0 && tid == 0) P.band_len[0] = P.prev_tile ? P.band_len[-1] : 0;
+        return;
+    }
     for (;;) {
-        if (tid == 0) s_chunk = (uint32_t)atomicAdd((unsigned long long *)&P.status[0], 1ull);
+        if (tid == 0) s_chunk = (uint32_t)atomicAdd(P.ticket, 1ull);
         __syncthreads();
-        const uint64_t chunk = s_chunk;
-        if (chunk >= (nchunks ? nchunks : 1)) break; // an empty stream still runs chunk 0 (header + EOI)
+        const uint64_t chunk = chunk_begin + s_chunk;
+        if (chunk >= chunk_end) break;
         const uint64_t at = chunk * STUFF_CHUNK + (uint64_t)tid * 16;
         uint4 v = make_uint4(0, 0, 0, 0);
         int nvalid = 0;
@@ -859,7 +876,7 @@ __global__ void __launch_bounds__(STUFF_THREADS) jfif_stuff_kernel(const __grid_
         }
         __syncthreads();
         const uint64_t base = HEADER_BYTES + s_base;
-        const bool is_last = chunk + 1 >= nchunks;
+        const bool is_last = P.final && chunk + 1 >= chunk_end;
         const uint64_t end = base + total + (is_last ? 2 : 0);
         if (is_last && tid == 0) {
             stage8[total] = 0xFF; // EOI
@@ -867,6 +884,7 @@ __global__ void __launch_bounds__(STUFF_THREADS) jfif_stuff_kernel(const __grid_
             P.result[0] = end;
             if (end > P.out_cap) atomicOr((unsigned long long *)&P.result[2], 1ull);
         }
+        if (chunk + 1 == chunk_end && tid == 0) P.band_len[0] = end <= P.out_cap ? end : 0;
         __syncthreads();
         if (end <= P.out_cap) {
             // copy stage8[0, n) to out + base: byte stores up to the first aligned word, then aligned 32-bit stores
@@ -1054,7 +1072,7 @@ extern "C" size_t ljb_jfif_bound(int w, int h)
 // on the context stream), then the stuffing kernel.  nbands == 1 with band_ready == nullptr is the device-resident call.
 static int jfif_run(ljb_ctx *ctx, const uint8_t *d_pixels, int w, int h, int comp, size_t stride, int quality, int subsample,
                     uint8_t *d_out, size_t out_cap, uint64_t *d_result, int16_t *d_coefs, int nbands, const int *band_end,
-                    const cudaEvent_t *band_ready)
+                    const cudaEvent_t *band_ready, uint64_t *band_len_host = nullptr, const cudaEvent_t *band_done = nullptr)
 {
     using namespace jfk;
     if (!ctx || !d_pixels || !d_out || !d_result || w <= 0 || h <= 0 || comp < 1 || comp > 4 || stride < (size_t)w * (size_t)comp ||
@@ -1091,8 +1109,8 @@ static int jfif_run(ljb_ctx *ctx, const uint8_t *d_pixels, int w, int h, int com
     const size_t o_st1 = o_total + 8;
     const size_t o_st2 = o_st1 + ((size_t)ntiles + 1) * 8;
     const size_t o_tailw = o_st2 + (nchunks_max + 1) * 8;
-    const size_t o_tick = (o_tailw + (size_t)ntiles * 4 + 7) & ~(size_t)7; // one ticket counter per band
-    const size_t o_end = o_tick + (size_t)nbands * 8;
+    const size_t o_tick = (o_tailw + (size_t)ntiles * 4 + 7) & ~(size_t)7; // per band: ticket of the encode launch, of the stuff launch, file bytes
+    const size_t o_end = o_tick + (size_t)(nbands + 1) * 3 * 8;
     // spill area: a tile is at most R rounds of 30 data units of 216 bytes
     const int spill_slots = (R * UNITS_PER_ROUND * 216 * 8) / (CAP_BITS - UNITS_PER_ROUND * 216 * 8 / 15) + 2;
     const size_t o_spill = (o_end + 15) & ~(size_t)15;
@@ -1137,6 +1155,18 @@ static int jfif_run(ljb_ctx *ctx, const uint8_t *d_pixels, int w, int h, int com
     }
     ctx->kernel_ms_summed = 0;
     const size_t full = (size_t)ctx->num_sms * 2;
+    StuffParams S;
+    S.ustream = P.ustream;
+    S.ucap = ucap;
+    S.total_bits = P.total_bits;
+    S.status = (uint64_t *)(sb + o_st2);
+    S.out = d_out;
+    S.out_cap = out_cap;
+    S.result = d_result;
+    S.tile_status = P.status; // word t = look-back word of tile t - 1 (its inclusive bit count once the tile is placed)
+    S.hdr = pl.hdr;
+    const size_t sfull = (size_t)ctx->num_sms * 8;
+    const int sgrid = (int)(nchunks_max < sfull ? nchunks_max : sfull);
     uint32_t t_begin = 0;
     for (int b = 0; b < nbands; ++b) {
         // tiles whose MCUs (and the one before the first: the DC halo) lie in the rows that are on the device by now
@@ -1158,24 +1188,26 @@ static int jfif_run(ljb_ctx *ctx, const uint8_t *d_pixels, int w, int h, int com
             else jfif_encode_kernel<false><<<grid, THREADS, SM_BYTES, ctx->stream>>>(P);
             LJB_CUDA(cudaGetLastError());
             ctx->launches += 1;
-            t_begin = t_end;
         }
+        if (b + 1 == nbands) LJB_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+        // stuffing of what this band completed (everything left, in the last band)
+        const bool final = b + 1 == nbands;
+        if (final || t_end > t_begin || band_len_host) {
+            S.prev_tile = t_begin;
+            S.upto_tile = t_end;
+            S.final = final ? 1 : 0;
+            S.ticket = (unsigned long long *)(sb + o_tick) + (nbands + 1) + b;
+            S.band_len = (uint64_t *)(sb + o_tick) + 2 * (nbands + 1) + 1 + b; // ([-1] of band 0 is never read)
+            jfif_stuff_kernel<<<sgrid, STUFF_THREADS, 0, ctx->stream>>>(S);
+            LJB_CUDA(cudaGetLastError());
+            ctx->launches += 1;
+            if (band_len_host) {
+                LJB_CUDA(cudaMemcpyAsync(band_len_host + b, S.band_len, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+                LJB_CUDA(cudaEventRecord(band_done[b], ctx->stream));
+            }
+        }
+        t_begin = t_end;
     }
-    LJB_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
-    StuffParams S;
-    S.ustream = P.ustream;
-    S.ucap = ucap;
-    S.total_bits = P.total_bits;
-    S.status = (uint64_t *)(sb + o_st2);
-    S.out = d_out;
-    S.out_cap = out_cap;
-    S.result = d_result;
-    S.hdr = pl.hdr;
-    const size_t sfull = (size_t)ctx->num_sms * 8;
-    const int sgrid = (int)(nchunks_max < sfull ? nchunks_max : sfull);
-    jfif_stuff_kernel<<<sgrid, STUFF_THREADS, 0, ctx->stream>>>(S);
-    LJB_CUDA(cudaGetLastError());
-    ctx->launches += 1;
     return LJB_OK;
 }
 
@@ -1190,7 +1222,8 @@ extern "C" int ljb_jfif_encode_dev(ljb_ctx *ctx, const uint8_t *d_pixels, int w,
 
 // Host-buffer entry point.  The image is one bit stream, but its tiles only look BACK (bit offsets, the DC of the data unit
 // before the tile): the rows are uploaded in bands on a second stream and the tiles of a band are encoded as soon as the
-// band has arrived, so the encode kernel hides behind the upload; stuffing and the download of the file follow.
+// band has arrived, so the encode kernel hides behind the upload; every band is followed by a stuffing launch over the 4 KiB
+// chunks its tiles completed, and that part of the file goes down on the third stream while later bands still come up.
 extern "C" int ljb_jfif_encode(ljb_ctx *ctx, const uint8_t *pixels, int w, int h, int comp, size_t stride, int quality, int subsample,
                                uint8_t *out, size_t out_cap, size_t *out_len)
 {
@@ -1208,13 +1241,15 @@ extern "C" int ljb_jfif_encode(ljb_ctx *ctx, const uint8_t *pixels, int w, int h
     if (dcap > bound) dcap = bound;
     if ((rc = ljb_ensure(&ctx->d_pout[0], &ctx->pout_bytes[0], dcap + 64)) != 0) return rc;
     if ((rc = ljb_ensure(&ctx->d_small, &ctx->small_bytes, 64)) != 0) return rc;
-    // bands of whole 16-row MCU rows, about one pipeline chunk of pixels each, at most MAXBANDS
-    constexpr int MAXBANDS = 16;
+    // bands of whole 16-row MCU rows, 3/8 of a pipeline chunk of pixels each (48 MiB: what follows the last upload — its tiles, their
+    // stuffing and download — is a band's worth; measured 18.1 / 16.7 / 16.3 / 16.4 ms at 128 / 64 / 48 / 32 MiB for 16384 x 16384 r g b),
+    // at most MAXBANDS
+    constexpr int MAXBANDS = 24;
     int band_end[MAXBANDS];
-    cudaEvent_t ready[MAXBANDS];
+    cudaEvent_t ready[2 * MAXBANDS]; // per band: its rows are on the device | its part of the file is complete
     int nbands = 0;
     {
-        size_t rows = ljb_pipe_chunk() / (dstride ? dstride : 1);
+        size_t rows = ljb_pipe_chunk() * 3 / 8 / (dstride ? dstride : 1);
         rows = (rows + 15) & ~(size_t)15;
         if (rows < 16) rows = 16;
         if (rows * MAXBANDS < (size_t)h) rows = (((size_t)h + MAXBANDS - 1) / MAXBANDS + 15) & ~(size_t)15;
@@ -1222,9 +1257,12 @@ extern "C" int ljb_jfif_encode(ljb_ctx *ctx, const uint8_t *pixels, int w, int h
     }
     int made = 0;
     int status = LJB_OK;
-    for (; made < nbands; ++made)
+    if ((rc = ljb_pipe_init(ctx, (size_t)nbands)) != 0) return rc;
+    for (; made < 2 * nbands; ++made)
         if (cudaEventCreateWithFlags(&ready[made], cudaEventDisableTiming) != cudaSuccess) break;
-    if (made < nbands) status = ljb_set_cuda_error(cudaGetLastError(), "cudaEventCreateWithFlags", __LINE__);
+    if (made < 2 * nbands) status = ljb_set_cuda_error(cudaGetLastError(), "cudaEventCreateWithFlags", __LINE__);
+    const cudaEvent_t *done = ready + nbands;
+    uint64_t *band_len = ctx->h_res; // pinned: the file bytes complete after each band
     if (status == LJB_OK) {
         // the upload stream must not overtake work still reading the buffer from an earlier call on the context stream
         cudaError_t e = cudaEventRecord(ctx->ev_kern[0], ctx->stream);
@@ -1238,20 +1276,31 @@ extern "C" int ljb_jfif_encode(ljb_ctx *ctx, const uint8_t *pixels, int w, int h
     }
     if (status == LJB_OK)
         status = jfif_run(ctx, (const uint8_t *)ctx->d_pin[0], w, h, comp, dstride, quality, subsample, (uint8_t *)ctx->d_pout[0], dcap,
-                          (uint64_t *)ctx->d_small, nullptr, nbands, band_end, ready);
+                          (uint64_t *)ctx->d_small, nullptr, nbands, band_end, ready, band_len, done);
     uint64_t res[3] = {0, 0, 0};
+    // the part of the file every band completed goes down on the third stream while later bands come up and are encoded
+    size_t sent = 0;
     if (status == LJB_OK) {
-        cudaError_t e = cudaMemcpyAsync(res, ctx->d_small, sizeof res, cudaMemcpyDeviceToHost, ctx->stream);
+        cudaError_t e = cudaSuccess;
+        for (int b = 0; b < nbands && e == cudaSuccess; ++b) {
+            e = cudaEventSynchronize(done[b]);
+            const size_t upto = e == cudaSuccess ? (size_t)band_len[b] : 0;
+            if (e == cudaSuccess && upto > sent && upto <= out_cap) {
+                e = cudaMemcpyAsync(out + sent, (const uint8_t *)ctx->d_pout[0] + sent, upto - sent, cudaMemcpyDeviceToHost, ctx->s_out);
+                sent = upto;
+            }
+        }
+        if (e == cudaSuccess) e = cudaMemcpyAsync(res, ctx->d_small, sizeof res, cudaMemcpyDeviceToHost, ctx->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-        if (e != cudaSuccess) status = ljb_set_cuda_error(e, "result download", __LINE__);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->s_out);
+        if (e != cudaSuccess) status = ljb_set_cuda_error(e, "file download", __LINE__);
     }
     cudaStreamSynchronize(ctx->s_in);
     cudaStreamSynchronize(ctx->stream);
+    cudaStreamSynchronize(ctx->s_out);
     for (int i = 0; i < made; ++i) cudaEventDestroy(ready[i]);
     if (status != LJB_OK) return status;
     *out_len = (size_t)res[0];
-    if (res[2] & 3) return LJB_E_CAPACITY;
-    LJB_CUDA(cudaMemcpyAsync(out, ctx->d_pout[0], (size_t)res[0], cudaMemcpyDeviceToHost, ctx->stream));
-    LJB_CUDA(cudaStreamSynchronize(ctx->stream));
+    if ((res[2] & 3) || sent != (size_t)res[0]) return LJB_E_CAPACITY;
     return LJB_OK;
 }

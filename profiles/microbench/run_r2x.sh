@@ -1,9 +1,4 @@
 set -x
 python -c "import lz4jpeg_b200 as l; l._native.lib()" || exit 1
-cd lz4-jpeg_b200
-for v in "-DLJB_SHORTCUT=4" "-DLJB_SHORTCUT=8" "-DLJB_SHORTCUT=4 -DLJB_TINYCROWD=33" "-DLJB_SHORTCUT=4 -DLJB_TINYCROWD=6" "-DLJB_SHORTCUT=6" "-DLJB_SHORTCUT=4"; do
-  nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC $v -c csrc/lz4_encode.cu -o build/lz4_encode.cu.o 2>/dev/null || exit 1
-  nvcc -gencode arch=compute_100a,code=sm_100a -shared -o liblz4jpeg_b200.so build/*.o -lcudart || exit 1
-  echo "variant $v"
-  (cd .. && timeout 120 python profiles/microbench/quick_lz4.py 268435456 2>&1 | tail -1; timeout 300 python profiles/microbench/degenerate_lz4.py 2>&1 | grep "random\|text")
-done
+timeout 900 python -m pytest tests/test_gpu_jfif.py tests/test_gpu_dropin.py tests/test_gpu_errors.py tests/test_gpu_compat.py -x -q 2>&1 | tail -3
+for c in 4 3; do for s in 0 1; do timeout 300 python profiles/tools/jfif_time.py --dim 16384 --sub $s --comp $c --iters 4 --e2e 2>&1 | tail -2; done; done > gpurun_out/jfif_timing_r2x.txt; cat gpurun_out/jfif_timing_r2x.txt
