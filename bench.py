@@ -42,7 +42,7 @@ BLOCK_LEN = 65536
 LZ4_BYTES = int(os.environ.get("LJB_BENCH_LZ4_BYTES", 4 * GIB))
 JPEG_DIM = int(os.environ.get("LJB_BENCH_JPEG_DIM", 16384))
 # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the ncu pass over this same command committed as
-# profiles/r2/launches_r2y_bench_steps2_warmup1.csv (the full-size launches of every kernel); bytes at the default workload sizes,
+# profiles/r2/launches_r2aa_bench_steps2_warmup1.csv (the full-size launches of every kernel); bytes at the default workload sizes,
 # None for other sizes.
 NCU_TRAFFIC = {"lz4": 4.374e9 + 5.915e9 if LZ4_BYTES == 4 * GIB else None, "lz4_decode": 45.6e9 + 4.49e9 if LZ4_BYTES == 4 * GIB else None,
                "jpeg": 1.086e9 + 0.504e9 if JPEG_DIM == 16384 else None,

@@ -106,7 +106,7 @@ def test_spilled_tiles(ljb, ctx, oracle, monkeypatch):
 @pytest.mark.parametrize("chunk", [1, 20000, 300000])
 def test_banded_upload(ljb, ctx, oracle, monkeypatch, chunk):
     """The host-buffer entry point uploads the rows in bands and encodes the tiles of a band as soon as it has arrived; a
-    small LJB_PIPE_CHUNK_BYTES drives up to sixteen bands (16-row bands, bands that hold no complete tile, ragged last
+    small LJB_PIPE_CHUNK_BYTES drives up to twenty-four bands (16-row bands, bands that hold no complete tile, ragged last
     bands) through small images; the file does not change."""
     monkeypatch.setenv("LJB_PIPE_CHUNK_BYTES", str(chunk))
     rng = np.random.default_rng(5)
