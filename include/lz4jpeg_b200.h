@@ -158,6 +158,12 @@ int ljb_jpeg_encode_batch(ljb_ctx *ctx, const uint8_t *rgba, int w, int h, size_
 int ljb_jpeg_encode_batch_dev(ljb_ctx *ctx, const uint8_t *d_rgba, int w, int h, size_t stride, size_t image_stride, size_t nimages,
                               uint8_t *d_out, size_t out_cap, uint64_t *d_group_offsets, uint16_t *d_group_bits, int16_t *d_coefs,
                               uint64_t *d_result);
+/* The batch calls for r g b pixels of three bytes (stride >= 3 * w). */
+int ljb_jpeg_encode_batch_rgb(ljb_ctx *ctx, const uint8_t *rgb, int w, int h, size_t stride, size_t image_stride, size_t nimages,
+                              uint8_t *out, size_t out_cap, uint64_t *group_offsets, uint16_t *group_bits, size_t *out_len);
+int ljb_jpeg_encode_batch_rgb_dev(ljb_ctx *ctx, const uint8_t *d_rgb, int w, int h, size_t stride, size_t image_stride, size_t nimages,
+                                  uint8_t *d_out, size_t out_cap, uint64_t *d_group_offsets, uint16_t *d_group_bits, int16_t *d_coefs,
+                                  uint64_t *d_result);
 
 /* process() of the reference's parallel build (Algorithms/parallel/JPEG/JPEG.c:1103-1252) on groups given by their samples
  * (PixelGroup, JPEG.c:42-46: lum_values[64], b_values[32], r_values[32] = 128 bytes per group):

@@ -1011,16 +1011,28 @@ extern "C" int ljb_jpeg_encode_rgb_dev(ljb_ctx *ctx, const uint8_t *d_rgb, int w
 
 // Batch of equal-sized images in ONE launch (one ticket counter, one look-back): image i holds groups
 // [i * G, (i + 1) * G) of the numbering, G = ljb_jpeg_group_count(w, h); its stream is out[group_offsets[i*G], group_offsets[(i+1)*G]).
-extern "C" int ljb_jpeg_encode_batch_dev(ljb_ctx *ctx, const uint8_t *d_rgba, int w, int h, size_t stride, size_t image_stride, size_t nimages,
-                                         uint8_t *d_out, size_t out_cap, uint64_t *d_group_offsets, uint16_t *d_group_bits, int16_t *d_coefs,
-                                         uint64_t *d_result)
+static int jpeg_batch_dev(ljb_ctx *ctx, const uint8_t *d_px, int bpp, int w, int h, size_t stride, size_t image_stride, size_t nimages,
+                          uint8_t *d_out, size_t out_cap, uint64_t *d_group_offsets, uint16_t *d_group_bits, int16_t *d_coefs, uint64_t *d_result)
 {
     if (nimages == 0) return LJB_E_ARG;
     BatchMode bm;
     bm.nimages = nimages;
     bm.img_stride = image_stride;
-    return jpeg_launch(ctx, d_rgba, w, h, stride, 0, nimages * ljb_jpeg_group_count(w, h), d_out, out_cap, d_group_offsets, d_group_bits,
+    bm.bpp = bpp;
+    return jpeg_launch(ctx, d_px, w, h, stride, 0, nimages * ljb_jpeg_group_count(w, h), d_out, out_cap, d_group_offsets, d_group_bits,
                        d_coefs, d_result, 0, bm);
+}
+extern "C" int ljb_jpeg_encode_batch_dev(ljb_ctx *ctx, const uint8_t *d_rgba, int w, int h, size_t stride, size_t image_stride, size_t nimages,
+                                         uint8_t *d_out, size_t out_cap, uint64_t *d_group_offsets, uint16_t *d_group_bits, int16_t *d_coefs,
+                                         uint64_t *d_result)
+{
+    return jpeg_batch_dev(ctx, d_rgba, 4, w, h, stride, image_stride, nimages, d_out, out_cap, d_group_offsets, d_group_bits, d_coefs, d_result);
+}
+extern "C" int ljb_jpeg_encode_batch_rgb_dev(ljb_ctx *ctx, const uint8_t *d_rgb, int w, int h, size_t stride, size_t image_stride, size_t nimages,
+                                             uint8_t *d_out, size_t out_cap, uint64_t *d_group_offsets, uint16_t *d_group_bits, int16_t *d_coefs,
+                                             uint64_t *d_result)
+{
+    return jpeg_batch_dev(ctx, d_rgb, 3, w, h, stride, image_stride, nimages, d_out, out_cap, d_group_offsets, d_group_bits, d_coefs, d_result);
 }
 
 // Groups given by their samples, as the reference's process() receives them (PixelGroup, JPEG.c:42-46: lum_values[64],
@@ -1169,21 +1181,21 @@ extern "C" int ljb_jpeg_encode_rgb(ljb_ctx *ctx, const uint8_t *rgb, int w, int 
 // Host-buffer batch: equal-sized images stored one after the other.  Images whose sides are multiples of 8 and that lie back to
 // back are, group for group, one tall image (8 | h: no group straddles two images; ceil(w*h/64) == tiles): they go through the
 // pipelined single-image path in one call.  Anything else is encoded image by image and the offsets are rebased.
-extern "C" int ljb_jpeg_encode_batch(ljb_ctx *ctx, const uint8_t *rgba, int w, int h, size_t stride, size_t image_stride, size_t nimages,
-                                     uint8_t *out, size_t out_cap, uint64_t *group_offsets, uint16_t *group_bits, size_t *out_len)
+static int jpeg_batch_host(ljb_ctx *ctx, const uint8_t *rgba, int bpp, int w, int h, size_t stride, size_t image_stride, size_t nimages,
+                           uint8_t *out, size_t out_cap, uint64_t *group_offsets, uint16_t *group_bits, size_t *out_len)
 {
-    if (!ctx || !rgba || !out || w <= 0 || h <= 0 || (w & 1) || nimages == 0 || stride < (size_t)w * 4 || image_stride < stride * (size_t)h)
+    if (!ctx || !rgba || !out || w <= 0 || h <= 0 || (w & 1) || nimages == 0 || stride < (size_t)w * (size_t)bpp || image_stride < stride * (size_t)h)
         return LJB_E_ARG;
     const size_t G = ljb_jpeg_group_count(w, h);
     if ((w % 8) == 0 && (h % 8) == 0 && image_stride == stride * (size_t)h && (size_t)h * nimages <= 0x7FFFFFFFull)
-        return ljb_jpeg_encode_rgba(ctx, rgba, w, (int)((size_t)h * nimages), stride, 0, G * nimages, out, out_cap, group_offsets, group_bits,
-                                    nullptr, out_len);
+        return jpeg_encode_host(ctx, rgba, bpp, w, (int)((size_t)h * nimages), stride, 0, G * nimages, out, out_cap, group_offsets, group_bits,
+                                nullptr, out_len);
     size_t running = 0;
     std::vector<uint64_t> offs(G + 1);
     for (size_t i = 0; i < nimages; ++i) {
         size_t len = 0;
-        const int rc = ljb_jpeg_encode_rgba(ctx, rgba + i * image_stride, w, h, stride, 0, G, out + running, out_cap - running,
-                                            group_offsets ? offs.data() : nullptr, group_bits ? group_bits + 3 * i * G : nullptr, nullptr, &len);
+        const int rc = jpeg_encode_host(ctx, rgba + i * image_stride, bpp, w, h, stride, 0, G, out + running, out_cap - running,
+                                        group_offsets ? offs.data() : nullptr, group_bits ? group_bits + 3 * i * G : nullptr, nullptr, &len);
         if (rc != LJB_OK) {
             if (out_len) *out_len = running + len;
             return rc;
@@ -1194,4 +1206,15 @@ extern "C" int ljb_jpeg_encode_batch(ljb_ctx *ctx, const uint8_t *rgba, int w, i
     }
     if (out_len) *out_len = running;
     return LJB_OK;
+}
+
+extern "C" int ljb_jpeg_encode_batch(ljb_ctx *ctx, const uint8_t *rgba, int w, int h, size_t stride, size_t image_stride, size_t nimages,
+                                     uint8_t *out, size_t out_cap, uint64_t *group_offsets, uint16_t *group_bits, size_t *out_len)
+{
+    return jpeg_batch_host(ctx, rgba, 4, w, h, stride, image_stride, nimages, out, out_cap, group_offsets, group_bits, out_len);
+}
+extern "C" int ljb_jpeg_encode_batch_rgb(ljb_ctx *ctx, const uint8_t *rgb, int w, int h, size_t stride, size_t image_stride, size_t nimages,
+                                         uint8_t *out, size_t out_cap, uint64_t *group_offsets, uint16_t *group_bits, size_t *out_len)
+{
+    return jpeg_batch_host(ctx, rgb, 3, w, h, stride, image_stride, nimages, out, out_cap, group_offsets, group_bits, out_len);
 }

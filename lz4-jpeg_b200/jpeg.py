@@ -138,11 +138,12 @@ def decode_huffman(enc: EncodedImage, trees, ctx: N.Context | None = None) -> np
 
 
 def process_batch(images, ctx: N.Context | None = None) -> EncodedImage:
-    """N equal-sized images (N x H x W x 4 uint8) in one call (ljb_jpeg_encode_batch): image i holds groups [i*G, (i+1)*G)."""
+    """N equal-sized images (N x H x W x 4 or N x H x W x 3 uint8) in one call (ljb_jpeg_encode_batch / _rgb): image i holds groups
+    [i*G, (i+1)*G)."""
     a = np.ascontiguousarray(images, dtype=np.uint8)
-    if a.ndim != 4 or a.shape[3] != 4:
-        raise ValueError("expect an N x H x W x 4 uint8 array")
-    n, h, w, _ = a.shape
+    if a.ndim != 4 or a.shape[3] not in (3, 4):
+        raise ValueError("expect an N x H x W x 4 or N x H x W x 3 uint8 array")
+    n, h, w, bpp = a.shape
     ctx = ctx or N.default_context()
     G = group_count(w, h)
     cap = int(N.lib().ljb_jpeg_bound(n * G))
@@ -150,18 +151,19 @@ def process_batch(images, ctx: N.Context | None = None) -> EncodedImage:
     offs = np.zeros(n * G + 1, dtype=np.uint64)
     bits = np.zeros((n * G, 3), dtype=np.uint16)
     out_len = C.c_size_t(0)
-    rc = N.lib().ljb_jpeg_encode_batch(ctx.handle, a.ctypes.data, w, h, 4 * w, 4 * w * h, n, out.ctypes.data, cap, offs.ctypes.data,
-                                       bits.ctypes.data, C.byref(out_len))
-    N.check(rc, "ljb_jpeg_encode_batch")
+    fn = N.lib().ljb_jpeg_encode_batch if bpp == 4 else N.lib().ljb_jpeg_encode_batch_rgb
+    rc = fn(ctx.handle, a.ctypes.data, w, h, bpp * w, bpp * w * h, n, out.ctypes.data, cap, offs.ctypes.data, bits.ctypes.data, C.byref(out_len))
+    N.check(rc, "ljb_jpeg_encode_batch" if bpp == 4 else "ljb_jpeg_encode_batch_rgb")
     return EncodedImage(out[: out_len.value].copy(), offs, bits, None, w, h, 0)
 
 
-def encode_batch_device(d_rgba, w: int, h: int, nimages: int, d_out, d_group_offsets, d_group_bits, d_result, ctx: N.Context) -> None:
-    """Asynchronous on ctx.stream: nimages back-to-back images in one launch (ljb_jpeg_encode_batch_dev)."""
-    rc = N.lib().ljb_jpeg_encode_batch_dev(ctx.handle, d_rgba.data_ptr(), w, h, 4 * w, 4 * w * h, nimages, d_out.data_ptr(), d_out.numel(),
-                                           d_group_offsets.data_ptr(), d_group_bits.data_ptr() if d_group_bits is not None else None, None,
-                                           d_result.data_ptr())
-    N.check(rc, "ljb_jpeg_encode_batch_dev")
+def encode_batch_device(d_rgba, w: int, h: int, nimages: int, d_out, d_group_offsets, d_group_bits, d_result, ctx: N.Context,
+                        bpp: int = 4) -> None:
+    """Asynchronous on ctx.stream: nimages back-to-back images in one launch (ljb_jpeg_encode_batch_dev / _rgb_dev)."""
+    fn = N.lib().ljb_jpeg_encode_batch_dev if bpp == 4 else N.lib().ljb_jpeg_encode_batch_rgb_dev
+    rc = fn(ctx.handle, d_rgba.data_ptr(), w, h, bpp * w, bpp * w * h, nimages, d_out.data_ptr(), d_out.numel(), d_group_offsets.data_ptr(),
+            d_group_bits.data_ptr() if d_group_bits is not None else None, None, d_result.data_ptr())
+    N.check(rc, "ljb_jpeg_encode_batch_dev" if bpp == 4 else "ljb_jpeg_encode_batch_rgb_dev")
 
 
 def process_groups(samples, ctx: N.Context | None = None):

@@ -50,6 +50,9 @@ def test_batch_entry_point_equals_per_image_calls():
                 assert np.array_equal(enc.stream[o0:o1], one.stream), (w, h, i)
                 assert np.array_equal(enc.group_bits[i * G:(i + 1) * G], one.group_bits)
                 assert np.array_equal(enc.group_offsets[i * G:(i + 1) * G + 1] - np.uint64(o0), one.group_offsets)
+            rgb = ljb.jpeg.process_batch(np.ascontiguousarray(imgs[:, :, :, :3]), ctx=ctx)  # the same frames as r g b, three bytes per pixel
+            assert np.array_equal(rgb.stream, enc.stream) and np.array_equal(rgb.group_offsets, enc.group_offsets), (w, h)
+            assert np.array_equal(rgb.group_bits, enc.group_bits)
     finally:
         ctx.close()
 
