@@ -53,6 +53,13 @@ int main(int argc, char **argv)
         die("ljb_jpeg_encode_rgba", rc);
     int jbad = jla != jlb || memcmp(ja, jb, jla) != 0 || memcmp(jao, jbo, (ng + 1) * 8) != 0 || memcmp(jab, jbb, ng * 6) != 0;
     printf("jpeg: %d GPUs %dx%d -> %zu bytes, %zu groups, %s\n", ngpus, w, h, jla, ng, jbad ? "MISMATCH" : "identical to 1 GPU");
+    /* the same image as r g b, three bytes per pixel: the same stream */
+    uint8_t *rgb = malloc((size_t)w * h * 3);
+    for (size_t i = 0; i < (size_t)w * h; ++i) memcpy(rgb + 3 * i, img + 4 * i, 3);
+    size_t jlc = 0;
+    if ((rc = ljb_comm_jpeg_encode_rgb(comm, rgb, w, h, (size_t)w * 3, ja, jcap, jao, jab, &jlc)) != LJB_OK) die("ljb_comm_jpeg_encode_rgb", rc);
+    int rbad = jlc != jlb || memcmp(ja, jb, jlc) != 0 || memcmp(jao, jbo, (ng + 1) * 8) != 0 || memcmp(jab, jbb, ng * 6) != 0;
+    printf("jpeg rgb: %d GPUs -> %zu bytes, %s\n", ngpus, jlc, rbad ? "MISMATCH" : "identical to 1 GPU");
     ljb_comm_destroy(comm);
-    return bad || jbad;
+    return bad || jbad || rbad;
 }

@@ -41,6 +41,9 @@ int ljb_comm_lz4_compress(ljb_comm *comm, const uint8_t *in, size_t n, size_t bl
 /* ljb_jpeg_encode_rgba over all GPUs: GPU r encodes a contiguous range of whole group rows of the one image. */
 int ljb_comm_jpeg_encode_rgba(ljb_comm *comm, const uint8_t *rgba, int w, int h, size_t stride, uint8_t *out, size_t out_cap,
                               uint64_t *group_offsets, uint16_t *group_bits, size_t *out_len);
+/* the same for r g b pixels of three bytes (ljb_jpeg_encode_rgb) */
+int ljb_comm_jpeg_encode_rgb(ljb_comm *comm, const uint8_t *rgb, int w, int h, size_t stride, uint8_t *out, size_t out_cap,
+                             uint64_t *group_offsets, uint16_t *group_bits, size_t *out_len);
 
 #ifdef __cplusplus
 }

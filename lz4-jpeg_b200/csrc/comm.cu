@@ -210,13 +210,13 @@ extern "C" int ljb_comm_lz4_compress(ljb_comm *c, const uint8_t *in, size_t n, s
     return LJB_OK;
 }
 
-extern "C" int ljb_comm_jpeg_encode_rgba(ljb_comm *c, const uint8_t *rgba, int w, int h, size_t stride, uint8_t *out, size_t out_cap,
-                                         uint64_t *group_offsets, uint16_t *group_bits, size_t *out_len)
+static int comm_jpeg_encode(ljb_comm *c, const uint8_t *rgba, int bpp, int w, int h, size_t stride, uint8_t *out, size_t out_cap,
+                            uint64_t *group_offsets, uint16_t *group_bits, size_t *out_len)
 {
-    if (!c || !rgba || !out || w <= 0 || h <= 0 || (w & 1) || stride < (size_t)w * 4) return LJB_E_ARG;
+    if (!c || !rgba || !out || w <= 0 || h <= 0 || (w & 1) || stride < (size_t)w * (size_t)bpp) return LJB_E_ARG;
     const size_t bpr = ((size_t)w + 7) / 8, total = ljb_jpeg_group_count(w, h), rows = (total + bpr - 1) / bpr;
     const size_t per = (rows + c->n - 1) / c->n;
-    const size_t dstride = ((size_t)w * 4 + 15) & ~(size_t)15;
+    const size_t dstride = ((size_t)w * (size_t)bpp + 15) & ~(size_t)15;
     struct Shard {
         size_t g0 = 0, g1 = 0, y0 = 0, y1 = 0, cap = 0;
     };
@@ -247,13 +247,13 @@ extern "C" int ljb_comm_jpeg_encode_rgba(ljb_comm *c, const uint8_t *rgba, int w
         const size_t ng = s.g1 - s.g0;
         uint64_t *d_res = (uint64_t *)c->d_small[r], *d_offs = d_res + 3;
         uint16_t *d_bits = (uint16_t *)(d_offs + ng + 1);
-        COMM_CUDA(cudaMemcpy2DAsync(c->d_in[r], dstride, rgba + s.y0 * stride, stride, (size_t)w * 4, s.y1 - s.y0, cudaMemcpyHostToDevice,
+        COMM_CUDA(cudaMemcpy2DAsync(c->d_in[r], dstride, rgba + s.y0 * stride, stride, (size_t)w * (size_t)bpp, s.y1 - s.y0, cudaMemcpyHostToDevice,
                                     c->ctx[r]->stream));
         // the kernel addresses rows of the whole image: bias the band's pointer by the rows before it (never dereferenced there)
         const uint8_t *biased = (const uint8_t *)c->d_in[r] - s.y0 * dstride;
-        if ((rc = ljb_jpeg_encode_rgba_dev(c->ctx[r], biased, w, h, dstride, s.g0, ng, (uint8_t *)c->d_out[r], s.cap, d_offs, d_bits, nullptr,
-                                           d_res)) != 0)
-            return rc;
+        rc = bpp == 3 ? ljb_jpeg_encode_rgb_dev(c->ctx[r], biased, w, h, dstride, s.g0, ng, (uint8_t *)c->d_out[r], s.cap, d_offs, d_bits, nullptr, d_res)
+                      : ljb_jpeg_encode_rgba_dev(c->ctx[r], biased, w, h, dstride, s.g0, ng, (uint8_t *)c->d_out[r], s.cap, d_offs, d_bits, nullptr, d_res);
+        if (rc != 0) return rc;
         COMM_CUDA(cudaMemcpyAsync(c->d_mine[r], d_res, sizeof(uint64_t), cudaMemcpyDeviceToDevice, c->ctx[r]->stream));
     }
     std::vector<const uint64_t *> totals(c->n);
@@ -292,4 +292,15 @@ extern "C" int ljb_comm_jpeg_encode_rgba(ljb_comm *c, const uint8_t *rgba, int w
         if (hres[r][2] & 1) return LJB_E_CAPACITY;
     }
     return LJB_OK;
+}
+
+extern "C" int ljb_comm_jpeg_encode_rgba(ljb_comm *c, const uint8_t *rgba, int w, int h, size_t stride, uint8_t *out, size_t out_cap,
+                                         uint64_t *group_offsets, uint16_t *group_bits, size_t *out_len)
+{
+    return comm_jpeg_encode(c, rgba, 4, w, h, stride, out, out_cap, group_offsets, group_bits, out_len);
+}
+extern "C" int ljb_comm_jpeg_encode_rgb(ljb_comm *c, const uint8_t *rgb, int w, int h, size_t stride, uint8_t *out, size_t out_cap,
+                                        uint64_t *group_offsets, uint16_t *group_bits, size_t *out_len)
+{
+    return comm_jpeg_encode(c, rgb, 3, w, h, stride, out, out_cap, group_offsets, group_bits, out_len);
 }

@@ -123,4 +123,4 @@ def test_c_host_on_n_gpus(tmp_path, ngpus):
     cases.synth_text(23 * 65536 + 999, seed=5).tofile(inp)
     r = subprocess.run([exe, str(ngpus), str(inp), "65536", "640", "328"], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
-    assert r.stdout.count("identical to 1 GPU") == 2, r.stdout
+    assert r.stdout.count("identical to 1 GPU") == 3, r.stdout
