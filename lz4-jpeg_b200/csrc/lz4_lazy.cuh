@@ -54,6 +54,11 @@ constexpr uint32_t HOT_USE = 512;                    // candidate lists longer t
 #ifndef LJB_MINFRONT
 #define LJB_MINFRONT 1024
 #endif
+#ifndef LJB_WIDE
+#define LJB_WIDE 8
+#endif
+constexpr uint32_t WIDE = LJB_WIDE;                   // walker segments of low-entropy blocks: this many times WG (even)
+static_assert(WIDE % 2 == 0 && WIDE >= 2, "a wide walker segment is a whole number of emission segments");
 constexpr int MINFRONT = LJB_MINFRONT;                         // buckets with more entries than this keep their earliest position in front
 constexpr uint32_t VLONG = LJB_VLONG;                      // a lane compares this much on its own; longer runs are compared by the whole warp
 static_assert(2 * WG == SEG, "an emission segment is two walker segments");
@@ -261,10 +266,15 @@ __device__ __forceinline__ void lazy_search(uint8_t *smem, const uint32_t nb, ui
     // Consecutive segments go to different warps (lane l of warp w parses segment 32 l + w): the expensive stretches of a block
     // (fresh text) and the cheap ones (capped runs) are then spread over all warps — with contiguous segments per warp the round
     // waited for its slowest warp for a quarter of the kernel.
-    const uint32_t nwalk = (nb + WG - 1) / WG;
+    // Low-entropy blocks (the ones that got the 8-gram index) take walker segments of WIDE x WG bytes: their matches are long (15 bytes
+    // on two-symbol data) and two chains that enter a 66-byte segment at different offsets rarely meet inside it, so every round
+    // corrected one more segment — half of such a block's cycles went to rounds >= 1.  (tune bit 1 forces, bit 2 forbids.)
+    const bool wide = ((hot && !(P.tune & 4u)) || (P.tune & 2u)) && nb > WIDE * (uint32_t)WG;
+    const uint32_t wg = wide ? WIDE * (uint32_t)WG : (uint32_t)WG;
+    const uint32_t nwalk = (nb + wg - 1) / wg;
     const uint32_t s = (P.tune & 1u) ? (uint32_t)tid : (uint32_t)lane * 32u + (uint32_t)(tid >> 5); // (tune bit 0: contiguous segments per warp, for measurements)
     const bool has = s < nwalk;
-    const uint32_t seg0 = s * WG, segend = min(seg0 + (uint32_t)WG, nb);
+    const uint32_t seg0 = s * wg, segend = min(seg0 + wg, nb);
     uint32_t my_in = 0, my_can = 0; // (own lane only) where the latest walk of the segment started; exit of its first walk
     bool my_split = false;          // a later walk left the segment without meeting an earlier one
     uint32_t d_search = 0, d_cand = 0, d_steps = 0, d_vl = 0, d_run = 0;
@@ -358,7 +368,7 @@ __device__ __forceinline__ void lazy_search(uint8_t *smem, const uint32_t nb, ui
                 run = true;
                 p = seg0;
             } else if (s > 0) {
-                const uint32_t e = (uint32_t)xout[s - 1] + (s - 1) * WG; // where the chain leaves the segment before this one
+                const uint32_t e = (uint32_t)xout[s - 1] + (s - 1) * wg; // where the chain leaves the segment before this one
                 if (e != my_in) {
                     run = true;
                     p = e;
@@ -662,11 +672,23 @@ __device__ __forceinline__ void lazy_search(uint8_t *smem, const uint32_t nb, ui
         for (uint32_t i = (uint32_t)tid; i < (nb + 15u) / 16u; i += THREADS) z[i] = __ldcg(&g4[i]);
         const uint32_t nseg = (nb + SEG - 1) / SEG;
         uint32_t e8 = 0xFFu;
-        if ((uint32_t)tid < nseg) {
+        if (!wide && (uint32_t)tid < nseg) {
             const uint32_t e = (uint32_t)xin[2 * tid] + 2u * (uint32_t)tid * WG; // first chain position at or behind the segment's start
             if (e < min(((uint32_t)tid + 1u) * SEG, nb)) e8 = e - (uint32_t)tid * SEG;
         }
         entry[tid] = (uint8_t)e8;
+        if (wide) { // a wide walker segment is WIDE / 2 emission segments: the entries of all but the first are found along the steps
+            __syncthreads(); // step[] and the defaults of entry[] are complete
+            if ((uint32_t)tid < nwalk) {
+                uint32_t e = (uint32_t)xin[tid] + (uint32_t)tid * wg;
+#pragma unroll 1
+                for (uint32_t g = (WIDE / 2u) * (uint32_t)tid; g < (WIDE / 2u) * ((uint32_t)tid + 1u) && g < nseg; ++g) {
+                    const uint32_t lo = g * SEG, hi = min(lo + (uint32_t)SEG, nb);
+                    while (e < lo) e += step[e] ? (uint32_t)step[e] : 1u;
+                    if (e < hi) entry[g] = (uint8_t)(e - lo);
+                }
+            }
+        }
     }
     if (P.phase_cycles) {
         const unsigned t_s = __reduce_add_sync(FULL, d_search), t_c = __reduce_add_sync(FULL, d_cand);

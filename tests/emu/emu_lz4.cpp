@@ -45,6 +45,7 @@ extern "C" int emu_lz4_compress(const uint8_t *in, size_t n, size_t block_len, u
     P.frame_byte = (uint32_t)(nblocks & 0xFF);
     P.dump_len = dump_len;
     P.dump_dist = dump_dist;
+    P.tune = getenv("LJB_LZ4_TUNE") ? (uint32_t)atoi(getenv("LJB_LZ4_TUNE")) : 0u; // the kernel's experiment switches, as the library reads them
     P.phase_cycles = phase24; // optional: 24 counters (the kernel's LJB_LZ4_PHASES probes; 'cycles' are emulator ticks)
     if (phase24) memset(phase24, 0, 24 * sizeof *phase24);
     result[0] = result[1] = result[2] = 0;

@@ -93,6 +93,20 @@ def test_chain_search_pathological_blocks(emu, oracle):
         assert np.array_equal(s, s0) and ph == p0
 
 
+def test_chain_search_wide_walker_segments(emu, oracle, monkeypatch):
+    """Two-symbol data takes the wide walker segments (8 x 66 bytes) by itself; LJB_LZ4_TUNE=2 forces them on text as well."""
+    rng = np.random.default_rng(11)
+    two = rng.integers(0, 2, 65536 + 900, dtype=np.uint8) + 48
+    s, offs, ph = _compress(emu, two, 65536, LAZY)
+    s0, o0, p0 = oracle.lz4_compress(two, 65536, 1)
+    assert np.array_equal(s, s0) and np.array_equal(offs, o0) and ph == p0
+    monkeypatch.setenv("LJB_LZ4_TUNE", "2")
+    for data in (cases.synth_text(65536 + 3000, seed=5), cases.synth_text(1000, seed=2), np.zeros(66000, np.uint8)):
+        s, offs, ph = _compress(emu, data, 65536, LAZY)
+        s0, o0, p0 = oracle.lz4_compress(data, 65536, 1)
+        assert np.array_equal(s, s0) and np.array_equal(offs, o0) and ph == p0
+
+
 def test_chain_search_benchmark_blocks(emu, oracle):
     """12 blocks of the benchmark distribution through one persistent CTA (ticket counter, look-back, deferred placement)."""
     data = cases.synth_text(12 * 65536, seed=42)

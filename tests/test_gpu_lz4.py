@@ -119,6 +119,20 @@ def test_pathological_blocks_terminate(ljb, ctx, oracle):
         assert np.array_equal(f.stream, s) and f.phantom == ph
 
 
+@pytest.mark.parametrize("tune", ["2", "4"])
+def test_wide_walker_segments_forced_and_forbidden(ljb, ctx, oracle, monkeypatch, tune):
+    """Low-entropy blocks are walked in segments of 528 bytes instead of 66 (lz4_lazy.cuh, `wide`): the same streams with that
+    mode forced on every block (LJB_LZ4_TUNE=2) and forbidden on every block (4) — text, two-symbol data, a ragged last block."""
+    monkeypatch.setenv("LJB_LZ4_TUNE", tune)
+    rng = np.random.default_rng(11)
+    for data in (cases.synth_text(3 * 65536 + 1234, seed=5), rng.integers(0, 2, 2 * 65536 + 700, dtype=np.uint8) + 48,
+                 rng.integers(0, 4, 65536, dtype=np.uint8), np.zeros(70000, np.uint8), cases.synth_text(5000, seed=1)):
+        bl = min(65536, data.size)
+        f = ljb.lz4.lz4_encode(data, bl, ctx=ctx)
+        s, offs, ph = oracle.lz4_compress(data, bl, 1)
+        assert np.array_equal(f.stream, s) and np.array_equal(f.block_offsets, offs) and f.phantom == ph
+
+
 def test_capacity_error(ljb, ctx):
     data = cases.synth_text(8192, seed=1)
     with pytest.raises(ljb.LjbError) as e:
