@@ -83,6 +83,7 @@ struct Misc {
     long long ticket;
     unsigned long long base;                 // output offset of this block
     int emit_ok;
+    unsigned int wdone[NWARPS];              // chain search: ticket + 1 of the block whose first walks warp w has finished
 };
 static_assert(sizeof(Misc) <= 1024, "Misc must fit its area");
 
@@ -242,6 +243,7 @@ __global__ void __launch_bounds__(THREADS, 1) lz4_encode_kernel(Params P)
         if (fw == 0) __syncthreads(); // M.base / M.emit_ok are reused (after a partial flush: the barrier behind the chain hop)
     };
 
+    if (tid < NWARPS) M.wdone[tid] = 0; // (read after the first block's barriers; a block's own value is its ticket + 1, never 0)
     long long t_prev = clock64();
 #define LJB_PHASE(idx)                                                                      \
     do {                                                                                    \

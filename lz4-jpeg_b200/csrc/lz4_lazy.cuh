@@ -27,6 +27,12 @@
 // benchmark text, 30 000-byte passages of a 118 KB corpus, has 10 k .. 30 k such positions per block).
 #pragma once
 
+#ifdef LJB_EMU // (the CPU emulation runs one fiber at a time: a spinning lane hands over)
+#define LJB_SPIN() emu_spin_yield()
+#define __threadfence_block() ((void)0)
+#else
+#define LJB_SPIN() ((void)0)
+#endif
 constexpr int WG = 66;                              // bytes per walker segment: two per emission segment
 constexpr int NWALK_MAX = (MAXB + WG - 1) / WG;     // 993
 constexpr int LCH = 12;                             // the index keeps a bucket ordered by 4096-position chunk
@@ -360,9 +366,25 @@ __device__ __forceinline__ void lazy_search(uint8_t *smem, const uint32_t nb, ui
         }
         return (res << 16) | (0xFFFFu - bc);
     };
+    // Rounds 0 and 1 run without a CTA barrier between them: what a walker of round 1 needs from the others is the exit of the
+    // segment before its own, and that segment belongs to the same lane of the warp before (lane - 1 of the last warp for the
+    // first one).  A warp that has written its exits of round 0 says so in wdone[] and goes on as soon as the warp before it has
+    // said the same: the re-walks of the fast warps fill the time they would have waited for the slowest one.  (Everything else
+    // a walk touches — known bits, steps, records — belongs to its own segment.)
+#ifndef LJB_FUSE_ROUNDS
+#define LJB_FUSE_ROUNDS 1
+#endif
+    volatile unsigned int *const wdone = M.wdone;
+    const unsigned int epoch = (unsigned int)M.ticket + 1u; // (tickets are unique: no flag has to be cleared between blocks)
     for (uint32_t round = 0;; ++round) {
         bool run = false;
         uint32_t p = 0;
+        if (LJB_FUSE_ROUNDS && round == 1) {
+            if (lane == 0)
+                while (wdone[((tid >> 5) + 31) & 31] != epoch) LJB_SPIN();
+            __syncwarp();
+            __threadfence_block();
+        }
         if (has) {
             if (round == 0) {
                 run = true;
@@ -375,7 +397,7 @@ __device__ __forceinline__ void lazy_search(uint8_t *smem, const uint32_t nb, ui
                 }
             }
         }
-        if (!__syncthreads_or(run)) break; // (also separates the reads above from this round's writes)
+        if (!(LJB_FUSE_ROUNDS && round == 1) && !__syncthreads_or(run)) break; // (also separates the reads above from this round's writes)
         if (run) my_in = p;
         uint32_t ex = p;                   // a chain that jumps over the segment leaves it where it enters it
         bool act = run && p < segend;
@@ -655,7 +677,13 @@ __device__ __forceinline__ void lazy_search(uint8_t *smem, const uint32_t nb, ui
             if (round == 0) my_can = ex;
             else if (walked && !met && ex != my_can) my_split = true;
         }
-        __syncthreads(); // the exits of this round are what the next round starts from
+        if (LJB_FUSE_ROUNDS && round == 0) { // this warp's exits of round 0 are written: the warp after it may start its round 1
+            __threadfence_block();
+            __syncwarp();
+            if (lane == 0) wdone[tid >> 5] = epoch;
+        } else {
+            __syncthreads(); // the exits of this round are what the next round starts from
+        }
         if (round == 0) phase(2); // first walks
     }
     phase(1); // later rounds

@@ -61,6 +61,11 @@ static void run_cta(Cta &c)
     unsigned done = 0;
     for (;;) {
         bool progress = false;
+        for (auto &f : c.fibers) // lanes that were spinning on a flag look at it again
+            if (f.state == YIELDED) {
+                f.state = RUNNABLE;
+                progress = true;
+            }
         for (unsigned w = 0; w < nw; ++w) {
             const unsigned l0 = w * 32, l1 = std::min(l0 + 32, c.nthreads);
             for (;;) {

@@ -37,7 +37,7 @@ static inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) {
 
 namespace emu {
 
-enum State { RUNNABLE, WAIT_WARP, WAIT_TEAM, WAIT_CTA, WAIT_NAMED, DONE };
+enum State { RUNNABLE, WAIT_WARP, WAIT_TEAM, WAIT_CTA, WAIT_NAMED, YIELDED, DONE };
 
 struct Fiber {
     void *sp = nullptr;
@@ -246,6 +246,8 @@ static inline int __syncthreads_or(int pred)
     emu::block(emu::WAIT_CTA);
     return (int)emu::g->cta_or_result;
 }
+// a lane that spins on a flag another warp will set: it gets its next turn after every other warp has had one
+static inline void emu_spin_yield() { emu::block(emu::YIELDED); }
 static inline void emu_named_barrier(unsigned nthr)
 {
     emu::g->named_need = nthr;
