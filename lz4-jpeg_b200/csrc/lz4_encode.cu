@@ -1501,10 +1501,11 @@ extern "C" int ljb_lz4_compress(ljb_ctx *ctx, const uint8_t *in, size_t n, size_
     const size_t nblocks = ljb_lz4_block_count(n, block_len);
     LJB_CUDA(cudaSetDevice(ctx->device));
     int rc;
-    // Chunk schedule: 4 x the base chunk (512 MiB) in the middle — every chunk is a kernel launch whose last wave leaves SMs
-    // idle, which at ~15 GB/s outweighs finer overlap — ramping up from 1/8 of that at the start and down to 1/8 at the end,
-    // because the first upload and the last download are the only transfers nothing hides.
-    size_t cblocks = 4 * ljb_pipe_chunk() / block_len; // blocks per full chunk
+    // Chunk schedule: 2 x the base chunk (256 MiB) in the middle — every chunk is a kernel launch whose last wave leaves SMs
+    // idle, which outweighs finer overlap — ramping up from 1/8 of that at the start and down to 1/8 at the end, because the
+    // first upload and the last download are the only transfers nothing hides.  (4 GiB at 28 GB/s of kernel: 165.8 / 159.5 /
+    // 157.8 / 159.7 / 164.1 ms with middle chunks of 1 GiB / 512 / 256 / 128 / 64 MiB.)
+    size_t cblocks = 2 * ljb_pipe_chunk() / block_len; // blocks per full chunk
     if (cblocks == 0) cblocks = 1;
     std::vector<size_t> start; // first block of every chunk, plus the end
     {
