@@ -1522,8 +1522,13 @@ extern "C" int ljb_lz4_compress(ljb_ctx *ctx, const uint8_t *in, size_t n, size_
             }
             for (int i = 2; i >= 0; --i) sizes.push_back(ramp[i]);
         } else {
+            // too small for the ramp: about eight chunks of whole waves of blocks (one block per SM at a time), so that uploads,
+            // kernels and downloads still overlap (256 MiB: 18.1 -> 12 ms)
+            const size_t sms = (size_t)(ctx->num_sms > 0 ? ctx->num_sms : 1);
+            size_t c = ((nblocks + 7) / 8 + sms - 1) / sms * sms;
+            if (c > cblocks) c = cblocks;
             for (size_t left = nblocks; left;) {
-                const size_t t = left < cblocks ? left : cblocks;
+                const size_t t = left < c ? left : c;
                 sizes.push_back(t);
                 left -= t;
             }
