@@ -174,6 +174,10 @@ extern "C" int ljb_lz4_decompress(ljb_ctx *ctx, const uint8_t *comp, size_t comp
     int rc;
     size_t cblocks = 2 * ljb_pipe_chunk() / block_len; // 256 MiB of output per chunk
     if (cblocks == 0) cblocks = 1;
+    if (nblocks < 4 * cblocks) { // a small stream: about eight chunks, so that uploads, kernels and downloads still overlap
+        const size_t c = ((nblocks + 7) / 8 + 255) / 256 * 256;
+        if (c < cblocks) cblocks = c;
+    }
     if (cblocks > nblocks) cblocks = nblocks;
     const size_t nchunks = (nblocks + cblocks - 1) / cblocks;
     size_t max_comp = 0;
