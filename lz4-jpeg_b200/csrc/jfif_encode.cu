@@ -12,24 +12,31 @@
 //                        units = 5 MCUs of 4:2:0 (4 Y + Cb + Cr) or 10 MCUs of 4:4:4; each data unit owns a 64-word block
 //                        of the warp's shared memory that holds, in turn, its pixels, its samples and its coefficients.
 //                          stage      cp.async of the round's pixels into the blocks (16 B per lane and instruction)
-//                          convert    float YCbCr in place, a rolled loop over rows (the Y lanes of 4:2:0 also write the
-//                                     2x2 chroma means into the blocks of the chroma lanes of their MCU)
-//                          transform  one data unit per lane: 64 samples to registers, AAN DCT rows/columns, quantise,
-//                                     DC difference against the neighbouring lane's DC (the data unit before the tile is
-//                                     recomputed, DC only), 64 int32 back into the block
-//                          entropy    two data units per iteration, two coefficients per lane: zero runs from ballots,
-//                                     (run, size) code + extra bits per lane, one warp scan for both units, every lane
-//                                     ORs its bits at its exact offset into the warp's bit buffer.  No divergence.
+//                          convert    float YCbCr.  4:4:4: the three lanes of an MCU read the same 64 pixels and keep one
+//                                     component each, straight in registers, through one branch-free form for the three
+//                                     components (no divergence between the lanes of an MCU).  4:2:0: in place, a rolled
+//                                     loop over rows; the Y lanes also write the 2x2 chroma means into the chroma lanes' blocks
+//                          transform  one data unit per lane: 64 samples in registers, AAN DCT rows/columns, quantise,
+//                                     DC difference against the neighbouring lane's DC
+//                          halo       before a tile: the DCs of the three data units in front of it, recomputed by the whole
+//                                     warp from the 64 pixels of the preceding MCU (shuffle trees in the DCT's own order)
+//                          entropy    every lane codes ITS data unit into a lane-private area of the blocks (the bits grow
+//                                     from word 0 over the coefficients already read), one warp scan of the bit counts, every
+//                                     lane copies its string to its bit offset of the warp's bit buffer (funnel shifts; an
+//                                     atomicOr only for the two words it shares with its neighbours)
 //                        A finished tile publishes its bit count and its last seven bits and keeps its bits in one of two
 //                        bit buffers; one tile later (every predecessor has published by then) the warp resolves the
 //                        decoupled look-back, funnel-shifts the buffer to the global bit offset and writes aligned 32-bit
 //                        words to the unstuffed stream.  The byte two tiles share is completed by the later one.
 //   jfif_stuff_kernel    persistent; 4 KiB chunks of the unstuffed stream: count 0xFF, block scan, look-back for the
 //                        output offset, expand in shared memory, coalesced copy-out; the first chunk also writes the
-//                        607-byte header (passed by value), the last one the EOI marker and the length.
+//                        607-byte header (passed by value), the last one the EOI marker and the length.  The host-buffer
+//                        entry point launches it once per band of uploaded rows, over the chunks the band's tiles completed,
+//                        and sends the finished part of the file down while later bands come up.
 //
-// Code size matters here: the B200 instruction cache holds 32 KB per SM and sixteen warps run in different phases, so
-// only the 8x8 transform is unrolled (it must be: its 64 values live in registers).
+// Code size matters here: sixteen warps per SM run in different phases, so only the 8x8 transform and the 4:4:4 conversion
+// are unrolled (they must be: their 64 values live in registers); 5 900 instructions, of which the out-of-line copies the
+// compiler makes for diverged shuffles are never fetched.
 //
 // Algorithmic bytes: comp*W*H read + N_out written; the unstuffed stream is one extra write + read of ~N_out.
 #include "common.cuh"

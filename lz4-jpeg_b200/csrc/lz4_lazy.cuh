@@ -18,8 +18,14 @@
 //            entry(s) = exit(s-1) for all s, entry(0) = 0, which is the reference's chain.
 //   Measured on the benchmark text: round 0 does 97 % of the searches, chains meet after a few steps, 2-3 rounds.
 //
-// A search is done by the warp for its 32 lanes together: teams of eight lanes take one lane's candidate list each, so the
-// lanes of a warp stay busy whatever the sizes of the 32 lists are (p50 = 3, p99 = 311 candidates on text).
+//   Rounds 0 and 1 have no CTA barrier between them (a walk needs one thing from another warp: the exit of the segment before
+//   its own); blocks of low entropy take segments of WIDE x WG bytes, because chains of long matches rarely meet inside 66 bytes.
+//
+// A search is done by the warp for its 32 lanes together, three ways by the length of the candidate list (p50 = 3, p99 = 311 on
+// text): short lists stay with their lane, lists up to 32 go to teams of eight lanes (four lists at a time), longer ones to the
+// whole warp; every tier keeps two candidates per lane in flight (probe of the first 8 bytes, extension only for pairs that
+// match them).  A bucket of more than MINFRONT entries keeps its earliest position in front: a search whose best pair reaches
+// the cap there is over.
 //
 // Capped matches.  A match of MAX_MATCH = 1024 bytes is a literal step ((uint8_t)1024 == 0, LZ4.c:317) whose distance is
 // never used, and if (c, p) match 1024 + j bytes then (c + j', p + j') match >= 1024 for j' <= j: those positions are
